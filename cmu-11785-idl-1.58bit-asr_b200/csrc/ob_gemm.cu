@@ -87,7 +87,11 @@ enum GemmMode { kFwdI8 = 0, kDxBf16 = 1 };
 
 constexpr int kBlockM = 128;
 constexpr int kATileBytes = kBlockM * 128;                 // 128 rows x one 128-byte swizzle span
-constexpr int kGemmThreads = 384;                          // 12 warps, see roles below
+constexpr int kExpandWarps = 8;
+constexpr int kExpandThreads = kExpandWarps * 32;
+constexpr int kEpiWarp0 = 4 + kExpandWarps;                // first epilogue warp (multiple of 4: TMEM lane quarters)
+constexpr int kGemmThreads = (kEpiWarp0 + 4) * 32;         // 16 warps, see roles below
+constexpr int kStageOutBytes = 32 * 128;                   // one epilogue chunk: 32 rows x 128 B
 
 template <int MODE, int BLOCK_N, int STAGES>
 struct GemmSmem {
@@ -96,68 +100,53 @@ struct GemmSmem {
   static constexpr int kBpTileBytes = BLOCK_N * kPackedRowBytes;
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kOffA + STAGES * kATileBytes;
-  static constexpr int kOffBp = kOffB + STAGES * kBTileBytes;
-  static constexpr int kOffBar = kOffBp + STAGES * kBpTileBytes;
+  static constexpr int kOffOut = kOffB + STAGES * kBTileBytes;       // 4 warps x 2 buffers x 4 KB, 1024-aligned
+  static constexpr int kOffBp = kOffOut + 8 * kStageOutBytes;
+  static constexpr int kOffBias = kOffBp + STAGES * kBpTileBytes;    // [2][BLOCK_N] floats
+  static constexpr int kOffBar = kOffBias + 2 * BLOCK_N * 4;
   static constexpr int kNumBars = 3 * STAGES + 4;
   static constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
   static constexpr int kBytes = kOffTmemSlot + 16;
   static constexpr int kDynBytes = kBytes + 1024;                    // slack for the 1024-byte alignment
 };
 
-template <typename OutT>
-__device__ __forceinline__ void store_row_chunk(OutT* dst, const float (&v)[32], int valid_cols);
-
-template <>
-__device__ __forceinline__ void store_row_chunk<float>(float* dst, const float (&v)[32], int valid_cols) {
-  if (valid_cols >= 32) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < valid_cols) dst[j] = v[j];
-  }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
-template <>
-__device__ __forceinline__ void store_row_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32],
-                                                               int valid_cols) {
-  if (valid_cols >= 32) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 o;
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-      __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-      o.x = *reinterpret_cast<uint32_t*>(&p0);
-      o.y = *reinterpret_cast<uint32_t*>(&p1);
-      o.z = *reinterpret_cast<uint32_t*>(&p2);
-      o.w = *reinterpret_cast<uint32_t*>(&p3);
-      reinterpret_cast<uint4*>(dst)[j] = o;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < valid_cols) dst[j] = __float2bfloat16_rn(v[j]);
-  }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..7 = expanders,
-// 8..11 = epilogue (warp % 4 selects the TMEM lane quarter).
-template <int MODE, int BLOCK_N, int STAGES, typename OutT>
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = expanders,
+// 12..15 = epilogue (warp % 4 selects the TMEM lane quarter).
+// OUT_BF16: output element type (0 = fp32, 1 = bf16); the epilogue moves 128 bytes of a row per chunk.
+template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bp,
-                   const float* __restrict__ row_scale, const float* __restrict__ alpha, int alpha_mode,
-                   const float* __restrict__ bias, OutT* __restrict__ out, int M, int NC, int KC) {
+                   const __grid_constant__ CUtensorMap map_out, const float* __restrict__ row_scale,
+                   const float* __restrict__ alpha, int alpha_mode, const float* __restrict__ bias, int M, int NC,
+                   int KC) {
   using L = GemmSmem<MODE, BLOCK_N, STAGES>;
   constexpr int kElemsPerKBlock = MODE == kFwdI8 ? 128 : 64;
+  constexpr int kChunkCols = OUT_BF16 ? 64 : 32;          // output columns per 128-byte chunk
   constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   constexpr uint32_t kIdesc = MODE == kFwdI8 ? make_idesc(kCFmtS32, kFmtS8, kFmtS8, 0, 0, kBlockM, BLOCK_N)
                                              : make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 0, 0, kBlockM, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the shared state space visible to the compiler: offset arithmetic on the original pointer
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* full_bar = bars;                      // TMA landed (A tile + packed B tile)
   uint64_t* bready_bar = bars + STAGES;           // expanders wrote the B tile
@@ -175,11 +164,12 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_bp);
+    tma_prefetch_desc(&map_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&bready_bar[s], 128);
+      mbar_init(&bready_bar[s], kExpandThreads);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -206,10 +196,10 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kATileBytes + L::kBpTileBytes);
-          tma_load_2d(smem + L::kOffA + stage * kATileBytes, &map_a, &full_bar[stage], kb * kElemsPerKBlock,
-                      m_blk * kBlockM);
           tma_load_2d(smem + L::kOffBp + stage * L::kBpTileBytes, &map_bp, &full_bar[stage],
                       kb * L::kPackedRowBytes, n_blk * BLOCK_N);
+          tma_load_2d(smem + L::kOffA + stage * kATileBytes, &map_a, &full_bar[stage], kb * kElemsPerKBlock,
+                      m_blk * kBlockM);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -228,8 +218,8 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           mbar_wait(&full_bar[stage], phase);
           mbar_wait(&bready_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + L::kOffA + stage * kATileBytes), 0, 1024);
-          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + L::kOffB + stage * L::kBTileBytes), 0, 1024);
+          const uint64_t a_desc = make_smem_desc_sw128(sbase + L::kOffA + stage * kATileBytes, 0, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(sbase + L::kOffB + stage * L::kBTileBytes, 0, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {        // 4 MMAs of 32 contraction bytes each; +32 B = +2 in the address field
             if (MODE == kFwdI8)
@@ -243,30 +233,44 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < kEpiWarp0) {
     // ------------------------------ expanders: packed 2-bit -> operand tile ------------------------------
+    // Thread te owns word column c of rows r0 + k*rows_per_pass: the swizzled chunk offset is loop-invariant.
     const int te = threadIdx.x - 128;
     uint32_t stage = 0, phase = 0;
+    uint32_t src_off, dst_off;
+    if (MODE == kFwdI8) {        // 8 words per row; word c -> 16-byte chunk c
+      const int r = te >> 3, c = te & 7;
+      src_off = te * 4;
+      dst_off = r * 128 + ((c ^ (r & 7)) << 4);
+    } else {                     // 4 words per row; word c -> chunks 2c, 2c+1
+      const int r = te >> 2, c = te & 3;
+      src_off = te * 4;
+      dst_off = r * 128 + (((2 * c) ^ (r & 7)) << 4);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(smem + L::kOffBp + stage * L::kBpTileBytes);
-        uint8_t* dst = smem + L::kOffB + stage * L::kBTileBytes;
+        const uint32_t src = sbase + L::kOffBp + stage * L::kBpTileBytes + src_off;
+        const uint32_t dst = sbase + L::kOffB + stage * L::kBTileBytes + dst_off;
         if (MODE == kFwdI8) {
-#pragma unroll 4
-          for (int i = te; i < BLOCK_N * 8; i += 128) {          // 8 words per row, word c -> 16-byte chunk c
-            const int row = i >> 3, c = i & 7;
-            const uint4 o = expand_word_i8(src[i]);
-            *reinterpret_cast<uint4*>(dst + row * 128 + ((c ^ (row & 7)) << 4)) = o;
-          }
+          constexpr int kIters = BLOCK_N * 8 / kExpandThreads;      // rows advance by 32 per pass
+          uint32_t w[kIters];
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) w[i] = lds32(src + i * kExpandThreads * 4);
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) sts128(dst + i * 32 * 128, expand_word_i8(w[i]));
         } else {
-#pragma unroll 4
-          for (int i = te; i < BLOCK_N * 4; i += 128) {          // 4 words per row, word c -> chunks 2c, 2c+1
-            const int row = i >> 2, c = i & 3;
+          constexpr int kIters = BLOCK_N * 4 / kExpandThreads;      // rows advance by 64 per pass
+          uint32_t w[kIters];
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) w[i] = lds32(src + i * kExpandThreads * 4);
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
             uint4 c0, c1;
-            expand_word_bf16(src[i], c0, c1);
-            *reinterpret_cast<uint4*>(dst + row * 128 + (((2 * c) ^ (row & 7)) << 4)) = c0;
-            *reinterpret_cast<uint4*>(dst + row * 128 + (((2 * c + 1) ^ (row & 7)) << 4)) = c1;
+            expand_word_bf16(w[i], c0, c1);
+            sts128(dst + i * 64 * 128, c0);
+            sts128((dst + i * 64 * 128) ^ 16u, c1);
           }
         }
         fence_proxy_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -274,10 +278,15 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 8) {
-    // ------------------------------ epilogue: TMEM -> registers -> global ------------------------------
-    const int e = warp - 8;
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------ epilogue: TMEM -> registers -> swizzled smem -> TMA store ------------------
+    const int e = warp - kEpiWarp0;
+    const int et = threadIdx.x - kEpiWarp0 * 32;            // 0..127
     const float a_eff = load_alpha_eff(alpha, alpha_mode);
+    const uint32_t out_buf = sbase + L::kOffOut + e * 2 * kStageOutBytes;
+    const uint32_t out_row = lane * 128;
+    const uint32_t swz = (lane & 7) << 4;
+    uint32_t buf = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
@@ -288,35 +297,92 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const float s = __ldg(row_scale + row);
         factor = MODE == kFwdI8 ? __fdiv_rn(a_eff, s) : a_eff * s;
       }
+      // bias slice of this tile -> smem (double-buffered by accumulator stage; the named barrier below orders it)
+      float* bias_s = reinterpret_cast<float*>(smem + L::kOffBias) + as * BLOCK_N;
+      for (int j = et; j < BLOCK_N; j += 128) {
+        const int col = n_blk * BLOCK_N + j;
+        bias_s[j] = (bias != nullptr && col < NC) ? __ldg(bias + col) : 0.f;
+      }
+      named_bar_sync(1, 128);
+      const uint32_t bias_addr = sbase + L::kOffBias + as * BLOCK_N * 4;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + as * BLOCK_N + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        const int valid = NC - col0;
-        if (row < M && valid > 0) {
-          float v[32];
+      for (int c = 0; c < BLOCK_N / kChunkCols; ++c) {
+        const int col0 = n_blk * BLOCK_N + c * kChunkCols;
+        if (col0 >= NC) break;                               // warp-uniform
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(e * 32) << 16) + as * BLOCK_N + c * kChunkCols;
+        // the staging buffer we are about to overwrite must have been read by its TMA store
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const uint32_t obuf = out_buf + buf * kStageOutBytes + out_row;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float acc = MODE == kFwdI8 ? __int2float_rn(static_cast<int>(r[j])) : __uint_as_float(r[j]);
-            const float b = (bias != nullptr && j < valid) ? __ldg(bias + col0 + j) : 0.f;
-            v[j] = fmaf(acc, factor, b);
+        for (int h = 0; h < (OUT_BF16 ? 2 : 1); ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + h * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = lds128f(bias_addr + (c * kChunkCols + h * 32 + j4 * 4) * 4);
+            float v0, v1, v2, v3;
+            if (MODE == kFwdI8) {
+              v0 = fmaf(__int2float_rn(static_cast<int>(r[4 * j4 + 0])), factor, b.x);
+              v1 = fmaf(__int2float_rn(static_cast<int>(r[4 * j4 + 1])), factor, b.y);
+              v2 = fmaf(__int2float_rn(static_cast<int>(r[4 * j4 + 2])), factor, b.z);
+              v3 = fmaf(__int2float_rn(static_cast<int>(r[4 * j4 + 3])), factor, b.w);
+            } else {
+              v0 = fmaf(__uint_as_float(r[4 * j4 + 0]), factor, b.x);
+              v1 = fmaf(__uint_as_float(r[4 * j4 + 1]), factor, b.y);
+              v2 = fmaf(__uint_as_float(r[4 * j4 + 2]), factor, b.z);
+              v3 = fmaf(__uint_as_float(r[4 * j4 + 3]), factor, b.w);
+            }
+            if (OUT_BF16) {
+              // two float4 groups make one 16-byte chunk of 8 bf16: stash the even group, emit on the odd one
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
+              r[4 * j4 + 0] = *reinterpret_cast<uint32_t*>(&p0);
+              r[4 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p1);
+              if (j4 & 1) {
+                const int chunk = h * 4 + (j4 >> 1);
+                sts128(obuf + ((chunk << 4) ^ swz),
+                       make_uint4(r[4 * (j4 - 1) + 0], r[4 * (j4 - 1) + 1], r[4 * j4 + 0], r[4 * j4 + 1]));
+              }
+            } else {
+              sts128(obuf + ((j4 << 4) ^ swz), make_uint4(__float_as_uint(v0), __float_as_uint(v1),
+                                                          __float_as_uint(v2), __float_as_uint(v3)));
+            }
           }
-          store_row_chunk<OutT>(out + static_cast<int64_t>(row) * NC + col0, v, valid);
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_out, smem + L::kOffOut + (e * 2 + buf) * kStageOutBytes, col0,
+                       m_blk * kBlockM + e * 32);
+          tma_store_commit();
+        }
+        buf ^= 1;
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[as]);
     }
+    if (lane == 0) tma_store_wait_all<0>();                  // global writes complete before the CTA retires
   }
 
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+__device__ __forceinline__ void store_row_chunk_f32(float* dst, const float (&v)[32], int valid_cols) {
+  if (valid_cols >= 32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid_cols) dst[j] = v[j];
   }
 }
 
@@ -350,7 +416,7 @@ dw_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ C
   constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 1, 1, 128, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* done_bar = full_bar + 2 * STAGES;
@@ -435,7 +501,7 @@ dw_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ C
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        store_row_chunk<float>(dst_row + col0, v, K - col0);
+        store_row_chunk_f32(dst_row + col0, v, K - col0);
       }
     }
     tc_fence_before();
@@ -453,24 +519,30 @@ dw_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------
 static int pick_block_n(int M, int NC) {
   if (g_dbg_force_block_n == 64 || g_dbg_force_block_n == 128 || g_dbg_force_block_n == 256) return g_dbg_force_block_n;
+  // widest tile whose tile count fills the persistent grid evenly (wave efficiency >= 0.9), else the most even one
   const int m_blocks = (M + kBlockM - 1) / kBlockM;
-  const int want = 2 * sm_count();
   const int cands[3] = {256, 128, 64};
+  int best = 64;
+  double best_eff = -1.0;
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (bn > 64 && NC <= bn / 2) continue;                 // do not pad a narrow output to a wide tile
-    if (m_blocks * ((NC + bn - 1) / bn) >= want || bn == 64) return bn;
+    const int tiles = m_blocks * ((NC + bn - 1) / bn);
+    const int waves = (tiles + sm_count() - 1) / sm_count();
+    const double eff = static_cast<double>(tiles) / (static_cast<double>(waves) * sm_count());
+    if (eff >= 0.9) return bn;
+    if (eff > best_eff + 0.05) { best_eff = eff; best = bn; }
   }
-  return 64;
+  return best;
 }
 
-template <int MODE, int BLOCK_N, int STAGES, typename OutT>
-static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_bp, const float* row_scale,
-                              const float* alpha, int alpha_mode, const float* bias, OutT* out, int M, int NC, int KC,
-                              cudaStream_t st) {
+template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16>
+static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_bp, const CUtensorMap& map_out,
+                              const float* row_scale, const float* alpha, int alpha_mode, const float* bias, int M,
+                              int NC, int KC, cudaStream_t st) {
   using L = GemmSmem<MODE, BLOCK_N, STAGES>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OutT>;
+  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OUT_BF16>;
   static bool attr_set = false;
   if (!attr_set) {
     OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
@@ -478,16 +550,16 @@ static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_b
   }
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((NC + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kGemmThreads, L::kDynBytes, st>>>(map_a, map_bp, row_scale, alpha, alpha_mode, bias, out, M, NC, KC);
+  kern<<<grid, kGemmThreads, L::kDynBytes, st>>>(map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC);
   OB_LAUNCH_CHECK("gemm_expand_kernel");
   return OB_OK;
 }
 
-template <int MODE, typename OutT>
+template <int MODE, int OUT_BF16>
 static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const float* row_scale, const float* alpha,
-                                int alpha_mode, const float* bias, OutT* out, int M, int NC, int KC, cudaStream_t st) {
+                                int alpha_mode, const float* bias, void* out, int M, int NC, int KC, cudaStream_t st) {
   const int bn = pick_block_n(M, NC);
-  CUtensorMap map_a, map_bp;
+  CUtensorMap map_a, map_bp, map_out;
   int rc;
   if (MODE == kFwdI8) {
     rc = make_map(&map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, KC, M, (uint64_t)KC, 128, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -502,10 +574,16 @@ static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const floa
                   CU_TENSOR_MAP_SWIZZLE_NONE);
   }
   if (rc != OB_OK) return rc;
+  // output: 32-row x 128-byte boxes written by the epilogue warps (TMA clips the M and N tails)
+  if (OUT_BF16)
+    rc = make_map(&map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out, NC, M, (uint64_t)NC * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    rc = make_map(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, NC, M, (uint64_t)NC * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != OB_OK) return rc;
   switch (bn) {
-    case 256: return launch_gemm_expand<MODE, 256, 4, OutT>(map_a, map_bp, row_scale, alpha, alpha_mode, bias, out, M, NC, KC, st);
-    case 128: return launch_gemm_expand<MODE, 128, 5, OutT>(map_a, map_bp, row_scale, alpha, alpha_mode, bias, out, M, NC, KC, st);
-    default:  return launch_gemm_expand<MODE, 64, 6, OutT>(map_a, map_bp, row_scale, alpha, alpha_mode, bias, out, M, NC, KC, st);
+    case 256: return launch_gemm_expand<MODE, 256, 3, OUT_BF16>(map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st);
+    case 128: return launch_gemm_expand<MODE, 128, 5, OUT_BF16>(map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st);
+    default:  return launch_gemm_expand<MODE, 64, 6, OUT_BF16>(map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st);
   }
 }
 
@@ -578,10 +656,9 @@ extern "C" int ob_gemm_tern_i8_fwd(const int8_t* q, const float* scale, const ui
   if (rc != OB_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (y_dtype == OB_F32)
-    return dispatch_gemm_expand<kFwdI8, float>(q, packed_i8, scale, alpha, alpha_mode, bias, static_cast<float*>(y), M, N, K, st);
+    return dispatch_gemm_expand<kFwdI8, 0>(q, packed_i8, scale, alpha, alpha_mode, bias, y, M, N, K, st);
   if (y_dtype == OB_BF16)
-    return dispatch_gemm_expand<kFwdI8, __nv_bfloat16>(q, packed_i8, scale, alpha, alpha_mode, bias,
-                                                       static_cast<__nv_bfloat16*>(y), M, N, K, st);
+    return dispatch_gemm_expand<kFwdI8, 1>(q, packed_i8, scale, alpha, alpha_mode, bias, y, M, N, K, st);
   OB_REQUIRE(false, "ob_gemm_tern_i8_fwd: unknown dtype tag %d", y_dtype);
 }
 
@@ -596,11 +673,9 @@ extern "C" int ob_bwd_dx(const void* dys_bf16, const float* scale, const uint8_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // contraction runs over the layer's N; the output has K columns
   if (dx_dtype == OB_F32)
-    return dispatch_gemm_expand<kDxBf16, float>(dys_bf16, packed_t, scale, alpha, alpha_mode, nullptr,
-                                                static_cast<float*>(dx), M, K, N, st);
+    return dispatch_gemm_expand<kDxBf16, 0>(dys_bf16, packed_t, scale, alpha, alpha_mode, nullptr, dx, M, K, N, st);
   if (dx_dtype == OB_BF16)
-    return dispatch_gemm_expand<kDxBf16, __nv_bfloat16>(dys_bf16, packed_t, scale, alpha, alpha_mode, nullptr,
-                                                        static_cast<__nv_bfloat16*>(dx), M, K, N, st);
+    return dispatch_gemm_expand<kDxBf16, 1>(dys_bf16, packed_t, scale, alpha, alpha_mode, nullptr, dx, M, K, N, st);
   OB_REQUIRE(false, "ob_bwd_dx: unknown dtype tag %d", dx_dtype);
 }
 

@@ -154,8 +154,9 @@ def test_layer_against_reference_fixture(ob, kat_layer, bw):
     assert np.array_equal(gw != 0, k[f"{tag}_gW"] != 0)                     # STE mask bit-exact
     assert rel_err(layer.bias.grad.cpu().numpy(), k[f"{tag}_gb"]) < 1e-4
     assert math.isclose(layer.alpha.grad.item(), float(k[f"{tag}_galpha"]), rel_tol=1e-2)
-    # against the PURE reference (fp32 activations, Oracle-A) only the int8 rounding separates us
-    assert rel_err(y.detach().cpu().numpy(), k[f"bw{bw}_A_y"]) < 3e-2
+    # against the PURE reference (fp32 activations, Oracle-A) only the int8 activation rounding separates us
+    # (the fixture holds an outlier token whose absmax step is 40/127, hence the loose bound)
+    assert rel_err(y.detach().cpu().numpy(), k[f"bw{bw}_A_y"]) < 6e-2
 
 
 def test_layer_fp32_bypass_matches_reference(ob, kat_layer):
