@@ -85,7 +85,7 @@ static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, 
 // ---------------------------------------------------------------------------------------------
 enum GemmMode { kFwdI8 = 0, kDxBf16 = 1 };
 
-constexpr int kBlockM = 128;
+constexpr int kBlockM = 128;                               // rows per CTA (UMMA M = 128 x CTAS)
 constexpr int kATileBytes = kBlockM * 128;                 // 128 rows x one 128-byte swizzle span
 constexpr int kExpandWarps = 8;
 constexpr int kExpandThreads = kExpandWarps * 32;
@@ -93,18 +93,22 @@ constexpr int kEpiWarp0 = 4 + kExpandWarps;                // first epilogue war
 constexpr int kGemmThreads = (kEpiWarp0 + 4) * 32;         // 16 warps, see roles below
 constexpr int kStageOutBytes = 32 * 128;                   // one epilogue chunk: 32 rows x 128 B
 
-template <int MODE, int BLOCK_N, int STAGES>
+// CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a [256 x BLOCK_N] tile; each CTA loads its own 128
+// rows of A and expands its own half (BLOCK_N/2 rows) of B, so the expansion work and the shared-memory operand
+// traffic per MMA are halved.
+template <int MODE, int BLOCK_N, int STAGES, int CTAS>
 struct GemmSmem {
   static constexpr int kPackedRowBytes = MODE == kFwdI8 ? 32 : 16;   // 128 int8 / 64 bf16 codes per k-block
-  static constexpr int kBTileBytes = BLOCK_N * 128;
-  static constexpr int kBpTileBytes = BLOCK_N * kPackedRowBytes;
+  static constexpr int kRowsB = BLOCK_N / CTAS;                      // B rows expanded by this CTA
+  static constexpr int kBTileBytes = kRowsB * 128;
+  static constexpr int kBpTileBytes = kRowsB * kPackedRowBytes;
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kOffA + STAGES * kATileBytes;
   static constexpr int kOffOut = kOffB + STAGES * kBTileBytes;       // 4 warps x 2 buffers x 4 KB, 1024-aligned
   static constexpr int kOffBp = kOffOut + 8 * kStageOutBytes;
   static constexpr int kOffBias = kOffBp + STAGES * kBpTileBytes;    // [2][BLOCK_N] floats
   static constexpr int kOffBar = kOffBias + 2 * BLOCK_N * 4;
-  static constexpr int kNumBars = 3 * STAGES + 4;
+  static constexpr int kNumBars = 4 * STAGES + 4;
   static constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
   static constexpr int kBytes = kOffTmemSlot + 16;
   static constexpr int kDynBytes = kBytes + 1024;                    // slack for the 1024-byte alignment
@@ -127,39 +131,43 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = expanders,
-// 12..15 = epilogue (warp % 4 selects the TMEM lane quarter).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator, 3 = idle,
+// 4..11 = expanders, 12..15 = epilogue (warp % 4 selects the TMEM lane quarter).
 // OUT_BF16: output element type (0 = fp32, 1 = bf16); the epilogue moves 128 bytes of a row per chunk.
-template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16>
+template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bp,
                    const __grid_constant__ CUtensorMap map_out, const float* __restrict__ row_scale,
                    const float* __restrict__ alpha, int alpha_mode, const float* __restrict__ bias, int M, int NC,
                    int KC) {
-  using L = GemmSmem<MODE, BLOCK_N, STAGES>;
+  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS>;
   constexpr int kElemsPerKBlock = MODE == kFwdI8 ? 128 : 64;
   constexpr int kChunkCols = OUT_BF16 ? 64 : 32;          // output columns per 128-byte chunk
+  constexpr int kTileM = kBlockM * CTAS;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  constexpr uint32_t kIdesc = MODE == kFwdI8 ? make_idesc(kCFmtS32, kFmtS8, kFmtS8, 0, 0, kBlockM, BLOCK_N)
-                                             : make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 0, 0, kBlockM, BLOCK_N);
+  constexpr uint32_t kIdesc = MODE == kFwdI8 ? make_idesc(kCFmtS32, kFmtS8, kFmtS8, 0, 0, kTileM, BLOCK_N)
+                                             : make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 0, 0, kTileM, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   // keep the shared state space visible to the compiler: offset arithmetic on the original pointer
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-  uint64_t* full_bar = bars;                      // TMA landed (A tile + packed B tile)
-  uint64_t* bready_bar = bars + STAGES;           // expanders wrote the B tile
-  uint64_t* empty_bar = bars + 2 * STAGES;        // MMAs that read the stage retired
-  uint64_t* tmem_full_bar = bars + 3 * STAGES;    // [2] accumulator ready for the epilogue
-  uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;
+  uint64_t* a_full_bar = bars;                    // A tiles landed (pair mode: both CTAs' tiles, leader's barrier)
+  uint64_t* bp_full_bar = bars + STAGES;          // this CTA's packed B tile landed
+  uint64_t* bready_bar = bars + 2 * STAGES;       // expanders wrote the B tile (pair mode: both CTAs', leader's barrier)
+  uint64_t* empty_bar = bars + 3 * STAGES;        // MMAs that read the stage retired
+  uint64_t* tmem_full_bar = bars + 4 * STAGES;    // [2] accumulator ready for the epilogue
+  uint64_t* tmem_empty_bar = bars + 4 * STAGES + 2;   // [2] epilogue drained the accumulator (leader's barrier)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blocks = (M + kBlockM - 1) / kBlockM;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int m_tiles = (M + kTileM - 1) / kTileM;
   const int n_blocks = (NC + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = m_blocks * n_blocks;
+  const int num_tiles = m_tiles * n_blocks;
   const int num_kb = (KC + kElemsPerKBlock - 1) / kElemsPerKBlock;
+  const int first_tile = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -168,22 +176,23 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&bready_bar[s], kExpandThreads);
+      mbar_init(&a_full_bar[s], 1);
+      mbar_init(&bp_full_bar[s], 1);
+      mbar_init(&bready_bar[s], kExpandWarps * CTAS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], 4 * CTAS);
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(tmem_slot, kTmemCols); tmem_relinquish_pair(); }
+    else           { tmem_alloc(tmem_slot, kTmemCols);      tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -191,44 +200,61 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        const int a_row = m_blk * kTileM + rank * kBlockM;
+        const int b_row = n_blk * BLOCK_N + rank * L::kRowsB;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kATileBytes + L::kBpTileBytes);
-          tma_load_2d(smem + L::kOffBp + stage * L::kBpTileBytes, &map_bp, &full_bar[stage],
-                      kb * L::kPackedRowBytes, n_blk * BLOCK_N);
-          tma_load_2d(smem + L::kOffA + stage * kATileBytes, &map_a, &full_bar[stage], kb * kElemsPerKBlock,
-                      m_blk * kBlockM);
+          mbar_expect_tx(&bp_full_bar[stage], L::kBpTileBytes);
+          tma_load_2d(smem + L::kOffBp + stage * L::kBpTileBytes, &map_bp, &bp_full_bar[stage],
+                      kb * L::kPackedRowBytes, b_row);
+          if (CTAS == 2) {
+            if (rank == 0) mbar_expect_tx(&a_full_bar[stage], 2 * kATileBytes);
+            tma_load_2d_pair(smem + L::kOffA + stage * kATileBytes, &map_a, mapa_u32(smem_u32(&a_full_bar[stage]), 0),
+                             kb * kElemsPerKBlock, a_row);
+          } else {
+            mbar_expect_tx(&a_full_bar[stage], kATileBytes);
+            tma_load_2d(smem + L::kOffA + stage * kATileBytes, &map_a, &a_full_bar[stage], kb * kElemsPerKBlock, a_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (one thread) ------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (one thread of the leader CTA) ------------------------------
+    if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        if (CTAS == 2) mbar_wait_cluster(&tmem_empty_bar[as], aphase ^ 1); else mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          mbar_wait(&bready_bar[stage], phase);
+          mbar_wait(&a_full_bar[stage], phase);
+          if (CTAS == 2) mbar_wait_cluster(&bready_bar[stage], phase); else mbar_wait(&bready_bar[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc_sw128(sbase + L::kOffA + stage * kATileBytes, 0, 1024);
           const uint64_t b_desc = make_smem_desc_sw128(sbase + L::kOffB + stage * L::kBTileBytes, 0, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {        // 4 MMAs of 32 contraction bytes each; +32 B = +2 in the address field
-            if (MODE == kFwdI8)
-              umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb | k) != 0);
-            else
-              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb | k) != 0);
+            const uint32_t acc = (kb | k) != 0;
+            if (MODE == kFwdI8) {
+              if (CTAS == 2) umma_i8_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, acc);
+              else           umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, acc);
+            } else {
+              if (CTAS == 2) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, acc);
+              else           umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, acc);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+          if (CTAS == 2) {
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -238,43 +264,52 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // Thread te owns word column c of rows r0 + k*rows_per_pass: the swizzled chunk offset is loop-invariant.
     const int te = threadIdx.x - 128;
     uint32_t stage = 0, phase = 0;
-    uint32_t src_off, dst_off;
+    uint32_t dst_off;
     if (MODE == kFwdI8) {        // 8 words per row; word c -> 16-byte chunk c
       const int r = te >> 3, c = te & 7;
-      src_off = te * 4;
       dst_off = r * 128 + ((c ^ (r & 7)) << 4);
     } else {                     // 4 words per row; word c -> chunks 2c, 2c+1
       const int r = te >> 2, c = te & 3;
-      src_off = te * 4;
       dst_off = r * 128 + (((2 * c) ^ (r & 7)) << 4);
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t bready_addr0 = CTAS == 2 ? mapa_u32(smem_u32(&bready_bar[0]), 0) : smem_u32(&bready_bar[0]);
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        const uint32_t src = sbase + L::kOffBp + stage * L::kBpTileBytes + src_off;
+        mbar_wait(&bp_full_bar[stage], phase);
+        const uint32_t src = sbase + L::kOffBp + stage * L::kBpTileBytes + te * 4;
         const uint32_t dst = sbase + L::kOffB + stage * L::kBTileBytes + dst_off;
         if (MODE == kFwdI8) {
-          constexpr int kIters = BLOCK_N * 8 / kExpandThreads;      // rows advance by 32 per pass
+          constexpr int kWords = L::kRowsB * 8;                     // rows advance by 32 per pass
+          constexpr int kIters = (kWords + kExpandThreads - 1) / kExpandThreads;
           uint32_t w[kIters];
 #pragma unroll
-          for (int i = 0; i < kIters; ++i) w[i] = lds32(src + i * kExpandThreads * 4);
+          for (int i = 0; i < kIters; ++i)
+            if (kWords % kExpandThreads == 0 || te + i * kExpandThreads < kWords) w[i] = lds32(src + i * kExpandThreads * 4);
 #pragma unroll
-          for (int i = 0; i < kIters; ++i) sts128(dst + i * 32 * 128, expand_word_i8(w[i]));
+          for (int i = 0; i < kIters; ++i)
+            if (kWords % kExpandThreads == 0 || te + i * kExpandThreads < kWords)
+              sts128(dst + i * 32 * 128, expand_word_i8(w[i]));
         } else {
-          constexpr int kIters = BLOCK_N * 4 / kExpandThreads;      // rows advance by 64 per pass
+          constexpr int kWords = L::kRowsB * 4;                     // rows advance by 64 per pass
+          constexpr int kIters = (kWords + kExpandThreads - 1) / kExpandThreads;
           uint32_t w[kIters];
 #pragma unroll
-          for (int i = 0; i < kIters; ++i) w[i] = lds32(src + i * kExpandThreads * 4);
+          for (int i = 0; i < kIters; ++i)
+            if (kWords % kExpandThreads == 0 || te + i * kExpandThreads < kWords) w[i] = lds32(src + i * kExpandThreads * 4);
 #pragma unroll
-          for (int i = 0; i < kIters; ++i) {
-            uint4 c0, c1;
-            expand_word_bf16(w[i], c0, c1);
-            sts128(dst + i * 64 * 128, c0);
-            sts128((dst + i * 64 * 128) ^ 16u, c1);
-          }
+          for (int i = 0; i < kIters; ++i)
+            if (kWords % kExpandThreads == 0 || te + i * kExpandThreads < kWords) {
+              uint4 c0, c1;
+              expand_word_bf16(w[i], c0, c1);
+              sts128(dst + i * 64 * 128, c0);
+              sts128((dst + i * 64 * 128) ^ 16u, c1);
+            }
         }
         fence_proxy_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&bready_bar[stage]);
+        __syncwarp();
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_cluster(bready_addr0 + stage * 8); else mbar_arrive(&bready_bar[stage]);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -286,12 +321,14 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t out_buf = sbase + L::kOffOut + e * 2 * kStageOutBytes;
     const uint32_t out_row = lane * 128;
     const uint32_t swz = (lane & 7) << 4;
+    const uint32_t tmem_empty_addr0 = CTAS == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
     uint32_t buf = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      const int row = m_blk * kBlockM + e * 32 + lane;
+      const int row0 = m_blk * kTileM + rank * kBlockM + e * 32;
+      const int row = row0 + lane;
       float factor = 0.f;
       if (row < M) {
         const float s = __ldg(row_scale + row);
@@ -355,22 +392,25 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&map_out, smem + L::kOffOut + (e * 2 + buf) * kStageOutBytes, col0,
-                       m_blk * kBlockM + e * 32);
+          tma_store_2d(&map_out, smem + L::kOffOut + (e * 2 + buf) * kStageOutBytes, col0, row0);
           tma_store_commit();
         }
         buf ^= 1;
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[as]);
+      __syncwarp();
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(tmem_empty_addr0 + as * 8); else mbar_arrive(&tmem_empty_bar[as]);
+      }
     }
     if (lane == 0) tma_store_wait_all<0>();                  // global writes complete before the CTA retires
   }
 
-  __syncthreads();
+  tc_fence_before();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -517,60 +557,86 @@ dw_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
-static int pick_block_n(int M, int NC) {
-  if (g_dbg_force_block_n == 64 || g_dbg_force_block_n == 128 || g_dbg_force_block_n == 256) return g_dbg_force_block_n;
-  // widest tile whose tile count fills the persistent grid evenly (wave efficiency >= 0.9), else the most even one
-  const int m_blocks = (M + kBlockM - 1) / kBlockM;
-  const int cands[3] = {256, 128, 64};
-  int best = 64;
-  double best_eff = -1.0;
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (bn > 64 && NC <= bn / 2) continue;                 // do not pad a narrow output to a wide tile
-    const int tiles = m_blocks * ((NC + bn - 1) / bn);
-    const int waves = (tiles + sm_count() - 1) / sm_count();
-    const double eff = static_cast<double>(tiles) / (static_cast<double>(waves) * sm_count());
-    if (eff >= 0.9) return bn;
-    if (eff > best_eff + 0.05) { best_eff = eff; best = bn; }
+struct GemmCfg { int ctas, block_n; };
+
+// Candidate tilings, widest first.  The CTA-pair kernel (cta_group::2, [256 x BLOCK_N] tiles) halves the per-CTA
+// expansion work and operand traffic; the single-CTA tilings fill the machine on small problems.
+static GemmCfg pick_gemm_cfg(int M, int NC) {
+  static const GemmCfg cands[5] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}, {1, 64}};
+  if (g_dbg_force_block_n > 0) {
+    GemmCfg c = {g_dbg_force_block_n >= 1000 ? 2 : 1, g_dbg_force_block_n % 1000};
+    if (c.block_n == 64 || c.block_n == 128 || c.block_n == 256) {
+      if (c.ctas == 2 && c.block_n == 64) c.ctas = 1;
+      return c;
+    }
+  }
+  // cost model: waves x (columns per tile) / relative tensor throughput of the tiling (measured at K = 2048);
+  // every tiling gives a CTA 128 rows, so the per-wave cost is proportional to BLOCK_N.
+  static const double kRelTput[5] = {1.0, 0.65, 0.85, 0.55, 0.30};
+  GemmCfg best = {1, 64};
+  double best_cost = 1e30;
+  for (int i = 0; i < 5; ++i) {
+    const GemmCfg c = cands[i];
+    if (c.block_n > 64 && NC <= c.block_n / 2) continue;             // do not pad a narrow output to a wide tile
+    const int tile_m = kBlockM * c.ctas;
+    const int units = sm_count() / c.ctas;                           // concurrently running tiles
+    const int tiles = ((M + tile_m - 1) / tile_m) * ((NC + c.block_n - 1) / c.block_n);
+    const int waves = (tiles + units - 1) / units;
+    const double cost = static_cast<double>(waves) * c.block_n / kRelTput[i];
+    if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
 }
 
-template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16>
+template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS>
 static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_bp, const CUtensorMap& map_out,
                               const float* row_scale, const float* alpha, int alpha_mode, const float* bias, int M,
                               int NC, int KC, cudaStream_t st) {
-  using L = GemmSmem<MODE, BLOCK_N, STAGES>;
+  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OUT_BF16>;
+  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OUT_BF16, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
     attr_set = true;
   }
-  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((NC + BLOCK_N - 1) / BLOCK_N);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kGemmThreads, L::kDynBytes, st>>>(map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC);
-  OB_LAUNCH_CHECK("gemm_expand_kernel");
+  const int tile_m = kBlockM * CTAS;
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((NC + BLOCK_N - 1) / BLOCK_N);
+  const int units = sm_count() / CTAS;
+  const int grid = (tiles < units ? tiles : units) * CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = L::kDynBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC));
   return OB_OK;
 }
 
 template <int MODE, int OUT_BF16>
 static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const float* row_scale, const float* alpha,
                                 int alpha_mode, const float* bias, void* out, int M, int NC, int KC, cudaStream_t st) {
-  const int bn = pick_block_n(M, NC);
+  const GemmCfg cfg = pick_gemm_cfg(M, NC);
+  const int bn = cfg.block_n;
   CUtensorMap map_a, map_bp, map_out;
   int rc;
   if (MODE == kFwdI8) {
     rc = make_map(&map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, KC, M, (uint64_t)KC, 128, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != OB_OK) return rc;
-    rc = make_map(&map_bp, CU_TENSOR_MAP_DATA_TYPE_UINT8, packed, KC / 4, NC, (uint64_t)KC / 4, 32, bn,
+    rc = make_map(&map_bp, CU_TENSOR_MAP_DATA_TYPE_UINT8, packed, KC / 4, NC, (uint64_t)KC / 4, 32, bn / cfg.ctas,
                   CU_TENSOR_MAP_SWIZZLE_NONE);
   } else {
     rc = make_map(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a, KC, M, (uint64_t)KC * 2, 64, kBlockM,
                   CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != OB_OK) return rc;
-    rc = make_map(&map_bp, CU_TENSOR_MAP_DATA_TYPE_UINT8, packed, KC / 4, NC, (uint64_t)KC / 4, 16, bn,
+    rc = make_map(&map_bp, CU_TENSOR_MAP_DATA_TYPE_UINT8, packed, KC / 4, NC, (uint64_t)KC / 4, 16, bn / cfg.ctas,
                   CU_TENSOR_MAP_SWIZZLE_NONE);
   }
   if (rc != OB_OK) return rc;
@@ -580,11 +646,17 @@ static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const floa
   else
     rc = make_map(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, NC, M, (uint64_t)NC * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != OB_OK) return rc;
-  switch (bn) {
-    case 256: return launch_gemm_expand<MODE, 256, 3, OUT_BF16>(map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st);
-    case 128: return launch_gemm_expand<MODE, 128, 5, OUT_BF16>(map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st);
-    default:  return launch_gemm_expand<MODE, 64, 6, OUT_BF16>(map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st);
+#define OB_GEMM_ARGS map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st
+  if (cfg.ctas == 2) {
+    if (bn == 256) return launch_gemm_expand<MODE, 256, 5, OUT_BF16, 2>(OB_GEMM_ARGS);
+    return launch_gemm_expand<MODE, 128, 6, OUT_BF16, 2>(OB_GEMM_ARGS);
   }
+  switch (bn) {
+    case 256: return launch_gemm_expand<MODE, 256, 3, OUT_BF16, 1>(OB_GEMM_ARGS);
+    case 128: return launch_gemm_expand<MODE, 128, 5, OUT_BF16, 1>(OB_GEMM_ARGS);
+    default:  return launch_gemm_expand<MODE, 64, 6, OUT_BF16, 1>(OB_GEMM_ARGS);
+  }
+#undef OB_GEMM_ARGS
 }
 
 struct DwPlan {

@@ -105,7 +105,7 @@ def test_act_quant_golden(ob, kat_layer, kat_layer_stats):
 # ------------------------------------------------------------------ forward GEMM
 @pytest.mark.parametrize("M,N,K", [(1, 64, 64), (128, 256, 256), (300, 256, 256), (996, 1024, 256),
                                    (996, 256, 1024), (2500, 512, 2048), (777, 192, 320)])
-@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+@pytest.mark.parametrize("block_n", [0, 64, 128, 256, 1128, 1256])   # 1xxx = CTA-pair kernel
 def test_forward_gemm_exact_integer_dot(ob, M, N, K, block_n):
     """The int8 x ternary contraction is exact: compare against an integer matmul, tight tolerance."""
     from onebit_b200 import _cabi, quant as obq

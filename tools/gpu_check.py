@@ -99,7 +99,7 @@ def case_fwd():
     shapes = [(128, 64, 128), (128, 256, 256), (300, 256, 256), (996, 1024, 256), (996, 256, 1024), (2048, 512, 512),
               (4096, 2048, 2048), (777, 192, 320)]
     for (M, N, K) in shapes:
-        for bn in (0, 64, 128, 256):
+        for bn in (0, 64, 128, 256, 1128, 1256):
             _cabi.lib.ob_debug_set(_cabi.DBG_FORCE_BLOCK_N, bn)
             g = torch.Generator().manual_seed(M + N + K)
             q = torch.randint(-127, 128, (M, K), generator=g, dtype=torch.int8).to(dev)
@@ -135,7 +135,7 @@ def case_dx():
     ok = True
     for (M, N, K) in [(128, 64, 64), (128, 256, 256), (300, 256, 256), (996, 1024, 256), (996, 256, 1024),
                       (2048, 512, 512), (777, 192, 320)]:
-        for bn in (0, 64, 128, 256):
+        for bn in (0, 64, 128, 256, 1128, 1256):
             lib.ob_debug_set(_cabi.DBG_FORCE_BLOCK_N, bn)
             g = torch.Generator().manual_seed(M + N + K + 1)
             dys = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev)
@@ -219,7 +219,7 @@ def main():
     for c in CASES:
         t0 = time.time()
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), c], timeout=300)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), c], timeout=240)
             summary[c] = "PASS" if r.returncode == 0 else f"FAIL(rc={r.returncode})"
         except subprocess.TimeoutExpired:
             summary[c] = "TIMEOUT"

@@ -100,6 +100,6 @@ if __name__ == "__main__":
     model = [(25536, 256, 256), (25536, 256, 1024), (25536, 1024, 256), (399, 256, 256)]
     big = [(65536, 2048, 2048), (65536, 1024, 1024), (65536, 256, 256), (4096, 2048, 2048)]
     if what in ("fwd", "all"):
-        fwd(big + model, bns=(0, 128, 256) if what == "fwd" else (0,))
+        fwd(big + model, bns=(0, 256, 1256, 1128) if what == "fwd" else (0,))
     if what in ("bwd", "all"):
         bwd(model + [(65536, 2048, 2048)])
