@@ -1,17 +1,21 @@
 #!/usr/bin/env python
-"""bench.py - the measurement contract (see DESIGN.md, "Measurement").
+"""bench.py - the measurement contract (DESIGN.md, "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gemm|layer] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|gemm] [--impl ours|reference]
 
-One "step" is one pass of the hot path over one batch of synthetic input.  Workloads:
+Workloads (one "step" = one pass of the hot path over one batch of synthetic input):
 
-  gemm   BASELINE.json configs[1]: the BitLinear forward at M = 65536 tokens, K = N = 2048, bitwidth 2
-         (act-quant + ternary x int8 tcgen05 GEMM, bf16 output).  metric = BitLinear int8 TOPS.
-  layer  the same layer forward+backward (adds bwd_prep, grad_x, grad_W + fused STE); metric = TFLOP/s-equivalent.
+  train  (default) BASELINE.json configs[2]/[3]: the Conformer co-training step of the reference
+         (onebit_asr/train.py:83-120: 2-bit + 1-bit + stochastic-precision passes, CTC + attention + KL losses,
+         one backward, clip, AdamW) with every routed projection on the B200 layer; batch 64 x 1600 frames x 80 mel
+         PER GPU (weak scaling: global batch 512 at 8 GPUs), NCCL all-reduce of the gradients overlapped with
+         backward.  metric = audio-seconds per second (1 frame = 10 ms).  At N = 1 the line also carries the
+         BitLinear int8 GEMM microbenchmark of configs[1] ("bitlinear_gemm").
+  gemm   BASELINE.json configs[1] alone: act-quant + ternary x int8 tcgen05 GEMM at M = 65536, K = N = 2048;
+         metric = BitLinear int8 TOPS.  `--sweep` adds the whole K/N sweep.
 
-Multi-GPU (torchrun): every rank runs the same per-rank workload (weak scaling, no data-path collective for the
-forward GEMM); the layer workload all-reduces the latent-weight gradients over NCCL each step.
-`--impl reference` times the CPU restatement of the reference path (oracle/) on the host cores.
+`--impl reference` times the reference's own path restated on the CPU (oracle/: the reference's fp32 layer inside
+the same module tree) on the host cores, on a bounded sample of the same workload.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -27,20 +31,28 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+FRAME_S = 0.010          # kaldi fbank frame shift (src/data/dataset.py:124-128): 1600 frames = 16 s of audio
+TRAIN = dict(batch=64, frames=1600, mel=80, vocab=5004, tokens=64)
+
 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
-    p.add_argument("--warmup", type=int, default=5)
-    p.add_argument("--workload", default="gemm", choices=["gemm", "layer"])
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--workload", default="train", choices=["train", "gemm"])
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--tokens", type=int, default=65536)
+    p.add_argument("--batch", type=int, default=TRAIN["batch"], help="utterances per GPU (train)")
+    p.add_argument("--frames", type=int, default=TRAIN["frames"])
+    p.add_argument("--dropout", type=float, default=0.1)
+    p.add_argument("--tokens", type=int, default=65536, help="GEMM microbench M")
     p.add_argument("--in-features", type=int, default=2048)
     p.add_argument("--out-features", type=int, default=2048)
     p.add_argument("--bitwidth", type=int, default=2)
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--sweep", action="store_true", help="also run the configs[1] K/N sweep (rank 0) and add it to the line")
+    p.add_argument("--no-gemm", action="store_true", help="skip the GEMM microbench inside the train line")
+    p.add_argument("--share-frontend", action="store_true", help="compute the conv subsampling once per step")
+    p.add_argument("--sweep", action="store_true", help="gemm workload: also run the configs[1] K/N sweep")
     return p.parse_args()
 
 
@@ -55,7 +67,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -71,6 +83,7 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -79,31 +92,39 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+
+        def num(s):
+            try:
+                return float(s)
+            except ValueError:
+                return None
+        sm = sorted(v for v in (num(r[0]) for r in self.rows if r) if v is not None)
+        mx = [v for v in (num(r[1]) for r in self.rows if len(r) > 1) if v is not None]
+        pw = [v for v in (num(r[2]) for r in self.rows if len(r) > 2) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower() == "active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 3 + i and r[3 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": int(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": int(max(mx)) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
-def dist_setup(args):
+def dist_setup():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
 
 
 def timed_region(world, fn, steps):
-    """barrier + sync, K steps between CUDA events on the current stream, max over ranks (ms)."""
-    import torch.distributed as dist
+    """barrier + sync, K steps between CUDA events on the current stream, max over ranks; returns ms."""
     if world > 1:
+        import torch.distributed as dist
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -114,6 +135,7 @@ def timed_region(world, fn, steps):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if world > 1:
+        import torch.distributed as dist
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
@@ -121,120 +143,300 @@ def timed_region(world, fn, steps):
     return ms
 
 
-# ------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_layer(args, sample_rows, steps, backward):
-    """The reference's path (fp32 weight quantiser + F.linear, quant.py:120-127) restated in oracle/, on the host."""
-    from oracle.torch_oracle import OracleQuantizedLinear
-    torch.set_num_threads(os.cpu_count())
-    torch.manual_seed(0)
-    layer = OracleQuantizedLinear(args.in_features, args.out_features, act_bits=32)   # Oracle-A: the pure reference
-    x = torch.randn(sample_rows, args.in_features)
-    gy = torch.randn(sample_rows, args.out_features)
-
-    def step():
-        if backward:
-            xr = x.requires_grad_(True)
-            layer(xr, args.bitwidth).backward(gy)
-        else:
-            with torch.no_grad():
-                layer(x, args.bitwidth)
-    step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    flops = 2.0 * sample_rows * args.in_features * args.out_features * (3 if backward else 1)
-    return flops / dt / 1e12, dt
+def int8_peak(peaks):
+    return 2.0 * peaks["bf16_tflops"], (f"2 x {peaks['source']} bf16 burst {peaks['bf16_tflops']} TFLOP/s (int8 dense is nominally "
+                                        "2x bf16; MEASURED_PEAKS.json has no int8 figure)")
 
 
-# ------------------------------------------------------------------------------------------ workloads
-def run_ours(args, world, rank):
+# ------------------------------------------------------------------------------------------ GEMM microbench
+def gemm_microbench(args, steps, sweep=False):
+    """configs[1]: forward hot path (activation quantiser + ternary x int8 GEMM) on device-resident operands."""
     import onebit_b200 as ob
-    from onebit_b200 import _cabi, quant as obq
+    from onebit_b200 import quant as obq
     peaks = load_peaks()
     dev = torch.device("cuda", torch.cuda.current_device())
     M, K, N, bw = args.tokens, args.in_features, args.out_features, args.bitwidth
     torch.manual_seed(0)
     layer = ob.QuantizedLinear(K, N).to(dev)
-    x = torch.randn(M, K, device=dev, generator=torch.Generator(device=dev).manual_seed(1234 + rank))
-    xb = x.to(torch.bfloat16)
-    packed, packed_t = layer.packed_weight(bw)
-    backward = args.workload == "layer"
-    launches_per_step = 0
+    xb = torch.randn(M, K, device=dev, generator=torch.Generator(device=dev).manual_seed(1234)).to(torch.bfloat16)
+    packed, _ = layer.packed_weight(bw)
 
-    if not backward:
-        # hot path of the forward: activation quantiser + ternary x int8 GEMM (bf16 in -> bf16 out)
-        def step():
-            q, s = ob.act_quant_int8(xb)
-            return obq.gemm_fwd(q, s, packed, layer.alpha, layer.bias, N, torch.bfloat16)
-        launches_per_step = 2
-        flops_per_step = 2.0 * M * N * K
-    else:
-        gy = torch.randn(M, N, device=dev, generator=torch.Generator(device=dev).manual_seed(99))
-        xr = x.requires_grad_(True)
-        grads = [layer.weight, layer.alpha, layer.bias]
-
-        def step():
-            obq._ActQuantCache.clear()
-            for p in grads:
-                p.grad = None
-            xr.grad = None
-            y = layer(xr, bw)
-            y.backward(gy)
-            if world > 1:
-                import torch.distributed as dist
-                flat = torch.cat([p.grad.reshape(-1) for p in grads])
-                dist.all_reduce(flat)
-        launches_per_step = 2 + 1 + 1 + 3     # act quant, fwd gemm | prep, dx, dw + ste + tail
-        flops_per_step = 6.0 * M * N * K
-
-    for _ in range(max(args.warmup, 3)):
+    def step():
+        q, s = ob.act_quant_int8(xb)
+        return obq.gemm_fwd(q, s, packed, layer.alpha, layer.bias, N, torch.bfloat16)
+    for _ in range(3):
         step()
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
-    ms = timed_region(world, step, args.steps)
-    clocks = sampler.stop()
-    ms_per_step = ms / args.steps
-    value = world * flops_per_step / (ms_per_step * 1e-3) / 1e12
-
-    # ---- dominant kernel alone (forward GEMM), CUDA events on its launch stream
+    step_ms = timed_region(1, step, steps) / steps
     q, s = ob.act_quant_int8(xb)
+
     def gemm_only():
         obq.gemm_fwd(q, s, packed, layer.alpha, layer.bias, N, torch.bfloat16)
     for _ in range(3):
         gemm_only()
-    gemm_ms = timed_region(1, gemm_only, args.steps) / args.steps
-    gemm_tops = 2.0 * M * N * K / (gemm_ms * 1e-3) / 1e12
-    gemm_bytes = M * K + N * K / 4 + 2.0 * M * N + 4 * M + 4 * N
-    int8_peak = 2.0 * peaks["bf16_tflops"]
-    # act quantiser alone (HBM-bound)
+    gemm_ms = timed_region(1, gemm_only, steps) / steps
+
     def act_only():
         ob.act_quant_int8(xb)
     for _ in range(3):
         act_only()
-    act_ms = timed_region(1, act_only, args.steps) / args.steps
+    act_ms = timed_region(1, act_only, steps) / steps
+    ops = 2.0 * M * N * K
+    gemm_bytes = M * K + N * K / 4 + 2.0 * M * N + 4 * M + 4 * N
+    peak, peak_src = int8_peak(peaks)
+    tops = ops / (gemm_ms * 1e-3) / 1e12
     act_gbs = (M * K * 2 + M * K + 4 * M) / (act_ms * 1e-3) / 1e9
-    ai = 2.0 * M * N * K / gemm_bytes
-    roofline = {"kernel": "gemm_expand_kernel<kFwdI8> (ternary x int8, tcgen05 kind::i8)", "bound": "tensor",
-                "achieved": round(gemm_tops, 1), "peak": round(int8_peak, 1), "unit": "TFLOP/s",
-                "frac": round(gemm_tops / int8_peak, 4), "traffic": None,
-                "peak_source": f"2 x {peaks['source']} bf16 burst {peaks['bf16_tflops']} (int8 dense is 2x bf16 nominally; "
-                               "no int8 figure in MEASURED_PEAKS.json)",
-                "gemm_ms": round(gemm_ms, 4), "arith_intensity_op_per_byte": round(ai, 1),
-                "hbm_gbs_of_gemm": round(gemm_bytes / (gemm_ms * 1e-3) / 1e9, 1),
-                "act_quant": {"bound": "hbm", "achieved": round(act_gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                              "frac": round(act_gbs / peaks["hbm_gbs"], 4), "ms": round(act_ms, 4)}}
-    try:   # cuBLASLt int8 cross-check for the int8 denominator (library GEMM, not the product)
+    out = {"shape": {"M": M, "K": K, "N": N, "bitwidth": bw, "in": "bf16", "out": "bf16"},
+           "step_ms": round(step_ms, 4), "step_tops": round(ops / (step_ms * 1e-3) / 1e12, 1),
+           "roofline": {"kernel": "gemm_expand_kernel<kFwdI8, 256, 5, bf16, cta_group::2> (ternary x int8, tcgen05 kind::i8)",
+                        "bound": "tensor", "achieved": round(tops, 1), "peak": round(peak, 1), "unit": "TFLOP/s",
+                        "frac": round(tops / peak, 4), "traffic": None, "peak_source": peak_src,
+                        "ms": round(gemm_ms, 4), "arith_intensity_op_per_byte": round(ops / gemm_bytes, 1),
+                        "algorithmic_bytes": int(gemm_bytes)},
+           "act_quant": {"kernel": "act_quant_reg_kernel<bf16,16>", "bound": "hbm", "achieved": round(act_gbs, 1),
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(act_gbs / peaks["hbm_gbs"], 4),
+                         "ms": round(act_ms, 4)}}
+    try:   # cuBLASLt int8 (a library GEMM, not the product) as a cross-check of the int8 denominator
         a8 = torch.randint(-127, 127, (8192, 8192), device=dev, dtype=torch.int8)
         b8 = torch.randint(-127, 127, (8192, 8192), device=dev, dtype=torch.int8).t()
         for _ in range(3):
             torch._int_mm(a8, b8)
         t = timed_region(1, lambda: torch._int_mm(a8, b8), 10) / 10
-        roofline["int_mm_8192_tops"] = round(2 * 8192 ** 3 / (t * 1e-3) / 1e12, 1)
+        out["roofline"]["cublaslt_int_mm_8192_tops"] = round(2 * 8192 ** 3 / (t * 1e-3) / 1e12, 1)
     except Exception as e:  # pragma: no cover
-        roofline["int_mm_8192_tops"] = f"unavailable: {type(e).__name__}"
+        out["roofline"]["cublaslt_int_mm_8192_tops"] = f"unavailable: {type(e).__name__}"
+    if sweep:
+        rows = []
+        for Ms in (4096, 65536):
+            for Ks in (256, 512, 1024, 2048):
+                for Ns in (256, 512, 1024, 2048):
+                    torch.manual_seed(0)
+                    l2 = ob.QuantizedLinear(Ks, Ns).to(dev)
+                    pk, _ = l2.packed_weight(bw)
+                    nbuf = max(1, int(400e6 // (Ms * Ks + 2 * Ms * Ns)))      # rotate operands: working set > L2
+                    qs = [ob.act_quant_int8(torch.randn(Ms, Ks, device=dev, dtype=torch.bfloat16)) for _ in range(nbuf)]
+                    g = torch.cuda.CUDAGraph()                                # graph replay: device time, no launch gaps
+                    ys = [torch.empty(Ms, Ns, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        obq.gemm_fwd(qs[0][0], qs[0][1], pk, l2.alpha, l2.bias, Ns, torch.bfloat16)
+                        with torch.cuda.graph(g, stream=side):
+                            for i in range(20):
+                                qq, ss = qs[i % nbuf]
+                                obq.gemm_fwd(qq, ss, pk, l2.alpha, l2.bias, Ns, torch.bfloat16)
+                    torch.cuda.current_stream().wait_stream(side)
+                    g.replay()
+                    t = timed_region(1, g.replay, 3) / 3 / 20
+                    by = Ms * Ks + Ns * Ks / 4 + 2.0 * Ms * Ns + 4 * Ms + 4 * Ns
+                    rows.append({"M": Ms, "K": Ks, "N": Ns, "us": round(t * 1e3, 2),
+                                 "tops": round(2.0 * Ms * Ns * Ks / (t * 1e-3) / 1e12, 1),
+                                 "gbs": round(by / (t * 1e-3) / 1e9, 1)})
+                    del ys
+        out["sweep"] = rows
+    return out
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+
+# ------------------------------------------------------------------------------------------ train workload
+def make_batch(B, T, seed, device=None, pinned=False):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(B, T, TRAIN["mel"], generator=g)
+    batch = {"feats": feats.pin_memory() if pinned else feats,
+             "feat_lens": torch.full((B,), T, dtype=torch.long),
+             "tokens": torch.randint(4, TRAIN["vocab"], (B, TRAIN["tokens"]), generator=g),
+             "token_lens": torch.full((B,), TRAIN["tokens"], dtype=torch.long)}
+    if device is not None:
+        host = batch
+        batch = {k: v.to(device) for k, v in host.items()}
+        batch["feat_lens_cpu"], batch["token_lens_cpu"] = host["feat_lens"], host["token_lens"]
+    return batch
+
+
+def hot_kernel_rooflines(peaks, M):
+    """Each kernel of the layer at the model's widest routed shape (256 -> 1024, M tokens), timed alone with CUDA
+    events over a rotating operand set that exceeds L2; algorithmic bytes per DESIGN.md."""
+    import onebit_b200 as ob
+    from onebit_b200 import _cabi, quant as obq
+    lib = _cabi.lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    K, N = 256, 1024
+    torch.manual_seed(0)
+    layer = ob.QuantizedLinear(K, N).to(dev)
+    pk, pkt = layer.packed_weight(2)
+    nbuf = 4
+    xs = [torch.randn(M, K, device=dev) for _ in range(nbuf)]
+    gys = [torch.randn(M, N, device=dev) for _ in range(nbuf)]
+    qs = [ob.act_quant_int8(x) for x in xs]
+    ys = [torch.empty(M, N, device=dev) for _ in range(nbuf)]
+    dys = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+    qbs = [torch.empty(M, K, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+    dxs = [torch.empty(M, K, device=dev) for _ in range(nbuf)]
+    colsum = torch.empty(lib.ob_bwd_colsum_blocks(M), N, device=dev)
+    gw, ga, gb = torch.empty(N, K, device=dev), torch.empty((), device=dev), torch.empty(N, device=dev)
+    nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    st = torch.cuda.current_stream().cuda_stream
+    a = layer.alpha
+    i = [0]
+
+    def nxt():
+        i[0] = (i[0] + 1) % nbuf
+        return i[0]
+    fns = {
+        "act_quant_i8": (lambda j: lib.ob_act_quant_i8(xs[j].data_ptr(), 0, M, K, qs[j][0].data_ptr(), qs[j][1].data_ptr(), st),
+                         4 * M * K + M * K + 4 * M, 0.0),
+        "gemm_fwd": (lambda j: lib.ob_gemm_tern_i8_fwd(qs[j][0].data_ptr(), qs[j][1].data_ptr(), pk.data_ptr(), a.data_ptr(), 1,
+                                                       layer.bias.data_ptr(), M, N, K, ys[j].data_ptr(), 0, st),
+                     M * K + N * K / 4 + 4.0 * M * N + 4 * M + 4 * N, 2.0 * M * N * K),
+        "bwd_prep": (lambda j: lib.ob_bwd_prep(gys[j].data_ptr(), 0, qs[j][1].data_ptr(), qs[j][0].data_ptr(), M, N, K,
+                                               dys[j].data_ptr(), qbs[j].data_ptr(), colsum.data_ptr(), st),
+                     6.0 * M * N + 3.0 * M * K + 4 * M, 0.0),
+        "bwd_dx": (lambda j: lib.ob_bwd_dx(dys[j].data_ptr(), qs[j][1].data_ptr(), pkt.data_ptr(), a.data_ptr(), 1, M, N, K,
+                                           dxs[j].data_ptr(), 0, st),
+                   2.0 * M * N + N * K / 4 + 4.0 * M * K + 4 * M, 2.0 * M * N * K),
+        "bwd_dw": (lambda j: lib.ob_bwd_dw(dys[j].data_ptr(), qbs[j].data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(),
+                                           a.data_ptr(), 1, 2, M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                           ws.data_ptr(), nbytes, st),
+                   2.0 * M * N + 2.0 * M * K + 8.0 * N * K, 2.0 * M * N * K),
+    }
+    out = {}
+    for name, (fn, nbytes_alg, flops) in fns.items():
+        for _ in range(3):
+            fn(nxt())
+        ms = timed_region(1, lambda: fn(nxt()), 20) / 20
+        gbs = nbytes_alg / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": round(gbs / peaks["hbm_gbs"], 4), "algorithmic_bytes": int(nbytes_alg),
+                     "tflops": round(flops / (ms * 1e-3) / 1e12, 1) if flops else None}
+    return {"shape": {"M": M, "K": K, "N": N}, "kernels": out}
+
+
+def cpu_reference_train(args, sample_batch, steps):
+    """The reference's training step on the host: the same module tree with the reference's fp32 layer (Oracle-A),
+    all host threads; a bounded sample (sample_batch utterances of the same length)."""
+    import onebit_b200 as ob
+    from onebit_b200.training import StepConfig, train_step
+    from oracle.torch_oracle import OracleQuantizedLinear
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    OracleQuantizedLinear.act_bits_default = 32
+    try:
+        model = ob.ConformerASR(TRAIN["mel"], TRAIN["vocab"], enc_dropout=args.dropout, dec_dropout=args.dropout,
+                                linear_cls=OracleQuantizedLinear).train()
+    finally:
+        OracleQuantizedLinear.act_bits_default = 8
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2)
+    batch = make_batch(sample_batch, args.frames, 1)
+    cfg = StepConfig()
+    train_step(model, batch, opt, cfg)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_step(model, batch, opt, cfg)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_batch * args.frames * FRAME_S / dt, dt
+
+
+def run_train(args, world, rank):
+    import onebit_b200 as ob
+    from onebit_b200 import _cabi
+    from onebit_b200.dp import GradAllReducer
+    from onebit_b200.training import StepConfig, train_step
+    peaks = load_peaks()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    B, T = args.batch, args.frames
+    torch.manual_seed(0)                                   # same weights and precision masks on every rank
+    model = ob.ConformerASR(TRAIN["mel"], TRAIN["vocab"], enc_dropout=args.dropout, dec_dropout=args.dropout).train().to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2)
+    sync = GradAllReducer(model.parameters()) if world > 1 else None
+    cfg = StepConfig(share_frontend=args.share_frontend)
+    batch = make_batch(B, T, 1000 + rank, device=dev)
+    warm = max(args.warmup, 3)
+
+    def step():
+        return train_step(model, batch, opt, cfg, grad_sync=sync)[0]
+    for _ in range(warm):
+        step()
+    l0 = _cabi.lib.ob_launch_count()
+    sampler = ClockSampler(torch.cuda.current_device()).start()
+    ms = timed_region(world, step, args.steps)
+    clocks = sampler.stop()
+    launches = _cabi.lib.ob_launch_count() - l0
+    ms_per_step = ms / args.steps
+    audio_s = world * B * T * FRAME_S
+    value = audio_s / (ms_per_step * 1e-3)
+
+    # end to end through the public API: host (pinned) batch -> device each step, loss read back each step
+    host = make_batch(B, T, 2000 + rank, pinned=True)
+
+    def e2e_step():
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        b["feat_lens_cpu"], b["token_lens_cpu"] = host["feat_lens"], host["token_lens"]
+        return train_step(model, b, opt, cfg, grad_sync=sync)[0].item()
+    e2e_step()
+    e2e_steps = max(2, min(args.steps, 5))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    last = 0.0
+    for _ in range(e2e_steps):
+        last = e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    e2e = {"value": round(audio_s / (e2e_ms * 1e-3), 1), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 2), "last_loss": round(last, 4),
+           "api": "onebit_b200.training.train_step(model, host_batch, AdamW) incl. H2D of the batch and loss.item()"}
+
+    out = {"metric": "conformer_train_audio_sec_per_sec", "value": round(value, 1), "unit": "audio-s/s", "n_gpus": world,
+           "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None,
+           "dtype": "int8 x ternary fwd (int32 accum), bf16 bwd (fp32 accum); non-routed ops fp32 as in the reference",
+           "data": "synthetic", "impl": "ours",
+           "config": {"workload": "Conformer BitLinear co-training step (BASELINE configs[2]; configs[3] at 8 GPUs): 12 blocks, "
+                                  "d_model 256, d_ff 1024, 4 heads, V=5004, 3 passes (2-bit, 1-bit, stochastic precision) + "
+                                  "CTC/attention/KL losses + clip + AdamW",
+                      "batch_per_gpu": B, "global_batch": B * world, "frames": T, "mel": TRAIN["mel"], "dropout": args.dropout,
+                      "audio_s_per_step": audio_s, "share_frontend": bool(args.share_frontend),
+                      "l2": "per-step activations (tens of GB) exceed the 126 MB L2; no explicit flush",
+                      "parallelism": f"dp{world}"},
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    if rank == 0:
+        M = B * (((T - 1) // 2 - 1) // 2)
+        hk = hot_kernel_rooflines(peaks, M)
+        # dominant kernel of the layer inside the step = the one with the largest per-layer time at this shape
+        dom = max(hk["kernels"].items(), key=lambda kv: kv[1]["ms"])
+        out["roofline"] = dict(kernel=dom[0], shape=hk["shape"], traffic=None,
+                               **{k: dom[1][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
+                               peak_source=f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)")
+        out["layer_kernels"] = hk
+        if world == 1 and not args.no_gemm:
+            out["bitlinear_gemm"] = gemm_microbench(args, 20)
+        if world == 1 and not args.no_cpu_baseline:
+            sample = 2
+            v, dt = cpu_reference_train(args, sample, 2)
+            out["cpu_baseline"] = {"value": round(v, 2), "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{sample} utterances x {T} frames per step (of {B}), same model/step, reference fp32 "
+                                             f"layer (oracle/torch_oracle.py, Oracle-A) on torch-CPU, {dt:.2f} s/step"}
+    return out
+
+
+def run_gemm(args, world, rank):
+    res = gemm_microbench(args, args.steps, sweep=args.sweep and rank == 0)
+    M, K, N, bw = args.tokens, args.in_features, args.out_features, args.bitwidth
+    # every rank runs the same GEMM (weak scaling, no collective on this path): aggregate = world x per-rank
+    ms = timed_region(world, lambda: None, 1)  # barrier only
+    del ms
+    import onebit_b200 as ob
+    from onebit_b200 import _cabi, quant as obq
+    dev = torch.device("cuda", torch.cuda.current_device())
+    layer = ob.QuantizedLinear(K, N).to(dev)
     x_host = torch.randn(M, K).to(torch.bfloat16).pin_memory()
     y_host = torch.empty(M, N, dtype=torch.bfloat16).pin_memory()
     x_dev = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
@@ -246,49 +448,24 @@ def run_ours(args, world, rank):
         y_host.copy_(y, non_blocking=True)
     for _ in range(3):
         e2e_step()
-    e2e_steps = max(3, min(args.steps, 10))
-    e2e_ms = timed_region(world, e2e_step, e2e_steps) / e2e_steps
-    e2e = {"value": round(world * 2.0 * M * N * K / (e2e_ms * 1e-3) / 1e12, 2), "unit": "TOPS",
-           "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,
-           "ms_per_step": round(e2e_ms, 3), "api": "QuantizedLinear.forward(x_bf16, 2) on host-pinned input/output"}
-
-    out = {"metric": "bitlinear_int8_tops" if not backward else "bitlinear_fwd_bwd_tflops",
-           "value": round(value, 2), "unit": "TOPS" if not backward else "TFLOP/s", "n_gpus": world,
-           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 x ternary (int32 accum)",
-           "data": "synthetic", "impl": "ours",
-           "config": {"workload": f"BitLinear {'fwd' if not backward else 'fwd+bwd'} M={M} K={K} N={N} bitwidth={bw} "
-                                  "(BASELINE configs[1], largest sweep point)",
-                      "tokens_per_gpu": M, "in_features": K, "out_features": N, "bitwidth": bw,
-                      "l2": "operands (q 134 MB, y 268 MB) exceed the 126 MB L2; no explicit flush",
-                      "parallelism": f"dp{world}"},
-           "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
-
-    if args.sweep and rank == 0:
-        sweep = []
-        for Ms in (4096, 65536):
-            for Ks in (256, 512, 1024, 2048):
-                for Ns in (256, 512, 1024, 2048):
-                    torch.manual_seed(0)
-                    l2 = ob.QuantizedLinear(Ks, Ns).to(dev)
-                    pk, _ = l2.packed_weight(bw)
-                    qs, ss = ob.act_quant_int8(torch.randn(Ms, Ks, device=dev, dtype=torch.bfloat16))
-                    f = lambda: obq.gemm_fwd(qs, ss, pk, l2.alpha, l2.bias, Ns, torch.bfloat16)
-                    for _ in range(3):
-                        f()
-                    t = timed_region(1, f, 20) / 20
-                    by = Ms * Ks + Ns * Ks / 4 + 2.0 * Ms * Ns + 4 * Ms + 4 * Ns
-                    sweep.append({"M": Ms, "K": Ks, "N": Ns, "us": round(t * 1e3, 2),
-                                  "tops": round(2.0 * Ms * Ns * Ks / (t * 1e-3) / 1e12, 1),
-                                  "gbs": round(by / (t * 1e-3) / 1e9, 1)})
-        out["sweep"] = sweep
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rows = 2048
-        tf, dt = cpu_reference_layer(args, rows, 3, backward)
-        out["cpu_baseline"] = {"value": round(tf, 4), "unit": out["unit"], "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"{rows} of {M} tokens, same K/N/bitwidth, fp32 torch-CPU restatement of "
-                                         f"quant.py:120-127 (Oracle-A), {dt:.3f} s/step"}
+    l0 = _cabi.lib.ob_launch_count()
+    sampler = ClockSampler(torch.cuda.current_device()).start()
+    e2e_ms = timed_region(world, e2e_step, max(3, args.steps)) / max(3, args.steps)
+    clocks = sampler.stop()
+    launches = _cabi.lib.ob_launch_count() - l0
+    ops = 2.0 * M * N * K
+    out = {"metric": "bitlinear_int8_tops", "value": round(world * res["step_tops"], 1), "unit": "TOPS", "n_gpus": world,
+           "steps": args.steps, "warmup": 3, "ms_per_step": res["step_ms"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int8 x ternary (int32 accum)", "data": "synthetic", "impl": "ours",
+           "config": {"workload": f"BitLinear fwd (act-quant + GEMM) M={M} K={K} N={N} bitwidth={bw} (BASELINE configs[1])",
+                      "l2": "operands (q 134 MB, y 268 MB) exceed the 126 MB L2; no explicit flush", "parallelism": f"dp{world}"},
+           "roofline": res["roofline"], "act_quant": res["act_quant"],
+           "e2e": {"value": round(world * ops / (e2e_ms * 1e-3) / 1e12, 2), "unit": "TOPS", "h2d_bytes_per_step": M * K * 2,
+                   "d2h_bytes_per_step": M * N * 2, "ms_per_step": round(e2e_ms, 3),
+                   "api": "QuantizedLinear.forward(x_bf16, 2) with host-pinned input and output"},
+           "gpu_launches": int(launches), "clocks": clocks}
+    if "sweep" in res:
+        out["sweep"] = res["sweep"]
     return out
 
 
@@ -296,41 +473,57 @@ def run_reference(args, world, rank):
     """Reference arm: the reference's own CPU implementation of the path (oracle port), all host threads."""
     if rank != 0:
         return None
-    backward = args.workload == "layer"
-    rows = 2048
-    steps = max(1, min(args.steps, 5))
-    tf, dt = cpu_reference_layer(args, rows, steps, backward)
-    unit = "TOPS" if not backward else "TFLOP/s"
-    M, K, N, bw = args.tokens, args.in_features, args.out_features, args.bitwidth
-    return {"metric": "bitlinear_int8_tops" if not backward else "bitlinear_fwd_bwd_tflops", "value": round(tf, 4),
-            "unit": unit, "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": round(dt * 1e3, 2),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "impl": "reference",
-            "config": {"workload": f"BitLinear {'fwd' if not backward else 'fwd+bwd'} M={M} K={K} N={N} bitwidth={bw} "
-                                   "(BASELINE configs[1], largest sweep point)",
-                       "tokens_per_gpu": M, "in_features": K, "out_features": N, "bitwidth": bw,
-                       "parallelism": "cpu"},
-            "cpu_baseline": {"value": round(tf, 4), "unit": unit, "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{rows} of {M} tokens per step (bounded sample), torch-CPU restatement of the "
-                                       "reference layer (oracle/torch_oracle.py, Oracle-A)"},
-            "e2e": {"value": round(tf, 4), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+    steps = max(1, min(args.steps, 3))
+    if args.workload == "train":
+        sample = 2
+        v, dt = cpu_reference_train(args, sample, steps)
+        unit, metric = "audio-s/s", "conformer_train_audio_sec_per_sec"
+        cfg = {"workload": "Conformer BitLinear co-training step (BASELINE configs[2]; configs[3] at 8 GPUs): 12 blocks, "
+                           "d_model 256, d_ff 1024, 4 heads, V=5004, 3 passes (2-bit, 1-bit, stochastic precision) + "
+                           "CTC/attention/KL losses + clip + AdamW",
+               "batch_per_gpu": args.batch, "frames": args.frames, "mel": TRAIN["mel"], "dropout": args.dropout,
+               "parallelism": "cpu"}
+        sample_txt = (f"{sample} utterances x {args.frames} frames per step (bounded sample of batch {args.batch}), reference fp32 "
+                      "layer restated in oracle/torch_oracle.py (Oracle-A) inside the same module tree, torch-CPU")
+    else:
+        from oracle.torch_oracle import OracleQuantizedLinear
+        torch.set_num_threads(os.cpu_count())
+        torch.manual_seed(0)
+        rows = 2048
+        layer = OracleQuantizedLinear(args.in_features, args.out_features, act_bits=32)
+        x = torch.randn(rows, args.in_features)
+        with torch.no_grad():
+            layer(x, args.bitwidth)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                layer(x, args.bitwidth)
+        dt = (time.perf_counter() - t0) / steps
+        v = 2.0 * rows * args.in_features * args.out_features / dt / 1e12
+        unit, metric = "TOPS", "bitlinear_int8_tops"
+        cfg = {"workload": f"BitLinear fwd M={args.tokens} K={args.in_features} N={args.out_features} bitwidth={args.bitwidth} "
+                           "(BASELINE configs[1])", "parallelism": "cpu"}
+        sample_txt = f"{rows} of {args.tokens} tokens per step, reference fp32 layer (Oracle-A) on torch-CPU"
+    return {"metric": metric, "value": round(v, 4), "unit": unit, "n_gpus": world, "steps": steps, "warmup": 1,
+            "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg,
+            "cpu_baseline": {"value": round(v, 4), "unit": unit, "cores": os.cpu_count(), "kind": "port", "sample": sample_txt},
+            "e2e": {"value": round(v, 4), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
 
 def main():
     args = parse()
     if args.impl == "reference":
-        rank = int(os.environ.get("RANK", "0"))
-        out = run_reference(args, int(os.environ.get("WORLD_SIZE", "1")), rank)
+        out = run_reference(args, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")))
         if out is not None:
             print(json.dumps(out), flush=True)
         return
-    world, rank, _ = dist_setup(args)
-    out = run_ours(args, world, rank)
+    world, rank, _ = dist_setup()
+    out = run_train(args, world, rank) if args.workload == "train" else run_gemm(args, world, rank)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
 
 

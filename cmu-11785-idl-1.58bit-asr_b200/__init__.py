@@ -5,7 +5,8 @@ name is not a Python identifier).  ``install_as_reference_quant()`` registers th
 the reference's ``conformer.py`` (which does ``from quant import QuantizedLinear``, conformer.py:12)
 picks this layer up unchanged.
 """
-from . import _cabi
+from . import _cabi, conformer, dp, training
+from .conformer import ConformerASR
 from .quant import BitLinear, QuantizedLinear, act_quant_int8, install_as_reference_quant, quantize_weight
 
-__all__ = ["QuantizedLinear", "BitLinear", "quantize_weight", "act_quant_int8", "install_as_reference_quant", "_cabi"]
+__all__ = ["ConformerASR", "conformer", "training", "dp", "QuantizedLinear", "BitLinear", "quantize_weight", "act_quant_int8", "install_as_reference_quant", "_cabi"]

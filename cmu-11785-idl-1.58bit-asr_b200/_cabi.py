@@ -22,6 +22,7 @@ _p, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size
 # name -> (restype, argtypes); mirrors include/onebit.h one to one
 SIGNATURES = {
     "ob_version": (_i, []),
+    "ob_launch_count": (_i64, []),
     "ob_last_error_string": (ctypes.c_char_p, []),
     "ob_absmean_workspace_bytes": (_sz, []),
     "ob_weight_absmean": (_i, [_p, _i64, _p, _p, _p]),

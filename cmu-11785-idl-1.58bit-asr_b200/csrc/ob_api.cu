@@ -1,11 +1,16 @@
 // ob_api.cu - library-level entry points: version, per-thread error string, device check.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "ob_common.cuh"
 
 namespace ob {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -37,4 +42,5 @@ int check_device() {
 }  // namespace ob
 
 extern "C" int ob_version(void) { return OB_VERSION; }
+extern "C" int64_t ob_launch_count(void) { return static_cast<int64_t>(ob::g_launches.load()); }
 extern "C" const char* ob_last_error_string(void) { return ob::g_err; }

@@ -17,6 +17,7 @@ namespace ob {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_device();   // OB_OK when the current device is sm_100
+void count_launch();  // bumps the library-wide kernel launch counter (ob_launch_count)
 
 #define OB_REQUIRE(cond, ...)                 \
   do {                                        \
@@ -43,6 +44,7 @@ int check_device();   // OB_OK when the current device is sm_100
       ::ob::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));            \
       return OB_ERR_CUDA;                                                                  \
     }                                                                                      \
+    ::ob::count_launch();                                                                  \
   } while (0)
 
 // ---------------------------------------------------------------------------------------------

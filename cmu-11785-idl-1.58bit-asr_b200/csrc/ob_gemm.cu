@@ -617,6 +617,7 @@ static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_b
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC));
+  count_launch();
   return OB_OK;
 }
 

@@ -1,0 +1,106 @@
+"""Data-parallel gradient exchange for the co-training step: one process per GPU, NCCL all-reduce over NVLink.
+
+The reference has no distributed code; the only exchange step of the path is the mean of
+the gradients.  Every parameter's AccumulateGrad fires exactly once per ``loss.backward()`` even though the latent
+weights are used by three passes, so a post-accumulate-grad hook per parameter is enough: gradients are copied into
+flat fp32 buckets (~25 MB, filled in reverse-autograd order) and each full bucket is all-reduced asynchronously on
+a side stream while the rest of backward runs.  ``finish()`` joins the side stream, averages and scatters the
+buckets back before ``clip_grad_norm_`` needs the global gradients (train.py:117).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+class GradAllReducer:
+    def __init__(self, params, bucket_bytes: int = 25 << 20, process_group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.cuda = bool(self.params) and self.params[0].is_cuda
+        self.stream = torch.cuda.Stream() if self.cuda else None
+        # buckets in reverse parameter order ~ the order gradients become ready
+        self.buckets = []                 # dicts: params, offsets, flat buffer, numel
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > bucket_bytes:
+                self._close_bucket(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._close_bucket(cur)
+        self._where = {}
+        for bi, b in enumerate(self.buckets):
+            for p, off in zip(b["params"], b["offsets"]):
+                self._where[p] = (bi, off)
+        self._handles = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._reset()
+
+    def _close_bucket(self, plist):
+        offsets, n = [], 0
+        for p in plist:
+            offsets.append(n)
+            n += p.numel()
+        flat = torch.zeros(n, dtype=torch.float32, device=plist[0].device)
+        self.buckets.append({"params": plist, "offsets": offsets, "flat": flat, "numel": n})
+
+    def _reset(self):
+        self._pending = [len(b["params"]) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+
+    def _on_grad(self, p: torch.nn.Parameter):
+        if self.world == 1:
+            return
+        bi, off = self._where[p]
+        b = self.buckets[bi]
+        b["flat"][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi: int):
+        b = self.buckets[bi]
+        self._launched[bi] = True
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                h = dist.all_reduce(b["flat"], group=self.group, async_op=True)
+        else:
+            h = dist.all_reduce(b["flat"], group=self.group, async_op=True)
+        self._handles.append(h)
+
+    def finish(self):
+        """Wait for every bucket, divide by the world size and write the averaged gradients back."""
+        if self.world == 1:
+            return
+        for bi, b in enumerate(self.buckets):           # parameters without a gradient this step (e.g. alpha at 32 bit)
+            if not self._launched[bi]:
+                for p, off in zip(b["params"], b["offsets"]):
+                    if p.grad is None:
+                        b["flat"][off:off + p.numel()].zero_()
+                self._launch(bi)
+        for h in self._handles:
+            h.wait()
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        inv = 1.0 / self.world
+        for b in self.buckets:
+            b["flat"].mul_(inv)
+            for p, off in zip(b["params"], b["offsets"]):
+                g = b["flat"][off:off + p.numel()].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+        self._reset()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()

@@ -57,6 +57,8 @@ extern "C" {
 typedef void* ob_stream_t; /* cudaStream_t */
 
 int ob_version(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+int64_t ob_launch_count(void);
 const char* ob_last_error_string(void);
 
 /* mean(|W|) over n elements -> out[0]; deterministic two-stage reduction.  Replaces the one-off

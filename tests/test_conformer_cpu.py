@@ -1,0 +1,165 @@
+"""CPU checks of the Conformer caller and the co-training step against the reference-generated fixture
+(tests/golden/make_golden_conformer.py), plus the data-parallel gradient exchange on gloo (world_size 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN, ROOT
+
+import onebit_b200 as ob
+from onebit_b200.training import StepConfig, WarmupCosine, cotraining_loss, sample_sp_mask
+from oracle.torch_oracle import OracleQuantizedLinear
+
+CFG = dict(input_dim=80, vocab_size=64, enc_layers=3, dec_layers=1, enc_dropout=0.0, dec_dropout=0.0)
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return dict(np.load(os.path.join(GOLDEN, "conformer_step.npz")))
+
+
+def load_batch(fx, device="cpu"):
+    b = {k: torch.from_numpy(fx[k]).to(device) for k in ("feats", "feat_lens", "tokens", "token_lens")}
+    b["feat_lens_cpu"] = torch.from_numpy(fx["feat_lens"])
+    b["token_lens_cpu"] = torch.from_numpy(fx["token_lens"])
+    return b
+
+
+def build(act_bits, seed):
+    torch.manual_seed(seed)
+    OracleQuantizedLinear.act_bits_default = act_bits
+    try:
+        return ob.ConformerASR(**CFG, linear_cls=OracleQuantizedLinear).train()
+    finally:
+        OracleQuantizedLinear.act_bits_default = 8
+
+
+def run_steps(model, batch, sp_masks, lr, cfg=StepConfig()):
+    opt = torch.optim.AdamW(model.parameters(), lr=lr, betas=(0.9, 0.98), weight_decay=1e-2)
+    out = []
+    for spm in sp_masks:
+        opt.zero_grad()
+        loss, _ = cotraining_loss(model, batch, cfg, list(spm))
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=5.0)
+        opt.step()
+        out.append(loss.item())
+    return out
+
+
+def test_training_run_reproduces_reference_losses(fx):
+    """Oracle-A through our module tree == the reference's run_epoch arithmetic, 4 optimiser steps, batch 3."""
+    torch.set_num_threads(1)
+    model = build(32, int(fx["seed"]))
+    losses = run_steps(model, load_batch(fx), fx["sp_masks"], float(fx["lr"]))
+    np.testing.assert_allclose(losses, fx["losses_A"], rtol=2e-4)
+
+
+def test_host_lengths_and_shared_frontend_do_not_change_the_loss(fx):
+    torch.set_num_threads(1)
+    batch = load_batch(fx)
+    plain = {k: v for k, v in batch.items() if not k.endswith("_cpu")}
+    m = build(8, 3)
+    l0, _ = cotraining_loss(m, plain, StepConfig(), [1, 0, 1])
+    l1, _ = cotraining_loss(m, batch, StepConfig(), [1, 0, 1])
+    l2, _ = cotraining_loss(m, batch, StepConfig(share_frontend=True), [1, 0, 1])
+    assert abs(l0.item() - l1.item()) < 1e-6 and abs(l0.item() - l2.item()) < 1e-5
+    g_ref = torch.autograd.grad(l1, m.encoder.subsample.out.weight, retain_graph=True)[0]
+    g_shared = torch.autograd.grad(l2, m.encoder.subsample.out.weight)[0]
+    assert torch.allclose(g_ref, g_shared, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/onebit_asr"), reason="reference tree not mounted")
+def test_module_tree_matches_reference_state_dict():
+    saved = {k: sys.modules.get(k) for k in ("quant", "conformer")}
+    sys.path.insert(0, "/root/reference/onebit_asr")
+    try:
+        for k in ("quant", "conformer"):
+            sys.modules.pop(k, None)
+        import conformer as refc
+        torch.manual_seed(5)
+        ref = refc.ConformerASR(80, 40, enc_layers=2, dec_layers=1)
+        torch.manual_seed(5)
+        ours = ob.ConformerASR(80, 40, enc_layers=2, dec_layers=1)
+        sd_r, sd_o = ref.state_dict(), ours.state_dict()
+        assert list(sd_r.keys()) == list(sd_o.keys())
+        assert all(torch.equal(sd_r[k], sd_o[k]) for k in sd_r)
+        ours.load_state_dict(sd_r)                                 # reference checkpoints load (eval.py:282)
+        batch = {"feats": torch.randn(2, 90, 80), "feat_lens": torch.tensor([90, 50])}
+        ref.eval(), ours.eval()
+        with torch.no_grad():
+            a, b = ref(batch, precision=32), ours(batch, precision=32)
+        assert torch.allclose(a[0], b[0], atol=1e-6) and torch.equal(a[1], b[1]) and torch.allclose(a[2], b[2], atol=1e-5)
+    finally:
+        sys.path.remove("/root/reference/onebit_asr")
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_schedule_helpers():
+    torch.manual_seed(0)
+    m = sample_sp_mask(12)
+    assert len(m) == 12 and set(m) <= {0, 1}
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=5e-4)
+    s = WarmupCosine(opt, warmup_steps=4, total_steps=12)
+    lrs = []
+    for _ in range(12):
+        s.step()
+        lrs.append(opt.param_groups[0]["lr"])
+    assert abs(lrs[0] - 5e-4 / 4) < 1e-12 and abs(max(lrs) - 5e-4) < 1e-12 and abs(lrs[-1] - 5e-5) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------ data parallel, gloo x2
+def _dp_worker(rank, world, port, fxpath, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    fx = dict(np.load(fxpath))
+    batch = load_batch(fx)
+    # rank r takes utterance r (ragged lengths): the two ranks see different data
+    shard = {k: (v[rank:rank + 1] if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
+    model = build(8, 3)
+    from onebit_b200.dp import GradAllReducer
+    sync = GradAllReducer(model.parameters(), bucket_bytes=1 << 20)
+    loss, _ = cotraining_loss(model, shard, StepConfig(), [1, 0, 1])
+    loss.backward()
+    sync.finish()
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+    if rank == 0:
+        q.put(flat.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_gradient_allreduce_gloo(fx):
+    """mean of per-rank gradients (overlapped bucketed all-reduce) == gradients of the averaged per-rank losses."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, os.path.join(GOLDEN, "conformer_step.npz"), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    torch.set_num_threads(1)
+    batch = load_batch(fx)
+    model = build(8, 3)
+    total = 0.0
+    for r in range(2):
+        shard = {k: (v[r:r + 1] if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
+        loss, _ = cotraining_loss(model, shard, StepConfig(), [1, 0, 1])
+        total = total + 0.5 * loss
+    total.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).numpy()
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-6)

@@ -1,0 +1,39 @@
+"""Probe the Conformer co-training step on a B200: step time, peak memory, top kernels.  python tools/gpu_train_probe.py [B] [T]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import onebit_b200 as ob  # noqa: E402
+from onebit_b200.training import StepConfig, train_step  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 1600
+share = len(sys.argv) > 3 and sys.argv[3] == "share"
+torch.manual_seed(0)
+model = ob.ConformerASR(80, 5004).train().cuda()
+opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2)
+g = torch.Generator().manual_seed(1)
+batch = {"feats": torch.randn(B, T, 80, generator=g).cuda(), "feat_lens": torch.full((B,), T).cuda(),
+         "tokens": torch.randint(4, 5004, (B, 64), generator=g).cuda(), "token_lens": torch.full((B,), 64).cuda(),
+         "feat_lens_cpu": torch.full((B,), T), "token_lens_cpu": torch.full((B,), 64)}
+cfg = StepConfig(share_frontend=share)
+for _ in range(2):
+    loss, _ = train_step(model, batch, opt, cfg)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+n = 3
+for _ in range(n):
+    loss, _ = train_step(model, batch, opt, cfg)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / n
+print(f"B={B} T={T} share_frontend={share}: {dt * 1e3:.1f} ms/step, {B * T * 0.01 / dt:.1f} audio-s/s, loss {loss.item():.4f}, "
+      f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    train_step(model, batch, opt, cfg)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=60))
