@@ -357,13 +357,21 @@ def run_train(args, world, rank):
         step()
     l0 = _cabi.lib.ob_launch_count()
     sampler = ClockSampler(torch.cuda.current_device()).start()
+    window = os.environ.get("OB_NCU_WINDOW") == "1"     # `ncu --profile-from-start off` then sees only the timed steps
+    if window:
+        torch.cuda.profiler.start()
     ms = timed_region(world, step, args.steps)
+    if window:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = _cabi.lib.ob_launch_count() - l0
     ms_per_step = ms / args.steps
     audio_s = world * B * T * FRAME_S
     value = audio_s / (ms_per_step * 1e-3)
 
+    if window:
+        return {"metric": "conformer_train_audio_sec_per_sec", "value": round(value, 1), "unit": "audio-s/s",
+                "ms_per_step": round(ms_per_step, 2), "gpu_launches": int(launches), "note": "OB_NCU_WINDOW run (profiling aid)"}
     # end to end through the public API: host (pinned) batch -> device each step, loss read back each step
     host = make_batch(B, T, 2000 + rank, pinned=True)
 
