@@ -11,6 +11,8 @@ Workloads (one "step" = one pass of the hot path over one batch of synthetic inp
          PER GPU (weak scaling: global batch 512 at 8 GPUs), NCCL all-reduce of the gradients overlapped with
          backward.  metric = audio-seconds per second (1 frame = 10 ms).  At N = 1 the line also carries the
          BitLinear int8 GEMM microbenchmark of configs[1] ("bitlinear_gemm").
+  infer  BASELINE.json configs[4]: packed 2-bit weights (PackedQuantizedLinear), batches of 1..256 utterances x 1000
+         frames, encoder forward at precision 2 + CTC head + greedy CTC decode on the device; metric = audio-s/s.
   gemm   BASELINE.json configs[1] alone: act-quant + ternary x int8 tcgen05 GEMM at M = 65536, K = N = 2048;
          metric = BitLinear int8 TOPS.  `--sweep` adds the whole K/N sweep.
 
@@ -40,7 +42,7 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--workload", default="train", choices=["train", "gemm"])
+    p.add_argument("--workload", default="train", choices=["train", "gemm", "infer"])
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=TRAIN["batch"], help="utterances per GPU (train)")
     p.add_argument("--frames", type=int, default=TRAIN["frames"])
@@ -435,6 +437,65 @@ def run_train(args, world, rank):
     return out
 
 
+def run_infer(args, world, rank):
+    """configs[4]: batched inference with packed 2-bit weights and device-side greedy CTC decoding."""
+    import onebit_b200 as ob
+    from onebit_b200 import _cabi
+    from onebit_b200.inference import pack_model_for_inference, transcribe_greedy
+    dev = torch.device("cuda", torch.cuda.current_device())
+    T = 1000
+    torch.manual_seed(0)
+    model = ob.ConformerASR(TRAIN["mel"], TRAIN["vocab"]).to(dev)
+    pack_model_for_inference(model, 2)
+    rows = []
+    clocks, launches, headline = None, 0, None
+    for B in (1, 8, 64, 256):
+        feats = torch.randn(B, T, TRAIN["mel"], generator=torch.Generator().manual_seed(B + rank))
+        host = {"feats": feats.pin_memory(), "feat_lens": torch.full((B,), T, dtype=torch.long)}
+        batch = {k: v.to(dev) for k, v in host.items()}
+
+        def step():
+            return transcribe_greedy(model, batch, precision=2)
+
+        def e2e_step():
+            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            toks, n = transcribe_greedy(model, b, precision=2)
+            return toks.cpu(), n.cpu()
+        for _ in range(3):
+            step()
+        l0 = _cabi.lib.ob_launch_count()
+        sampler = ClockSampler(torch.cuda.current_device()).start() if B == 256 else None
+        ms = timed_region(world, step, args.steps) / args.steps
+        if sampler is not None:
+            clocks = sampler.stop()
+            launches = _cabi.lib.ob_launch_count() - l0
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+        row = {"batch": B, "ms": round(ms, 3), "utt_per_s": round(world * B / (ms * 1e-3), 1),
+               "audio_s_per_s": round(world * B * T * FRAME_S / (ms * 1e-3), 1),
+               "e2e_audio_s_per_s": round(world * B * T * FRAME_S / (e2e_ms * 1e-3), 1),
+               "h2d_bytes": feats.numel() * 4, "d2h_bytes": B * (((T - 1) // 2 - 1) // 2) * 4 + B * 4}
+        rows.append(row)
+        headline = row
+    out = {"metric": "conformer_infer_audio_sec_per_sec", "value": headline["audio_s_per_s"], "unit": "audio-s/s", "n_gpus": world,
+           "steps": args.steps, "warmup": 3, "ms_per_step": headline["ms"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int8 x ternary (int32 accum); non-routed ops fp32 as in the reference", "data": "synthetic",
+           "impl": "ours",
+           "config": {"workload": "Conformer batched inference (BASELINE configs[4]): packed 2-bit weights, precision 2, 1000 frames, "
+                                  "greedy CTC decode on the device; headline = batch 256", "batches": rows,
+                      "parallelism": f"dp{world}"},
+           "e2e": {"value": headline["e2e_audio_s_per_s"], "unit": "audio-s/s", "h2d_bytes_per_step": headline["h2d_bytes"],
+                   "d2h_bytes_per_step": headline["d2h_bytes"], "api": "onebit_b200.inference.transcribe_greedy on a host-pinned batch, "
+                   "tokens copied back to the host"},
+           "gpu_launches": int(launches), "clocks": clocks}
+    return out
+
+
 def run_gemm(args, world, rank):
     res = gemm_microbench(args, args.steps, sweep=args.sweep and rank == 0)
     M, K, N, bw = args.tokens, args.in_features, args.out_features, args.bitwidth
@@ -526,7 +587,7 @@ def main():
             print(json.dumps(out), flush=True)
         return
     world, rank, _ = dist_setup()
-    out = run_train(args, world, rank) if args.workload == "train" else run_gemm(args, world, rank)
+    out = {"train": run_train, "gemm": run_gemm, "infer": run_infer}[args.workload](args, world, rank)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -15,6 +15,7 @@
 
 namespace ob {
 
+size_t bwd_tail_workspace_bytes(int N);
 int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const float* alpha, int alpha_mode, int64_t n,
                         int bitwidth, float* grad_W, float* grad_alpha, float* alpha_parts, const float* colsum,
                         int n_col_blocks, int N, float* grad_bias, cudaStream_t st);
@@ -756,7 +757,7 @@ extern "C" size_t ob_bwd_dw_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const DwPlan p = plan_dw(M, N, K);
   const size_t partials = (size_t)p.splits * N * K * sizeof(float);
-  return partials + ob_ste_workspace_bytes((int64_t)N * K) + 256;
+  return partials + ob_ste_workspace_bytes((int64_t)N * K) + bwd_tail_workspace_bytes(N) + 256;
 }
 
 extern "C" int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float* colsum, const float* W,

@@ -211,12 +211,67 @@ __global__ void __launch_bounds__(256) ste_backward_kernel(const float* __restri
   if (threadIdx.x == 0) alpha_parts[blockIdx.x] = s;
 }
 
+// grad_W finaliser for many token splits: 256 elements per block; thread (eg, sl) sums splits sl, sl+4, ... of one
+// float4, the four split lanes are combined through shared memory in fixed order (deterministic), then the STE.
+constexpr int kFinBlockElems = 256;
+
+__global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restrict__ g_parts, int splits,
+                                                          const float* __restrict__ W, const float* __restrict__ alpha,
+                                                          int alpha_mode, int64_t n, int bitwidth,
+                                                          float* __restrict__ grad_W, float* __restrict__ alpha_parts) {
+  __shared__ float4 part[3][64];
+  __shared__ float red[8];
+  const int eg = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int64_t i = (int64_t)blockIdx.x * kFinBlockElems + eg * 4;      // n % 256 == 0 (N, K multiples of 64)
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  int s = sl;
+  for (; s + 4 < splits; s += 8) {
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)s * n + i));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)(s + 4) * n + i));
+    a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
+    a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
+  }
+  if (s < splits) {
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)s * n + i));
+    a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
+  }
+  a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
+  if (sl > 0) part[sl - 1][eg] = a0;
+  __syncthreads();
+  float acc = 0.f;
+  if (sl == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float4 o = part[j][eg];
+      a0.x += o.x; a0.y += o.y; a0.z += o.z; a0.w += o.w;
+    }
+    const float a_eff = load_alpha_eff(alpha, alpha_mode);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W + i));
+    float4 o;
+    o.x = ste_elem(a0.x, w.x, a_eff, bitwidth, acc);
+    o.y = ste_elem(a0.y, w.y, a_eff, bitwidth, acc);
+    o.z = ste_elem(a0.z, w.z, a_eff, bitwidth, acc);
+    o.w = ste_elem(a0.w, w.w, a_eff, bitwidth, acc);
+    *reinterpret_cast<float4*>(grad_W + i) = o;
+  }
+  const float tot = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) alpha_parts[blockIdx.x] = tot;
+}
+
 // tail: block 0 reduces the alpha partials; blocks >= 1 reduce the column-sum partials into grad_bias
+constexpr int kTailRowChunks = 8;   // the column-sum partial rows are reduced by 8 blocks per 32-column group
+
+// block 0: alpha partials -> grad_alpha.  blocks >= 1: (column group, row chunk) pairs reduce the per-row-block
+// column sums of dY; the last chunk to finish (ticket) adds the 8 chunk sums in fixed order -> grad_bias.
+// tail_ws: [kTailRowChunks][N] floats followed by ceil(N/32) int tickets (zeroed by the finaliser, self-resetting).
 __global__ void __launch_bounds__(256) bwd_tail_kernel(const float* __restrict__ alpha_parts, int n_alpha_parts,
                                                        const float* __restrict__ alpha, int alpha_mode,
                                                        float* __restrict__ grad_alpha, const float* __restrict__ colsum,
-                                                       int n_col_blocks, int N, float* __restrict__ grad_bias) {
+                                                       int n_col_blocks, int N, float* __restrict__ grad_bias,
+                                                       float* __restrict__ tail_ws) {
   __shared__ float red[8];
+  __shared__ float col_red[8][33];
+  __shared__ int is_last;
   if (blockIdx.x == 0) {
     if (grad_alpha == nullptr) return;
     float acc = 0.f;
@@ -229,14 +284,46 @@ __global__ void __launch_bounds__(256) bwd_tail_kernel(const float* __restrict__
       }
       grad_alpha[0] = s;
     }
-  } else {
-    if (grad_bias == nullptr) return;
-    const int c = (blockIdx.x - 1) * 256 + threadIdx.x;
-    if (c < N) {
-      float acc = 0.f;
-      for (int b = 0; b < n_col_blocks; ++b) acc += colsum[(int64_t)b * N + c];
-      grad_bias[c] = acc;
+    return;
+  }
+  if (grad_bias == nullptr) return;
+  const int bx = (blockIdx.x - 1) / kTailRowChunks, by = (blockIdx.x - 1) % kTailRowChunks;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = bx * 32 + cx;
+  const int rows_per_chunk = (n_col_blocks + kTailRowChunks - 1) / kTailRowChunks;
+  const int b0 = by * rows_per_chunk, b1 = min(n_col_blocks, b0 + rows_per_chunk);
+  float a0 = 0.f, a1 = 0.f;
+  if (c < N) {
+    int b = b0 + ry;
+    for (; b + 8 < b1; b += 16) {
+      a0 += colsum[(int64_t)b * N + c];
+      a1 += colsum[(int64_t)(b + 8) * N + c];
     }
+    if (b < b1) a0 += colsum[(int64_t)b * N + c];
+  }
+  col_red[ry][cx] = a0 + a1;
+  __syncthreads();
+  float* chunk_part = tail_ws;                                   // [kTailRowChunks][N]
+  int* tickets = reinterpret_cast<int*>(tail_ws + (int64_t)kTailRowChunks * N);
+  if (ry == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += col_red[j][cx];
+    chunk_part[(int64_t)by * N + c] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&tickets[bx], 1) == kTailRowChunks - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (ry == 0 && c < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < kTailRowChunks; ++j) t += __ldcg(&chunk_part[(int64_t)j * N + c]);
+      grad_bias[c] = t;
+    }
+    if (threadIdx.x == 0) tickets[bx] = 0;
   }
 }
 
@@ -368,7 +455,20 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ dY,
     const int c = c0 + (threadIdx.x - rg * tpr) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (rg < rpi) {
-      for (int r = rg; r < rows; r += rpi) {
+      int r = rg;
+      for (; r + 3 * rpi < rows; r += 4 * rpi) {                 // 4 independent 16-byte loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = load4<T>(dY + (int64_t)(r0 + r + u * rpi) * N + c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+          const float is = inv_s[r + u * rpi];
+          *reinterpret_cast<uint2*>(dys + (int64_t)(r0 + r + u * rpi) * N + c) =
+              pack_bf16x4(v[u].x * is, v[u].y * is, v[u].z * is, v[u].w * is);
+        }
+      }
+      for (; r < rows; r += rpi) {
         const int64_t off = (int64_t)(r0 + r) * N + c;
         float4 v = load4<T>(dY + off);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -464,19 +564,36 @@ extern "C" int ob_weight_quant_dense(const float* W, const float* alpha, int alp
 
 static int ste_blocks(int64_t n) { return (int)((n + kSteBlockElems - 1) / kSteBlockElems); }
 
-extern "C" size_t ob_ste_workspace_bytes(int64_t n) { return (size_t)ste_blocks(n) * sizeof(float); }
+extern "C" size_t ob_ste_workspace_bytes(int64_t n) {
+  const size_t fin = (size_t)((n + kFinBlockElems - 1) / kFinBlockElems);
+  const size_t ste = (size_t)ste_blocks(n);
+  return (fin > ste ? fin : ste) * sizeof(float);
+}
+// extra floats the grad_bias tail needs behind the alpha partials
+static size_t tail_workspace_bytes(int N) { return ((size_t)kTailRowChunks * N + (size_t)(N + 31) / 32 + 8) * sizeof(float); }
+namespace ob { size_t bwd_tail_workspace_bytes(int N) { return tail_workspace_bytes(N); } }
 
 namespace ob {
 // shared with ob_gemm.cu (grad_W finalizer)
 int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const float* alpha, int alpha_mode, int64_t n,
                         int bitwidth, float* grad_W, float* grad_alpha, float* alpha_parts, const float* colsum,
                         int n_col_blocks, int N, float* grad_bias, cudaStream_t st) {
-  const int blocks = ste_blocks(n);
-  ste_backward_kernel<<<blocks, 256, 0, st>>>(g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
-  OB_LAUNCH_CHECK("ste_backward_kernel");
-  const int bias_blocks = (grad_bias != nullptr) ? (N + 255) / 256 : 0;
-  bwd_tail_kernel<<<1 + bias_blocks, 256, 0, st>>>(alpha_parts, blocks, alpha, alpha_mode, grad_alpha, colsum,
-                                                   n_col_blocks, N, grad_bias);
+  int blocks;
+  if (splits >= 4 && n % kFinBlockElems == 0) {
+    blocks = (int)(n / kFinBlockElems);
+    dw_finalize_kernel<<<blocks, 256, 0, st>>>(g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
+    OB_LAUNCH_CHECK("dw_finalize_kernel");
+  } else {
+    blocks = ste_blocks(n);
+    ste_backward_kernel<<<blocks, 256, 0, st>>>(g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
+    OB_LAUNCH_CHECK("ste_backward_kernel");
+  }
+  const int col_groups = (grad_bias != nullptr) ? (N + 31) / 32 : 0;
+  float* tail_ws = alpha_parts + blocks;                           // [kTailRowChunks][N] floats + col_groups tickets
+  if (col_groups > 0)
+    OB_CUDA(cudaMemsetAsync(tail_ws + (size_t)kTailRowChunks * N, 0, (size_t)col_groups * sizeof(int), st));
+  bwd_tail_kernel<<<1 + col_groups * kTailRowChunks, 256, 0, st>>>(alpha_parts, blocks, alpha, alpha_mode, grad_alpha,
+                                                                   colsum, n_col_blocks, N, grad_bias, tail_ws);
   OB_LAUNCH_CHECK("bwd_tail_kernel");
   return OB_OK;
 }

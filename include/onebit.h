@@ -127,6 +127,14 @@ int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float* colsum, co
               const float* alpha, int alpha_mode, int bitwidth, int M, int N, int K, float* grad_W,
               float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream);
 
+/* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
+ * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded
+ * with -1), out_lens [B].  ws: at least ob_ctc_decode_workspace_bytes(B, T) bytes. */
+size_t ob_ctc_decode_workspace_bytes(int B, int T);
+int ob_ctc_greedy_decode(const void* logits, int dtype, int B, int T, int V, const int32_t* lens,
+                         int blank_id, int32_t* out_tokens, int32_t* out_lens, void* ws,
+                         ob_stream_t stream);
+
 /* Debug/tuning knob (tests and profiling only): key/value pairs, see csrc/ob_gemm.cu. */
 int ob_debug_set(int key, int value);
 

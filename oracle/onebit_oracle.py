@@ -222,6 +222,26 @@ def unpack_codes(P: np.ndarray, order: str = "i8") -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# greedy CTC decode (onebit_asr/metrics.py:51-60)
+# --------------------------------------------------------------------------
+
+
+def ctc_greedy_decode(logits: np.ndarray, blank_id: int = 3):
+    """logits [T, V] -> token ids: argmax per frame (first maximal index), drop blanks, collapse repeats."""
+    pred = np.argmax(np.asarray(logits), axis=-1).tolist()
+    out, prev = [], None
+    for t in pred:
+        if t != blank_id and t != prev:
+            out.append(int(t))
+        prev = t
+    return out
+
+
+def ctc_greedy_decode_batch(logits: np.ndarray, lens, blank_id: int = 3):
+    return [ctc_greedy_decode(logits[b, : int(lens[b])], blank_id) for b in range(logits.shape[0])]
+
+
+# --------------------------------------------------------------------------
 # layer init (quant.py:100-118) — needs torch for the RNG stream; imported lazily
 # --------------------------------------------------------------------------
 

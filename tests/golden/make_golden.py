@@ -4,7 +4,7 @@ Run in the build container only (needs /root/reference, which is not present on 
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{kat_edges.json,kat_seeded.json,kat_layer.npz,kat_layer_stats.json}.
+Writes tests/golden/{kat_edges.json,kat_seeded.json,kat_layer.npz,kat_layer_stats.json,kat_decode.npz}.
 Nothing from the reference is copied: it is imported from where it lies and only its
 numerical outputs are stored.  Recipes follow SURVEY.md section 8(c).
 """
@@ -165,6 +165,25 @@ def kat_layer_stats():
     return out
 
 
+def kat_decode():
+    """Greedy CTC decode of the reference (onebit_asr/metrics.py:51-60) on logits with ties, blanks and repeats."""
+    import metrics as refm          # reference onebit_asr/metrics.py
+    g = torch.Generator().manual_seed(77)
+    B, T, V = 4, 61, 40
+    logits = torch.randn(B, T, V, generator=g)
+    steer = torch.randint(0, 8, (B, T), generator=g)                 # small alphabet -> many repeats and blanks (id 3)
+    logits.scatter_(2, steer.unsqueeze(-1), 6.0)
+    logits[0, 5, 9] = logits[0, 5, 2] = 9.0                           # exact tie -> first maximal index
+    logits[1, 0, 3] = 12.0                                            # starts with a blank
+    lens = torch.tensor([61, 40, 1, 17])
+    hyps = [refm.ctc_greedy_decode(logits[b, : int(lens[b])], blank_id=3) for b in range(B)]
+    pad = np.full((B, T), -1, dtype=np.int32)
+    for b, h in enumerate(hyps):
+        pad[b, : len(h)] = h
+    return {"logits": logits.numpy(), "lens": lens.numpy().astype(np.int32), "tokens": pad,
+            "out_lens": np.array([len(h) for h in hyps], dtype=np.int32)}
+
+
 def main():
     torch.set_num_threads(1)           # fixed summation order for the stored float sums
     with open(os.path.join(HERE, "kat_edges.json"), "w") as f:
@@ -174,6 +193,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_layer.npz"), **kat_layer_small())
     with open(os.path.join(HERE, "kat_layer_stats.json"), "w") as f:
         json.dump(kat_layer_stats(), f, indent=1)
+    np.savez_compressed(os.path.join(HERE, "kat_decode.npz"), **kat_decode())
     print("golden fixtures written to", HERE, "torch", torch.__version__)
 
 

@@ -214,7 +214,10 @@ def test_layer_vs_oracle(ob, M, K, N, bw):
     assert rel_err(layer.weight.grad.cpu().numpy(), g_ref["weight"]) < 1e-2
     assert np.array_equal(layer.weight.grad.cpu().numpy() != 0, g_ref["weight"] != 0)
     assert rel_err(layer.bias.grad.cpu().numpy(), g_ref["bias"]) < 1e-4
-    assert math.isclose(layer.alpha.grad.item(), float(g_ref["alpha"]), rel_tol=1e-2, abs_tol=1e-2 * np.abs(g_ref["weight"]).max())
+    # grad_alpha = sum over N*K of grad_W_hat * term is cancellation-prone: its error scales with ||grad_W_hat||_2
+    # (bf16 operand rounding, 2^-9 per element), not with its own value -> absolute bound of 1e-2 of that norm
+    g_hat_norm = float(np.linalg.norm(g_ref["weight"].astype(np.float64))) * 2 ** 0.5      # ~half the entries are masked
+    assert math.isclose(layer.alpha.grad.item(), float(g_ref["alpha"]), rel_tol=1e-2, abs_tol=1e-2 * g_hat_norm)
 
 
 def test_size_independent_properties_at_bench_size(ob):

@@ -125,3 +125,12 @@ def test_pack_roundtrip(order):
     assert np.array_equal(ob.unpack_codes(P, order), Q)
     # zero bytes decode to zero codes (TMA out-of-bounds fill is therefore harmless)
     assert not ob.unpack_codes(np.zeros((2, 8), np.uint8), order).any()
+
+
+def test_greedy_decode_matches_reference_fixture():
+    import os
+    from conftest import GOLDEN
+    fx = dict(np.load(os.path.join(GOLDEN, "kat_decode.npz")))
+    hyps = ob.ctc_greedy_decode_batch(fx["logits"], fx["lens"], blank_id=3)
+    for b, h in enumerate(hyps):
+        assert len(h) == fx["out_lens"][b] and h == fx["tokens"][b, : len(h)].tolist()

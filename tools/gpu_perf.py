@@ -103,3 +103,33 @@ if __name__ == "__main__":
         fwd(big + model, bns=(0, 256, 1256, 1128) if what == "fwd" else (0,))
     if what in ("bwd", "all"):
         bwd(model + [(65536, 2048, 2048)])
+
+
+def kern(shapes):
+    """Per-kernel device times (CUPTI via torch.profiler) of one layer forward+backward at each shape."""
+    from torch.profiler import ProfilerActivity, profile
+    for (M, K, N) in shapes:
+        torch.manual_seed(0)
+        layer = ob.QuantizedLinear(K, N).cuda()
+        x = torch.randn(M, K, device="cuda", requires_grad=True)
+        gy = torch.randn(M, N, device="cuda")
+        for _ in range(3):
+            obq._ActQuantCache.clear()
+            layer(x, 2).backward(gy)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(10):
+                obq._ActQuantCache.clear()
+                layer(x, 2).backward(gy)
+            torch.cuda.synchronize()
+        print(f"--- layer fwd+bwd M={M} K={K} N={N}")
+        tot = 0.0
+        for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total):
+            if e.device_time_total > 0:
+                tot += e.device_time_total / 10
+                print(f"   {e.device_time_total / e.count:9.1f} us x{e.count // 10:2d}  {e.key[:110]}")
+        print(f"   total {tot:.1f} us per fwd+bwd", flush=True)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "kern":
+    kern([(25536, 256, 256), (25536, 256, 1024), (25536, 1024, 256), (399, 256, 256)])
