@@ -53,7 +53,9 @@ def parse():
     p.add_argument("--bitwidth", type=int, default=2)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-gemm", action="store_true", help="skip the GEMM microbench inside the train line")
-    p.add_argument("--share-frontend", action="store_true", help="compute the conv subsampling once per step")
+    p.add_argument("--no-share-frontend", dest="share_frontend", action="store_false",
+                   help="recompute the (bitwidth-independent, dropout-free) conv subsampling in each of the three passes, as the "
+                        "reference does; by default it is computed once per step and shared - identical loss and gradients")
     p.add_argument("--sweep", action="store_true", help="gemm workload: also run the configs[1] K/N sweep")
     return p.parse_args()
 
@@ -412,7 +414,11 @@ def run_train(args, world, rank):
                                   "d_model 256, d_ff 1024, 4 heads, V=5004, 3 passes (2-bit, 1-bit, stochastic precision) + "
                                   "CTC/attention/KL losses + clip + AdamW",
                       "batch_per_gpu": B, "global_batch": B * world, "frames": T, "mel": TRAIN["mel"], "dropout": args.dropout,
-                      "audio_s_per_step": audio_s, "share_frontend": bool(args.share_frontend),
+                      "audio_s_per_step": audio_s,
+                      "share_frontend": bool(args.share_frontend),
+                      "share_frontend_note": "conv subsampling (no dropout, no bitwidth) evaluated once per step for the three passes: "
+                                             "common-subexpression sharing inside the step, same loss and gradients "
+                                             "(tests/test_conformer_cpu.py); --no-share-frontend restores the 3x evaluation",
                       "l2": "per-step activations (tens of GB) exceed the 126 MB L2; no explicit flush",
                       "parallelism": f"dp{world}"},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -49,8 +49,12 @@ class FeedForwardModule(nn.Module):
 
     def forward(self, x, bitwidth: int, mask=None):
         h = self.lin1(self.ln(x), bitwidth)
-        h = self.dropout(swish(h))
-        h = self.dropout(self.lin2(h, bitwidth))
+        if hasattr(self.lin2, "forward_swish_dropout"):
+            # B200 layer: swish + dropout + activation quantiser fused in front of lin2's GEMM (same math)
+            h = self.lin2.forward_swish_dropout(h, bitwidth, self.dropout.p, self.training)
+        else:
+            h = self.lin2(self.dropout(swish(h)), bitwidth)
+        h = self.dropout(h)
         if mask is not None:                                   # zero padded frames (conformer.py:42-44)
             h = h * mask[:, :, 0].unsqueeze(-1)
         return x + 0.5 * h

@@ -422,6 +422,68 @@ __global__ void __launch_bounds__(256) act_quant_generic_kernel(const T* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused FFN mid-section (conformer.py:36-39): z = dropout(swish(h)), then the activation quantiser of lin2.
+// One read of h (+ the keep mask), one write of int8 codes: replaces sigmoid, mul, dropout and act-quant kernels.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float swish_f(float h) { return h * (1.0f / (1.0f + expf(-h))); }
+
+template <int V>
+__global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __restrict__ h, const uint8_t* __restrict__ keep,
+                                                               float inv_keep, int64_t M, int K, int8_t* __restrict__ q,
+                                                               float* __restrict__ scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    const float* hr = h + row * K;
+    float4 v[V];
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int e = (lane + 32 * j) * 4;
+      float4 t = __ldg(reinterpret_cast<const float4*>(hr + e));
+      t.x = swish_f(t.x); t.y = swish_f(t.y); t.z = swish_f(t.z); t.w = swish_f(t.w);
+      if (keep != nullptr) {
+        const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep + row * K + e));
+        t.x = m.x ? t.x * inv_keep : 0.f; t.y = m.y ? t.y * inv_keep : 0.f;
+        t.z = m.z ? t.z * inv_keep : 0.f; t.w = m.w ? t.w * inv_keep : 0.f;
+      }
+      v[j] = t;
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+    }
+    amax = warp_max(amax);
+    const float s = act_scale_from_amax(amax);
+    uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * K);
+#pragma unroll
+    for (int j = 0; j < V; ++j) qr[lane + 32 * j] = quant4(v[j], s);
+    if (lane == 0) scale[row] = s;
+  }
+}
+
+// g_h = g_z * keep * inv_keep * swish'(h),  swish'(h) = sig + h * sig * (1 - sig)
+__global__ void __launch_bounds__(256) swish_drop_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ h,
+                                                             const uint8_t* __restrict__ keep, float inv_keep, int64_t n4,
+                                                             float* __restrict__ gh) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gz) + i);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(h) + i);
+    float mk[4] = {inv_keep, inv_keep, inv_keep, inv_keep};
+    if (keep != nullptr) {
+      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep) + i);
+      mk[0] = m.x ? inv_keep : 0.f; mk[1] = m.y ? inv_keep : 0.f; mk[2] = m.z ? inv_keep : 0.f; mk[3] = m.w ? inv_keep : 0.f;
+    }
+    const float xs[4] = {x.x, x.y, x.z, x.w}, gs[4] = {g.x, g.y, g.z, g.w};
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float sg = 1.0f / (1.0f + expf(-xs[u]));
+      o[u] = gs[u] * mk[u] * (sg + xs[u] * sg * (1.0f - sg));
+    }
+    reinterpret_cast<float4*>(gh)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward prep: dys = bf16(dY / s_m), qb = bf16(q), column sums of dY per row block
 // ---------------------------------------------------------------------------------------------
 constexpr int kPrepRows = 64;
@@ -668,5 +730,32 @@ extern "C" int ob_bwd_prep(const void* dY, int dy_dtype, const float* scale, con
   else
     OB_REQUIRE(false, "ob_bwd_prep: unknown dtype tag %d", dy_dtype);
   OB_LAUNCH_CHECK("bwd_prep_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_swish_drop_quant(const float* h, const uint8_t* keep, float inv_keep, int64_t M, int K, int8_t* q,
+                                   float* scale, ob_stream_t stream) {
+  OB_REQUIRE(h && q && scale && M > 0, "ob_swish_drop_quant: null pointer or M <= 0");
+  OB_REQUIRE(K == 256 || K == 512 || K == 1024 || K == 2048, "ob_swish_drop_quant: K (%d) must be 256, 512, 1024 or 2048", K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t want = (M + 7) / 8;
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  switch (K) {
+    case 256:  swish_drop_quant_kernel<2><<<blocks, 256, 0, st>>>(h, keep, inv_keep, M, K, q, scale); break;
+    case 512:  swish_drop_quant_kernel<4><<<blocks, 256, 0, st>>>(h, keep, inv_keep, M, K, q, scale); break;
+    case 1024: swish_drop_quant_kernel<8><<<blocks, 256, 0, st>>>(h, keep, inv_keep, M, K, q, scale); break;
+    default:   swish_drop_quant_kernel<16><<<blocks, 256, 0, st>>>(h, keep, inv_keep, M, K, q, scale); break;
+  }
+  OB_LAUNCH_CHECK("swish_drop_quant_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_swish_drop_bwd(const float* gz, const float* h, const uint8_t* keep, float inv_keep, int64_t n,
+                                 float* gh, ob_stream_t stream) {
+  OB_REQUIRE(gz && h && gh && n > 0 && n % 4 == 0, "ob_swish_drop_bwd: null pointer or n not a positive multiple of 4");
+  const int64_t want = (n / 4 + 255) / 256;
+  const int blocks = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  swish_drop_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(gz, h, keep, inv_keep, n / 4, gh);
+  OB_LAUNCH_CHECK("swish_drop_bwd_kernel");
   return OB_OK;
 }

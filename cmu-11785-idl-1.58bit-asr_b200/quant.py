@@ -153,39 +153,93 @@ class _QuantLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         q, s, weight, alpha, packed_t = ctx.saved_tensors
-        M, K = q.shape
-        N = weight.shape[0]
         need_x, need_w, need_a, need_b = ctx.needs_input_grad[:4]
-        need_w = need_w or need_a
-        need_b = need_b and ctx.has_bias
-        g2 = gy.reshape(M, N)
-        if not g2.is_contiguous():
-            g2 = g2.contiguous()
-        dev, st = g2.device, _stream()
-        dys = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
-        qb = torch.empty((M, K), device=dev, dtype=torch.bfloat16) if need_w else None
-        colsum = torch.empty((lib.ob_bwd_colsum_blocks(M), N), device=dev, dtype=torch.float32) if need_b else None
-        check(lib.ob_bwd_prep(g2.data_ptr(), _tag(g2), s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(),
-                              None if qb is None else qb.data_ptr(), None if colsum is None else colsum.data_ptr(), st))
-        gx = gw = ga = gb = None
-        if need_x:
-            gx = torch.empty((M, K), device=dev, dtype=gy.dtype)
-            check(lib.ob_bwd_dx(dys.data_ptr(), s.data_ptr(), packed_t.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW,
-                                M, N, K, gx.data_ptr(), _tag(gx), st))
+        gx, gw, ga, gb = _linear_backward(gy, q, s, weight, alpha, packed_t, ctx.bitwidth, need_x, need_w or need_a,
+                                          need_b and ctx.has_bias)
+        if gx is not None:
             gx = gx.view(ctx.x_shape)
-        if need_w:
-            gw = torch.empty((N, K), device=dev, dtype=torch.float32)
-            ga = torch.empty((), device=dev, dtype=torch.float32)
-            gb = torch.empty((N,), device=dev, dtype=torch.float32) if need_b else None
-            nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
-            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-            check(lib.ob_bwd_dw(dys.data_ptr(), qb.data_ptr(), None if colsum is None else colsum.data_ptr(),
-                                weight.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW, ctx.bitwidth, M, N, K,
-                                gw.data_ptr(), ga.data_ptr(), None if gb is None else gb.data_ptr(), ws.data_ptr(),
-                                nbytes, st))
-        elif need_b:
-            gb = g2.sum(0, dtype=torch.float32)
         return gx, gw, ga, gb, None, None, None
+
+
+def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w, need_b):
+    """Shared backward of the quantised linear: prep (bf16 casts + column sums), grad_x GEMM, grad_W GEMM + fused
+    STE / alpha / bias reductions.  Returns (grad_x [M,K] | None, grad_W | None, grad_alpha | None, grad_bias | None)."""
+    M, K = q.shape
+    N = weight.shape[0]
+    g2 = gy.reshape(M, N)
+    if not g2.is_contiguous():
+        g2 = g2.contiguous()
+    dev, st = g2.device, _stream()
+    dys = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+    qb = torch.empty((M, K), device=dev, dtype=torch.bfloat16) if need_w else None
+    colsum = torch.empty((lib.ob_bwd_colsum_blocks(M), N), device=dev, dtype=torch.float32) if need_b else None
+    check(lib.ob_bwd_prep(g2.data_ptr(), _tag(g2), s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(),
+                          None if qb is None else qb.data_ptr(), None if colsum is None else colsum.data_ptr(), st))
+    gx = gw = ga = gb = None
+    if need_x:
+        gx = torch.empty((M, K), device=dev, dtype=gy.dtype)
+        check(lib.ob_bwd_dx(dys.data_ptr(), s.data_ptr(), packed_t.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW,
+                            M, N, K, gx.data_ptr(), _tag(gx), st))
+    if need_w:
+        gw = torch.empty((N, K), device=dev, dtype=torch.float32)
+        ga = torch.empty((), device=dev, dtype=torch.float32)
+        gb = torch.empty((N,), device=dev, dtype=torch.float32) if need_b else None
+        nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        check(lib.ob_bwd_dw(dys.data_ptr(), qb.data_ptr(), None if colsum is None else colsum.data_ptr(),
+                            weight.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW, bitwidth, M, N, K,
+                            gw.data_ptr(), ga.data_ptr(), None if gb is None else gb.data_ptr(), ws.data_ptr(),
+                            nbytes, st))
+    elif need_b:
+        gb = g2.sum(0, dtype=torch.float32)
+    return gx, gw, ga, gb
+
+
+_FUSED_SWISH_K = (256, 512, 1024, 2048)
+
+
+class _SwishDropQuantLinearFn(torch.autograd.Function):
+    """lin(dropout(swish(h))) with the element-wise chain fused into the activation quantiser (forward) and into one
+    kernel behind the grad_x GEMM (backward): the FFN mid-section of conformer.py:36-39."""
+
+    @staticmethod
+    def forward(ctx, h, weight, alpha, bias, bitwidth, packed, packed_t, keep, inv_keep):
+        K = h.shape[-1]
+        N = weight.shape[0]
+        h2 = h.reshape(-1, K)
+        if not h2.is_contiguous():
+            h2 = h2.contiguous()
+        M = h2.shape[0]
+        q = torch.empty((M, K), device=h.device, dtype=torch.int8)
+        s = torch.empty((M,), device=h.device, dtype=torch.float32)
+        st = _stream()
+        check(lib.ob_swish_drop_quant(h2.data_ptr(), None if keep is None else keep.data_ptr(), inv_keep, M, K,
+                                      q.data_ptr(), s.data_ptr(), st))
+        y = torch.empty((M, N), device=h.device, dtype=h.dtype)
+        check(lib.ob_gemm_tern_i8_fwd(q.data_ptr(), s.data_ptr(), packed.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW,
+                                      None if bias is None else bias.data_ptr(), M, N, K, y.data_ptr(), _tag(y), st))
+        if keep is None:
+            ctx.save_for_backward(h2, q, s, weight, alpha, packed_t)
+        else:
+            ctx.save_for_backward(h2, q, s, weight, alpha, packed_t, keep)
+        ctx.bitwidth, ctx.has_bias, ctx.h_shape, ctx.inv_keep = bitwidth, bias is not None, h.shape, inv_keep
+        return y.view(*h.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        saved = ctx.saved_tensors
+        h2, q, s, weight, alpha, packed_t = saved[:6]
+        keep = saved[6] if len(saved) > 6 else None
+        need_h, need_w, need_a, need_b = ctx.needs_input_grad[:4]
+        gz, gw, ga, gb = _linear_backward(gy, q, s, weight, alpha, packed_t, ctx.bitwidth, need_h, need_w or need_a,
+                                          need_b and ctx.has_bias)
+        gh = None
+        if need_h:
+            gh = torch.empty_like(h2)
+            check(lib.ob_swish_drop_bwd(gz.data_ptr(), h2.data_ptr(), None if keep is None else keep.data_ptr(),
+                                        ctx.inv_keep, h2.numel(), gh.data_ptr(), _stream()))
+            gh = gh.view(ctx.h_shape)
+        return gh, gw, ga, gb, None, None, None, None, None
 
 
 class _QuantizeWeightFn(torch.autograd.Function):
@@ -270,6 +324,31 @@ class QuantizedLinear(nn.Module):
             raise ValueError(f"onebit_b200: unsupported input dtype {x.dtype}")
         packed, packed_t = self.packed_weight(bitwidth)
         return _QuantLinearFn.apply(x, self.weight, self.alpha, self.bias, bitwidth, packed, packed_t)
+
+
+    def forward_swish_dropout(self, h: torch.Tensor, bitwidth: int, p: float = 0.0, training: bool = False,
+                              keep: torch.Tensor = None) -> torch.Tensor:
+        """``self(dropout(swish(h)), bitwidth)`` (conformer.py:37-39) with swish, dropout and the activation quantiser
+        fused into one kernel.  ``keep`` (bool [.., K]) overrides the sampled dropout mask (tests)."""
+        fused = (bitwidth in (1, 2) and h.is_cuda and h.dtype == torch.float32 and self.in_features in _FUSED_SWISH_K)
+        if not fused:
+            z = h * torch.sigmoid(h)
+            if keep is not None:
+                z = z * keep.to(z.dtype) * (1.0 / (1.0 - p))
+            else:
+                z = F.dropout(z, p, training)
+            return self.forward(z, bitwidth)
+        _require_cuda(self.weight, "weight")
+        inv_keep = 1.0
+        if keep is not None:
+            keep, inv_keep = keep.reshape(-1, self.in_features).contiguous(), 1.0 / (1.0 - p)
+        elif training and p > 0.0:
+            keep = torch.empty(h.numel() // self.in_features, self.in_features, device=h.device,
+                               dtype=torch.bool).bernoulli_(1.0 - p)
+            inv_keep = 1.0 / (1.0 - p)
+        packed, packed_t = self.packed_weight(bitwidth)
+        return _SwishDropQuantLinearFn.apply(h, self.weight, self.alpha, self.bias, bitwidth, packed, packed_t, keep,
+                                             inv_keep)
 
 
 BitLinear = QuantizedLinear   # the north_star's name for the same layer

@@ -127,6 +127,14 @@ int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float* colsum, co
               const float* alpha, int alpha_mode, int bitwidth, int M, int N, int K, float* grad_W,
               float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream);
 
+/* Fused FFN mid-section (conformer.py:36-39): z = dropout(swish(h)) followed by the
+ * activation quantiser of the next layer, in one pass.  h [M, K] fp32; keep [M, K] bytes (1 = keep) or NULL for no
+ * dropout; inv_keep = 1/(1-p).  K in {256, 512, 1024, 2048}.  ob_swish_drop_bwd: g_h = g_z * keep*inv_keep * swish'(h). */
+int ob_swish_drop_quant(const float* h, const uint8_t* keep, float inv_keep, int64_t M, int K, int8_t* q,
+                        float* scale, ob_stream_t stream);
+int ob_swish_drop_bwd(const float* gz, const float* h, const uint8_t* keep, float inv_keep, int64_t n,
+                      float* gh, ob_stream_t stream);
+
 /* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
  * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded
  * with -1), out_lens [B].  ws: at least ob_ctc_decode_workspace_bytes(B, T) bytes. */

@@ -244,3 +244,45 @@ def test_no_fallback_on_bad_shape(ob):
     layer = ob.QuantizedLinear(100, 64).cuda()              # K % 64 != 0: refused loudly, never silently emulated
     with pytest.raises(ValueError):
         layer(torch.randn(4, 100, device="cuda"), 2)
+
+
+# ------------------------------------------------------------------ fused FFN mid-section
+@pytest.mark.parametrize("p", [0.0, 0.1])
+@pytest.mark.parametrize("bw", [1, 2])
+def test_fused_swish_dropout_quant_matches_unfused(ob, p, bw):
+    """lin2(dropout(swish(h))) through the fused kernels == the same chain through separate torch ops + our layer
+    (same int8 codes up to expf rounding; outputs and gradients within the layer tolerances)."""
+    torch.manual_seed(5)
+    layer = ob.QuantizedLinear(1024, 256).cuda()
+    with torch.no_grad():
+        layer.bias.normal_(0, 0.1)
+    g = torch.Generator().manual_seed(6)
+    h0 = (torch.randn(3, 111, 1024, generator=g) * 2).cuda()
+    gy = torch.randn(3, 111, 256, generator=g).cuda()
+    keep = (torch.rand(3, 111, 1024, generator=g) > p).cuda() if p > 0 else None
+
+    def run(fused):
+        layer.zero_grad()
+        h = h0.clone().requires_grad_(True)
+        if fused:
+            y = layer.forward_swish_dropout(h, bw, p, True, keep=keep)
+        else:
+            z = h * torch.sigmoid(h)
+            if keep is not None:
+                z = z * keep.float() * (1.0 / (1.0 - p))
+            y = layer(z, bw)
+        y.backward(gy)
+        return y.detach(), h.grad.clone(), layer.weight.grad.clone(), layer.alpha.grad.clone(), layer.bias.grad.clone()
+
+    yf, ghf, gwf, gaf, gbf = run(True)
+    yu, ghu, gwu, gau, gbu = run(False)
+    scale = yu.abs().max().item()
+    assert (yf - yu).abs().max().item() < 2e-3 * scale           # a code may flip by one step where expf rounds differently
+    assert (yf - yu).abs().mean().item() < 1e-5 * scale
+    assert (ghf - ghu).abs().max().item() < 1e-2 * ghu.abs().max().item()
+    assert (gwf - gwu).abs().max().item() < 1e-2 * gwu.abs().max().item()
+    assert torch.equal(gwf != 0, gwu != 0)
+    assert torch.allclose(gbf, gbu, rtol=1e-5, atol=1e-5)
+    if p > 0:
+        dropped = ~keep
+        assert ghf[dropped].abs().max().item() == 0.0              # no gradient through dropped activations
