@@ -23,7 +23,8 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
 // ---------------------------------------------------------------------------------------------
 // debug / tuning knobs (ob_debug_set)
 // ---------------------------------------------------------------------------------------------
-enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4 };
+enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5 };
+static int g_dbg_kernel_flags = 0;   // bit0 skip TMA stores, bit1 skip epilogue math/STS, bit2 skip expansion (timing experiments)
 static int g_dbg_swap_lbo_sbo = 0;
 static int g_dbg_force_block_n = 0;
 static int g_dbg_force_splits = 0;
@@ -91,13 +92,14 @@ constexpr int kATileBytes = kBlockM * 128;                 // 128 rows x one 128
 constexpr int kExpandWarps = 8;
 constexpr int kExpandThreads = kExpandWarps * 32;
 constexpr int kEpiWarp0 = 4 + kExpandWarps;                // first epilogue warp (multiple of 4: TMEM lane quarters)
-constexpr int kGemmThreads = (kEpiWarp0 + 4) * 32;         // 16 warps, see roles below
+constexpr int kEpiWarps = 8;                               // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kGemmThreads = (kEpiWarp0 + kEpiWarps) * 32; // 20 warps, see roles below
 constexpr int kStageOutBytes = 32 * 128;                   // one epilogue chunk: 32 rows x 128 B
 
 // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a [256 x BLOCK_N] tile; each CTA loads its own 128
 // rows of A and expands its own half (BLOCK_N/2 rows) of B, so the expansion work and the shared-memory operand
 // traffic per MMA are halved.
-template <int MODE, int BLOCK_N, int STAGES, int CTAS>
+template <int MODE, int BLOCK_N, int STAGES, int CTAS, int OUT_BUFS>
 struct GemmSmem {
   static constexpr int kPackedRowBytes = MODE == kFwdI8 ? 32 : 16;   // 128 int8 / 64 bf16 codes per k-block
   static constexpr int kRowsB = BLOCK_N / CTAS;                      // B rows expanded by this CTA
@@ -105,8 +107,8 @@ struct GemmSmem {
   static constexpr int kBpTileBytes = kRowsB * kPackedRowBytes;
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kOffA + STAGES * kATileBytes;
-  static constexpr int kOffOut = kOffB + STAGES * kBTileBytes;       // 4 warps x 2 buffers x 4 KB, 1024-aligned
-  static constexpr int kOffBp = kOffOut + 8 * kStageOutBytes;
+  static constexpr int kOffOut = kOffB + STAGES * kBTileBytes;       // 8 warps x OUT_BUFS buffers x 4 KB, 1024-aligned
+  static constexpr int kOffBp = kOffOut + kEpiWarps * OUT_BUFS * kStageOutBytes;
   static constexpr int kOffBias = kOffBp + STAGES * kBpTileBytes;    // [2][BLOCK_N] floats
   static constexpr int kOffBar = kOffBias + 2 * BLOCK_N * 4;
   static constexpr int kNumBars = 4 * STAGES + 4;
@@ -133,15 +135,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator, 3 = idle,
-// 4..11 = expanders, 12..15 = epilogue (warp % 4 selects the TMEM lane quarter).
+// 4..11 = expanders, 12..19 = epilogue (warp % 4 selects the TMEM lane quarter, (warp-12)/4 the column half).
 // OUT_BF16: output element type (0 = fp32, 1 = bf16); the epilogue moves 128 bytes of a row per chunk.
-template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS>
+// OUT_BUFS: staging buffers per epilogue warp; the TMA stores of up to OUT_BUFS-1 earlier chunks stay in flight
+// (the store-read latency, not the instruction count, bounds the output rate with only two).
+template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS, int OUT_BUFS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bp,
                    const __grid_constant__ CUtensorMap map_out, const float* __restrict__ row_scale,
                    const float* __restrict__ alpha, int alpha_mode, const float* __restrict__ bias, int M, int NC,
-                   int KC) {
-  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS>;
+                   int KC, int dbg) {
+  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS, OUT_BUFS>;
   constexpr int kElemsPerKBlock = MODE == kFwdI8 ? 128 : 64;
   constexpr int kChunkCols = OUT_BF16 ? 64 : 32;          // output columns per 128-byte chunk
   constexpr int kTileM = kBlockM * CTAS;
@@ -184,7 +188,7 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4 * CTAS);
+      mbar_init(&tmem_empty_bar[s], kEpiWarps * CTAS);
     }
     mbar_fence_init();
   }
@@ -279,7 +283,8 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(&bp_full_bar[stage], phase);
         const uint32_t src = sbase + L::kOffBp + stage * L::kBpTileBytes + te * 4;
         const uint32_t dst = sbase + L::kOffB + stage * L::kBTileBytes + dst_off;
-        if (MODE == kFwdI8) {
+        if (dbg & 4) {
+        } else if (MODE == kFwdI8) {
           constexpr int kWords = L::kRowsB * 8;                     // rows advance by 32 per pass
           constexpr int kIters = (kWords + kExpandThreads - 1) / kExpandThreads;
           uint32_t w[kIters];
@@ -316,10 +321,11 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------ epilogue: TMEM -> registers -> swizzled smem -> TMA store ------------------
-    const int e = warp - kEpiWarp0;
-    const int et = threadIdx.x - kEpiWarp0 * 32;            // 0..127
+    const int ew = warp - kEpiWarp0;                        // 0..7
+    const int e = ew & 3, half = ew >> 2;
+    const int et = threadIdx.x - kEpiWarp0 * 32;            // 0..255
     const float a_eff = load_alpha_eff(alpha, alpha_mode);
-    const uint32_t out_buf = sbase + L::kOffOut + e * 2 * kStageOutBytes;
+    const uint32_t out_buf = sbase + L::kOffOut + ew * OUT_BUFS * kStageOutBytes;   // [NG groups][G chunks][4 KB]
     const uint32_t out_row = lane * 128;
     const uint32_t swz = (lane & 7) << 4;
     const uint32_t tmem_empty_addr0 = CTAS == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
@@ -337,66 +343,86 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       // bias slice of this tile -> smem (double-buffered by accumulator stage; the named barrier below orders it)
       float* bias_s = reinterpret_cast<float*>(smem + L::kOffBias) + as * BLOCK_N;
-      for (int j = et; j < BLOCK_N; j += 128) {
+      for (int j = et; j < BLOCK_N; j += kEpiWarps * 32) {
         const int col = n_blk * BLOCK_N + j;
         bias_s[j] = (bias != nullptr && col < NC) ? __ldg(bias + col) : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiWarps * 32);
       const uint32_t bias_addr = sbase + L::kOffBias + as * BLOCK_N * 4;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
+      // chunks are staged and stored in groups of G (one fence / commit per group, NG groups in flight); the two
+      // warps of a lane quarter split the tile's chunks in halves
+      constexpr int NG = OUT_BUFS >= 2 ? 2 : 1;
+      constexpr int G = OUT_BUFS / NG;
+      constexpr int kChunks = BLOCK_N / kChunkCols;
+      constexpr int kPerHalf = (kChunks + 1) / 2;
+      const int c_begin = half * kPerHalf, c_end = min(kChunks, c_begin + kPerHalf);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / kChunkCols; ++c) {
-        const int col0 = n_blk * BLOCK_N + c * kChunkCols;
-        if (col0 >= NC) break;                               // warp-uniform
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(e * 32) << 16) + as * BLOCK_N + c * kChunkCols;
-        // the staging buffer we are about to overwrite must have been read by its TMA store
-        if (lane == 0) tma_store_wait_read<1>();
+      for (int c0 = c_begin; c0 < c_end; c0 += G) {
+        if (n_blk * BLOCK_N + c0 * kChunkCols >= NC) break;  // warp-uniform
+        // the staging group we are about to overwrite must have been read by its TMA stores
+        if (lane == 0) tma_store_wait_read<NG - 1>();
         __syncwarp();
-        const uint32_t obuf = out_buf + buf * kStageOutBytes + out_row;
 #pragma unroll
-        for (int h = 0; h < (OUT_BF16 ? 2 : 1); ++h) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + h * 32, r);
-          tmem_ld_wait();
+        for (int g = 0; g < G; ++g) {
+          const int c = c0 + g;
+          const int col0 = n_blk * BLOCK_N + c * kChunkCols;
+          if (c >= c_end || col0 >= NC) break;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(e * 32) << 16) + as * BLOCK_N + c * kChunkCols;
+          const uint32_t obuf = out_buf + (buf * G + g) * kStageOutBytes + out_row;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = lds128f(bias_addr + (c * kChunkCols + h * 32 + j4 * 4) * 4);
-            float v0, v1, v2, v3;
-            if (MODE == kFwdI8) {
-              v0 = fmaf(__int2float_rn(static_cast<int>(r[4 * j4 + 0])), factor, b.x);
-              v1 = fmaf(__int2float_rn(static_cast<int>(r[4 * j4 + 1])), factor, b.y);
-              v2 = fmaf(__int2float_rn(static_cast<int>(r[4 * j4 + 2])), factor, b.z);
-              v3 = fmaf(__int2float_rn(static_cast<int>(r[4 * j4 + 3])), factor, b.w);
-            } else {
-              v0 = fmaf(__uint_as_float(r[4 * j4 + 0]), factor, b.x);
-              v1 = fmaf(__uint_as_float(r[4 * j4 + 1]), factor, b.y);
-              v2 = fmaf(__uint_as_float(r[4 * j4 + 2]), factor, b.z);
-              v3 = fmaf(__uint_as_float(r[4 * j4 + 3]), factor, b.w);
-            }
-            if (OUT_BF16) {
-              // two float4 groups make one 16-byte chunk of 8 bf16: stash the even group, emit on the odd one
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
-              r[4 * j4 + 0] = *reinterpret_cast<uint32_t*>(&p0);
-              r[4 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p1);
-              if (j4 & 1) {
-                const int chunk = h * 4 + (j4 >> 1);
-                sts128(obuf + ((chunk << 4) ^ swz),
-                       make_uint4(r[4 * (j4 - 1) + 0], r[4 * (j4 - 1) + 1], r[4 * j4 + 0], r[4 * j4 + 1]));
+          for (int h = 0; h < (OUT_BF16 ? 2 : 1); ++h) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + h * 32, r);
+            tmem_ld_wait();
+            if (dbg & 2) continue;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b = lds128f(bias_addr + (c * kChunkCols + h * 32 + j4 * 4) * 4);
+              float v0, v1, v2, v3;
+              if (MODE == kFwdI8) {
+                // exact int32 -> fp32 for |acc| < 2^22 (|acc| <= 128 K, K <= 32768) with two full-rate ops
+                // instead of the quarter-rate I2F: bits(1.5 * 2^23 + acc) = 0x4B400000 + acc
+                v0 = fmaf(__uint_as_float(r[4 * j4 + 0] + 0x4B400000u) - 12582912.0f, factor, b.x);
+                v1 = fmaf(__uint_as_float(r[4 * j4 + 1] + 0x4B400000u) - 12582912.0f, factor, b.y);
+                v2 = fmaf(__uint_as_float(r[4 * j4 + 2] + 0x4B400000u) - 12582912.0f, factor, b.z);
+                v3 = fmaf(__uint_as_float(r[4 * j4 + 3] + 0x4B400000u) - 12582912.0f, factor, b.w);
+              } else {
+                v0 = fmaf(__uint_as_float(r[4 * j4 + 0]), factor, b.x);
+                v1 = fmaf(__uint_as_float(r[4 * j4 + 1]), factor, b.y);
+                v2 = fmaf(__uint_as_float(r[4 * j4 + 2]), factor, b.z);
+                v3 = fmaf(__uint_as_float(r[4 * j4 + 3]), factor, b.w);
               }
-            } else {
-              sts128(obuf + ((j4 << 4) ^ swz), make_uint4(__float_as_uint(v0), __float_as_uint(v1),
-                                                          __float_as_uint(v2), __float_as_uint(v3)));
+              if (OUT_BF16) {
+                // two float4 groups make one 16-byte chunk of 8 bf16: stash the even group, emit on the odd one
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
+                r[4 * j4 + 0] = *reinterpret_cast<uint32_t*>(&p0);
+                r[4 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p1);
+                if (j4 & 1) {
+                  const int chunk = h * 4 + (j4 >> 1);
+                  sts128(obuf + ((chunk << 4) ^ swz),
+                         make_uint4(r[4 * (j4 - 1) + 0], r[4 * (j4 - 1) + 1], r[4 * j4 + 0], r[4 * j4 + 1]));
+                }
+              } else {
+                sts128(obuf + ((j4 << 4) ^ swz), make_uint4(__float_as_uint(v0), __float_as_uint(v1),
+                                                            __float_as_uint(v2), __float_as_uint(v3)));
+              }
             }
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&map_out, smem + L::kOffOut + (e * 2 + buf) * kStageOutBytes, col0, row0);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int col0 = n_blk * BLOCK_N + (c0 + g) * kChunkCols;
+            if (c0 + g < c_end && col0 < NC && !(dbg & 1))
+              tma_store_2d(&map_out, smem + L::kOffOut + ((ew * NG + buf) * G + g) * kStageOutBytes, col0, row0);
+          }
           tma_store_commit();
         }
-        buf ^= 1;
+        buf = (buf + 1 == NG) ? 0 : buf + 1;
       }
       tc_fence_before();
       __syncwarp();
@@ -589,13 +615,13 @@ static GemmCfg pick_gemm_cfg(int M, int NC) {
   return best;
 }
 
-template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS>
+template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS, int OUT_BUFS>
 static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_bp, const CUtensorMap& map_out,
                               const float* row_scale, const float* alpha, int alpha_mode, const float* bias, int M,
                               int NC, int KC, cudaStream_t st) {
-  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS>;
+  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS, OUT_BUFS>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OUT_BF16, CTAS>;
+  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OUT_BF16, CTAS, OUT_BUFS>;
   static bool attr_set = false;
   if (!attr_set) {
     OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
@@ -617,7 +643,8 @@ static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_b
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC));
+  OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC,
+                             g_dbg_kernel_flags));
   count_launch();
   return OB_OK;
 }
@@ -650,13 +677,17 @@ static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const floa
   if (rc != OB_OK) return rc;
 #define OB_GEMM_ARGS map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st
   if (cfg.ctas == 2) {
-    if (bn == 256) return launch_gemm_expand<MODE, 256, 5, OUT_BF16, 2>(OB_GEMM_ARGS);
-    return launch_gemm_expand<MODE, 128, 6, OUT_BF16, 2>(OB_GEMM_ARGS);
+    if (bn == 256) {
+      // long contractions want the deeper operand ring; short ones are output-bound and want double-buffered staging
+      if (KC >= 1024) return launch_gemm_expand<MODE, 256, 5, OUT_BF16, 2, 1>(OB_GEMM_ARGS);
+      return launch_gemm_expand<MODE, 256, 4, OUT_BF16, 2, 2>(OB_GEMM_ARGS);
+    }
+    return launch_gemm_expand<MODE, 128, 6, OUT_BF16, 2, 2>(OB_GEMM_ARGS);
   }
   switch (bn) {
-    case 256: return launch_gemm_expand<MODE, 256, 3, OUT_BF16, 1>(OB_GEMM_ARGS);
-    case 128: return launch_gemm_expand<MODE, 128, 5, OUT_BF16, 1>(OB_GEMM_ARGS);
-    default:  return launch_gemm_expand<MODE, 64, 6, OUT_BF16, 1>(OB_GEMM_ARGS);
+    case 256: return launch_gemm_expand<MODE, 256, 3, OUT_BF16, 1, 1>(OB_GEMM_ARGS);
+    case 128: return launch_gemm_expand<MODE, 128, 4, OUT_BF16, 1, 2>(OB_GEMM_ARGS);
+    default:  return launch_gemm_expand<MODE, 64, 6, OUT_BF16, 1, 2>(OB_GEMM_ARGS);
   }
 #undef OB_GEMM_ARGS
 }
@@ -713,6 +744,7 @@ extern "C" int ob_debug_set(int key, int value) {
     case kDbgForceBlockN: g_dbg_force_block_n = value; return OB_OK;
     case kDbgForceSplits: g_dbg_force_splits = value; return OB_OK;
     case kDbgMaxCtas: g_dbg_max_ctas = value; return OB_OK;
+    case kDbgKernelFlags: g_dbg_kernel_flags = value; return OB_OK;
     default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;
   }
 }
@@ -723,8 +755,8 @@ extern "C" int ob_gemm_tern_i8_fwd(const int8_t* q, const float* scale, const ui
                                    int alpha_mode, const float* bias, int M, int N, int K, void* y, int y_dtype,
                                    ob_stream_t stream) {
   OB_REQUIRE(q && scale && packed_i8 && alpha && y, "ob_gemm_tern_i8_fwd: null pointer");
-  OB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0,
-             "ob_gemm_tern_i8_fwd: need K %% 64 == 0 and N %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  OB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0 && K <= 32768,
+             "ob_gemm_tern_i8_fwd: need K %% 64 == 0, K <= 32768 and N %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
   OB_REQUIRE(aligned16(q) && aligned16(packed_i8) && aligned16(y), "ob_gemm_tern_i8_fwd: pointers must be 16-byte aligned");
   int rc = check_device();
   if (rc != OB_OK) return rc;
