@@ -1,0 +1,206 @@
+// ob_norm.cu - LayerNorm in front of the routed projections (conformer.py:35, 109).
+// One warp per token row held in registers (C = 128 V), fp32 throughout; the backward fuses dx with per-block
+// partial sums of d-gamma / d-beta, reduced in fixed order (deterministic).  HBM-bound streaming kernels.
+#include "ob_common.cuh"
+
+namespace ob {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, int64_t M, int C,
+                                                     float* __restrict__ y, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 g[V], b[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    g[j] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+    b[j] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j] = __ldg(xr + lane + 32 * j);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = wsum(s) * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float a = v[j].x - mean, c = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+      ss += (a * a + c * c) + (d * d + e * e);
+    }
+    const float rstd = 1.0f / sqrtf(wsum(ss) * inv_c + eps);
+    float4* yr = reinterpret_cast<float4*>(y + row * C);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float4 o;
+      o.x = (v[j].x - mean) * rstd * g[j].x + b[j].x;
+      o.y = (v[j].y - mean) * rstd * g[j].y + b[j].y;
+      o.z = (v[j].z - mean) * rstd * g[j].z + b[j].z;
+      o.w = (v[j].w - mean) * rstd * g[j].w + b[j].w;
+      yr[lane + 32 * j] = o;
+    }
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+constexpr int kLnBwdBlocks = 296;      // persistent grid; fixed so the parameter-gradient sum order is fixed
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  partial d-gamma += dy * xhat, d-beta += dy
+template <int V>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                     const float* __restrict__ gamma, int64_t M, int C,
+                                                     float* __restrict__ dx, float* __restrict__ part /* [2][blocks][C] */) {
+  __shared__ float4 red[8][32 * V];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 g[V], dg[V], db[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    g[j] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+    dg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    const float4* dr = reinterpret_cast<const float4*>(dy + row * C);
+    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    float4 xh[V], gg[V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float4 xv = __ldg(xr + lane + 32 * j), dv = __ldg(dr + lane + 32 * j);
+      xh[j] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      gg[j] = make_float4(dv.x * g[j].x, dv.y * g[j].y, dv.z * g[j].z, dv.w * g[j].w);
+      s1 += (gg[j].x + gg[j].y) + (gg[j].z + gg[j].w);
+      s2 += (gg[j].x * xh[j].x + gg[j].y * xh[j].y) + (gg[j].z * xh[j].z + gg[j].w * xh[j].w);
+      dg[j].x += dv.x * xh[j].x; dg[j].y += dv.y * xh[j].y; dg[j].z += dv.z * xh[j].z; dg[j].w += dv.w * xh[j].w;
+      db[j].x += dv.x; db[j].y += dv.y; db[j].z += dv.z; db[j].w += dv.w;
+    }
+    const float m1 = wsum(s1) * inv_c, m2 = wsum(s2) * inv_c;
+    float4* oxr = reinterpret_cast<float4*>(dx + row * C);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float4 o;
+      o.x = rstd * (gg[j].x - m1 - xh[j].x * m2);
+      o.y = rstd * (gg[j].y - m1 - xh[j].y * m2);
+      o.z = rstd * (gg[j].z - m1 - xh[j].z * m2);
+      o.w = rstd * (gg[j].w - m1 - xh[j].w * m2);
+      oxr[lane + 32 * j] = o;
+    }
+  }
+  // block partials: warps combined in fixed order
+  float* part_g = part + (int64_t)blockIdx.x * C;
+  float* part_b = part + ((int64_t)gridDim.x + blockIdx.x) * C;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[wid][lane + 32 * j] = which == 0 ? dg[j] : db[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * V; i += 256) {
+      float4 a = red[0][i];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) {
+        const float4 o = red[w][i];
+        a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+      }
+      reinterpret_cast<float4*>(which == 0 ? part_g : part_b)[i] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// [2][nblocks][C] partials -> d-gamma, d-beta: 32 columns x 8 row groups per block, fixed order
+__global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restrict__ part, int nblocks, int C,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int which = blockIdx.y;
+  const float* p = part + (int64_t)which * nblocks * C;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    int b = ry;
+    for (; b + 8 < nblocks; b += 16) {
+      a0 += p[(int64_t)b * C + c];
+      a1 += p[(int64_t)(b + 8) * C + c];
+    }
+    if (b < nblocks) a0 += p[(int64_t)b * C + c];
+  }
+  red[ry][cx] = a0 + a1;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][cx];
+    (which == 0 ? dgamma : dbeta)[c] = t;
+  }
+}
+
+}  // namespace ob
+
+using namespace ob;
+
+static int ln_blocks(int64_t M) {
+  const int64_t want = (M + 7) / 8;
+  return (int)(want < 148 * 8 ? want : 148 * 8);
+}
+
+extern "C" int ob_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int C,
+                                float* y, float* mean, float* rstd, ob_stream_t stream) {
+  OB_REQUIRE(x && gamma && beta && y && mean && rstd && M > 0, "ob_layernorm_fwd: null pointer or M <= 0");
+  OB_REQUIRE(C == 128 || C == 256 || C == 512 || C == 1024, "ob_layernorm_fwd: C (%d) must be 128, 256, 512 or 1024", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = ln_blocks(M);
+  switch (C) {
+    case 128:  ln_fwd_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, y, mean, rstd); break;
+    case 256:  ln_fwd_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, y, mean, rstd); break;
+    case 512:  ln_fwd_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, y, mean, rstd); break;
+    default:   ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, y, mean, rstd); break;
+  }
+  OB_LAUNCH_CHECK("ln_fwd_kernel");
+  return OB_OK;
+}
+
+extern "C" size_t ob_layernorm_bwd_workspace_bytes(int C) { return (size_t)2 * kLnBwdBlocks * C * sizeof(float); }
+
+extern "C" int ob_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                int64_t M, int C, float* dx, float* dgamma, float* dbeta, void* ws, ob_stream_t stream) {
+  OB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws && M > 0,
+             "ob_layernorm_bwd: null pointer or M <= 0");
+  OB_REQUIRE(C == 128 || C == 256 || C == 512 || C == 1024, "ob_layernorm_bwd: C (%d) must be 128, 256, 512 or 1024", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t want = (M + 7) / 8;
+  const int blocks = (int)(want < kLnBwdBlocks ? want : kLnBwdBlocks);
+  float* part = static_cast<float*>(ws);
+  switch (C) {
+    case 128:  ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, C, dx, part); break;
+    case 256:  ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, C, dx, part); break;
+    case 512:  ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, C, dx, part); break;
+    default:   ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, C, dx, part); break;
+  }
+  OB_LAUNCH_CHECK("ln_bwd_kernel");
+  dim3 grid((C + 31) / 32, 2);
+  ln_param_grad_kernel<<<grid, 256, 0, st>>>(part, blocks, C, dgamma, dbeta);
+  OB_LAUNCH_CHECK("ln_param_grad_kernel");
+  return OB_OK;
+}

@@ -135,6 +135,16 @@ int ob_swish_drop_quant(const float* h, const uint8_t* keep, float inv_keep, int
 int ob_swish_drop_bwd(const float* gz, const float* h, const uint8_t* keep, float inv_keep, int64_t n,
                       float* gh, ob_stream_t stream);
 
+/* LayerNorm in front of the routed projections (conformer.py:35, 109): y = (x - mean) * rstd * gamma + beta over the
+ * last axis C in {128, 256, 512, 1024}, fp32; mean/rstd [M] are kept for the backward.  ob_layernorm_bwd writes dx and
+ * the parameter gradients (deterministic two-stage reduction; ws >= ob_layernorm_bwd_workspace_bytes(C)). */
+int ob_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int C,
+                     float* y, float* mean, float* rstd, ob_stream_t stream);
+size_t ob_layernorm_bwd_workspace_bytes(int C);
+int ob_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                     const float* gamma, int64_t M, int C, float* dx, float* dgamma, float* dbeta,
+                     void* ws, ob_stream_t stream);
+
 /* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
  * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded
  * with -1), out_lens [B].  ws: at least ob_ctc_decode_workspace_bytes(B, T) bytes. */

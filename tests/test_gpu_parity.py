@@ -286,3 +286,28 @@ def test_fused_swish_dropout_quant_matches_unfused(ob, p, bw):
     if p > 0:
         dropped = ~keep
         assert ghf[dropped].abs().max().item() == 0.0              # no gradient through dropped activations
+
+
+# ------------------------------------------------------------------ LayerNorm in front of the routed projections
+@pytest.mark.parametrize("shape", [(4, 249, 256), (25536, 256), (3, 7, 128), (1000, 1024), (5, 512)])
+def test_layernorm_matches_torch(ob, shape):
+    from onebit_b200.norm import layer_norm
+    g = torch.Generator().manual_seed(sum(shape))
+    C = shape[-1]
+    x0 = (torch.randn(*shape, generator=g) * 3 + 1).cuda()
+    w = (torch.randn(C, generator=g) * 0.5 + 1).cuda().requires_grad_(True)
+    b = torch.randn(C, generator=g).cuda().requires_grad_(True)
+    gy = torch.randn(*shape, generator=g).cuda()
+    outs = []
+    for fn in (lambda t: layer_norm(t, w, b, 1e-5), lambda t: torch.nn.functional.layer_norm(t, (C,), w, b, 1e-5)):
+        w.grad = b.grad = None
+        x = x0.clone().requires_grad_(True)
+        y = fn(x)
+        y.backward(gy)
+        outs.append((y.detach(), x.grad, w.grad.clone(), b.grad.clone()))
+    (y1, gx1, gw1, gb1), (y2, gx2, gw2, gb2) = outs
+    assert torch.allclose(y1, y2, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(gx1, gx2, rtol=1e-4, atol=1e-5)
+    rows = x0.numel() // C
+    assert (gw1 - gw2).abs().max().item() < 1e-5 * rows ** 0.5 * gw2.abs().max().clamp_min(1).item()
+    assert (gb1 - gb2).abs().max().item() < 1e-5 * rows ** 0.5 * gb2.abs().max().clamp_min(1).item()
