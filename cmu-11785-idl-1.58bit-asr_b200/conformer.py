@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import attention
 from .norm import layer_norm
 from .quant import QuantizedLinear
 
@@ -128,12 +129,17 @@ class MHSA(nn.Module):
         v = self._heads(self.v_proj(y, bitwidth), B)
         p = self._heads(self.pos_proj(pos_emb, bitwidth), 1)
         ac = torch.matmul(q + self.pos_bias_u.view(1, self.n_heads, 1, self.d_head), k.transpose(-2, -1))
-        bd = self.rel_shift(torch.matmul(q + self.pos_bias_v.view(1, self.n_heads, 1, self.d_head), p.transpose(-2, -1)))
-        scores = (ac + bd) / math.sqrt(self.d_head)
-        if mask is not None:
-            scores = scores.masked_fill(mask[:, None, :, :] == 0, float("-inf"))
-        attn = torch.nan_to_num(torch.softmax(scores, dim=-1), nan=0.0)     # fully padded rows -> 0 (conformer.py:127)
-        attn = self.dropout(attn)
+        bd_raw = torch.matmul(q + self.pos_bias_v.view(1, self.n_heads, 1, self.d_head), p.transpose(-2, -1))
+        if attention.usable(ac, mask):
+            # shift + scale + mask + softmax + nan_to_num + dropout in one kernel each way (same formulas)
+            attn = attention.rel_attention_probs(ac, bd_raw, mask, 1.0 / math.sqrt(self.d_head), self.dropout.p,
+                                                 self.training)
+        else:
+            scores = (ac + self.rel_shift(bd_raw)) / math.sqrt(self.d_head)
+            if mask is not None:
+                scores = scores.masked_fill(mask[:, None, :, :] == 0, float("-inf"))
+            attn = torch.nan_to_num(torch.softmax(scores, dim=-1), nan=0.0)  # fully padded rows -> 0 (conformer.py:127)
+            attn = self.dropout(attn)
         h = (attn @ v).transpose(1, 2).contiguous().view(B, T, C)
         h = self.dropout(self.out_proj(h, bitwidth))
         if mask is not None:

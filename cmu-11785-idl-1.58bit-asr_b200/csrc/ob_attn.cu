@@ -1,0 +1,164 @@
+// ob_attn.cu - the element-wise chain between the attention matmuls of the reference's MHSA (conformer.py:118-128):
+//   scores = (ac + rel_shift(bd)) / sqrt(d_head) -> masked_fill(-inf) -> softmax -> nan_to_num -> dropout
+// fused into one forward and one backward kernel (nine / twelve torch kernels over [B,H,T,T] fp32 otherwise).
+// One warp per (b, h, i) row held in registers; the relative shift (conformer.py:96-103: pad one column, view as
+// [T+1, T], drop the first row) is pure index arithmetic: element (i, j) reads P[f / (T+1)][f % (T+1)] with
+// f = T + i*T + j, P = [0 | bd].  SURVEY.md section 8f ranks 1/3 (callers around the routed projections).
+#include "ob_common.cuh"
+
+namespace ob {
+
+__device__ __forceinline__ float wmax_(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float wsum_(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// NJ = ceil(T / 32) elements per lane
+template <int NJ>
+__global__ void __launch_bounds__(256) relattn_softmax_fwd_kernel(const float* __restrict__ ac, const float* __restrict__ bd,
+                                                                  const uint8_t* __restrict__ mask /* [B,T,T] */,
+                                                                  const uint8_t* __restrict__ keep /* [B,H,T,T] | null */,
+                                                                  float inv_keep, float scale, int B, int H, int T,
+                                                                  float* __restrict__ y, float* __restrict__ attn_d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)B * H * T;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    const int i = (int)(row % T);
+    const int64_t bh = row / T;
+    const int b = (int)(bh / H);
+    const float* ac_r = ac + row * T;
+    const float* bd_bh = bd + bh * (int64_t)T * T;
+    const uint8_t* m_r = mask + ((int64_t)b * T + i) * T;
+    const int f0 = T + i * T;
+    const int r0 = f0 / (T + 1), c0 = f0 - r0 * (T + 1);
+    float s[NJ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) {
+      const int j = lane + 32 * u;
+      s[u] = -INFINITY;
+      if (j < T && m_r[j]) {
+        int c = c0 + j, r = r0;
+        if (c >= T + 1) { c -= T + 1; r += 1; }
+        const float bdv = c == 0 ? 0.f : __ldg(bd_bh + (int64_t)r * T + (c - 1));
+        s[u] = (__ldg(ac_r + j) + bdv) * scale;
+        mx = fmaxf(mx, s[u]);
+      }
+    }
+    mx = wmax_(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) {
+      s[u] = (s[u] == -INFINITY) ? 0.f : expf(s[u] - mx);      // fully masked row: mx = -inf, every term 0
+      sum += s[u];
+    }
+    sum = wsum_(sum);
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;               // nan_to_num(nan = 0) of the reference (conformer.py:127)
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) {
+      const int j = lane + 32 * u;
+      if (j < T) {
+        const float p = s[u] * inv;
+        y[row * T + j] = p;
+        if (attn_d != nullptr) attn_d[row * T + j] = keep[row * T + j] ? p * inv_keep : 0.f;
+      }
+    }
+  }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256) relattn_softmax_bwd_kernel(const float* __restrict__ gd, const float* __restrict__ y,
+                                                                  const uint8_t* __restrict__ keep, float inv_keep,
+                                                                  float scale, int B, int H, int T,
+                                                                  float* __restrict__ d_ac, float* __restrict__ d_bd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)B * H * T;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    const int i = (int)(row % T);
+    const int64_t bh = row / T;
+    float* dbd_bh = d_bd + bh * (int64_t)T * T;
+    const int f0 = T + i * T;
+    const int r0 = f0 / (T + 1), c0 = f0 - r0 * (T + 1);
+    float g[NJ], p[NJ];
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) {
+      const int j = lane + 32 * u;
+      g[u] = 0.f;
+      p[u] = 0.f;
+      if (j < T) {
+        p[u] = __ldg(y + row * T + j);
+        float gv = __ldg(gd + row * T + j);
+        if (keep != nullptr) gv = keep[row * T + j] ? gv * inv_keep : 0.f;
+        g[u] = gv;
+        dot += gv * p[u];
+      }
+    }
+    dot = wsum_(dot);
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) {
+      const int j = lane + 32 * u;
+      if (j < T) {
+        const float ds = p[u] * (g[u] - dot) * scale;
+        d_ac[row * T + j] = ds;
+        int c = c0 + j, r = r0;
+        if (c >= T + 1) { c -= T + 1; r += 1; }
+        if (c > 0) dbd_bh[(int64_t)r * T + (c - 1)] = ds;        // c == 0 is the padded column: no gradient
+      }
+    }
+    if (i == 0)                                                   // positions of [0 | bd] in front of the dropped row
+      for (int j = lane; j < T - 1; j += 32) dbd_bh[j] = 0.f;
+  }
+}
+
+}  // namespace ob
+
+using namespace ob;
+
+static int attn_blocks(int64_t rows) {
+  const int64_t want = (rows + 7) / 8;
+  return (int)(want < 148 * 16 ? want : 148 * 16);
+}
+
+#define OB_ATTN_DISPATCH(KERNEL, ...)                                         \
+  do {                                                                        \
+    const int nj = (T + 31) / 32;                                             \
+    if (nj <= 8) KERNEL<8><<<blocks, 256, 0, st>>>(__VA_ARGS__);              \
+    else if (nj <= 16) KERNEL<16><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
+    else if (nj <= 32) KERNEL<32><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
+    else KERNEL<64><<<blocks, 256, 0, st>>>(__VA_ARGS__);                     \
+  } while (0)
+
+extern "C" int ob_relattn_softmax_fwd(const float* ac, const float* bd, const uint8_t* mask, const uint8_t* keep,
+                                      float inv_keep, float scale, int B, int H, int T, float* y, float* attn_d,
+                                      ob_stream_t stream) {
+  OB_REQUIRE(ac && bd && mask && y, "ob_relattn_softmax_fwd: null pointer");
+  OB_REQUIRE((keep == nullptr) == (attn_d == nullptr), "ob_relattn_softmax_fwd: keep and attn_d go together");
+  OB_REQUIRE(B > 0 && H > 0 && T > 0 && T <= 2048, "ob_relattn_softmax_fwd: need 0 < T <= 2048 (T=%d)", T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = attn_blocks((int64_t)B * H * T);
+  OB_ATTN_DISPATCH(relattn_softmax_fwd_kernel, ac, bd, mask, keep, inv_keep, scale, B, H, T, y, attn_d);
+  OB_LAUNCH_CHECK("relattn_softmax_fwd_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep, float inv_keep, float scale,
+                                      int B, int H, int T, float* d_ac, float* d_bd, ob_stream_t stream) {
+  OB_REQUIRE(gd && y && d_ac && d_bd, "ob_relattn_softmax_bwd: null pointer");
+  OB_REQUIRE(B > 0 && H > 0 && T > 0 && T <= 2048, "ob_relattn_softmax_bwd: need 0 < T <= 2048 (T=%d)", T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = attn_blocks((int64_t)B * H * T);
+  OB_ATTN_DISPATCH(relattn_softmax_bwd_kernel, gd, y, keep, inv_keep, scale, B, H, T, d_ac, d_bd);
+  OB_LAUNCH_CHECK("relattn_softmax_bwd_kernel");
+  return OB_OK;
+}

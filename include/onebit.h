@@ -145,6 +145,16 @@ int ob_layernorm_bwd(const float* dy, const float* x, const float* mean, const f
                      const float* gamma, int64_t M, int C, float* dx, float* dgamma, float* dbeta,
                      void* ws, ob_stream_t stream);
 
+/* Element-wise chain between the attention matmuls of the reference MHSA (conformer.py:118-128), fused:
+ * y = nan_to_num(softmax(masked_fill((ac + rel_shift(bd)) * scale))), attn_d = dropout(y).  ac, bd [B,H,T,T] fp32 (bd
+ * BEFORE the relative shift), mask [B,T,T] bytes (0 = masked), keep [B,H,T,T] bytes or NULL (then attn_d NULL), T <= 2048.
+ * Backward: gradients w.r.t. ac and the un-shifted bd from the gradient w.r.t. attn_d (or y when keep is NULL). */
+int ob_relattn_softmax_fwd(const float* ac, const float* bd, const uint8_t* mask, const uint8_t* keep,
+                           float inv_keep, float scale, int B, int H, int T, float* y, float* attn_d,
+                           ob_stream_t stream);
+int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep, float inv_keep,
+                           float scale, int B, int H, int T, float* d_ac, float* d_bd, ob_stream_t stream);
+
 /* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
  * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded
  * with -1), out_lens [B].  ws: at least ob_ctc_decode_workspace_bytes(B, T) bytes. */

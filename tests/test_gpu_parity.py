@@ -311,3 +311,43 @@ def test_layernorm_matches_torch(ob, shape):
     rows = x0.numel() // C
     assert (gw1 - gw2).abs().max().item() < 1e-5 * rows ** 0.5 * gw2.abs().max().clamp_min(1).item()
     assert (gb1 - gb2).abs().max().item() < 1e-5 * rows ** 0.5 * gb2.abs().max().clamp_min(1).item()
+
+
+# ------------------------------------------------------------------ fused relative-position attention chain
+@pytest.mark.parametrize("B,H,T", [(2, 4, 49), (3, 2, 249), (1, 4, 399), (2, 1, 33), (1, 2, 700)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_rel_attention_probs_matches_reference_chain(ob, B, H, T, p):
+    """Against the reference's own op sequence (conformer.py:96-128) written with torch ops, incl. padded utterances
+    (fully masked rows -> zeros) and the relative shift."""
+    import math as _m
+    from onebit_b200.attention import rel_attention_probs
+    from onebit_b200.conformer import MHSA
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    ac0 = (torch.randn(B, H, T, T, generator=g) * 3).cuda()
+    bd0 = (torch.randn(B, H, T, T, generator=g) * 3).cuda()
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    km = (torch.arange(T)[None, :] < lens[:, None]).cuda()
+    mask = km[:, :, None] & km[:, None, :]
+    keep = (torch.rand(B, H, T, T, generator=g) > p).cuda() if p > 0 else None
+    gy = torch.randn(B, H, T, T, generator=g).cuda()
+    scale = 1.0 / _m.sqrt(64)
+
+    def reference(ac, bd):
+        scores = (ac + MHSA.rel_shift(bd)) / _m.sqrt(64)
+        scores = scores.masked_fill(mask[:, None, :, :] == 0, float("-inf"))
+        a = torch.nan_to_num(torch.softmax(scores, dim=-1), nan=0.0)
+        return a if keep is None else a * keep.float() * (1.0 / (1.0 - p))
+
+    outs = []
+    for fn in (lambda a, b: rel_attention_probs(a, b, mask, scale, p, True, keep=keep), reference):
+        ac, bd = ac0.clone().requires_grad_(True), bd0.clone().requires_grad_(True)
+        out = fn(ac, bd)
+        out.backward(gy)
+        outs.append((out.detach(), ac.grad, bd.grad))
+    (o1, ga1, gb1), (o2, ga2, gb2) = outs
+    assert torch.allclose(o1, o2, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ga1, ga2, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(gb1, gb2, rtol=1e-4, atol=1e-6)
+    if (~km).any():
+        assert o1.transpose(1, 2)[~km].abs().max().item() == 0.0        # padded query rows are exactly zero
