@@ -322,6 +322,10 @@ class QuantizedLinear(nn.Module):
         _require_cuda(self.weight, "weight")
         if x.dtype not in _DTYPE_TAG:
             raise ValueError(f"onebit_b200: unsupported input dtype {x.dtype}")
+        if x.shape[-1] != self.in_features:
+            raise ValueError(f"onebit_b200: expected last dimension {self.in_features}, got {x.shape[-1]}")
+        if x.numel() == 0:                                # empty batch: nothing to launch (F.linear returns an empty tensor too)
+            return x.new_zeros(*x.shape[:-1], self.out_features) + 0.0 * (self.weight.sum() + self.alpha)
         packed, packed_t = self.packed_weight(bitwidth)
         return _QuantLinearFn.apply(x, self.weight, self.alpha, self.bias, bitwidth, packed, packed_t)
 

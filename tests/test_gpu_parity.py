@@ -351,3 +351,37 @@ def test_rel_attention_probs_matches_reference_chain(ob, B, H, T, p):
     assert torch.allclose(gb1, gb2, rtol=1e-4, atol=1e-6)
     if (~km).any():
         assert o1.transpose(1, 2)[~km].abs().max().item() == 0.0        # padded query rows are exactly zero
+
+
+# ------------------------------------------------------------------ edge cases of the layer interface
+def test_layer_edge_cases(ob):
+    torch.manual_seed(2)
+    layer = ob.QuantizedLinear(128, 64).cuda()
+    # empty batch
+    y = layer(torch.empty(0, 7, 128, device="cuda"), 2)
+    assert y.shape == (0, 7, 64)
+    # a single token, 1-D input
+    x1 = torch.randn(128, device="cuda")
+    y1 = layer(x1, 1)
+    assert y1.shape == (64,)
+    ref = orc.linear_forward(x1.cpu().numpy()[None], layer.weight.detach().cpu().numpy(), layer.alpha.item(),
+                             layer.bias.detach().cpu().numpy(), 1, 8)[0]
+    assert rel_err(y1.detach().cpu().numpy(), ref) < 1e-4
+    # non-contiguous input (a transposed view) and a bf16 input
+    xt = torch.randn(128, 33, device="cuda").t()
+    assert torch.equal(layer(xt, 2), layer(xt.contiguous(), 2))
+    yb = layer(xt.contiguous().to(torch.bfloat16), 2)
+    assert yb.dtype == torch.bfloat16 and rel_err(yb.float().cpu().numpy(), layer(xt.contiguous().to(torch.bfloat16).float(), 2).detach().cpu().numpy()) < 2e-2
+    # wrong feature size, wrong bitwidth
+    with pytest.raises(ValueError):
+        layer(torch.randn(4, 64, device="cuda"), 2)
+    with pytest.raises(ValueError, match="bitwidth must be one of"):
+        layer(torch.randn(4, 128, device="cuda"), 8)
+    # no-bias layer, gradient only w.r.t. the weight
+    nb = ob.QuantizedLinear(128, 64, bias=False).cuda()
+    x = torch.randn(10, 128, device="cuda")
+    nb(x, 2).sum().backward()
+    assert nb.weight.grad is not None and nb.alpha.grad is not None and nb.bias is None
+    # all-zero input: scale clamp path, output == bias
+    z = layer(torch.zeros(3, 128, device="cuda"), 2)
+    assert torch.allclose(z, layer.bias.expand(3, 64))
