@@ -21,7 +21,7 @@ __device__ __forceinline__ float wsum_(float v) {
 
 // NJ = ceil(T / 32) elements per lane
 template <int NJ>
-__global__ void __launch_bounds__(256) relattn_softmax_fwd_kernel(const float* __restrict__ ac, const float* __restrict__ bd,
+__global__ void __launch_bounds__(256, 2) relattn_softmax_fwd_kernel(const float* __restrict__ ac, const float* __restrict__ bd,
                                                                   const uint8_t* __restrict__ mask /* [B,T,T] */,
                                                                   const uint8_t* __restrict__ keep /* [B,H,T,T] | null */,
                                                                   float inv_keep, float scale, int B, int H, int T,
@@ -41,15 +41,25 @@ __global__ void __launch_bounds__(256) relattn_softmax_fwd_kernel(const float* _
     const int r0 = f0 / (T + 1), c0 = f0 - r0 * (T + 1);
     float s[NJ];
     float mx = -INFINITY;
+    // phase 1: every load of the row is issued up front with a clamped (always in-bounds) index and no predicate,
+    // so ~3 NJ requests per lane are in flight at once; phase 2 applies the bounds and the mask
+    float av[NJ], bv[NJ];
+    uint8_t mk[NJ];
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
-      const int j = lane + 32 * u;
+      const int j = min(lane + 32 * u, T - 1);
+      int c = c0 + j, r = r0;
+      if (c >= T + 1) { c -= T + 1; r += 1; }
+      mk[u] = __ldg(m_r + j);
+      av[u] = __ldg(ac_r + j);
+      bv[u] = __ldg(bd_bh + (int64_t)r * T + max(c - 1, 0));
+      if (c == 0) bv[u] = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) {
       s[u] = -INFINITY;
-      if (j < T && m_r[j]) {
-        int c = c0 + j, r = r0;
-        if (c >= T + 1) { c -= T + 1; r += 1; }
-        const float bdv = c == 0 ? 0.f : __ldg(bd_bh + (int64_t)r * T + (c - 1));
-        s[u] = (__ldg(ac_r + j) + bdv) * scale;
+      if (lane + 32 * u < T && mk[u]) {
+        s[u] = (av[u] + bv[u]) * scale;
         mx = fmaxf(mx, s[u]);
       }
     }
@@ -62,20 +72,25 @@ __global__ void __launch_bounds__(256) relattn_softmax_fwd_kernel(const float* _
     }
     sum = wsum_(sum);
     const float inv = sum > 0.f ? 1.0f / sum : 0.f;               // nan_to_num(nan = 0) of the reference (conformer.py:127)
+    uint8_t kp[NJ];
+    if (attn_d != nullptr) {
+#pragma unroll
+      for (int u = 0; u < NJ; ++u) kp[u] = __ldg(keep + row * T + min(lane + 32 * u, T - 1));
+    }
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
       const int j = lane + 32 * u;
       if (j < T) {
         const float p = s[u] * inv;
         y[row * T + j] = p;
-        if (attn_d != nullptr) attn_d[row * T + j] = keep[row * T + j] ? p * inv_keep : 0.f;
+        if (attn_d != nullptr) attn_d[row * T + j] = kp[u] ? p * inv_keep : 0.f;
       }
     }
   }
 }
 
 template <int NJ>
-__global__ void __launch_bounds__(256) relattn_softmax_bwd_kernel(const float* __restrict__ gd, const float* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) relattn_softmax_bwd_kernel(const float* __restrict__ gd, const float* __restrict__ y,
                                                                   const uint8_t* __restrict__ keep, float inv_keep,
                                                                   float scale, int B, int H, int T,
                                                                   float* __restrict__ d_ac, float* __restrict__ d_bd) {
@@ -90,18 +105,23 @@ __global__ void __launch_bounds__(256) relattn_softmax_bwd_kernel(const float* _
     const int f0 = T + i * T;
     const int r0 = f0 / (T + 1), c0 = f0 - r0 * (T + 1);
     float g[NJ], p[NJ];
+    uint8_t kp[NJ];
     float dot = 0.f;
 #pragma unroll
+    for (int u = 0; u < NJ; ++u) {                                // all loads first, clamped index, no predicate
+      const int j = min(lane + 32 * u, T - 1);
+      p[u] = __ldg(y + row * T + j);
+      g[u] = __ldg(gd + row * T + j);
+      kp[u] = keep != nullptr ? __ldg(keep + row * T + j) : (uint8_t)1;
+    }
+#pragma unroll
     for (int u = 0; u < NJ; ++u) {
-      const int j = lane + 32 * u;
-      g[u] = 0.f;
-      p[u] = 0.f;
-      if (j < T) {
-        p[u] = __ldg(y + row * T + j);
-        float gv = __ldg(gd + row * T + j);
-        if (keep != nullptr) gv = keep[row * T + j] ? gv * inv_keep : 0.f;
-        g[u] = gv;
-        dot += gv * p[u];
+      if (lane + 32 * u < T) {
+        g[u] = kp[u] ? g[u] * (keep != nullptr ? inv_keep : 1.0f) : 0.f;
+        dot += g[u] * p[u];
+      } else {
+        g[u] = 0.f;
+        p[u] = 0.f;
       }
     }
     dot = wsum_(dot);
@@ -134,6 +154,7 @@ static int attn_blocks(int64_t rows) {
   do {                                                                        \
     const int nj = (T + 31) / 32;                                             \
     if (nj <= 8) KERNEL<8><<<blocks, 256, 0, st>>>(__VA_ARGS__);              \
+    else if (nj <= 13) KERNEL<13><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
     else if (nj <= 16) KERNEL<16><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
     else if (nj <= 32) KERNEL<32><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
     else KERNEL<64><<<blocks, 256, 0, st>>>(__VA_ARGS__);                     \

@@ -151,3 +151,30 @@ def modelshape():
 
 if len(sys.argv) > 1 and sys.argv[1] == "modelshape":
     modelshape()
+
+
+def attn():
+    """The fused attention chain at the bench shape (B=64, H=4, T=399), forward + backward, a few launches."""
+    from onebit_b200.attention import rel_attention_probs
+    B, H, T = 64, 4, 399
+    ac = torch.randn(B, H, T, T, device="cuda", requires_grad=True)
+    bd = torch.randn(B, H, T, T, device="cuda", requires_grad=True)
+    mask = torch.ones(B, T, T, device="cuda", dtype=torch.bool)
+    gy = torch.randn(B, H, T, T, device="cuda")
+    for _ in range(3):
+        rel_attention_probs(ac, bd, mask, 0.125, 0.1, True).backward(gy)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    out = rel_attention_probs(ac, bd, mask, 0.125, 0.1, True)
+    e[1].record()
+    out.backward(gy)
+    e[2].record()
+    torch.cuda.synchronize()
+    nb = B * H * T * T
+    print(f"attn chain fwd(+bernoulli) {e[0].elapsed_time(e[1]) * 1e3:.0f} us, bwd {e[1].elapsed_time(e[2]) * 1e3:.0f} us "
+          f"({nb * 18 / 1e6:.0f} MB each way)")
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "attn":
+    attn()
