@@ -302,6 +302,43 @@ def hot_kernel_rooflines(peaks, M):
                                            ws.data_ptr(), nbytes, st),
                    2.0 * M * N + 2.0 * M * K + 8.0 * N * K, 2.0 * M * N * K),
     }
+    # kernels around the layer (same token count): FFN mid-section, LayerNorm, attention chain, weight quantiser
+    from onebit_b200.attention import rel_attention_probs  # noqa: F401
+    h_mid = [torch.randn(M, N, device=dev) for _ in range(2)]
+    q_mid = torch.empty(M, N, device=dev, dtype=torch.int8)
+    s_mid = torch.empty(M, device=dev)
+    keep = torch.rand(M, N, device=dev) > 0.1
+    gh = torch.empty(M, N, device=dev)
+    ln_w, ln_b = torch.ones(K, device=dev), torch.zeros(K, device=dev)
+    ln_y, ln_stats = torch.empty(M, K, device=dev), torch.empty(2, M, device=dev)
+    ln_dx, ln_dp = torch.empty(M, K, device=dev), torch.empty(2, K, device=dev)
+    ln_ws = torch.empty(lib.ob_layernorm_bwd_workspace_bytes(K), device=dev, dtype=torch.uint8)
+    Bq, Hh, Tt = max(1, M // 399), 4, 399
+    att = [torch.randn(Bq, Hh, Tt, Tt, device=dev) for _ in range(4)]
+    att_keep = torch.rand(Bq, Hh, Tt, Tt, device=dev) > 0.1
+    att_mask = torch.ones(Bq, Tt, Tt, device=dev, dtype=torch.bool)
+    att_y, att_o = torch.empty_like(att[0]), torch.empty_like(att[0])
+    nat = Bq * Hh * Tt * Tt
+    pk2, pkt2 = torch.empty_like(pk), torch.empty_like(pkt)
+    fns.update({
+        "swish_drop_quant": (lambda j: lib.ob_swish_drop_quant(h_mid[j % 2].data_ptr(), keep.data_ptr(), 1.0 / 0.9, M, N,
+                                                                q_mid.data_ptr(), s_mid.data_ptr(), st), 4.0 * M * N + 2.0 * M * N + 4 * M, 0.0),
+        "swish_drop_bwd": (lambda j: lib.ob_swish_drop_bwd(gys[j].data_ptr(), h_mid[j % 2].data_ptr(), keep.data_ptr(), 1.0 / 0.9,
+                                                            M * N, gh.data_ptr(), st), 12.0 * M * N + M * N, 0.0),
+        "layernorm_fwd": (lambda j: lib.ob_layernorm_fwd(xs[j].data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), 1e-5, M, K, ln_y.data_ptr(),
+                                                         ln_stats[0].data_ptr(), ln_stats[1].data_ptr(), st), 8.0 * M * K + 8 * M, 0.0),
+        "layernorm_bwd": (lambda j: lib.ob_layernorm_bwd(dxs[j].data_ptr(), xs[j].data_ptr(), ln_stats[0].data_ptr(), ln_stats[1].data_ptr(),
+                                                         ln_w.data_ptr(), M, K, ln_dx.data_ptr(), ln_dp[0].data_ptr(), ln_dp[1].data_ptr(),
+                                                         ln_ws.data_ptr(), st), 12.0 * M * K + 8 * M, 0.0),
+        "relattn_softmax_fwd": (lambda j: lib.ob_relattn_softmax_fwd(att[j % 2].data_ptr(), att[2 + j % 2].data_ptr(), att_mask.data_ptr(),
+                                                                     att_keep.data_ptr(), 1.0 / 0.9, 0.125, Bq, Hh, Tt, att_y.data_ptr(),
+                                                                     att_o.data_ptr(), st), 17.0 * nat, 0.0),
+        "relattn_softmax_bwd": (lambda j: lib.ob_relattn_softmax_bwd(att[j % 2].data_ptr(), att_y.data_ptr(), att_keep.data_ptr(), 1.0 / 0.9,
+                                                                     0.125, Bq, Hh, Tt, att[2].data_ptr(), att[3].data_ptr(), st),
+                                17.0 * nat, 0.0),
+        "weight_quant_pack": (lambda j: lib.ob_weight_quant_pack(layer.weight.data_ptr(), a.data_ptr(), 1, N, K, 2, pk2.data_ptr(),
+                                                                 pkt2.data_ptr(), st), 4.5 * N * K, 0.0),
+    })
     out = {}
     for name, (fn, nbytes_alg, flops) in fns.items():
         for _ in range(3):
@@ -311,7 +348,7 @@ def hot_kernel_rooflines(peaks, M):
         out[name] = {"ms": round(ms, 4), "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": round(gbs / peaks["hbm_gbs"], 4), "algorithmic_bytes": int(nbytes_alg),
                      "tflops": round(flops / (ms * 1e-3) / 1e12, 1) if flops else None}
-    return {"shape": {"M": M, "K": K, "N": N}, "kernels": out}
+    return {"shape": {"M": M, "K": K, "N": N, "attention": [Bq, Hh, Tt, Tt]}, "kernels": out}
 
 
 def cpu_reference_train(args, sample_batch, steps):
@@ -427,7 +464,8 @@ def run_train(args, world, rank):
         M = B * (((T - 1) // 2 - 1) // 2)
         hk = hot_kernel_rooflines(peaks, M)
         # dominant kernel of the layer inside the step = the one with the largest per-layer time at this shape
-        dom = max(hk["kernels"].items(), key=lambda kv: kv[1]["ms"])
+        core = ("act_quant_i8", "gemm_fwd", "bwd_prep", "bwd_dx", "bwd_dw")
+        dom = max(((k, v) for k, v in hk["kernels"].items() if k in core), key=lambda kv: kv[1]["ms"])
         out["roofline"] = dict(kernel=dom[0], shape=hk["shape"], traffic=None,
                                **{k: dom[1][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
                                peak_source=f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)")

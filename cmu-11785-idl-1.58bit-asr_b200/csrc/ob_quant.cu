@@ -437,17 +437,22 @@ __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __re
   for (int64_t row = warp0; row < M; row += nwarps) {
     const float* hr = h + row * K;
     float4 v[V];
+    uchar4 mk[V];
     float amax = 0.f;
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
+    for (int j = 0; j < V; ++j) {                       // all loads of the row first (memory-level parallelism)
       const int e = (lane + 32 * j) * 4;
-      float4 t = __ldg(reinterpret_cast<const float4*>(hr + e));
-      t.x = swish_f(t.x); t.y = swish_f(t.y); t.z = swish_f(t.z); t.w = swish_f(t.w);
-      if (keep != nullptr) {
-        const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep + row * K + e));
-        t.x = m.x ? t.x * inv_keep : 0.f; t.y = m.y ? t.y * inv_keep : 0.f;
-        t.z = m.z ? t.z * inv_keep : 0.f; t.w = m.w ? t.w * inv_keep : 0.f;
-      }
+      v[j] = __ldg(reinterpret_cast<const float4*>(hr + e));
+      mk[j] = keep != nullptr ? __ldg(reinterpret_cast<const uchar4*>(keep + row * K + e)) : make_uchar4(1, 1, 1, 1);
+    }
+    const float ik = keep != nullptr ? inv_keep : 1.0f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float4 t = v[j];
+      t.x = mk[j].x ? swish_f(t.x) * ik : 0.f;
+      t.y = mk[j].y ? swish_f(t.y) * ik : 0.f;
+      t.z = mk[j].z ? swish_f(t.z) * ik : 0.f;
+      t.w = mk[j].w ? swish_f(t.w) * ik : 0.f;
       v[j] = t;
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
     }
@@ -486,7 +491,7 @@ __global__ void __launch_bounds__(256) swish_drop_bwd_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------
 // backward prep: dys = bf16(dY / s_m), qb = bf16(q), column sums of dY per row block
 // ---------------------------------------------------------------------------------------------
-constexpr int kPrepRows = 64;
+constexpr int kPrepRows = 32;
 
 __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
   __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
@@ -518,12 +523,12 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ dY,
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (rg < rpi) {
       int r = rg;
-      for (; r + 3 * rpi < rows; r += 4 * rpi) {                 // 4 independent 16-byte loads in flight per thread
-        float4 v[4];
+      for (; r + 7 * rpi < rows; r += 8 * rpi) {                 // 8 independent 16-byte loads in flight per thread
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = load4<T>(dY + (int64_t)(r0 + r + u * rpi) * N + c);
+        for (int u = 0; u < 8; ++u) v[u] = load4<T>(dY + (int64_t)(r0 + r + u * rpi) * N + c);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
           const float is = inv_s[r + u * rpi];
           *reinterpret_cast<uint2*>(dys + (int64_t)(r0 + r + u * rpi) * N + c) =

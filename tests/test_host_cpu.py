@@ -46,7 +46,7 @@ def test_argument_validation_without_gpu():
     assert lib.ob_bwd_dx(16, 16, 16, 16, 1, 8, 60, 64, 16, 0, None) == _cabi.OB_ERR_ARG                   # N % 64
     assert lib.ob_debug_set(999, 1) == _cabi.OB_ERR_ARG
     assert lib.ob_bwd_dw_workspace_bytes(1000, 256, 256) >= 256 * 256 * 4
-    assert lib.ob_bwd_colsum_blocks(129) == 3
+    assert lib.ob_bwd_colsum_blocks(129) == (129 + 31) // 32
 
 
 def test_constructor_matches_reference_fixtures(kat_seeded):
