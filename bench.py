@@ -57,6 +57,9 @@ def parse():
                    help="recompute the (bitwidth-independent, dropout-free) conv subsampling in each of the three passes, as the "
                         "reference does; by default it is computed once per step and shared - identical loss and gradients")
     p.add_argument("--sweep", action="store_true", help="gemm workload: also run the configs[1] K/N sweep")
+    p.add_argument("--tf32-nonrouted", action="store_true",
+                   help="NOT the reference's numerics: let the non-routed fp32 matmuls (attention, vocabulary projections) use "
+                        "TF32 tensor cores; reported with this flag in `config`, never the default")
     return p.parse_args()
 
 
@@ -384,6 +387,8 @@ def run_train(args, world, rank):
     peaks = load_peaks()
     dev = torch.device("cuda", torch.cuda.current_device())
     B, T = args.batch, args.frames
+    if args.tf32_nonrouted:
+        torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(0)                                   # same weights and precision masks on every rank
     model = ob.ConformerASR(TRAIN["mel"], TRAIN["vocab"], enc_dropout=args.dropout, dec_dropout=args.dropout).train().to(dev)
     opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2)
@@ -451,7 +456,7 @@ def run_train(args, world, rank):
                                   "d_model 256, d_ff 1024, 4 heads, V=5004, 3 passes (2-bit, 1-bit, stochastic precision) + "
                                   "CTC/attention/KL losses + clip + AdamW",
                       "batch_per_gpu": B, "global_batch": B * world, "frames": T, "mel": TRAIN["mel"], "dropout": args.dropout,
-                      "audio_s_per_step": audio_s,
+                      "audio_s_per_step": audio_s, "tf32_nonrouted": bool(args.tf32_nonrouted),
                       "share_frontend": bool(args.share_frontend),
                       "share_frontend_note": "conv subsampling (no dropout, no bitwidth) evaluated once per step for the three passes: "
                                              "common-subexpression sharing inside the step, same loss and gradients "
@@ -625,15 +630,23 @@ def run_reference(args, world, rank):
 
 def main():
     args = parse()
+    # exactly ONE line on stdout: anything libraries print to fd 1 meanwhile (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         out = run_reference(args, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")))
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
         return
     world, rank, _ = dist_setup()
     out = {"train": run_train, "gemm": run_gemm, "infer": run_infer}[args.workload](args, world, rank)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
