@@ -150,6 +150,14 @@ def timed_region(world, fn, steps):
     return ms
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch measured by ncu for a named kernel/shape (profiles/ncu_traffic.json), else None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]["bytes"]
+    except Exception:
+        return None
+
+
 def int8_peak(peaks):
     return 2.0 * peaks["bf16_tflops"], (f"2 x {peaks['source']} bf16 burst {peaks['bf16_tflops']} TFLOP/s (int8 dense is nominally "
                                         "2x bf16; MEASURED_PEAKS.json has no int8 figure)")
@@ -196,7 +204,8 @@ def gemm_microbench(args, steps, sweep=False):
            "step_ms": round(step_ms, 4), "step_tops": round(ops / (step_ms * 1e-3) / 1e12, 1),
            "roofline": {"kernel": "gemm_expand_kernel<kFwdI8, 256, 5, bf16, cta_group::2> (ternary x int8, tcgen05 kind::i8)",
                         "bound": "tensor", "achieved": round(tops, 1), "peak": round(peak, 1), "unit": "TFLOP/s",
-                        "frac": round(tops / peak, 4), "traffic": None, "peak_source": peak_src,
+                        "frac": round(tops / peak, 4),
+                        "traffic": ncu_traffic(f"gemm_fwd_{M}x{K}x{N}_bf16"), "peak_source": peak_src,
                         "ms": round(gemm_ms, 4), "arith_intensity_op_per_byte": round(ops / gemm_bytes, 1),
                         "algorithmic_bytes": int(gemm_bytes)},
            "act_quant": {"kernel": "act_quant_reg_kernel<bf16,16>", "bound": "hbm", "achieved": round(act_gbs, 1),
@@ -471,7 +480,8 @@ def run_train(args, world, rank):
         # dominant kernel of the layer inside the step = the one with the largest per-layer time at this shape
         core = ("act_quant_i8", "gemm_fwd", "bwd_prep", "bwd_dx", "bwd_dw")
         dom = max(((k, v) for k, v in hk["kernels"].items() if k in core), key=lambda kv: kv[1]["ms"])
-        out["roofline"] = dict(kernel=dom[0], shape=hk["shape"], traffic=None,
+        out["roofline"] = dict(kernel=dom[0], shape=hk["shape"],
+                               traffic=ncu_traffic(f"{dom[0]}_{M}x{hk['shape']['K']}x{hk['shape']['N']}_f32"),
                                **{k: dom[1][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
                                peak_source=f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)")
         out["layer_kernels"] = hk
