@@ -535,7 +535,16 @@ def run_infer(args, world, rank):
             e2e_step()
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
-        row = {"batch": B, "ms": round(ms, 3), "utt_per_s": round(world * B / (ms * 1e-3), 1),
+        # the same pass replayed from a CUDA graph (one driver call instead of ~1300 launches)
+        from onebit_b200.inference import GraphedTranscriber
+        runner = GraphedTranscriber(model, B, T, TRAIN["mel"], precision=2)
+        for _ in range(3):
+            runner(batch["feats"], batch["feat_lens"])
+        graph_ms = timed_region(world, lambda: runner(batch["feats"], batch["feat_lens"]), args.steps) / args.steps
+        del runner
+        row = {"batch": B, "ms": round(ms, 3), "graph_ms": round(graph_ms, 3),
+               "graph_audio_s_per_s": round(world * B * T * FRAME_S / (graph_ms * 1e-3), 1),
+               "utt_per_s": round(world * B / (ms * 1e-3), 1),
                "audio_s_per_s": round(world * B * T * FRAME_S / (ms * 1e-3), 1),
                "e2e_audio_s_per_s": round(world * B * T * FRAME_S / (e2e_ms * 1e-3), 1),
                "h2d_bytes": feats.numel() * 4, "d2h_bytes": B * (((T - 1) // 2 - 1) // 2) * 4 + B * 4}

@@ -127,3 +127,37 @@ def transcribe_greedy(model, batch, precision: int = 2, blank_id: int = 3):
     Python beam search replaced by the device-side greedy decoder)."""
     _, mask, ctc_logits = model(batch, precision)
     return ctc_greedy_decode(ctc_logits, mask.sum(dim=1), blank_id)
+
+
+class GraphedTranscriber:
+    """``transcribe_greedy`` captured in a CUDA graph for one (batch, frames) shape: the ~1300 launches of an inference
+    pass are replayed with one driver call, which is what bounds small batches (the pass is launch-latency-bound
+    below batch ~64).  Weights must be frozen (packed); feed inputs through ``__call__`` - they are copied into the
+    static buffers the graph was captured on."""
+
+    def __init__(self, model, batch_size: int, frames: int, mel: int = 80, precision: int = 2, blank_id: int = 3,
+                 device=None):
+        device = device or next(model.parameters()).device
+        self.model, self.precision, self.blank_id = model.eval(), precision, blank_id
+        self.feats = torch.zeros(batch_size, frames, mel, device=device)
+        self.feat_lens = torch.full((batch_size,), frames, device=device, dtype=torch.long)
+        batch = {"feats": self.feats, "feat_lens": self.feat_lens}
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                                  # warm-up: lazy initialisations outside the capture
+                _ActQuantCache.clear()
+                transcribe_greedy(model, batch, precision, blank_id)
+            _ActQuantCache.clear()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.tokens, self.out_lens = transcribe_greedy(model, batch, precision, blank_id)
+            _ActQuantCache.clear()                              # the cache must not hand captured buffers to eager calls
+        torch.cuda.current_stream(device).wait_stream(side)
+
+    @torch.no_grad()
+    def __call__(self, feats: torch.Tensor, feat_lens: torch.Tensor):
+        self.feats.copy_(feats, non_blocking=True)
+        self.feat_lens.copy_(feat_lens, non_blocking=True)
+        self.graph.replay()
+        return self.tokens, self.out_lens

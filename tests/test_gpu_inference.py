@@ -72,3 +72,18 @@ def test_packed_model_roundtrip_and_transcribe(ob):
     toks, n = transcribe_greedy(fresh, batch, precision=2)
     assert torch.equal(n, n_ref) and torch.equal(toks, toks_ref)
     assert n.tolist() == [min(int(x), 49) for x in n.tolist()] and toks.shape == (3, 49)
+
+
+def test_graphed_transcriber_matches_eager(ob):
+    from onebit_b200.inference import GraphedTranscriber, pack_model_for_inference, transcribe_greedy
+    cfg = dict(input_dim=80, vocab_size=64, enc_layers=2, dec_layers=1, enc_dropout=0.0, dec_dropout=0.0)
+    torch.manual_seed(8)
+    model = pack_model_for_inference(ob.ConformerASR(**cfg).cuda(), 2)
+    runner = GraphedTranscriber(model, batch_size=3, frames=200, precision=2)
+    for seed in (1, 2):
+        g = torch.Generator().manual_seed(seed)
+        feats = torch.randn(3, 200, 80, generator=g).cuda()
+        lens = torch.tensor([200, 120 + seed, 64]).cuda()
+        toks, n = runner(feats, lens)
+        toks_e, n_e = transcribe_greedy(model, {"feats": feats, "feat_lens": lens}, precision=2)
+        assert torch.equal(n, n_e) and torch.equal(toks, toks_e)
