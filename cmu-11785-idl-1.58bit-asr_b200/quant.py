@@ -326,8 +326,24 @@ class QuantizedLinear(nn.Module):
             raise ValueError(f"onebit_b200: expected last dimension {self.in_features}, got {x.shape[-1]}")
         if x.numel() == 0:                                # empty batch: nothing to launch (F.linear returns an empty tensor too)
             return x.new_zeros(*x.shape[:-1], self.out_features) + 0.0 * (self.weight.sum() + self.alpha)
+        if self.in_features % 64 or self.out_features % 64:
+            return self._forward_padded(x, bitwidth)
         packed, packed_t = self.packed_weight(bitwidth)
         return _QuantLinearFn.apply(x, self.weight, self.alpha, self.bias, bitwidth, packed, packed_t)
+
+    def _forward_padded(self, x: torch.Tensor, bitwidth: int) -> torch.Tensor:
+        """Feature counts that are not multiples of 64 (the tensor-core kernels' granularity): zero-pad the operands
+        to the next multiple, run the same kernels, slice the result.  Zero activations in the padded columns and
+        zero upstream gradients in the padded rows make the padding invisible to y and to every gradient (incl.
+        alpha); the packed codes of the padded weight are rebuilt per call (this is the rare path)."""
+        K, N = self.in_features, self.out_features
+        Kp, Np = -(-K // 64) * 64, -(-N // 64) * 64
+        w = F.pad(self.weight, (0, Kp - K, 0, Np - N))
+        b = None if self.bias is None else F.pad(self.bias, (0, Np - N))
+        xp = F.pad(x, (0, Kp - K))
+        packed, packed_t = pack_weight(w, self.alpha, bitwidth, OB_ALPHA_RAW, transposed=True)
+        y = _QuantLinearFn.apply(xp, w, self.alpha, b, bitwidth, packed, packed_t)
+        return y[..., :N]
 
 
     def forward_swish_dropout(self, h: torch.Tensor, bitwidth: int, p: float = 0.0, training: bool = False,

@@ -240,10 +240,32 @@ def test_size_independent_properties_at_bench_size(ob):
     assert (got - chk).abs().max().item() < 1e-3 * chk.abs().max().item()
 
 
-def test_no_fallback_on_bad_shape(ob):
-    layer = ob.QuantizedLinear(100, 64).cuda()              # K % 64 != 0: refused loudly, never silently emulated
-    with pytest.raises(ValueError):
-        layer(torch.randn(4, 100, device="cuda"), 2)
+@pytest.mark.parametrize("K,N", [(100, 70), (80, 256), (256, 5004 % 1000)])
+@pytest.mark.parametrize("bw", [1, 2])
+def test_unaligned_feature_counts_are_padded_not_emulated(ob, K, N, bw):
+    """Feature counts that are not multiples of 64 run on the same kernels through zero padding (no other code path):
+    outputs and every gradient still match the oracle."""
+    torch.manual_seed(K + N)
+    layer = ob.QuantizedLinear(K, N)
+    with torch.no_grad():
+        layer.bias.normal_(0, 0.1)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(37, K, generator=g)
+    gy = torch.randn(37, N, generator=g)
+    W, a, b = (t.detach().numpy().copy() for t in (layer.weight, layer.alpha, layer.bias))
+    layer = layer.cuda()
+    xd = x.cuda().requires_grad_(True)
+    y = layer(xd, bw)
+    assert y.shape == (37, N)
+    y.backward(gy.cuda())
+    y_ref = orc.linear_forward(x.numpy(), W, a, b, bw, 8)
+    g_ref = orc.linear_backward(gy.numpy(), x.numpy(), W, a, b, bw, 8)
+    assert rel_err(y.detach().cpu().numpy(), y_ref) < 1e-4
+    assert rel_err(xd.grad.cpu().numpy(), g_ref["x"]) < 1e-2
+    assert layer.weight.grad.shape == (N, K) and rel_err(layer.weight.grad.cpu().numpy(), g_ref["weight"]) < 1e-2
+    assert rel_err(layer.bias.grad.cpu().numpy(), g_ref["bias"]) < 1e-4
+    g_hat_norm = float(np.linalg.norm(g_ref["weight"].astype(np.float64))) * 2 ** 0.5
+    assert math.isclose(layer.alpha.grad.item(), float(g_ref["alpha"]), rel_tol=1e-2, abs_tol=1e-2 * g_hat_norm)
 
 
 # ------------------------------------------------------------------ fused FFN mid-section
