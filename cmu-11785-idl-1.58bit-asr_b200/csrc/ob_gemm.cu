@@ -362,7 +362,7 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int c0 = c_begin; c0 < c_end; c0 += G) {
         if (n_blk * BLOCK_N + c0 * kChunkCols >= NC) break;  // warp-uniform
         // the staging group we are about to overwrite must have been read by its TMA stores
-        if (lane == 0) tma_store_wait_read<NG - 1>();
+        if (lane == 0 && !(dbg & 16)) tma_store_wait_read<NG - 1>();
         __syncwarp();
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -411,7 +411,7 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
           }
         }
-        fence_proxy_async_smem();
+        if (!(dbg & 8)) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
 #pragma unroll

@@ -322,6 +322,9 @@ class QuantizedLinear(nn.Module):
         _require_cuda(self.weight, "weight")
         if x.dtype not in _DTYPE_TAG:
             raise ValueError(f"onebit_b200: unsupported input dtype {x.dtype}")
+        if self.weight.dtype != torch.float32 or self.alpha.dtype != torch.float32:
+            raise ValueError("onebit_b200: the latent weight, alpha and bias must stay float32 (the quantiser works on the fp32 "
+                             f"latent weights, quant.py:49); got weight {self.weight.dtype}")
         if x.shape[-1] != self.in_features:
             raise ValueError(f"onebit_b200: expected last dimension {self.in_features}, got {x.shape[-1]}")
         if x.numel() == 0:                                # empty batch: nothing to launch (F.linear returns an empty tensor too)

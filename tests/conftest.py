@@ -13,6 +13,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _ensure_library():
+    """The CUDA library is a build artefact (git-ignored): build it once if this checkout does not have it yet."""
+    so = os.path.join(ROOT, "cmu-11785-idl-1.58bit-asr_b200", "libonebit.so")
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.run(["bash", os.path.join(ROOT, "cmu-11785-idl-1.58bit-asr_b200", "csrc", "build.sh")], check=True)
+
+
+_ensure_library()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
