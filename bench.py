@@ -662,6 +662,10 @@ def main():
         if out is not None:
             emit(out)
         return
+    if args.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) != args.gpus:
+        sys.stderr.write(f"bench.py --gpus {args.gpus} must be launched with one rank per GPU: python -m torch.distributed.run "
+                         f"--nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...\n")
+        sys.exit(2)
     world, rank, _ = dist_setup()
     out = {"train": run_train, "gemm": run_gemm, "infer": run_infer}[args.workload](args, world, rank)
     if rank == 0:

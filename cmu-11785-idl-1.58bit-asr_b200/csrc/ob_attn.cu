@@ -44,13 +44,14 @@ __global__ void __launch_bounds__(256, 2) relattn_softmax_fwd_kernel(const float
     // phase 1: every load of the row is issued up front with a clamped (always in-bounds) index and no predicate,
     // so ~3 NJ requests per lane are in flight at once; phase 2 applies the bounds and the mask
     float av[NJ], bv[NJ];
-    uint8_t mk[NJ];
+    uint8_t mk[NJ], kp[NJ];
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
       const int j = min(lane + 32 * u, T - 1);
       int c = c0 + j, r = r0;
       if (c >= T + 1) { c -= T + 1; r += 1; }
       mk[u] = __ldg(m_r + j);
+      kp[u] = attn_d != nullptr ? __ldg(keep + row * T + j) : (uint8_t)1;
       av[u] = __ldg(ac_r + j);
       bv[u] = __ldg(bd_bh + (int64_t)r * T + max(c - 1, 0));
       if (c == 0) bv[u] = 0.f;
@@ -72,11 +73,6 @@ __global__ void __launch_bounds__(256, 2) relattn_softmax_fwd_kernel(const float
     }
     sum = wsum_(sum);
     const float inv = sum > 0.f ? 1.0f / sum : 0.f;               // nan_to_num(nan = 0) of the reference (conformer.py:127)
-    uint8_t kp[NJ];
-    if (attn_d != nullptr) {
-#pragma unroll
-      for (int u = 0; u < NJ; ++u) kp[u] = __ldg(keep + row * T + min(lane + 32 * u, T - 1));
-    }
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
       const int j = lane + 32 * u;

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   }
 }
 
-constexpr int kLnBwdBlocks = 296;      // persistent grid; fixed so the parameter-gradient sum order is fixed
+constexpr int kLnBwdBlocks = 296;      // persistent grid (2 per SM); fixed so the parameter-gradient sum order is fixed
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  partial d-gamma += dy * xhat, d-beta += dy
 template <int V>

@@ -365,12 +365,17 @@ __device__ __forceinline__ float act_scale_from_amax(float amax) {
   // torch evaluates `127.0 / t` as reciprocal(t) * 127 (two roundings); pinned bit-exactly by the oracle
   return __fmul_rn(__frcp_rn(fmaxf(amax, 1e-5f)), 127.0f);
 }
+// q = clamp(rint(v * s), -128, 127) for four values, packed little-endian.  Clamping to the (integer) bounds first and
+// then adding 1.5 * 2^23 rounds to the nearest integer, ties to even, exactly like rint() - the sum's low mantissa
+// byte IS the int8 two's-complement code - and it stays on the full-rate FP pipes (FRND and F2I run on the
+// quarter-rate XU pipe, which ncu showed ~50-60 % busy in these kernels).
 __device__ __forceinline__ uint32_t quant4(float4 v, float s) {
-  int a = (int)fminf(fmaxf(rintf(__fmul_rn(v.x, s)), -128.f), 127.f);
-  int b = (int)fminf(fmaxf(rintf(__fmul_rn(v.y, s)), -128.f), 127.f);
-  int c = (int)fminf(fmaxf(rintf(__fmul_rn(v.z, s)), -128.f), 127.f);
-  int d = (int)fminf(fmaxf(rintf(__fmul_rn(v.w, s)), -128.f), 127.f);
-  return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+  constexpr float kMagic = 12582912.0f;
+  const uint32_t a = __float_as_uint(fminf(fmaxf(__fmul_rn(v.x, s), -128.f), 127.f) + kMagic);
+  const uint32_t b = __float_as_uint(fminf(fmaxf(__fmul_rn(v.y, s), -128.f), 127.f) + kMagic);
+  const uint32_t c = __float_as_uint(fminf(fmaxf(__fmul_rn(v.z, s), -128.f), 127.f) + kMagic);
+  const uint32_t d = __float_as_uint(fminf(fmaxf(__fmul_rn(v.w, s), -128.f), 127.f) + kMagic);
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
 // K == 128*V: lane l holds float4 index l + 32*j, j < V (coalesced 512-byte warp loads)
@@ -425,7 +430,10 @@ __global__ void __launch_bounds__(256) act_quant_generic_kernel(const T* __restr
 // fused FFN mid-section (conformer.py:36-39): z = dropout(swish(h)), then the activation quantiser of lin2.
 // One read of h (+ the keep mask), one write of int8 codes: replaces sigmoid, mul, dropout and act-quant kernels.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float swish_f(float h) { return h * (1.0f / (1.0f + expf(-h))); }
+// swish with the SFU exponential (ex2.approx, ~2 ulp) and an IEEE reciprocal: the full-precision expf made this
+// kernel ALU-bound (26 M exponentials per launch at the FFN width); the result differs from torch's sigmoid*x in
+// the last bits only, which moves an int8 code by at most one step on a ~1e-5 fraction of elements
+__device__ __forceinline__ float swish_f(float h) { return h * __frcp_rn(1.0f + __expf(-h)); }
 
 template <int V>
 __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __restrict__ h, const uint8_t* __restrict__ keep,
