@@ -2,10 +2,11 @@
 //
 //   gemm_expand_kernel<kFwdI8>   y  = (q . Q^T) * alpha/s + b     int8 x ternary, kind::i8, S32 accumulators
 //   gemm_expand_kernel<kDxBf16>  dx = (dys . Q) * alpha*s         bf16 x ternary, kind::f16, F32 accumulators
-//        A tile: TMA, SWIZZLE_128B, K-major.  B tile: packed 2-bit codes land in shared memory by TMA, four
-//        expander warps rewrite them as int8 / bf16 in the UMMA K-major SWIZZLE_128B layout (one PRMT per
-//        output word), fence.proxy.async, then the single MMA thread consumes them.  Persistent CTAs, static
-//        tile schedule (n fastest so co-resident CTAs share A rows in L2), double-buffered TMEM accumulators.
+//        A tile: TMA, SWIZZLE_128B, K-major.  B tile: packed 2-bit codes land in shared memory by TMA, eight
+//        expander warps rewrite them as int8 / bf16 in the UMMA K-major SWIZZLE_128B layout (one PRMT per output
+//        word), fence.proxy.async, then the single MMA thread consumes them.  Persistent CTAs (optionally CTA pairs,
+//        cta_group::2), static tile schedule (n fastest so co-resident CTAs share A rows in L2), double-buffered
+//        TMEM accumulators, eight epilogue warps storing through swizzled shared memory with TMA.
 //   dw_kernel                     dW_hat partials = dys^T . qb     bf16, both operands MN-major straight from the
 //        row-major [tokens, features] tensors (no transposes in HBM), split over tokens; the STE mask, the
 //        alpha reduction and grad_bias are fused into the finalizer (ob_quant.cu).
