@@ -211,16 +211,91 @@ __global__ void __launch_bounds__(256) ste_backward_kernel(const float* __restri
   if (threadIdx.x == 0) alpha_parts[blockIdx.x] = s;
 }
 
+constexpr int kTailRowChunks = 8;   // the column-sum partial rows are reduced by 8 blocks per 32-column group
+
+// grad_bias from the per-row-block column sums of dY: block (bx = 32-column group, by = row chunk) reduces its chunk;
+// the last chunk to finish (ticket) adds the 8 chunk sums in fixed order.  chunk_part: [kTailRowChunks][N] floats,
+// tickets: one int per column group, zero on entry, reset on exit.
+__device__ __forceinline__ void bias_tail_block(int bx, int by, const float* __restrict__ colsum, int n_col_blocks, int N,
+                                                float* __restrict__ grad_bias, float* __restrict__ chunk_part,
+                                                int* __restrict__ tickets) {
+  __shared__ float col_red[8][33];
+  __shared__ int is_last;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = bx * 32 + cx;
+  const int rows_per_chunk = (n_col_blocks + kTailRowChunks - 1) / kTailRowChunks;
+  const int b0 = by * rows_per_chunk, b1 = min(n_col_blocks, b0 + rows_per_chunk);
+  float a0 = 0.f, a1 = 0.f;
+  if (c < N) {
+    int b = b0 + ry;
+    for (; b + 8 < b1; b += 16) {
+      a0 += colsum[(int64_t)b * N + c];
+      a1 += colsum[(int64_t)(b + 8) * N + c];
+    }
+    if (b < b1) a0 += colsum[(int64_t)b * N + c];
+  }
+  col_red[ry][cx] = a0 + a1;
+  __syncthreads();
+  if (ry == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += col_red[j][cx];
+    chunk_part[(int64_t)by * N + c] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&tickets[bx], 1) == kTailRowChunks - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (ry == 0 && c < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < kTailRowChunks; ++j) t += __ldcg(&chunk_part[(int64_t)j * N + c]);
+      grad_bias[c] = t;
+    }
+    if (threadIdx.x == 0) tickets[bx] = 0;
+  }
+}
+
+// sum of the per-block alpha partials in fixed order, sign(alpha) chained in OB_ALPHA_RAW mode (quant.py:124)
+__device__ __forceinline__ void alpha_final(const float* __restrict__ alpha_parts, int n_parts, const float* __restrict__ alpha,
+                                            int alpha_mode, float* __restrict__ grad_alpha, float* red) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_parts; i += 256) acc += __ldcg(alpha_parts + i);
+  float s = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) {
+    if (alpha_mode == OB_ALPHA_RAW) {
+      const float a = __ldg(alpha);
+      s = a > 0.f ? s : (a < 0.f ? -s : 0.f);
+    }
+    grad_alpha[0] = s;
+  }
+}
+
 // grad_W finaliser for many token splits: 256 elements per block; thread (eg, sl) sums splits sl, sl+4, ... of one
 // float4, the four split lanes are combined through shared memory in fixed order (deterministic), then the STE.
 constexpr int kFinBlockElems = 256;
 
+// Blocks [0, fin_blocks) finalise 256 elements each; the last of them to finish (ticket) reduces the alpha partials.
+// Blocks >= fin_blocks reduce the grad_bias column sums.  One launch for the whole tail of the backward.
+// tail_ws: [kTailRowChunks][N] floats, then 1 + ceil(N/32) int tickets (zero on entry, reset on exit).
 __global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restrict__ g_parts, int splits,
                                                           const float* __restrict__ W, const float* __restrict__ alpha,
                                                           int alpha_mode, int64_t n, int bitwidth,
-                                                          float* __restrict__ grad_W, float* __restrict__ alpha_parts) {
+                                                          float* __restrict__ grad_W, float* __restrict__ alpha_parts,
+                                                          int fin_blocks, float* __restrict__ grad_alpha,
+                                                          const float* __restrict__ colsum, int n_col_blocks, int N,
+                                                          float* __restrict__ grad_bias, float* __restrict__ tail_ws) {
   __shared__ float4 part[3][64];
   __shared__ float red[8];
+  __shared__ int last_fin;
+  int* tickets = reinterpret_cast<int*>(tail_ws + (int64_t)kTailRowChunks * N);
+  if (static_cast<int>(blockIdx.x) >= fin_blocks) {
+    const int t = blockIdx.x - fin_blocks;
+    bias_tail_block(t / kTailRowChunks, t % kTailRowChunks, colsum, n_col_blocks, N, grad_bias, tail_ws, tickets + 1);
+    return;
+  }
   const int eg = threadIdx.x & 63, sl = threadIdx.x >> 6;
   const int64_t i = (int64_t)blockIdx.x * kFinBlockElems + eg * 4;      // n % 256 == 0 (N, K multiples of 64)
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
@@ -255,76 +330,35 @@ __global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restric
     *reinterpret_cast<float4*>(grad_W + i) = o;
   }
   const float tot = block_sum<256>(acc, red);
-  if (threadIdx.x == 0) alpha_parts[blockIdx.x] = tot;
+  if (threadIdx.x == 0) {
+    alpha_parts[blockIdx.x] = tot;
+    __threadfence();
+    last_fin = atomicAdd(&tickets[0], 1) == fin_blocks - 1;
+  }
+  __syncthreads();
+  if (last_fin) {
+    __threadfence();
+    alpha_final(alpha_parts, fin_blocks, alpha, alpha_mode, grad_alpha, red);
+    if (threadIdx.x == 0) tickets[0] = 0;
+  }
 }
 
-// tail: block 0 reduces the alpha partials; blocks >= 1 reduce the column-sum partials into grad_bias
-constexpr int kTailRowChunks = 8;   // the column-sum partial rows are reduced by 8 blocks per 32-column group
-
-// block 0: alpha partials -> grad_alpha.  blocks >= 1: (column group, row chunk) pairs reduce the per-row-block
-// column sums of dY; the last chunk to finish (ticket) adds the 8 chunk sums in fixed order -> grad_bias.
-// tail_ws: [kTailRowChunks][N] floats followed by ceil(N/32) int tickets (zeroed by the finaliser, self-resetting).
+// stand-alone tail (dense quantize_weight backward, or few splits): block 0 reduces the alpha partials, blocks >= 1
+// the grad_bias column sums.  tail_ws as above (tickets start one int later to share the layout).
 __global__ void __launch_bounds__(256) bwd_tail_kernel(const float* __restrict__ alpha_parts, int n_alpha_parts,
                                                        const float* __restrict__ alpha, int alpha_mode,
                                                        float* __restrict__ grad_alpha, const float* __restrict__ colsum,
                                                        int n_col_blocks, int N, float* __restrict__ grad_bias,
                                                        float* __restrict__ tail_ws) {
   __shared__ float red[8];
-  __shared__ float col_red[8][33];
-  __shared__ int is_last;
   if (blockIdx.x == 0) {
-    if (grad_alpha == nullptr) return;
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < n_alpha_parts; i += 256) acc += alpha_parts[i];
-    float s = block_sum<256>(acc, red);
-    if (threadIdx.x == 0) {
-      if (alpha_mode == OB_ALPHA_RAW) {                 // d(|a|+eps)/da = sign(a), sign(0) = 0 (autograd of quant.py:124)
-        const float a = __ldg(alpha);
-        s = a > 0.f ? s : (a < 0.f ? -s : 0.f);
-      }
-      grad_alpha[0] = s;
-    }
+    if (grad_alpha != nullptr) alpha_final(alpha_parts, n_alpha_parts, alpha, alpha_mode, grad_alpha, red);
     return;
   }
   if (grad_bias == nullptr) return;
-  const int bx = (blockIdx.x - 1) / kTailRowChunks, by = (blockIdx.x - 1) % kTailRowChunks;
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = bx * 32 + cx;
-  const int rows_per_chunk = (n_col_blocks + kTailRowChunks - 1) / kTailRowChunks;
-  const int b0 = by * rows_per_chunk, b1 = min(n_col_blocks, b0 + rows_per_chunk);
-  float a0 = 0.f, a1 = 0.f;
-  if (c < N) {
-    int b = b0 + ry;
-    for (; b + 8 < b1; b += 16) {
-      a0 += colsum[(int64_t)b * N + c];
-      a1 += colsum[(int64_t)(b + 8) * N + c];
-    }
-    if (b < b1) a0 += colsum[(int64_t)b * N + c];
-  }
-  col_red[ry][cx] = a0 + a1;
-  __syncthreads();
-  float* chunk_part = tail_ws;                                   // [kTailRowChunks][N]
   int* tickets = reinterpret_cast<int*>(tail_ws + (int64_t)kTailRowChunks * N);
-  if (ry == 0 && c < N) {
-    float t = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t += col_red[j][cx];
-    chunk_part[(int64_t)by * N + c] = t;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&tickets[bx], 1) == kTailRowChunks - 1;
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    if (ry == 0 && c < N) {
-      float t = 0.f;
-#pragma unroll
-      for (int j = 0; j < kTailRowChunks; ++j) t += __ldcg(&chunk_part[(int64_t)j * N + c]);
-      grad_bias[c] = t;
-    }
-    if (threadIdx.x == 0) tickets[bx] = 0;
-  }
+  const int t = blockIdx.x - 1;
+  bias_tail_block(t / kTailRowChunks, t % kTailRowChunks, colsum, n_col_blocks, N, grad_bias, tail_ws, tickets + 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -645,7 +679,7 @@ extern "C" size_t ob_ste_workspace_bytes(int64_t n) {
   return (fin > ste ? fin : ste) * sizeof(float);
 }
 // extra floats the grad_bias tail needs behind the alpha partials
-static size_t tail_workspace_bytes(int N) { return ((size_t)kTailRowChunks * N + (size_t)(N + 31) / 32 + 8) * sizeof(float); }
+static size_t tail_workspace_bytes(int N) { return ((size_t)kTailRowChunks * N + (size_t)(N + 31) / 32 + 9) * sizeof(float); }
 namespace ob { size_t bwd_tail_workspace_bytes(int N) { return tail_workspace_bytes(N); } }
 
 namespace ob {
@@ -653,20 +687,21 @@ namespace ob {
 int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const float* alpha, int alpha_mode, int64_t n,
                         int bitwidth, float* grad_W, float* grad_alpha, float* alpha_parts, const float* colsum,
                         int n_col_blocks, int N, float* grad_bias, cudaStream_t st) {
-  int blocks;
-  if (splits >= 4 && n % kFinBlockElems == 0) {
-    blocks = (int)(n / kFinBlockElems);
-    dw_finalize_kernel<<<blocks, 256, 0, st>>>(g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
-    OB_LAUNCH_CHECK("dw_finalize_kernel");
-  } else {
-    blocks = ste_blocks(n);
-    ste_backward_kernel<<<blocks, 256, 0, st>>>(g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
-    OB_LAUNCH_CHECK("ste_backward_kernel");
-  }
   const int col_groups = (grad_bias != nullptr) ? (N + 31) / 32 : 0;
-  float* tail_ws = alpha_parts + blocks;                           // [kTailRowChunks][N] floats + col_groups tickets
-  if (col_groups > 0)
-    OB_CUDA(cudaMemsetAsync(tail_ws + (size_t)kTailRowChunks * N, 0, (size_t)col_groups * sizeof(int), st));
+  const bool fused = splits >= 4 && n % kFinBlockElems == 0;
+  const int blocks = fused ? (int)(n / kFinBlockElems) : ste_blocks(n);
+  float* tail_ws = alpha_parts + blocks;                           // [kTailRowChunks][N] floats + (1 + col_groups) tickets
+  if (fused || col_groups > 0)
+    OB_CUDA(cudaMemsetAsync(tail_ws + (size_t)kTailRowChunks * N, 0, (size_t)(1 + col_groups) * sizeof(int), st));
+  if (fused) {
+    dw_finalize_kernel<<<blocks + col_groups * kTailRowChunks, 256, 0, st>>>(
+        g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts, blocks, grad_alpha, colsum, n_col_blocks,
+        N, grad_bias, tail_ws);
+    OB_LAUNCH_CHECK("dw_finalize_kernel");
+    return OB_OK;
+  }
+  ste_backward_kernel<<<blocks, 256, 0, st>>>(g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
+  OB_LAUNCH_CHECK("ste_backward_kernel");
   bwd_tail_kernel<<<1 + col_groups * kTailRowChunks, 256, 0, st>>>(alpha_parts, blocks, alpha, alpha_mode, grad_alpha,
                                                                    colsum, n_col_blocks, N, grad_bias, tail_ws);
   OB_LAUNCH_CHECK("bwd_tail_kernel");
