@@ -21,7 +21,7 @@ __device__ __forceinline__ float wsum_(float v) {
 
 // NJ = ceil(T / 32) elements per lane
 template <int NJ>
-__global__ void __launch_bounds__(256, 2) relattn_softmax_fwd_kernel(const float* __restrict__ ac, const float* __restrict__ bd,
+__global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float* __restrict__ ac, const float* __restrict__ bd,
                                                                   const uint8_t* __restrict__ mask /* [B,T,T] */,
                                                                   const uint8_t* __restrict__ keep /* [B,H,T,T] | null */,
                                                                   float inv_keep, float scale, int B, int H, int T,
@@ -35,32 +35,35 @@ __global__ void __launch_bounds__(256, 2) relattn_softmax_fwd_kernel(const float
     const int64_t bh = row / T;
     const int b = (int)(bh / H);
     const float* ac_r = ac + row * T;
-    const float* bd_bh = bd + bh * (int64_t)T * T;
     const uint8_t* m_r = mask + ((int64_t)b * T + i) * T;
+    const uint8_t* k_r = attn_d != nullptr ? keep + row * T : m_r;
     const int f0 = T + i * T;
     const int r0 = f0 / (T + 1), c0 = f0 - r0 * (T + 1);
+    // element j of the shifted row is P[r0][c0 + j] or, past the end of that row of [0 | bd], P[r0 + 1][c0 + j - (T+1)];
+    // relative to bd row r0 both are one linear offset: c0 + j - 1 (same row) or c0 + j - 2 (next row)
+    const float* bd_r0 = bd + bh * (int64_t)T * T + (int64_t)r0 * T;
     float s[NJ];
     float mx = -INFINITY;
-    // phase 1: every load of the row is issued up front with a clamped (always in-bounds) index and no predicate,
-    // so ~3 NJ requests per lane are in flight at once; phase 2 applies the bounds and the mask
     float av[NJ], bv[NJ];
-    uint8_t mk[NJ], kp[NJ];
+    uint32_t mbits = 0, kbits = 0, zbits = 0;                   // mask / keep / zero-column flags, one bit per element
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
       const int j = min(lane + 32 * u, T - 1);
-      int c = c0 + j, r = r0;
-      if (c >= T + 1) { c -= T + 1; r += 1; }
-      mk[u] = __ldg(m_r + j);
-      kp[u] = attn_d != nullptr ? __ldg(keep + row * T + j) : (uint8_t)1;
+      const int t = c0 + j;
+      const int wrapped = t >= T + 1;
+      const uint32_t mk = __ldg(m_r + j);
+      const uint32_t kp = __ldg(k_r + j);
       av[u] = __ldg(ac_r + j);
-      bv[u] = __ldg(bd_bh + (int64_t)r * T + max(c - 1, 0));
-      if (c == 0) bv[u] = 0.f;
+      bv[u] = __ldg(bd_r0 + max(t - 1 - wrapped, 0));
+      zbits |= ((t == 0 || t == T + 1) ? 1u : 0u) << u;          // the zero column of [0 | bd]
+      mbits |= (mk != 0u ? 1u : 0u) << u;
+      kbits |= (kp != 0u ? 1u : 0u) << u;
     }
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
       s[u] = -INFINITY;
-      if (lane + 32 * u < T && mk[u]) {
-        s[u] = (av[u] + bv[u]) * scale;
+      if (lane + 32 * u < T && ((mbits >> u) & 1u)) {
+        s[u] = (av[u] + (((zbits >> u) & 1u) ? 0.f : bv[u])) * scale;
         mx = fmaxf(mx, s[u]);
       }
     }
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(256, 2) relattn_softmax_fwd_kernel(const float
     float sum = 0.f;
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
-      s[u] = (s[u] == -INFINITY) ? 0.f : expf(s[u] - mx);      // fully masked row: mx = -inf, every term 0
+      s[u] = (s[u] == -INFINITY) ? 0.f : __expf(s[u] - mx);    // SFU exponential (2 ulp); masked terms are exactly 0
       sum += s[u];
     }
     sum = wsum_(sum);
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(256, 2) relattn_softmax_fwd_kernel(const float
       if (j < T) {
         const float p = s[u] * inv;
         y[row * T + j] = p;
-        if (attn_d != nullptr) attn_d[row * T + j] = kp[u] ? p * inv_keep : 0.f;
+        if (attn_d != nullptr) attn_d[row * T + j] = ((kbits >> u) & 1u) ? p * inv_keep : 0.f;
       }
     }
   }
