@@ -485,6 +485,26 @@ def run_train(args, world, rank):
                                **{k: dom[1][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
                                peak_source=f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)")
         out["layer_kernels"] = hk
+        if world == 1:
+            # SURVEY.md section 8(d) also asks for ONE precision-2 pass (forward + backward + AdamW), next to the full step
+            from onebit_b200.training import att_ce_loss, ctc_loss_from_logits, make_att_targets
+
+            def one_pass():
+                opt.zero_grad(set_to_none=True)
+                enc, mask, ctc = model(batch, 2)
+                t_inp, t_out, t_pad = make_att_targets(batch["tokens"], cfg.bos_id, cfg.eos_id, cfg.pad_id)
+                logits = model.decode_logits(enc, mask, t_inp, t_pad)
+                lens = torch.clamp(batch["feat_lens_cpu"] // 4, max=enc.size(1))
+                loss = 0.8 * att_ce_loss(logits, t_out, cfg.pad_id, 0.1) + 0.2 * ctc_loss_from_logits(
+                    ctc, lens, batch["tokens"], batch["token_lens_cpu"], cfg.blank_id)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=cfg.max_grad_norm)
+                opt.step()
+            for _ in range(2):
+                one_pass()
+            ms1 = timed_region(1, one_pass, 3) / 3
+            out["variants"] = {"one_precision2_pass": {"ms_per_step": round(ms1, 2),
+                                                       "audio_s_per_s": round(B * T * FRAME_S / (ms1 * 1e-3), 1)}}
         if world == 1 and not args.no_gemm:
             out["bitlinear_gemm"] = gemm_microbench(args, 20)
         if world == 1 and not args.no_cpu_baseline:
