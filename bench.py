@@ -319,7 +319,6 @@ def hot_kernel_rooflines(peaks, M):
     h_mid = [torch.randn(M, N, device=dev) for _ in range(2)]
     q_mid = torch.empty(M, N, device=dev, dtype=torch.int8)
     s_mid = torch.empty(M, device=dev)
-    keep = torch.rand(M, N, device=dev) > 0.1
     gh = torch.empty(M, N, device=dev)
     ln_w, ln_b = torch.ones(K, device=dev), torch.zeros(K, device=dev)
     ln_y, ln_stats = torch.empty(M, K, device=dev), torch.empty(2, M, device=dev)
@@ -327,27 +326,27 @@ def hot_kernel_rooflines(peaks, M):
     ln_ws = torch.empty(lib.ob_layernorm_bwd_workspace_bytes(K), device=dev, dtype=torch.uint8)
     Bq, Hh, Tt = max(1, M // 399), 4, 399
     att = [torch.randn(Bq, Hh, Tt, Tt, device=dev) for _ in range(4)]
-    att_keep = torch.rand(Bq, Hh, Tt, Tt, device=dev) > 0.1
+    drop_thr = int(round(0.1 * 2 ** 16))              # in-kernel Philox dropout, p = 0.1 (no stored mask)
     att_mask = torch.ones(Bq, Tt, Tt, device=dev, dtype=torch.bool)
     att_y, att_o = torch.empty_like(att[0]), torch.empty_like(att[0])
     nat = Bq * Hh * Tt * Tt
     pk2, pkt2 = torch.empty_like(pk), torch.empty_like(pkt)
     fns.update({
-        "swish_drop_quant": (lambda j: lib.ob_swish_drop_quant(h_mid[j % 2].data_ptr(), keep.data_ptr(), 1.0 / 0.9, M, N,
-                                                                q_mid.data_ptr(), s_mid.data_ptr(), st), 4.0 * M * N + 2.0 * M * N + 4 * M, 0.0),
-        "swish_drop_bwd": (lambda j: lib.ob_swish_drop_bwd(gys[j].data_ptr(), h_mid[j % 2].data_ptr(), keep.data_ptr(), 1.0 / 0.9,
-                                                            M * N, gh.data_ptr(), st), 12.0 * M * N + M * N, 0.0),
+        "swish_drop_quant": (lambda j: lib.ob_swish_drop_quant(h_mid[j % 2].data_ptr(), None, 1.0 / 0.9, 1234, 4 * j, drop_thr, M, N,
+                                                                q_mid.data_ptr(), s_mid.data_ptr(), st), 5.0 * M * N + 4 * M, 0.0),
+        "swish_drop_bwd": (lambda j: lib.ob_swish_drop_bwd(gys[j].data_ptr(), h_mid[j % 2].data_ptr(), None, 1.0 / 0.9, 1234, 4 * j,
+                                                            drop_thr, M * N, gh.data_ptr(), st), 12.0 * M * N, 0.0),
         "layernorm_fwd": (lambda j: lib.ob_layernorm_fwd(xs[j].data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), 1e-5, M, K, ln_y.data_ptr(),
                                                          ln_stats[0].data_ptr(), ln_stats[1].data_ptr(), st), 8.0 * M * K + 8 * M, 0.0),
         "layernorm_bwd": (lambda j: lib.ob_layernorm_bwd(dxs[j].data_ptr(), xs[j].data_ptr(), ln_stats[0].data_ptr(), ln_stats[1].data_ptr(),
                                                          ln_w.data_ptr(), M, K, ln_dx.data_ptr(), ln_dp[0].data_ptr(), ln_dp[1].data_ptr(),
                                                          ln_ws.data_ptr(), st), 12.0 * M * K + 8 * M, 0.0),
         "relattn_softmax_fwd": (lambda j: lib.ob_relattn_softmax_fwd(att[j % 2].data_ptr(), att[2 + j % 2].data_ptr(), att_mask.data_ptr(),
-                                                                     att_keep.data_ptr(), 1.0 / 0.9, 0.125, Bq, Hh, Tt, att_y.data_ptr(),
-                                                                     att_o.data_ptr(), st), 17.0 * nat, 0.0),
-        "relattn_softmax_bwd": (lambda j: lib.ob_relattn_softmax_bwd(att[j % 2].data_ptr(), att_y.data_ptr(), att_keep.data_ptr(), 1.0 / 0.9,
-                                                                     0.125, Bq, Hh, Tt, att[2].data_ptr(), att[3].data_ptr(), st),
-                                17.0 * nat, 0.0),
+                                                                     None, 1.0 / 0.9, 1234, 4 * j, drop_thr, 0.125, Bq, Hh, Tt,
+                                                                     att_y.data_ptr(), att_o.data_ptr(), st), 16.0 * nat, 0.0),
+        "relattn_softmax_bwd": (lambda j: lib.ob_relattn_softmax_bwd(att[j % 2].data_ptr(), att_y.data_ptr(), None, 1.0 / 0.9, 1234, 4 * j,
+                                                                     drop_thr, 0.125, Bq, Hh, Tt, att[2].data_ptr(), att[3].data_ptr(), st),
+                                16.0 * nat, 0.0),
         "weight_quant_pack": (lambda j: lib.ob_weight_quant_pack(layer.weight.data_ptr(), a.data_ptr(), 1, N, K, 2, pk2.data_ptr(),
                                                                  pkt2.data_ptr(), st), 4.5 * N * K, 0.0),
     })

@@ -18,6 +18,7 @@ OB_ORDER_I8, OB_ORDER_BF16 = 0, 1
 DBG_SWAP_LBO_SBO, DBG_FORCE_BLOCK_N, DBG_FORCE_SPLITS, DBG_MAX_CTAS = 1, 2, 3, 4
 
 _p, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+_u64, _u32 = ctypes.c_uint64, ctypes.c_uint32
 
 # name -> (restype, argtypes); mirrors include/onebit.h one to one
 SIGNATURES = {
@@ -38,13 +39,14 @@ SIGNATURES = {
     "ob_bwd_dx": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
     "ob_bwd_dw_workspace_bytes": (_sz, [_i, _i, _i]),
     "ob_bwd_dw": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
-    "ob_swish_drop_quant": (_i, [_p, _p, ctypes.c_float, _i64, _i, _p, _p, _p]),
-    "ob_swish_drop_bwd": (_i, [_p, _p, _p, ctypes.c_float, _i64, _p, _p]),
+    "ob_swish_drop_quant": (_i, [_p, _p, ctypes.c_float, _u64, _u64, _u32, _i64, _i, _p, _p, _p]),
+    "ob_swish_drop_bwd": (_i, [_p, _p, _p, ctypes.c_float, _u64, _u64, _u32, _i64, _p, _p]),
     "ob_layernorm_fwd": (_i, [_p, _p, _p, ctypes.c_float, _i64, _i, _p, _p, _p, _p]),
     "ob_layernorm_bwd_workspace_bytes": (_sz, [_i]),
     "ob_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p]),
-    "ob_relattn_softmax_fwd": (_i, [_p, _p, _p, _p, ctypes.c_float, ctypes.c_float, _i, _i, _i, _p, _p, _p]),
-    "ob_relattn_softmax_bwd": (_i, [_p, _p, _p, ctypes.c_float, ctypes.c_float, _i, _i, _i, _p, _p, _p]),
+    "ob_relattn_softmax_fwd": (_i, [_p, _p, _p, _p, ctypes.c_float, _u64, _u64, _u32, ctypes.c_float, _i, _i, _i, _p, _p,
+                                    _p]),
+    "ob_relattn_softmax_bwd": (_i, [_p, _p, _p, ctypes.c_float, _u64, _u64, _u32, ctypes.c_float, _i, _i, _i, _p, _p, _p]),
     "ob_ctc_decode_workspace_bytes": (_sz, [_i, _i]),
     "ob_ctc_greedy_decode": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
     "ob_debug_set": (_i, [_i, _i]),

@@ -10,26 +10,26 @@ from __future__ import annotations
 import torch
 
 from ._cabi import check, lib
-from .quant import _stream
+from .quant import _NO_RNG, _stream, draw_dropout_stream
 
 MAX_T = 2048
 
 
 class _RelAttnSoftmaxFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ac, bd_raw, mask, keep, inv_keep, scale):
+    def forward(ctx, ac, bd_raw, mask, keep, inv_keep, scale, rng):
         B, H, T, _ = ac.shape
         ac, bd_raw = ac.contiguous(), bd_raw.contiguous()
         y = torch.empty_like(ac)
-        attn_d = torch.empty_like(ac) if keep is not None else None
+        attn_d = torch.empty_like(ac) if (keep is not None or rng[2] != 0) else None
         check(lib.ob_relattn_softmax_fwd(ac.data_ptr(), bd_raw.data_ptr(), mask.data_ptr(),
-                                         None if keep is None else keep.data_ptr(), inv_keep, scale, B, H, T,
+                                         None if keep is None else keep.data_ptr(), inv_keep, *rng, scale, B, H, T,
                                          y.data_ptr(), None if attn_d is None else attn_d.data_ptr(), _stream()))
         if keep is None:
             ctx.save_for_backward(y)
         else:
             ctx.save_for_backward(y, keep)
-        ctx.inv_keep, ctx.scale = inv_keep, scale
+        ctx.inv_keep, ctx.scale, ctx.rng = inv_keep, scale, rng
         return y if attn_d is None else attn_d
 
     @staticmethod
@@ -42,8 +42,9 @@ class _RelAttnSoftmaxFn(torch.autograd.Function):
         d_ac = torch.empty_like(y)
         d_bd = torch.empty_like(y)
         check(lib.ob_relattn_softmax_bwd(g.data_ptr(), y.data_ptr(), None if keep is None else keep.data_ptr(),
-                                         ctx.inv_keep, ctx.scale, B, H, T, d_ac.data_ptr(), d_bd.data_ptr(), _stream()))
-        return d_ac, d_bd, None, None, None, None
+                                         ctx.inv_keep, *ctx.rng, ctx.scale, B, H, T, d_ac.data_ptr(), d_bd.data_ptr(),
+                                         _stream()))
+        return d_ac, d_bd, None, None, None, None, None
 
 
 def usable(ac: torch.Tensor, mask) -> bool:
@@ -55,10 +56,9 @@ def rel_attention_probs(ac, bd_raw, mask, scale: float, p: float = 0.0, training
     """ac, bd_raw: [B, H, T, T] fp32 (bd_raw BEFORE the relative shift); mask: [B, T, T] bool (False = masked).
     ``keep`` (bool [B,H,T,T]) overrides the sampled dropout mask (tests)."""
     mask = mask.contiguous()
-    inv_keep = 1.0
+    inv_keep, rng = 1.0, _NO_RNG
     if keep is not None:
         keep, inv_keep = keep.contiguous(), 1.0 / (1.0 - p)
     elif training and p > 0.0:
-        keep = torch.empty(ac.shape, device=ac.device, dtype=torch.bool).bernoulli_(1.0 - p)
-        inv_keep = 1.0 / (1.0 - p)
-    return _RelAttnSoftmaxFn.apply(ac, bd_raw, mask, keep, inv_keep, scale)
+        inv_keep, rng = draw_dropout_stream(ac.device, p)                      # mask generated inside the kernels
+    return _RelAttnSoftmaxFn.apply(ac, bd_raw, mask, keep, inv_keep, scale, rng)

@@ -19,12 +19,29 @@ __device__ __forceinline__ float wsum_(float v) {
   return v;
 }
 
+template <int NJ>
+struct RowBits { using type = uint32_t; };                       // one flag per element a lane owns
+template <>
+struct RowBits<64> { using type = unsigned long long; };
+
+// dropout keep flags of the NJ elements a lane owns in one row: element u is lane u % 8 of the Philox block with counter
+// ((row * 32 + lane) * 8 + u / 8, offset)
+template <int NJ>
+__device__ __forceinline__ typename RowBits<NJ>::type rng_keep_bits(const DropRng& rng, int64_t row, int lane) {
+  using bits_t = typename RowBits<NJ>::type;
+  bits_t bits = 0;
+#pragma unroll
+  for (int g = 0; g < (NJ + 7) / 8; ++g)
+    bits |= static_cast<bits_t>(philox_keep8((static_cast<unsigned long long>(row) * 32 + lane) * 8 + g, rng)) << (8 * g);
+  return bits;
+}
+
 // NJ = ceil(T / 32) elements per lane
 template <int NJ>
 __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float* __restrict__ ac, const float* __restrict__ bd,
                                                                   const uint8_t* __restrict__ mask /* [B,T,T] */,
                                                                   const uint8_t* __restrict__ keep /* [B,H,T,T] | null */,
-                                                                  float inv_keep, float scale, int B, int H, int T,
+                                                                  float inv_keep, DropRng rng, float scale, int B, int H, int T,
                                                                   float* __restrict__ y, float* __restrict__ attn_d) {
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * T;
@@ -36,7 +53,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
     const int b = (int)(bh / H);
     const float* ac_r = ac + row * T;
     const uint8_t* m_r = mask + ((int64_t)b * T + i) * T;
-    const uint8_t* k_r = attn_d != nullptr ? keep + row * T : m_r;
+    const uint8_t* k_r = keep != nullptr ? keep + row * T : m_r;
     const int f0 = T + i * T;
     const int r0 = f0 / (T + 1), c0 = f0 - r0 * (T + 1);
     // element j of the shifted row is P[r0][c0 + j] or, past the end of that row of [0 | bd], P[r0 + 1][c0 + j - (T+1)];
@@ -45,7 +62,8 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
     float s[NJ];
     float mx = -INFINITY;
     float av[NJ], bv[NJ];
-    uint32_t mbits = 0, kbits = 0, zbits = 0;                   // mask / keep / zero-column flags, one bit per element
+    using bits_t = typename RowBits<NJ>::type;
+    bits_t mbits = 0, kbits = 0, zbits = 0;                     // mask / keep / zero-column flags, one bit per element
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
       const int j = min(lane + 32 * u, T - 1);
@@ -55,9 +73,9 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
       const uint32_t kp = __ldg(k_r + j);
       av[u] = __ldg(ac_r + j);
       bv[u] = __ldg(bd_r0 + max(t - 1 - wrapped, 0));
-      zbits |= ((t == 0 || t == T + 1) ? 1u : 0u) << u;          // the zero column of [0 | bd]
-      mbits |= (mk != 0u ? 1u : 0u) << u;
-      kbits |= (kp != 0u ? 1u : 0u) << u;
+      zbits |= static_cast<bits_t>(t == 0 || t == T + 1) << u;   // the zero column of [0 | bd]
+      mbits |= static_cast<bits_t>(mk != 0u) << u;
+      kbits |= static_cast<bits_t>(kp != 0u) << u;
     }
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
@@ -76,6 +94,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
     }
     sum = wsum_(sum);
     const float inv = sum > 0.f ? 1.0f / sum : 0.f;               // nan_to_num(nan = 0) of the reference (conformer.py:127)
+    if (keep == nullptr && rng.threshold != 0u) kbits = rng_keep_bits<NJ>(rng, row, lane);
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
       const int j = lane + 32 * u;
@@ -91,7 +110,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
 template <int NJ>
 __global__ void __launch_bounds__(256, 3) relattn_softmax_bwd_kernel(const float* __restrict__ gd, const float* __restrict__ y,
                                                                   const uint8_t* __restrict__ keep, float inv_keep,
-                                                                  float scale, int B, int H, int T,
+                                                                  DropRng rng, float scale, int B, int H, int T,
                                                                   float* __restrict__ d_ac, float* __restrict__ d_bd) {
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * T;
@@ -113,10 +132,14 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_bwd_kernel(const float
       g[u] = __ldg(gd + row * T + j);
       kp[u] = keep != nullptr ? __ldg(keep + row * T + j) : (uint8_t)1;
     }
+    const bool use_rng = keep == nullptr && rng.threshold != 0u;
+    const typename RowBits<NJ>::type rbits = use_rng ? rng_keep_bits<NJ>(rng, row, lane) : 0;
+    const float gscale = (keep != nullptr || use_rng) ? inv_keep : 1.0f;
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {
       if (lane + 32 * u < T) {
-        g[u] = kp[u] ? g[u] * (keep != nullptr ? inv_keep : 1.0f) : 0.f;
+        const bool kept = use_rng ? ((rbits >> u) & 1u) != 0u : kp[u] != 0;
+        g[u] = kept ? g[u] * gscale : 0.f;
         dot += g[u] * p[u];
       } else {
         g[u] = 0.f;
@@ -160,25 +183,31 @@ static int attn_blocks(int64_t rows) {
   } while (0)
 
 extern "C" int ob_relattn_softmax_fwd(const float* ac, const float* bd, const uint8_t* mask, const uint8_t* keep,
-                                      float inv_keep, float scale, int B, int H, int T, float* y, float* attn_d,
-                                      ob_stream_t stream) {
+                                      float inv_keep, uint64_t seed, uint64_t offset, uint32_t drop_threshold, float scale,
+                                      int B, int H, int T, float* y, float* attn_d, ob_stream_t stream) {
   OB_REQUIRE(ac && bd && mask && y, "ob_relattn_softmax_fwd: null pointer");
-  OB_REQUIRE((keep == nullptr) == (attn_d == nullptr), "ob_relattn_softmax_fwd: keep and attn_d go together");
+  OB_REQUIRE((keep != nullptr || drop_threshold != 0u) == (attn_d != nullptr),
+             "ob_relattn_softmax_fwd: attn_d is written exactly when dropout (mask or RNG) is on");
+  const DropRng rng = {seed, offset, drop_threshold};
+  OB_REQUIRE(drop_threshold < 65536u, "ob_relattn_softmax_fwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
   OB_REQUIRE(B > 0 && H > 0 && T > 0 && T <= 2048, "ob_relattn_softmax_fwd: need 0 < T <= 2048 (T=%d)", T);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = attn_blocks((int64_t)B * H * T);
-  OB_ATTN_DISPATCH(relattn_softmax_fwd_kernel, ac, bd, mask, keep, inv_keep, scale, B, H, T, y, attn_d);
+  OB_ATTN_DISPATCH(relattn_softmax_fwd_kernel, ac, bd, mask, keep, inv_keep, rng, scale, B, H, T, y, attn_d);
   OB_LAUNCH_CHECK("relattn_softmax_fwd_kernel");
   return OB_OK;
 }
 
-extern "C" int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep, float inv_keep, float scale,
-                                      int B, int H, int T, float* d_ac, float* d_bd, ob_stream_t stream) {
+extern "C" int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep, float inv_keep, uint64_t seed,
+                                      uint64_t offset, uint32_t drop_threshold, float scale, int B, int H, int T, float* d_ac,
+                                      float* d_bd, ob_stream_t stream) {
   OB_REQUIRE(gd && y && d_ac && d_bd, "ob_relattn_softmax_bwd: null pointer");
+  const DropRng rng = {seed, offset, drop_threshold};
+  OB_REQUIRE(drop_threshold < 65536u, "ob_relattn_softmax_bwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
   OB_REQUIRE(B > 0 && H > 0 && T > 0 && T <= 2048, "ob_relattn_softmax_bwd: need 0 < T <= 2048 (T=%d)", T);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = attn_blocks((int64_t)B * H * T);
-  OB_ATTN_DISPATCH(relattn_softmax_bwd_kernel, gd, y, keep, inv_keep, scale, B, H, T, d_ac, d_bd);
+  OB_ATTN_DISPATCH(relattn_softmax_bwd_kernel, gd, y, keep, inv_keep, rng, scale, B, H, T, d_ac, d_bd);
   OB_LAUNCH_CHECK("relattn_softmax_bwd_kernel");
   return OB_OK;
 }

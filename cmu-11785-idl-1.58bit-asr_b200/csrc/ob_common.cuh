@@ -96,6 +96,48 @@ __device__ __forceinline__ void expand_word_bf16(uint32_t w, uint4& c0, uint4& c
 }
 
 // ---------------------------------------------------------------------------------------------
+// counter-based dropout masks: Philox4x32-10 (Salmon et al., SC'11).  One call yields four 32-bit words for the counter
+// (group index, call offset) under the key `seed`, read as eight 16-bit lanes (lane k = half k % 2 of word k / 2, low half
+// first); an element is kept when its lane is >= threshold (= p * 2^16, so p is realised to 2^-17 and the caller rescales
+// by the exact 65536 / (65536 - threshold)).  The backward regenerates the same lanes instead of reading a stored mask.
+// ---------------------------------------------------------------------------------------------
+struct DropRng {
+  unsigned long long seed;
+  unsigned long long offset;
+  uint32_t threshold;          // 16-bit; 0 -> dropout off
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(unsigned long long group, unsigned long long offset, unsigned long long seed) {
+  uint32_t c0 = static_cast<uint32_t>(group), c1 = static_cast<uint32_t>(group >> 32);
+  uint32_t c2 = static_cast<uint32_t>(offset), c3 = static_cast<uint32_t>(offset >> 32);
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// keep flags of the eight lanes of one block: bit k set = lane k kept
+__device__ __forceinline__ uint32_t philox_keep8(unsigned long long group, const DropRng& rng) {
+  const uint4 w = philox4x32_10(group, rng.offset, rng.seed);
+  const uint32_t t = rng.threshold;
+  uint32_t bits = 0;
+  bits |= ((w.x & 0xFFFFu) >= t ? 1u : 0u) | ((w.x >> 16) >= t ? 2u : 0u);
+  bits |= ((w.y & 0xFFFFu) >= t ? 4u : 0u) | ((w.y >> 16) >= t ? 8u : 0u);
+  bits |= ((w.z & 0xFFFFu) >= t ? 16u : 0u) | ((w.z >> 16) >= t ? 32u : 0u);
+  bits |= ((w.w & 0xFFFFu) >= t ? 64u : 0u) | ((w.w >> 16) >= t ? 128u : 0u);
+  return bits;
+}
+
+// ---------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

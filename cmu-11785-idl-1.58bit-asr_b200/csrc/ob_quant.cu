@@ -467,34 +467,50 @@ __global__ void __launch_bounds__(256) act_quant_generic_kernel(const T* __restr
 // swish with the SFU exponential (ex2.approx, ~2 ulp) and an IEEE reciprocal: the full-precision expf made this
 // kernel ALU-bound (26 M exponentials per launch at the FFN width); the result differs from torch's sigmoid*x in
 // the last bits only, which moves an int8 code by at most one step on a ~1e-5 fraction of elements
-__device__ __forceinline__ float swish_f(float h) { return h * __frcp_rn(1.0f + __expf(-h)); }
+// swish(h) = h * sigmoid(h) on the SFU (ex2 + rcp, ~2 ulp); exp(-h) = inf for h < -88 gives h * 0 = -0
+__device__ __forceinline__ float swish_f(float h) { return h * __fdividef(1.0f, 1.0f + __expf(-h)); }
 
 template <int V>
 __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __restrict__ h, const uint8_t* __restrict__ keep,
-                                                               float inv_keep, int64_t M, int K, int8_t* __restrict__ q,
-                                                               float* __restrict__ scale) {
+                                                               float inv_keep, DropRng rng, int64_t M, int K,
+                                                               int8_t* __restrict__ q, float* __restrict__ scale) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = warp0; row < M; row += nwarps) {
     const float* hr = h + row * K;
     float4 v[V];
-    uchar4 mk[V];
+    uint32_t kb[V];                                     // keep flags of float4 j in bits 0..3
     float amax = 0.f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {                       // all loads of the row first (memory-level parallelism)
       const int e = (lane + 32 * j) * 4;
       v[j] = __ldg(reinterpret_cast<const float4*>(hr + e));
-      mk[j] = keep != nullptr ? __ldg(reinterpret_cast<const uchar4*>(keep + row * K + e)) : make_uchar4(1, 1, 1, 1);
+      kb[j] = 0xFu;
+      if (keep != nullptr) {
+        const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep + row * K + e));
+        kb[j] = (m.x ? 1u : 0u) | (m.y ? 2u : 0u) | (m.z ? 4u : 0u) | (m.w ? 8u : 0u);
+      }
     }
-    const float ik = keep != nullptr ? inv_keep : 1.0f;
+    if (keep == nullptr && rng.threshold != 0u) {
+      // float4 f of the flat [M, K] tensor uses lanes 4*((f >> 5) & 1) .. +3 of the block with counter f & ~32: one
+      // Philox call serves this thread's float4s j and j + 1
+#pragma unroll
+      for (int j = 0; j < V; j += 2) {
+        const unsigned long long f = static_cast<unsigned long long>(row) * (K >> 2) + lane + 32 * j;
+        const uint32_t b8 = philox_keep8(f, rng);
+        kb[j] = b8 & 0xFu;
+        kb[j + 1] = b8 >> 4;
+      }
+    }
+    const float ik = (keep != nullptr || rng.threshold != 0u) ? inv_keep : 1.0f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float4 t = v[j];
-      t.x = mk[j].x ? swish_f(t.x) * ik : 0.f;
-      t.y = mk[j].y ? swish_f(t.y) * ik : 0.f;
-      t.z = mk[j].z ? swish_f(t.z) * ik : 0.f;
-      t.w = mk[j].w ? swish_f(t.w) * ik : 0.f;
+      t.x = (kb[j] & 1u) ? swish_f(t.x) * ik : 0.f;
+      t.y = (kb[j] & 2u) ? swish_f(t.y) * ik : 0.f;
+      t.z = (kb[j] & 4u) ? swish_f(t.z) * ik : 0.f;
+      t.w = (kb[j] & 8u) ? swish_f(t.w) * ik : 0.f;
       v[j] = t;
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
     }
@@ -507,26 +523,39 @@ __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __re
   }
 }
 
-// g_h = g_z * keep * inv_keep * swish'(h),  swish'(h) = sig + h * sig * (1 - sig)
+// g_h = g_z * keep * inv_keep * swish'(h),  swish'(h) = sig + h * sig * (1 - sig).  A thread owns the float4 pair
+// (f, f + 32) that shares one Philox block (see swish_drop_quant_kernel); a warp still reads 512 contiguous bytes per load.
 __global__ void __launch_bounds__(256) swish_drop_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ h,
-                                                             const uint8_t* __restrict__ keep, float inv_keep, int64_t n4,
-                                                             float* __restrict__ gh) {
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gz) + i);
-    const float4 x = __ldg(reinterpret_cast<const float4*>(h) + i);
-    float mk[4] = {inv_keep, inv_keep, inv_keep, inv_keep};
-    if (keep != nullptr) {
-      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep) + i);
-      mk[0] = m.x ? inv_keep : 0.f; mk[1] = m.y ? inv_keep : 0.f; mk[2] = m.z ? inv_keep : 0.f; mk[3] = m.w ? inv_keep : 0.f;
-    }
-    const float xs[4] = {x.x, x.y, x.z, x.w}, gs[4] = {g.x, g.y, g.z, g.w};
-    float o[4];
+                                                             const uint8_t* __restrict__ keep, float inv_keep, DropRng rng,
+                                                             int64_t npairs, float* __restrict__ gh) {
+  const float ik = (keep != nullptr || rng.threshold != 0u) ? inv_keep : 1.0f;
+  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * 256) {
+    const int64_t f0 = ((p >> 5) << 6) + (p & 31);
+    float4 g[2], x[2];
+    uint32_t kb = 0xFFu;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float sg = 1.0f / (1.0f + expf(-xs[u]));
-      o[u] = gs[u] * mk[u] * (sg + xs[u] * sg * (1.0f - sg));
+    for (int c = 0; c < 2; ++c) {
+      g[c] = __ldg(reinterpret_cast<const float4*>(gz) + f0 + 32 * c);
+      x[c] = __ldg(reinterpret_cast<const float4*>(h) + f0 + 32 * c);
     }
-    reinterpret_cast<float4*>(gh)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (keep != nullptr) {
+      const uchar4 m0 = __ldg(reinterpret_cast<const uchar4*>(keep) + f0), m1 = __ldg(reinterpret_cast<const uchar4*>(keep) + f0 + 32);
+      kb = (m0.x ? 1u : 0u) | (m0.y ? 2u : 0u) | (m0.z ? 4u : 0u) | (m0.w ? 8u : 0u) | (m1.x ? 16u : 0u) | (m1.y ? 32u : 0u) |
+           (m1.z ? 64u : 0u) | (m1.w ? 128u : 0u);
+    } else if (rng.threshold != 0u) {
+      kb = philox_keep8(static_cast<unsigned long long>(f0), rng);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float xs[4] = {x[c].x, x[c].y, x[c].z, x[c].w}, gs[4] = {g[c].x, g[c].y, g[c].z, g[c].w};
+      float o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float sg = __fdividef(1.0f, 1.0f + __expf(-xs[u]));
+        o[u] = ((kb >> (4 * c + u)) & 1u) ? gs[u] * ik * (sg + xs[u] * sg * (1.0f - sg)) : 0.f;
+      }
+      reinterpret_cast<float4*>(gh)[f0 + 32 * c] = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -781,29 +810,34 @@ extern "C" int ob_bwd_prep(const void* dY, int dy_dtype, const float* scale, con
   return OB_OK;
 }
 
-extern "C" int ob_swish_drop_quant(const float* h, const uint8_t* keep, float inv_keep, int64_t M, int K, int8_t* q,
-                                   float* scale, ob_stream_t stream) {
+extern "C" int ob_swish_drop_quant(const float* h, const uint8_t* keep, float inv_keep, uint64_t seed, uint64_t offset,
+                                   uint32_t drop_threshold, int64_t M, int K, int8_t* q, float* scale, ob_stream_t stream) {
+  OB_REQUIRE(drop_threshold < 65536u, "ob_swish_drop_quant: drop_threshold (%u) is a 16-bit value", drop_threshold);
+  const DropRng rng = {seed, offset, drop_threshold};
   OB_REQUIRE(h && q && scale && M > 0, "ob_swish_drop_quant: null pointer or M <= 0");
   OB_REQUIRE(K == 256 || K == 512 || K == 1024 || K == 2048, "ob_swish_drop_quant: K (%d) must be 256, 512, 1024 or 2048", K);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t want = (M + 7) / 8;
   const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
   switch (K) {
-    case 256:  swish_drop_quant_kernel<2><<<blocks, 256, 0, st>>>(h, keep, inv_keep, M, K, q, scale); break;
-    case 512:  swish_drop_quant_kernel<4><<<blocks, 256, 0, st>>>(h, keep, inv_keep, M, K, q, scale); break;
-    case 1024: swish_drop_quant_kernel<8><<<blocks, 256, 0, st>>>(h, keep, inv_keep, M, K, q, scale); break;
-    default:   swish_drop_quant_kernel<16><<<blocks, 256, 0, st>>>(h, keep, inv_keep, M, K, q, scale); break;
+    case 256:  swish_drop_quant_kernel<2><<<blocks, 256, 0, st>>>(h, keep, inv_keep, rng, M, K, q, scale); break;
+    case 512:  swish_drop_quant_kernel<4><<<blocks, 256, 0, st>>>(h, keep, inv_keep, rng, M, K, q, scale); break;
+    case 1024: swish_drop_quant_kernel<8><<<blocks, 256, 0, st>>>(h, keep, inv_keep, rng, M, K, q, scale); break;
+    default:   swish_drop_quant_kernel<16><<<blocks, 256, 0, st>>>(h, keep, inv_keep, rng, M, K, q, scale); break;
   }
   OB_LAUNCH_CHECK("swish_drop_quant_kernel");
   return OB_OK;
 }
 
-extern "C" int ob_swish_drop_bwd(const float* gz, const float* h, const uint8_t* keep, float inv_keep, int64_t n,
-                                 float* gh, ob_stream_t stream) {
-  OB_REQUIRE(gz && h && gh && n > 0 && n % 4 == 0, "ob_swish_drop_bwd: null pointer or n not a positive multiple of 4");
-  const int64_t want = (n / 4 + 255) / 256;
+extern "C" int ob_swish_drop_bwd(const float* gz, const float* h, const uint8_t* keep, float inv_keep, uint64_t seed,
+                                 uint64_t offset, uint32_t drop_threshold, int64_t n, float* gh, ob_stream_t stream) {
+  OB_REQUIRE(gz && h && gh && n > 0 && n % 256 == 0, "ob_swish_drop_bwd: null pointer or n not a positive multiple of 256");
+  OB_REQUIRE(drop_threshold < 65536u, "ob_swish_drop_bwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
+  const DropRng rng = {seed, offset, drop_threshold};
+  const int64_t npairs = n / 8;
+  const int64_t want = (npairs + 255) / 256;
   const int blocks = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
-  swish_drop_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(gz, h, keep, inv_keep, n / 4, gh);
+  swish_drop_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(gz, h, keep, inv_keep, rng, npairs, gh);
   OB_LAUNCH_CHECK("swish_drop_bwd_kernel");
   return OB_OK;
 }

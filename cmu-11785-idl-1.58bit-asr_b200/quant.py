@@ -196,6 +196,23 @@ def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w
 
 
 _FUSED_SWISH_K = (256, 512, 1024, 2048)
+_NO_RNG = (0, 0, 0)
+_DROP_DOMAIN = 0x6F6E656269743135   # keeps these Philox streams apart from torch's own use of the same seed
+
+
+def draw_dropout_stream(device: torch.device, p: float):
+    """``inv_keep, (seed, offset, threshold)`` of a fresh Philox stream for one fused dropout (``include/onebit.h``), taken
+    from the device's default generator: reproducible under ``torch.manual_seed`` and never repeated, because the
+    generator's offset moves on.  An element is dropped iff its 16-bit lane is below ``threshold = round(p * 2^16)``, so
+    the realised rate is ``threshold / 65536`` (within 2^-17 of p) and ``inv_keep`` is exact for it.  Nothing here touches
+    the device; the backward regenerates the mask from the same triple instead of reading a stored one."""
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[index]
+    seed = (gen.initial_seed() ^ _DROP_DOMAIN) & 0xFFFFFFFFFFFFFFFF
+    offset = gen.get_offset()
+    gen.set_offset(offset + 4)
+    threshold = min(max(int(round(p * 65536.0)), 1), 65535)
+    return 65536.0 / (65536 - threshold), (seed, offset, threshold)
 
 
 class _SwishDropQuantLinearFn(torch.autograd.Function):
@@ -203,7 +220,7 @@ class _SwishDropQuantLinearFn(torch.autograd.Function):
     kernel behind the grad_x GEMM (backward): the FFN mid-section of conformer.py:36-39."""
 
     @staticmethod
-    def forward(ctx, h, weight, alpha, bias, bitwidth, packed, packed_t, keep, inv_keep):
+    def forward(ctx, h, weight, alpha, bias, bitwidth, packed, packed_t, keep, inv_keep, rng):
         K = h.shape[-1]
         N = weight.shape[0]
         h2 = h.reshape(-1, K)
@@ -213,7 +230,7 @@ class _SwishDropQuantLinearFn(torch.autograd.Function):
         q = torch.empty((M, K), device=h.device, dtype=torch.int8)
         s = torch.empty((M,), device=h.device, dtype=torch.float32)
         st = _stream()
-        check(lib.ob_swish_drop_quant(h2.data_ptr(), None if keep is None else keep.data_ptr(), inv_keep, M, K,
+        check(lib.ob_swish_drop_quant(h2.data_ptr(), None if keep is None else keep.data_ptr(), inv_keep, *rng, M, K,
                                       q.data_ptr(), s.data_ptr(), st))
         y = torch.empty((M, N), device=h.device, dtype=h.dtype)
         check(lib.ob_gemm_tern_i8_fwd(q.data_ptr(), s.data_ptr(), packed.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW,
@@ -222,7 +239,7 @@ class _SwishDropQuantLinearFn(torch.autograd.Function):
             ctx.save_for_backward(h2, q, s, weight, alpha, packed_t)
         else:
             ctx.save_for_backward(h2, q, s, weight, alpha, packed_t, keep)
-        ctx.bitwidth, ctx.has_bias, ctx.h_shape, ctx.inv_keep = bitwidth, bias is not None, h.shape, inv_keep
+        ctx.bitwidth, ctx.has_bias, ctx.h_shape, ctx.inv_keep, ctx.rng = bitwidth, bias is not None, h.shape, inv_keep, rng
         return y.view(*h.shape[:-1], N)
 
     @staticmethod
@@ -237,9 +254,9 @@ class _SwishDropQuantLinearFn(torch.autograd.Function):
         if need_h:
             gh = torch.empty_like(h2)
             check(lib.ob_swish_drop_bwd(gz.data_ptr(), h2.data_ptr(), None if keep is None else keep.data_ptr(),
-                                        ctx.inv_keep, h2.numel(), gh.data_ptr(), _stream()))
+                                        ctx.inv_keep, *ctx.rng, h2.numel(), gh.data_ptr(), _stream()))
             gh = gh.view(ctx.h_shape)
-        return gh, gw, ga, gb, None, None, None, None, None
+        return gh, gw, ga, gb, None, None, None, None, None, None
 
 
 class _QuantizeWeightFn(torch.autograd.Function):
@@ -362,16 +379,14 @@ class QuantizedLinear(nn.Module):
                 z = F.dropout(z, p, training)
             return self.forward(z, bitwidth)
         _require_cuda(self.weight, "weight")
-        inv_keep = 1.0
+        inv_keep, rng = 1.0, _NO_RNG
         if keep is not None:
             keep, inv_keep = keep.reshape(-1, self.in_features).contiguous(), 1.0 / (1.0 - p)
         elif training and p > 0.0:
-            keep = torch.empty(h.numel() // self.in_features, self.in_features, device=h.device,
-                               dtype=torch.bool).bernoulli_(1.0 - p)
-            inv_keep = 1.0 / (1.0 - p)
+            inv_keep, rng = draw_dropout_stream(h.device, p)                    # mask generated inside the kernels
         packed, packed_t = self.packed_weight(bitwidth)
         return _SwishDropQuantLinearFn.apply(h, self.weight, self.alpha, self.bias, bitwidth, packed, packed_t, keep,
-                                             inv_keep)
+                                             inv_keep, rng)
 
 
 BitLinear = QuantizedLinear   # the north_star's name for the same layer

@@ -128,12 +128,21 @@ int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float* colsum, co
               float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream);
 
 /* Fused FFN mid-section (conformer.py:36-39): z = dropout(swish(h)) followed by the
- * activation quantiser of the next layer, in one pass.  h [M, K] fp32; keep [M, K] bytes (1 = keep) or NULL for no
- * dropout; inv_keep = 1/(1-p).  K in {256, 512, 1024, 2048}.  ob_swish_drop_bwd: g_h = g_z * keep*inv_keep * swish'(h). */
-int ob_swish_drop_quant(const float* h, const uint8_t* keep, float inv_keep, int64_t M, int K, int8_t* q,
-                        float* scale, ob_stream_t stream);
-int ob_swish_drop_bwd(const float* gz, const float* h, const uint8_t* keep, float inv_keep, int64_t n,
-                      float* gh, ob_stream_t stream);
+ * activation quantiser of the next layer, in one pass.  h [M, K] fp32, K in {256, 512, 1024, 2048}; inv_keep = 1/(1-p).
+ * The dropout mask (nn.Dropout of conformer.py:38) comes from one of two places:
+ *   keep != NULL          : [M, K] bytes, 1 = keep (explicit mask, used by the parity tests);
+ *   keep == NULL, thr != 0: counter-based Philox4x32-10 keyed by `seed`; a block of four 32-bit words is read as eight
+ *                           16-bit lanes (lane k = half k % 2, low first, of word k / 2).  With f = element / 4 the
+ *                           128-bit counter is (f & ~32, offset) and the element's lane is 4 * ((f >> 5) & 1) +
+ *                           element % 4; it is kept iff lane >= thr, thr = round(p * 2^16) < 2^16, and the caller passes
+ *                           the exact inv_keep = 65536 / (65536 - thr).  The backward regenerates the same bits from
+ *                           (seed, offset): no mask is stored;
+ *   keep == NULL, thr == 0: no dropout (inv_keep ignored).
+ * ob_swish_drop_bwd: g_h = g_z * keep * inv_keep * swish'(h), n = M * K elements (n % 256 == 0). */
+int ob_swish_drop_quant(const float* h, const uint8_t* keep, float inv_keep, uint64_t seed, uint64_t offset,
+                        uint32_t drop_threshold, int64_t M, int K, int8_t* q, float* scale, ob_stream_t stream);
+int ob_swish_drop_bwd(const float* gz, const float* h, const uint8_t* keep, float inv_keep, uint64_t seed,
+                      uint64_t offset, uint32_t drop_threshold, int64_t n, float* gh, ob_stream_t stream);
 
 /* LayerNorm in front of the routed projections (conformer.py:35, 109): y = (x - mean) * rstd * gamma + beta over the
  * last axis C in {128, 256, 512, 1024}, fp32; mean/rstd [M] are kept for the backward.  ob_layernorm_bwd writes dx and
@@ -147,13 +156,17 @@ int ob_layernorm_bwd(const float* dy, const float* x, const float* mean, const f
 
 /* Element-wise chain between the attention matmuls of the reference MHSA (conformer.py:118-128), fused:
  * y = nan_to_num(softmax(masked_fill((ac + rel_shift(bd)) * scale))), attn_d = dropout(y).  ac, bd [B,H,T,T] fp32 (bd
- * BEFORE the relative shift), mask [B,T,T] bytes (0 = masked), keep [B,H,T,T] bytes or NULL (then attn_d NULL), T <= 2048.
- * Backward: gradients w.r.t. ac and the un-shifted bd from the gradient w.r.t. attn_d (or y when keep is NULL). */
+ * BEFORE the relative shift), mask [B,T,T] bytes (0 = masked), T <= 2048.  Dropout as in ob_swish_drop_quant: explicit
+ * keep [B,H,T,T] bytes, or keep == NULL with drop_threshold != 0 for the Philox stream (element lane + 32 u of row
+ * r = (b*H + h)*T + i is 16-bit lane u % 8 of the block with counter ((r * 32 + lane) * 8 + u / 8, offset)), or neither
+ * (then attn_d must be NULL and only y is written).
+ * Backward: gradients w.r.t. ac and the un-shifted bd from the gradient w.r.t. attn_d (or y without dropout). */
 int ob_relattn_softmax_fwd(const float* ac, const float* bd, const uint8_t* mask, const uint8_t* keep,
-                           float inv_keep, float scale, int B, int H, int T, float* y, float* attn_d,
-                           ob_stream_t stream);
-int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep, float inv_keep,
-                           float scale, int B, int H, int T, float* d_ac, float* d_bd, ob_stream_t stream);
+                           float inv_keep, uint64_t seed, uint64_t offset, uint32_t drop_threshold, float scale,
+                           int B, int H, int T, float* y, float* attn_d, ob_stream_t stream);
+int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep, float inv_keep, uint64_t seed,
+                           uint64_t offset, uint32_t drop_threshold, float scale, int B, int H, int T, float* d_ac,
+                           float* d_bd, ob_stream_t stream);
 
 /* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
  * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded

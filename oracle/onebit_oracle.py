@@ -258,3 +258,67 @@ def init_layer_params(in_features: int, out_features: int, bias: bool = True):
     a = w.abs().mean()
     b = torch.zeros(out_features) if bias else None
     return w, a, b
+
+
+# ---------------------------------------------------------------------------------------------
+# Dropout streams of the fused kernels (include/onebit.h: ob_swish_drop_quant, ob_relattn_softmax_fwd).
+# The reference draws nn.Dropout masks from torch's generator (conformer.py:38, 128); any Bernoulli(1-p) stream is
+# equivalent, so the kernels' stream is OUR spec: Philox4x32-10 (Salmon et al., SC'11), restated here from the
+# published algorithm and pinned to the Random123 known-answer vectors in tests/test_oracle.py.
+# ---------------------------------------------------------------------------------------------
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+_U32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
+    """Ten rounds of Philox-4x32 on arrays of counter words (uint32 values held in uint64); returns four uint32 arrays."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & _U32 for c in (c0, c1, c2, c3))
+    for r in range(10):
+        ka = np.uint64((k0 + r * _PHILOX_W0) & 0xFFFFFFFF)
+        kb = np.uint64((k1 + r * _PHILOX_W1) & 0xFFFFFFFF)
+        p0, p1 = _PHILOX_M0 * c0, _PHILOX_M1 * c2
+        c0, c1, c2, c3 = ((p1 >> np.uint64(32)) ^ c1 ^ ka, p1 & _U32, (p0 >> np.uint64(32)) ^ c3 ^ kb, p0 & _U32)
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def _philox_words(group: np.ndarray, offset: int, seed: int) -> np.ndarray:
+    """[..., 4] words of the block with counter (group, offset) and key seed, as the kernels lay them out."""
+    group = np.asarray(group, dtype=np.uint64)
+    zero = np.zeros_like(group)
+    w = philox4x32_10(group & _U32, group >> np.uint64(32), zero + np.uint64(offset & 0xFFFFFFFF),
+                      zero + np.uint64((offset >> 32) & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return np.stack(w, axis=-1)
+
+
+def _philox_lanes16(group: np.ndarray, offset: int, seed: int) -> np.ndarray:
+    """[..., 8] 16-bit lanes of the block: lane k = half k % 2 (low first) of word k // 2."""
+    w = _philox_words(group, offset, seed)
+    return np.stack([w & np.uint32(0xFFFF), w >> np.uint32(16)], axis=-1).reshape(*w.shape[:-1], 8)
+
+
+def dropout_keep_flat(n: int, seed: int, offset: int, threshold: int) -> np.ndarray:
+    """Keep mask of the fused swish/dropout kernels over a flat tensor of n (multiple of 256) elements: with f = e // 4,
+    element e is lane 4 * ((f >> 5) & 1) + e % 4 of the block with counter (f & ~32, offset); kept iff lane >= threshold
+    (16-bit)."""
+    assert n % 256 == 0 and 0 <= threshold < 65536
+    e = np.arange(n, dtype=np.uint64)
+    f = e >> np.uint64(2)
+    lanes = _philox_lanes16(np.arange(n // 4, dtype=np.uint64), offset, seed)          # block of every f (half are unused)
+    pick = (np.uint64(4) * ((f >> np.uint64(5)) & np.uint64(1)) + (e & np.uint64(3))).astype(np.int64)
+    return lanes[(f & ~np.uint64(32)).astype(np.int64), pick] >= threshold
+
+
+def dropout_keep_relattn(B: int, H: int, T: int, seed: int, offset: int, threshold: int) -> np.ndarray:
+    """Keep mask [B,H,T,T] of the fused attention chain: column j = lane + 32 u of row r = (b*H + h)*T + i is 16-bit lane
+    u % 8 of the block with counter ((r * 32 + lane) * 8 + u // 8, offset)."""
+    assert 0 <= threshold < 65536
+    rows = B * H * T
+    nu = (T + 31) // 32
+    r = np.arange(rows, dtype=np.uint64)[:, None, None]
+    lane = np.arange(32, dtype=np.uint64)[None, :, None]
+    g = np.arange((nu + 7) // 8, dtype=np.uint64)[None, None, :]
+    lanes = _philox_lanes16((r * np.uint64(32) + lane) * np.uint64(8) + g, offset, seed)    # [rows, 32, G, 8]
+    keep_lu = (lanes >= threshold).reshape(rows, 32, -1)                                   # [rows, lane, u]
+    keep = keep_lu.transpose(0, 2, 1).reshape(rows, -1)[:, :T]                             # column = u * 32 + lane
+    return keep.reshape(B, H, T, T)

@@ -375,6 +375,103 @@ def test_rel_attention_probs_matches_reference_chain(ob, B, H, T, p):
         assert o1.transpose(1, 2)[~km].abs().max().item() == 0.0        # padded query rows are exactly zero
 
 
+# ------------------------------------------------------------------ in-kernel dropout streams (Philox4x32-10)
+@pytest.mark.parametrize("M,K", [(37, 256), (333, 1024), (64, 2048), (5, 512)])
+def test_swish_dropout_rng_path_equals_explicit_mask(ob, M, K):
+    """The mask the kernels generate from (seed, offset, threshold) is the oracle's Philox mask: forward codes/scales and
+    backward gradients are bit-identical to the explicit-mask path fed with the oracle mask."""
+    from onebit_b200._cabi import lib, check
+    seed, offset, thr = 0x1234567890ABCDEF, 4 * M + (1 << 33), int(round(0.1 * 2 ** 16))
+    keep = torch.from_numpy(orc.dropout_keep_flat(M * K, seed, offset, thr).reshape(M, K)).cuda()
+    g = torch.Generator().manual_seed(M + K)
+    h = (torch.randn(M, K, generator=g) * 2).cuda()
+    gz = torch.randn(M, K, generator=g).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for kp, rng in ((keep, (0, 0, 0)), (None, (seed, offset, thr))):
+        q = torch.empty(M, K, dtype=torch.int8, device="cuda")
+        s = torch.empty(M, device="cuda")
+        gh = torch.empty(M, K, device="cuda")
+        kptr = None if kp is None else kp.data_ptr()
+        check(lib.ob_swish_drop_quant(h.data_ptr(), kptr, 1 / 0.9, *rng, M, K, q.data_ptr(), s.data_ptr(), st))
+        check(lib.ob_swish_drop_bwd(gz.data_ptr(), h.data_ptr(), kptr, 1 / 0.9, *rng, M * K, gh.data_ptr(), st))
+        outs.append((q, s, gh))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert 0.85 < keep.float().mean().item() < 0.95
+    assert torch.equal(outs[1][2] == 0, ~keep | (gz == 0))
+
+
+@pytest.mark.parametrize("B,H,T", [(2, 3, 49), (1, 2, 399), (1, 1, 700), (1, 1, 1100)])
+def test_rel_attention_rng_path_equals_explicit_mask(ob, B, H, T):
+    from onebit_b200._cabi import lib, check
+    seed, offset, thr = 99, 12 + (7 << 32), int(round(0.25 * 2 ** 16))
+    keep = torch.from_numpy(orc.dropout_keep_relattn(B, H, T, seed, offset, thr)).cuda()
+    g = torch.Generator().manual_seed(T)
+    ac, bd, gd = ((torch.randn(B, H, T, T, generator=g) * 2).cuda() for _ in range(3))
+    mask = torch.ones(B, T, T, dtype=torch.bool, device="cuda")
+    mask[0, :, T - 3:] = False
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for kp, rng in ((keep, (0, 0, 0)), (None, (seed, offset, thr))):
+        y, ad, d_ac, d_bd = (torch.empty_like(ac) for _ in range(4))
+        kptr = None if kp is None else kp.data_ptr()
+        check(lib.ob_relattn_softmax_fwd(ac.data_ptr(), bd.data_ptr(), mask.data_ptr(), kptr, 4 / 3, *rng, 0.125, B, H, T,
+                                         y.data_ptr(), ad.data_ptr(), st))
+        check(lib.ob_relattn_softmax_bwd(gd.data_ptr(), y.data_ptr(), kptr, 4 / 3, *rng, 0.125, B, H, T, d_ac.data_ptr(),
+                                         d_bd.data_ptr(), st))
+        outs.append((y, ad, d_ac, d_bd))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert 0.70 < keep.float().mean().item() < 0.80
+
+
+def test_layer_dropout_is_seeded_and_advances(ob):
+    """forward_swish_dropout / rel_attention_probs draw their stream from the device generator: same seed -> same result,
+    consecutive calls -> different masks, and the backward drops exactly what the forward dropped."""
+    from onebit_b200.attention import rel_attention_probs
+    layer = ob.QuantizedLinear(256, 256).cuda()
+    h = torch.randn(4, 50, 256, device="cuda")
+    gy = torch.randn(4, 50, 256, device="cuda")
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+
+    def run():
+        hh = h.clone().requires_grad_(True)
+        y = layer.forward_swish_dropout(hh, 2, 0.1, True)
+        y.backward(gy)
+        return y.detach(), hh.grad
+
+    torch.manual_seed(1234)
+    off0 = gen.get_offset()
+    y1, g1 = run()
+    assert gen.get_offset() == off0 + 4
+    y2, g2 = run()
+    torch.manual_seed(1234)
+    y3, g3 = run()
+    assert torch.equal(y1, y3) and torch.equal(g1, g3)
+    assert not torch.equal(y1, y2)
+    seed = (1234 ^ ob.quant._DROP_DOMAIN) & (2 ** 64 - 1)
+    keep = torch.from_numpy(orc.dropout_keep_flat(h.numel(), seed, off0, int(round(0.1 * 2 ** 16)))).cuda().view_as(h)
+    assert (g1[~keep] == 0).all() and (g1[keep] != 0).float().mean().item() > 0.99
+    # eval mode / p = 0: no stream is drawn
+    off = gen.get_offset()
+    layer.forward_swish_dropout(h, 2, 0.1, False)
+    layer.forward_swish_dropout(h, 2, 0.0, True)
+    assert gen.get_offset() == off
+    ac, bd = torch.randn(2, 2, 40, 40, device="cuda"), torch.randn(2, 2, 40, 40, device="cuda")
+    mask = torch.ones(2, 40, 40, dtype=torch.bool, device="cuda")
+    torch.manual_seed(5)
+    a1 = rel_attention_probs(ac, bd, mask, 0.125, 0.1, True)
+    a2 = rel_attention_probs(ac, bd, mask, 0.125, 0.1, True)
+    torch.manual_seed(5)
+    a3 = rel_attention_probs(ac, bd, mask, 0.125, 0.1, True)
+    assert torch.equal(a1, a3) and not torch.equal(a1, a2)
+    frac = (a1 == 0).float().mean().item()
+    assert 0.07 < frac < 0.13
+    assert torch.allclose(rel_attention_probs(ac, bd, mask, 0.125, 0.1, False).sum(-1), torch.ones(2, 2, 40, device="cuda"),
+                          atol=1e-5)
+
+
 # ------------------------------------------------------------------ edge cases of the layer interface
 def test_layer_edge_cases(ob):
     torch.manual_seed(2)

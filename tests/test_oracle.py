@@ -134,3 +134,26 @@ def test_greedy_decode_matches_reference_fixture():
     hyps = ob.ctc_greedy_decode_batch(fx["logits"], fx["lens"], blank_id=3)
     for b, h in enumerate(hyps):
         assert len(h) == fx["out_lens"][b] and h == fx["tokens"][b, : len(h)].tolist()
+
+
+# ------------------------------------------------------------------ dropout stream of the fused kernels
+def test_philox_known_answers():
+    """Philox4x32-10 restatement against the Random123 known-answer vectors (counter, key -> output)."""
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = ob.philox4x32_10(*[np.array([c]) for c in ctr], *key)
+        assert tuple(int(w[0]) for w in got) == want
+
+
+def test_dropout_masks_are_bernoulli_and_keyed():
+    thr = int(round(0.1 * 2 ** 16))
+    a = ob.dropout_keep_flat(1 << 18, seed=7, offset=0, threshold=thr)
+    b = ob.dropout_keep_flat(1 << 18, seed=7, offset=4, threshold=thr)
+    assert abs(a.mean() - 0.9) < 5e-3 and abs(b.mean() - 0.9) < 5e-3
+    assert 0.75 < (a == b).mean() < 0.89                      # independent streams agree on 0.81 + 0.01 of the elements
+    k = ob.dropout_keep_relattn(2, 3, 70, seed=7, offset=0, threshold=thr)
+    assert k.shape == (2, 3, 70, 70) and abs(k.mean() - 0.9) < 1e-2
+    assert ob.dropout_keep_flat(256, 1, 0, 0).all()            # threshold 0 keeps everything

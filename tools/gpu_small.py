@@ -24,7 +24,7 @@ y, stats = torch.empty(M, K, device=dev), torch.empty(2, M, device=dev)
 dx, dp = torch.empty(M, K, device=dev), torch.empty(2, K, device=dev)
 ws = torch.empty(lib.ob_layernorm_bwd_workspace_bytes(K), device=dev, dtype=torch.uint8)
 for _ in range(4):
-    lib.ob_swish_drop_quant(h.data_ptr(), keep.data_ptr(), 1 / 0.9, M, N, q.data_ptr(), s.data_ptr(), st)
+    lib.ob_swish_drop_quant(h.data_ptr(), keep.data_ptr(), 1 / 0.9, 0, 0, 0, M, N, q.data_ptr(), s.data_ptr(), st)
     lib.ob_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), 1e-5, M, K, y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), st)
     lib.ob_layernorm_bwd(dy.data_ptr(), x.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), w.data_ptr(), M, K, dx.data_ptr(),
                          dp[0].data_ptr(), dp[1].data_ptr(), ws.data_ptr(), st)
