@@ -342,10 +342,10 @@ def hot_kernel_rooflines(peaks, M):
                                                          ln_w.data_ptr(), M, K, ln_dx.data_ptr(), ln_dp[0].data_ptr(), ln_dp[1].data_ptr(),
                                                          ln_ws.data_ptr(), st), 12.0 * M * K + 8 * M, 0.0),
         "relattn_softmax_fwd": (lambda j: lib.ob_relattn_softmax_fwd(att[j % 2].data_ptr(), att[2 + j % 2].data_ptr(), att_mask.data_ptr(),
-                                                                     None, 1.0 / 0.9, 1234, 4 * j, drop_thr, 0.125, Bq, Hh, Tt,
+                                                                     None, 1.0 / 0.9, 1234, 4 * j, drop_thr, 0.125, Bq, Hh, Tt, Tt,
                                                                      att_y.data_ptr(), att_o.data_ptr(), st), 16.0 * nat, 0.0),
         "relattn_softmax_bwd": (lambda j: lib.ob_relattn_softmax_bwd(att[j % 2].data_ptr(), att_y.data_ptr(), None, 1.0 / 0.9, 1234, 4 * j,
-                                                                     drop_thr, 0.125, Bq, Hh, Tt, att[2].data_ptr(), att[3].data_ptr(), st),
+                                                                     drop_thr, 0.125, Bq, Hh, Tt, Tt, att[2].data_ptr(), att[3].data_ptr(), st),
                                 16.0 * nat, 0.0),
         "weight_quant_pack": (lambda j: lib.ob_weight_quant_pack(layer.weight.data_ptr(), a.data_ptr(), 1, N, K, 2, pk2.data_ptr(),
                                                                  pkt2.data_ptr(), st), 4.5 * N * K, 0.0),

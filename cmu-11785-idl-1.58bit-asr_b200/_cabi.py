@@ -44,11 +44,14 @@ SIGNATURES = {
     "ob_layernorm_fwd": (_i, [_p, _p, _p, ctypes.c_float, _i64, _i, _p, _p, _p, _p]),
     "ob_layernorm_bwd_workspace_bytes": (_sz, [_i]),
     "ob_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p]),
-    "ob_relattn_softmax_fwd": (_i, [_p, _p, _p, _p, ctypes.c_float, _u64, _u64, _u32, ctypes.c_float, _i, _i, _i, _p, _p,
+    "ob_relattn_softmax_fwd": (_i, [_p, _p, _p, _p, ctypes.c_float, _u64, _u64, _u32, ctypes.c_float, _i, _i, _i, _i, _p, _p,
                                     _p]),
-    "ob_relattn_softmax_bwd": (_i, [_p, _p, _p, ctypes.c_float, _u64, _u64, _u32, ctypes.c_float, _i, _i, _i, _p, _p, _p]),
+    "ob_relattn_softmax_bwd": (_i, [_p, _p, _p, ctypes.c_float, _u64, _u64, _u32, ctypes.c_float, _i, _i, _i, _i, _p, _p,
+                                    _p]),
     "ob_ctc_decode_workspace_bytes": (_sz, [_i, _i]),
     "ob_ctc_greedy_decode": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "ob_gemm_f32": (_i, [_p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, ctypes.c_float, _i,
+                         _i, _i, _i, _i, _i, _i, _p]),
     "ob_debug_set": (_i, [_i, _i]),
 }
 

@@ -171,6 +171,12 @@ class MHSA(nn.Module):
         if width != self.d_model:
             raise AssertionError(f"Expected {self.d_model}, got {width}")
         normed = self.ln(x)
+        if attention.rel_attention_usable(normed, mask, self.n_heads) and pos_emb.shape[:2] == (1, frames):
+            # tensor-core path: the projections are consumed in their [B, T, H*d] layout, no head transposes
+            mixed = attention.rel_attention(self.q_proj(normed, bitwidth), self.k_proj(normed, bitwidth),
+                                            self.v_proj(normed, bitwidth), self.pos_proj(pos_emb, bitwidth), self.pos_bias_u,
+                                            self.pos_bias_v, mask, self.n_heads, self.dropout.p, self.training)
+            return self._finish(x, mixed, mask, bitwidth)
         q = self._split(self.q_proj(normed, bitwidth), batch)
         k = self._split(self.k_proj(normed, bitwidth), batch)
         v = self._split(self.v_proj(normed, bitwidth), batch)
@@ -179,6 +185,9 @@ class MHSA(nn.Module):
         w = self.pos_bias_v.view(1, self.n_heads, 1, self.d_head)
         probs = self._probabilities(torch.matmul(q + u, k.transpose(-2, -1)), torch.matmul(q + w, pos.transpose(-2, -1)), mask)
         mixed = (probs @ v).transpose(1, 2).contiguous().view(batch, frames, width)
+        return self._finish(x, mixed, mask, bitwidth)
+
+    def _finish(self, x, mixed, mask, bitwidth):
         mixed = self.dropout(self.out_proj(mixed, bitwidth))
         keep = _frame_mask(mask)
         if keep is not None:

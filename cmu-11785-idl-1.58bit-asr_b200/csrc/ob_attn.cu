@@ -41,7 +41,7 @@ template <int NJ>
 __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float* __restrict__ ac, const float* __restrict__ bd,
                                                                   const uint8_t* __restrict__ mask /* [B,T,T] */,
                                                                   const uint8_t* __restrict__ keep /* [B,H,T,T] | null */,
-                                                                  float inv_keep, DropRng rng, float scale, int B, int H, int T,
+                                                                  float inv_keep, DropRng rng, float scale, int B, int H, int T, int ld,
                                                                   float* __restrict__ y, float* __restrict__ attn_d) {
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * T;
@@ -51,14 +51,15 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
     const int i = (int)(row % T);
     const int64_t bh = row / T;
     const int b = (int)(bh / H);
-    const float* ac_r = ac + row * T;
+    const float* ac_r = ac + row * ld;                           // ac, bd, y, attn_d: rows of T floats, pitch ld
     const uint8_t* m_r = mask + ((int64_t)b * T + i) * T;
     const uint8_t* k_r = keep != nullptr ? keep + row * T : m_r;
     const int f0 = T + i * T;
     const int r0 = f0 / (T + 1), c0 = f0 - r0 * (T + 1);
     // element j of the shifted row is P[r0][c0 + j] or, past the end of that row of [0 | bd], P[r0 + 1][c0 + j - (T+1)];
-    // relative to bd row r0 both are one linear offset: c0 + j - 1 (same row) or c0 + j - 2 (next row)
-    const float* bd_r0 = bd + bh * (int64_t)T * T + (int64_t)r0 * T;
+    // relative to bd row r0 both are one linear offset: c0 + j - 1 (same row) or c0 + j - 1 + ld - (T+1) (next row)
+    const float* bd_r0 = bd + (bh * (int64_t)T + r0) * ld;
+    const int wrap_off = ld - T - 1;
     float s[NJ];
     float mx = -INFINITY;
     float av[NJ], bv[NJ];
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
       const uint32_t mk = __ldg(m_r + j);
       const uint32_t kp = __ldg(k_r + j);
       av[u] = __ldg(ac_r + j);
-      bv[u] = __ldg(bd_r0 + max(t - 1 - wrapped, 0));
+      bv[u] = __ldg(bd_r0 + max(t - 1 + (wrapped ? wrap_off : 0), 0));
       zbits |= static_cast<bits_t>(t == 0 || t == T + 1) << u;   // the zero column of [0 | bd]
       mbits |= static_cast<bits_t>(mk != 0u) << u;
       kbits |= static_cast<bits_t>(kp != 0u) << u;
@@ -100,8 +101,8 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
       const int j = lane + 32 * u;
       if (j < T) {
         const float p = s[u] * inv;
-        y[row * T + j] = p;
-        if (attn_d != nullptr) attn_d[row * T + j] = ((kbits >> u) & 1u) ? p * inv_keep : 0.f;
+        y[row * ld + j] = p;
+        if (attn_d != nullptr) attn_d[row * ld + j] = ((kbits >> u) & 1u) ? p * inv_keep : 0.f;
       }
     }
   }
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
 template <int NJ>
 __global__ void __launch_bounds__(256, 3) relattn_softmax_bwd_kernel(const float* __restrict__ gd, const float* __restrict__ y,
                                                                   const uint8_t* __restrict__ keep, float inv_keep,
-                                                                  DropRng rng, float scale, int B, int H, int T,
+                                                                  DropRng rng, float scale, int B, int H, int T, int ld,
                                                                   float* __restrict__ d_ac, float* __restrict__ d_bd) {
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * T;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_bwd_kernel(const float
   for (int64_t row = warp0; row < rows; row += nwarps) {
     const int i = (int)(row % T);
     const int64_t bh = row / T;
-    float* dbd_bh = d_bd + bh * (int64_t)T * T;
+    float* dbd_bh = d_bd + bh * (int64_t)T * ld;
     const int f0 = T + i * T;
     const int r0 = f0 / (T + 1), c0 = f0 - r0 * (T + 1);
     float g[NJ], p[NJ];
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_bwd_kernel(const float
 #pragma unroll
     for (int u = 0; u < NJ; ++u) {                                // all loads first, clamped index, no predicate
       const int j = min(lane + 32 * u, T - 1);
-      p[u] = __ldg(y + row * T + j);
-      g[u] = __ldg(gd + row * T + j);
+      p[u] = __ldg(y + row * ld + j);
+      g[u] = __ldg(gd + row * ld + j);
       kp[u] = keep != nullptr ? __ldg(keep + row * T + j) : (uint8_t)1;
     }
     const bool use_rng = keep == nullptr && rng.threshold != 0u;
@@ -152,10 +153,10 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_bwd_kernel(const float
       const int j = lane + 32 * u;
       if (j < T) {
         const float ds = p[u] * (g[u] - dot) * scale;
-        d_ac[row * T + j] = ds;
+        d_ac[row * ld + j] = ds;
         int c = c0 + j, r = r0;
         if (c >= T + 1) { c -= T + 1; r += 1; }
-        if (c > 0) dbd_bh[(int64_t)r * T + (c - 1)] = ds;        // c == 0 is the padded column: no gradient
+        if (c > 0) dbd_bh[(int64_t)r * ld + (c - 1)] = ds;        // c == 0 is the padded column: no gradient
       }
     }
     if (i == 0)                                                   // positions of [0 | bd] in front of the dropped row
@@ -184,30 +185,32 @@ static int attn_blocks(int64_t rows) {
 
 extern "C" int ob_relattn_softmax_fwd(const float* ac, const float* bd, const uint8_t* mask, const uint8_t* keep,
                                       float inv_keep, uint64_t seed, uint64_t offset, uint32_t drop_threshold, float scale,
-                                      int B, int H, int T, float* y, float* attn_d, ob_stream_t stream) {
+                                      int B, int H, int T, int ld, float* y, float* attn_d, ob_stream_t stream) {
   OB_REQUIRE(ac && bd && mask && y, "ob_relattn_softmax_fwd: null pointer");
   OB_REQUIRE((keep != nullptr || drop_threshold != 0u) == (attn_d != nullptr),
              "ob_relattn_softmax_fwd: attn_d is written exactly when dropout (mask or RNG) is on");
   const DropRng rng = {seed, offset, drop_threshold};
   OB_REQUIRE(drop_threshold < 65536u, "ob_relattn_softmax_fwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
   OB_REQUIRE(B > 0 && H > 0 && T > 0 && T <= 2048, "ob_relattn_softmax_fwd: need 0 < T <= 2048 (T=%d)", T);
+  OB_REQUIRE(ld >= T, "ob_relattn_softmax_fwd: row pitch ld (%d) must be >= T (%d)", ld, T);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = attn_blocks((int64_t)B * H * T);
-  OB_ATTN_DISPATCH(relattn_softmax_fwd_kernel, ac, bd, mask, keep, inv_keep, rng, scale, B, H, T, y, attn_d);
+  OB_ATTN_DISPATCH(relattn_softmax_fwd_kernel, ac, bd, mask, keep, inv_keep, rng, scale, B, H, T, ld, y, attn_d);
   OB_LAUNCH_CHECK("relattn_softmax_fwd_kernel");
   return OB_OK;
 }
 
 extern "C" int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep, float inv_keep, uint64_t seed,
-                                      uint64_t offset, uint32_t drop_threshold, float scale, int B, int H, int T, float* d_ac,
-                                      float* d_bd, ob_stream_t stream) {
+                                      uint64_t offset, uint32_t drop_threshold, float scale, int B, int H, int T, int ld,
+                                      float* d_ac, float* d_bd, ob_stream_t stream) {
   OB_REQUIRE(gd && y && d_ac && d_bd, "ob_relattn_softmax_bwd: null pointer");
   const DropRng rng = {seed, offset, drop_threshold};
   OB_REQUIRE(drop_threshold < 65536u, "ob_relattn_softmax_bwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
   OB_REQUIRE(B > 0 && H > 0 && T > 0 && T <= 2048, "ob_relattn_softmax_bwd: need 0 < T <= 2048 (T=%d)", T);
+  OB_REQUIRE(ld >= T, "ob_relattn_softmax_bwd: row pitch ld (%d) must be >= T (%d)", ld, T);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = attn_blocks((int64_t)B * H * T);
-  OB_ATTN_DISPATCH(relattn_softmax_bwd_kernel, gd, y, keep, inv_keep, rng, scale, B, H, T, d_ac, d_bd);
+  OB_ATTN_DISPATCH(relattn_softmax_bwd_kernel, gd, y, keep, inv_keep, rng, scale, B, H, T, ld, d_ac, d_bd);
   OB_LAUNCH_CHECK("relattn_softmax_bwd_kernel");
   return OB_OK;
 }

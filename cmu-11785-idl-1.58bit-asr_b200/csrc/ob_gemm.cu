@@ -24,7 +24,9 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
 // ---------------------------------------------------------------------------------------------
 // debug / tuning knobs (ob_debug_set)
 // ---------------------------------------------------------------------------------------------
-enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5 };
+enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5,
+                kDbgF32SplitMode = 6 };
+void f32_gemm_debug(int split_mode);   // ob_gemm_f32.cu
 static int g_dbg_kernel_flags = 0;   // bit0 skip TMA stores, bit1 skip epilogue math/STS, bit2 skip expansion (timing experiments)
 static int g_dbg_swap_lbo_sbo = 0;
 static int g_dbg_force_block_n = 0;
@@ -32,7 +34,7 @@ static int g_dbg_force_splits = 0;
 static int g_dbg_max_ctas = 0;
 
 static int g_sms = 0;
-static int sm_count() {
+int sm_count() {
   if (g_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -45,11 +47,7 @@ static int sm_count() {
 // ---------------------------------------------------------------------------------------------
 // tensor maps (driver entry point resolved at run time: no link-time dependency on libcuda)
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;
@@ -117,23 +115,6 @@ struct GemmSmem {
   static constexpr int kBytes = kOffTmemSlot + 16;
   static constexpr int kDynBytes = kBytes + 1024;                    // slack for the 1024-byte alignment
 };
-
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator, 3 = idle,
 // 4..11 = expanders, 12..19 = epilogue (warp % 4 selects the TMEM lane quarter, (warp-12)/4 the column half).
@@ -746,6 +727,7 @@ extern "C" int ob_debug_set(int key, int value) {
     case kDbgForceSplits: g_dbg_force_splits = value; return OB_OK;
     case kDbgMaxCtas: g_dbg_max_ctas = value; return OB_OK;
     case kDbgKernelFlags: g_dbg_kernel_flags = value; return OB_OK;
+    case kDbgF32SplitMode: f32_gemm_debug(value); return OB_OK;
     default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;
   }
 }

@@ -159,14 +159,15 @@ int ob_layernorm_bwd(const float* dy, const float* x, const float* mean, const f
  * BEFORE the relative shift), mask [B,T,T] bytes (0 = masked), T <= 2048.  Dropout as in ob_swish_drop_quant: explicit
  * keep [B,H,T,T] bytes, or keep == NULL with drop_threshold != 0 for the Philox stream (element lane + 32 u of row
  * r = (b*H + h)*T + i is 16-bit lane u % 8 of the block with counter ((r * 32 + lane) * 8 + u / 8, offset)), or neither
- * (then attn_d must be NULL and only y is written).
+ * (then attn_d must be NULL and only y is written).  ac, bd, y, attn_d and the gradients are [B,H,T] rows of T floats with a
+ * common row pitch ld >= T (elements), so they can be the padded outputs / inputs of ob_gemm_f32.
  * Backward: gradients w.r.t. ac and the un-shifted bd from the gradient w.r.t. attn_d (or y without dropout). */
 int ob_relattn_softmax_fwd(const float* ac, const float* bd, const uint8_t* mask, const uint8_t* keep,
                            float inv_keep, uint64_t seed, uint64_t offset, uint32_t drop_threshold, float scale,
-                           int B, int H, int T, float* y, float* attn_d, ob_stream_t stream);
+                           int B, int H, int T, int ld, float* y, float* attn_d, ob_stream_t stream);
 int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep, float inv_keep, uint64_t seed,
-                           uint64_t offset, uint32_t drop_threshold, float scale, int B, int H, int T, float* d_ac,
-                           float* d_bd, ob_stream_t stream);
+                           uint64_t offset, uint32_t drop_threshold, float scale, int B, int H, int T, int ld,
+                           float* d_ac, float* d_bd, ob_stream_t stream);
 
 /* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
  * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded
@@ -175,6 +176,23 @@ size_t ob_ctc_decode_workspace_bytes(int B, int T);
 int ob_ctc_greedy_decode(const void* logits, int dtype, int B, int T, int V, const int32_t* lens,
                          int blank_id, int32_t* out_tokens, int32_t* out_lens, void* ws,
                          ob_stream_t stream);
+
+/* Batched fp32 GEMM on the tensor cores for the non-routed matmuls of the model (attention products conformer.py:113-129,
+ * vocabulary projections, 1x1 convolutions - fp32 torch.matmul / nn.Linear / nn.Conv1d in the reference):
+ *   D[b0,b1](m, n) (+)= scale * sum_k A[b0,b1](m, k) * B[b0,b1](n, k) + bias[n]
+ * passes = 3: every operand is split into tf32 hi + lo parts in shared memory and three products are accumulated in
+ * fp32 (error ~2^-22 relative per term: fp32-level); passes = 1: plain tf32.  Operand element (m, k) of A lives at
+ * A + b0*a_bs0 + b1*a_bs1 + m*lda + k (K-major) or ... + k*lda + m (a_mn_major = 1); B likewise with (n, k) (K-major
+ * B is an [N, K] weight; MN-major B is a [K, N] matrix); D is row-major [M, N] with pitch ldd.  A batch stride of 0
+ * broadcasts an input over that batch axis.  All pointers 16-byte aligned, leading dimensions and batch strides
+ * multiples of 4 elements; M, N, K arbitrary (> 0).  accumulate = 1 adds into D with vector atomics; a D batch stride of
+ * 0 then sums the products of that batch axis (order of the fp32 additions not fixed).  Contractions of K >= 2048 with
+ * few output tiles are split over K in chunks of 1024 (atomic adds into the zeroed D): this fills the SMs and keeps the
+ * truncating in-tensor-core accumulation chains short.  Measured error vs fp64: <= 1e-5 of max|D| (passes = 3). */
+int ob_gemm_f32(const float* A, int a_mn_major, int64_t lda, int64_t a_bs0, int64_t a_bs1, const float* B,
+                int b_mn_major, int64_t ldb, int64_t b_bs0, int64_t b_bs1, float* D, int64_t ldd, int64_t d_bs0,
+                int64_t d_bs1, const float* bias, float scale, int accumulate, int M, int N, int K, int nb0, int nb1,
+                int passes, ob_stream_t stream);
 
 /* Debug/tuning knob (tests and profiling only): key/value pairs, see csrc/ob_gemm.cu. */
 int ob_debug_set(int key, int value);

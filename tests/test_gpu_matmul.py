@@ -1,0 +1,138 @@
+"""fp32 tensor-core GEMM (ob_gemm_f32, 3 x tf32 split) and the attention core built on it, against fp64 / the reference's op
+sequence in fp32.  Tolerance: 2e-5 of max|result| (measured <= 1e-5; plain tf32 is ~8e-4, torch's fp32 SIMT path ~5e-7)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def ob():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import onebit_b200
+    return onebit_b200
+
+
+def rel(got, ref64):
+    return ((got.double() - ref64).abs().max() / ref64.abs().max().clamp_min(1e-30)).item()
+
+
+def R(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g).cuda()
+
+
+CASES = {
+    "nt_square": lambda: (R(256, 256), R(256, 256, seed=1)),
+    "nt_tiny": lambda: (R(1, 8), R(3, 8, seed=1)),
+    "nt_ragged_batched": lambda: (R(3, 4, 399, 64), R(3, 4, 399, 64, seed=1)),
+    "nt_wide_n": lambda: (R(1000, 256), R(5004, 256, seed=1)),
+    "nn_b_mn_major": lambda: (R(2, 4, 399, 400)[..., :399], R(2, 4, 399, 64, seed=1).transpose(-1, -2)),
+    "tn_both_mn_major": lambda: (R(1000, 64).t(), R(1000, 256, seed=1).t()),
+    "tn_batched": lambda: (R(2, 4, 399, 400)[..., :399].transpose(-1, -2), R(2, 4, 399, 64, seed=1).transpose(-1, -2)),
+    "tk_a_mn_major": lambda: (R(500, 300).t(), R(200, 500, seed=1)),
+    "deep_k_split": lambda: (R(25536, 512).t(), R(25536, 256, seed=1).t()),
+    "k_not_multiple_of_32": lambda: (R(77, 45), R(130, 45, seed=1)),
+    "broadcast_b": lambda: (R(3, 4, 100, 64), R(1, 4, 100, 64, seed=1)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_bmm_nt_matches_fp64(ob, name):
+    from onebit_b200.matmul import bmm_nt
+    a, b = CASES[name]()
+    ref = torch.matmul(a.double(), b.double().transpose(-1, -2))
+    got = bmm_nt(a, b)
+    assert got.shape == ref.shape
+    assert rel(got, ref) < TOL
+    assert rel(bmm_nt(a, b, passes=1), ref) < 3e-3                    # plain tf32, for comparison
+
+
+def test_bmm_nt_strided_views_bias_scale_accumulate(ob):
+    from onebit_b200.matmul import bmm_nt
+    qkv = R(3, 399, 256)
+    q = qkv.view(3, 399, 4, 64).permute(0, 2, 1, 3)                   # [B, H, T, d] view of [B, T, H*d]
+    ref = torch.matmul(q.double(), q.double().transpose(-1, -2))
+    assert rel(bmm_nt(q, q), ref) < TOL
+    out = torch.empty(3, 399, 256, device="cuda")
+    probs = torch.softmax(R(3, 4, 399, 399, seed=2), -1)
+    bmm_nt(probs, q.transpose(-1, -2), out=out.view(3, 399, 4, 64).permute(0, 2, 1, 3))     # written through a strided view
+    ref = torch.matmul(probs.double(), q.double()).permute(0, 2, 1, 3).reshape(3, 399, 256)
+    assert rel(out, ref) < TOL
+    x, w, bias = R(300, 256), R(512, 256, seed=1), R(512, seed=2)
+    ref = torch.nn.functional.linear(x.double(), w.double(), bias.double()) * 1.0
+    assert rel(bmm_nt(x, w, bias=bias), ref) < TOL
+    ref2 = 0.5 * torch.matmul(x.double(), w.double().t())
+    y = bmm_nt(x, w, scale=0.5)
+    assert rel(y, ref2) < TOL
+    bmm_nt(x, w, out=y, scale=0.5, accumulate=True)
+    assert rel(y, 2 * ref2) < TOL
+    # sum over a batch axis: output shared by the batch (stride 0) + accumulate
+    a, b = R(5, 1, 64, 40), R(5, 1, 32, 40, seed=1)
+    acc = torch.zeros(1, 1, 64, 32, device="cuda")
+    bmm_nt(a, b, out=acc.expand(5, 1, 64, 32), accumulate=True)
+    assert rel(acc[0, 0], torch.matmul(a.double(), b.double().transpose(-1, -2)).sum(0)[0]) < TOL
+
+
+def test_bmm_nt_rejects_bad_arguments(ob):
+    from onebit_b200.matmul import bmm_nt
+    with pytest.raises(RuntimeError):
+        bmm_nt(torch.randn(4, 4), torch.randn(4, 4))                  # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        bmm_nt(R(4, 8), R(4, 12))
+    with pytest.raises(ValueError):
+        bmm_nt(R(4, 8), R(4, 8), accumulate=True)
+
+
+@pytest.mark.parametrize("B,H,T,p", [(2, 4, 49, 0.0), (3, 4, 249, 0.1), (2, 2, 399, 0.1), (1, 4, 33, 0.0)])
+def test_rel_attention_matches_reference_sequence(ob, B, H, T, p):
+    """The attention core (three products + chain forward, six products + chain backward) against the reference's op
+    sequence (conformer.py:113-129) in torch fp32 with the same dropout mask."""
+    from onebit_b200.attention import rel_attention
+    from onebit_b200.conformer import MHSA
+    d = 64
+    W = H * d
+    g = torch.Generator().manual_seed(B * 100 + T)
+    mk = lambda *s: torch.randn(*s, generator=g).cuda()  # noqa: E731
+    q0, k0, v0, pos0 = mk(B, T, W), mk(B, T, W), mk(B, T, W), mk(1, T, W)
+    u0, w0 = mk(H, d) * 0.5, mk(H, d) * 0.5
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    km = (torch.arange(T)[None, :] < lens[:, None]).cuda()
+    mask = km[:, :, None] & km[:, None, :]
+    keep = (torch.rand(B, H, T, T, generator=g) > p).cuda() if p > 0 else None
+    go = mk(B, T, W)
+
+    def reference(q, k, v, pos, u, w):
+        split = lambda t, b: t.view(b, -1, H, d).transpose(1, 2)  # noqa: E731
+        qh, kh, vh, ph = split(q, B), split(k, B), split(v, B), split(pos, 1)
+        ac = torch.matmul(qh + u.view(1, H, 1, d), kh.transpose(-2, -1))
+        bd = MHSA.rel_shift(torch.matmul(qh + w.view(1, H, 1, d), ph.transpose(-2, -1)))
+        s = ((ac + bd) / math.sqrt(d)).masked_fill(mask[:, None] == 0, float("-inf"))
+        a = torch.nan_to_num(torch.softmax(s, dim=-1), nan=0.0)
+        if keep is not None:
+            a = a * keep.float() * (1.0 / (1.0 - p))
+        return torch.matmul(a, vh).transpose(1, 2).contiguous().view(B, T, W)
+
+    outs = []
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for fn in (lambda *a: rel_attention(*a, mask, H, p, True, keep=keep), reference):
+            leaves = [t.clone().requires_grad_(True) for t in (q0, k0, v0, pos0, u0, w0)]
+            out = fn(*leaves)
+            out.backward(go)
+            outs.append([out.detach()] + [t.grad for t in leaves])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    names = ["out", "g_q", "g_k", "g_v", "g_pos", "g_u", "g_w"]
+    for name, a, b in zip(names, *outs):
+        err = ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+        assert err < 5e-5, (name, err)
+    if (~km).any():
+        assert outs[0][0][~km].abs().max().item() == 0.0              # padded query rows are exactly zero

@@ -416,9 +416,9 @@ def test_rel_attention_rng_path_equals_explicit_mask(ob, B, H, T):
     for kp, rng in ((keep, (0, 0, 0)), (None, (seed, offset, thr))):
         y, ad, d_ac, d_bd = (torch.empty_like(ac) for _ in range(4))
         kptr = None if kp is None else kp.data_ptr()
-        check(lib.ob_relattn_softmax_fwd(ac.data_ptr(), bd.data_ptr(), mask.data_ptr(), kptr, 4 / 3, *rng, 0.125, B, H, T,
+        check(lib.ob_relattn_softmax_fwd(ac.data_ptr(), bd.data_ptr(), mask.data_ptr(), kptr, 4 / 3, *rng, 0.125, B, H, T, T,
                                          y.data_ptr(), ad.data_ptr(), st))
-        check(lib.ob_relattn_softmax_bwd(gd.data_ptr(), y.data_ptr(), kptr, 4 / 3, *rng, 0.125, B, H, T, d_ac.data_ptr(),
+        check(lib.ob_relattn_softmax_bwd(gd.data_ptr(), y.data_ptr(), kptr, 4 / 3, *rng, 0.125, B, H, T, T, d_ac.data_ptr(),
                                          d_bd.data_ptr(), st))
         outs.append((y, ad, d_ac, d_bd))
     for a, b in zip(*outs):

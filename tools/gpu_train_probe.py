@@ -37,3 +37,14 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     train_step(model, batch, opt, cfg)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=60))
+# device kernels only, by name
+kern = {}
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        k = kern.setdefault(ev.name, [0, 0.0])
+        k[0] += 1
+        k[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+tot = sum(v[1] for v in kern.values())
+print(f"device kernels: {sum(v[0] for v in kern.values())} launches, {tot / 1e3:.1f} ms")
+for name, (cnt, us) in sorted(kern.items(), key=lambda kv: -kv[1][1])[:70]:
+    print(f"{us / 1e3:9.2f} ms {100 * us / tot:5.1f}% {cnt:5d} x {us / cnt:8.1f} us  {name[:150]}")
