@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import attention
+from . import attention, matmul
 from .norm import layer_norm
 from .quant import QuantizedLinear
 
@@ -235,7 +235,7 @@ class Conv2dSubsampling(nn.Module):
     def forward(self, feats):
         maps = self.conv(feats.unsqueeze(1))              # [B, C, T', F']
         b, c, t, f = maps.shape
-        return self.out(maps.transpose(1, 2).contiguous().view(b, t, c * f))
+        return matmul.linear(maps.transpose(1, 2).contiguous().view(b, t, c * f), self.out.weight, self.out.bias)
 
 
 class ConformerBlock(nn.Module):
@@ -306,7 +306,7 @@ class TransformerDecoder(nn.Module):
         causal = ahead.float().masked_fill(ahead, float("-inf"))
         hidden = self.dec(self.emb(tgt_inp), memory, tgt_mask=causal, memory_key_padding_mask=(memory_mask == 0),
                           tgt_key_padding_mask=tgt_key_padding_mask)
-        return self.out(self.ln(hidden))
+        return matmul.linear(self.ln(hidden), self.out.weight, self.out.bias)
 
 
 class ConformerASR(nn.Module):
@@ -325,7 +325,7 @@ class ConformerASR(nn.Module):
     def forward(self, batch, precision: int, sp_mask: Optional[List[int]] = None, frontend_out=None):
         """batch: dict with ``feats [B,T,F]`` and ``feat_lens [B]`` -> (encoder output, frame validity, CTC logits)."""
         memory, valid = self.encoder(batch["feats"], batch["feat_lens"], precision, sp_mask, frontend_out)
-        return memory, valid, self.ctc_head(memory)
+        return memory, valid, matmul.linear(memory, self.ctc_head.weight, self.ctc_head.bias)
 
     def decode_logits(self, enc_out, enc_mask, tgt_inp, tgt_pad_mask):
         return self.decoder(tgt_inp, enc_out, enc_mask, tgt_pad_mask)

@@ -88,3 +88,45 @@ def bmm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None, bias: tor
                           d_bs0, d_bs1, None if bias is None else bias.data_ptr(), float(scale), int(accumulate), M, N, K, nb0,
                           nb1, passes, _stream()))
     return result
+
+
+class _LinearFn(torch.autograd.Function):
+    """``F.linear`` of the non-routed fp32 layers (vocabulary projections, front-end output) on ``bmm_nt``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        y = bmm_nt(x2, weight, bias=bias)
+        if not y.is_contiguous():                          # out_features not a multiple of 4: drop the padded pitch
+            y = y.contiguous()
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias, ctx.x_shape = bias is not None, x.shape
+        return y.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = bmm_nt(g2, weight.t()).contiguous().reshape(ctx.x_shape)                    # dY . W      (W read as an MN-major operand)
+        if ctx.needs_input_grad[1]:
+            gw = bmm_nt(g2.t(), x2.t())                                         # dY^T . X    (both MN-major, split over the rows)
+            if not gw.is_contiguous():
+                gw = gw.contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb
+
+
+def linear_usable(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.numel() > 0
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None) -> torch.Tensor:
+    """``x @ weight.T + bias`` in fp32 on the tensor cores (3 x tf32 split); ``torch.nn.functional.linear`` elsewhere."""
+    if not linear_usable(x, weight):
+        return torch.nn.functional.linear(x, weight, bias)
+    return _LinearFn.apply(x, weight, bias)

@@ -136,3 +136,24 @@ def test_rel_attention_matches_reference_sequence(ob, B, H, T, p):
         assert err < 5e-5, (name, err)
     if (~km).any():
         assert outs[0][0][~km].abs().max().item() == 0.0              # padded query rows are exactly zero
+
+
+@pytest.mark.parametrize("shape,n_out", [((4, 249, 256), 5004), ((1000, 4864), 256), ((3, 7, 64), 10)])
+def test_linear_matches_torch_fp32(ob, shape, n_out):
+    from onebit_b200.matmul import linear
+    x0, w0, b0, gy = R(*shape), R(n_out, shape[-1], seed=1) * 0.1, R(n_out, seed=2), R(*shape[:-1], n_out, seed=3)
+    outs = []
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for fn in (linear, torch.nn.functional.linear):
+            x, w, b = (t.clone().requires_grad_(True) for t in (x0, w0, b0))
+            y = fn(x, w, b)
+            y.backward(gy)
+            outs.append((y.detach(), x.grad, w.grad, b.grad))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    for name, a, b in zip(("y", "g_x", "g_w", "g_b"), *outs):
+        assert a.shape == b.shape and a.is_contiguous()
+        err = ((a - b).abs().max() / b.abs().max()).item()
+        assert err < TOL, (name, err)
