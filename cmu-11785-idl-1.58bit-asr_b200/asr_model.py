@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import attention, matmul
+from . import attention, convmod, matmul
 from .norm import layer_norm
 from .quant import QuantizedLinear
 
@@ -210,9 +210,16 @@ class ConvModule(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x, mask=None):
-        t = self.ln(x).transpose(1, 2)                    # channels first for the convolutions
-        t = self.bn(self.dw(self.glu(self.pw1(t))))
-        t = self.dropout(self.pw2(swish(t))).transpose(1, 2)
+        taps = self.dw.kernel_size[0]
+        if convmod.usable(x, x.shape[-1], taps) and self.bn.affine and self.dw.padding[0] == taps // 2:
+            # channel-last path: 1x1 convolutions as matrix products over the channel axis, B200 kernels in between
+            a = matmul.linear(self.ln(x), self.pw1.weight.squeeze(-1), self.pw1.bias)
+            s = convmod.glu_dwconv_bn_swish(a, self.dw.weight, self.dw.bias, self.bn.weight, self.bn.bias, self.bn.eps)
+            t = self.dropout(matmul.linear(s, self.pw2.weight.squeeze(-1), self.pw2.bias))
+        else:
+            t = self.ln(x).transpose(1, 2)                # channels first for torch's convolutions
+            t = self.bn(self.dw(self.glu(self.pw1(t))))
+            t = self.dropout(self.pw2(swish(t))).transpose(1, 2)
         keep = _frame_mask(mask)
         if keep is not None:
             t = t * keep

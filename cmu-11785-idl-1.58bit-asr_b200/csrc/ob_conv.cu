@@ -1,0 +1,423 @@
+// ob_conv.cu - the middle of the reference's convolution module (conformer.py:141-167) in the [B, T, C] layout of the
+// rest of the encoder:   a = pw1(ln(x))  ->  g = GLU(a)  ->  d = depthwise_conv1d(g)  ->  y = BatchNorm(d)  ->  s = swish(y).
+// The two 1x1 convolutions around it are plain matrix products over the channel axis (ob_gemm_f32); everything between
+// them is HBM-bound stencil / element-wise / reduction work, done here in as few passes as the data dependencies allow:
+//
+//   glu_dwconv_fwd      a -> d (+ per-tile BatchNorm partials: sum and centred sum of squares, Chan-combined in fp64)
+//   bn_swish_fwd        d -> s
+//   bn_swish_bwd_reduce g_s, d -> per-row-block sums of g_y and g_y * xhat        (g_y = g_s * swish'(y))
+//   bn_swish_bwd_apply  g_s, d -> g_d
+//   dwconv_bwd_data_glu g_d, a -> g_a (depthwise transposed convolution + GLU backward)
+//   dwconv_bwd_weight   g_d, a -> per-utterance partials of g_w and g_bias, reduced in fixed order
+//
+// BatchNorm uses batch statistics over all B*T frames including padding, biased variance, exactly as
+// nn.BatchNorm1d(track_running_stats=False) does in the reference (conformer.py:148), in training and in eval mode.
+// The depthwise kernel has ks <= 31 odd taps (reference default 31); shorter kernels are centred in the 31-tap window.
+#include "ob_common.cuh"
+
+namespace ob {
+
+constexpr int kCvT = 64;                  // frames per tile
+constexpr int kCvC = 64;                  // channels per tile
+constexpr int kCvHalo = 15;
+constexpr int kCvTaps = 31;
+constexpr int kCvRows = kCvT + 2 * kCvHalo;   // 94
+constexpr int kCvPer = kCvT / 4;          // outputs per thread (4 time groups of 64 channels = 256 threads)
+constexpr int kCvWin = kCvPer + kCvTaps - 1;
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// centred 31-tap window of channel c; flip = 1 for the transposed convolution
+__device__ __forceinline__ void load_taps(const float* __restrict__ w, int c, int ks, bool flip, float (&wr)[kCvTaps]) {
+  const int off = (kCvTaps - ks) / 2;
+#pragma unroll
+  for (int j = 0; j < kCvTaps; ++j) {
+    const int jj = flip ? kCvTaps - 1 - j : j;
+    wr[j] = (jj >= off && jj < off + ks) ? __ldg(w + c * ks + jj - off) : 0.f;
+  }
+}
+
+// tile of g = GLU(a) with halo into shared memory: rows t0-15 .. t0+78, zero outside the utterance
+__device__ __forceinline__ void load_glu_tile(const float* __restrict__ a, int b, int T, int C, int t0, int c0, float* tile) {
+  const int c = threadIdx.x & 63;
+  for (int r = threadIdx.x >> 6; r < kCvRows; r += 4) {
+    const int t = t0 - kCvHalo + r;
+    float v = 0.f;
+    if (t >= 0 && t < T) {
+      const float* row = a + (static_cast<int64_t>(b) * T + t) * (2 * C) + c0 + c;
+      v = __ldg(row) * sigmoid_f(__ldg(row + C));
+    }
+    tile[r * kCvC + c] = v;
+  }
+}
+
+__device__ __forceinline__ void load_plain_tile(const float* __restrict__ x, int b, int T, int C, int t0, int c0, float* tile) {
+  const int c = threadIdx.x & 63;
+  for (int r = threadIdx.x >> 6; r < kCvRows; r += 4) {
+    const int t = t0 - kCvHalo + r;
+    tile[r * kCvC + c] = (t >= 0 && t < T) ? __ldg(x + (static_cast<int64_t>(b) * T + t) * C + c0 + c) : 0.f;
+  }
+}
+
+// grid: x = b * tblocks + tb, y = channel tile.  part: [B * tblocks][2][C] = (sum, centred sum of squares) per tile.
+__global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, int B, int T, int C, int ks,
+                                                             float* __restrict__ d, float* __restrict__ part) {
+  __shared__ float tile[kCvRows * kCvC];
+  __shared__ float red[4][kCvC];
+  const int tblocks = (T + kCvT - 1) / kCvT;
+  const int b = blockIdx.x / tblocks, tb = blockIdx.x % tblocks;
+  const int t0 = tb * kCvT, c0 = blockIdx.y * kCvC;
+  const int c = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  load_glu_tile(a, b, T, C, t0, c0, tile);
+  float wr[kCvTaps];
+  load_taps(w, c0 + c, ks, false, wr);
+  const float bv = bias != nullptr ? __ldg(bias + c0 + c) : 0.f;
+  __syncthreads();
+  float win[kCvWin];
+#pragma unroll
+  for (int i = 0; i < kCvWin; ++i) win[i] = tile[(tg * kCvPer + i) * kCvC + c];
+  float out[kCvPer];
+  float sum = 0.f;
+#pragma unroll
+  for (int o = 0; o < kCvPer; ++o) {
+    float acc = bv;
+#pragma unroll
+    for (int j = 0; j < kCvTaps; ++j) acc = fmaf(wr[j], win[o + j], acc);
+    out[o] = acc;
+    const int t = t0 + tg * kCvPer + o;
+    if (t < T) {
+      d[(static_cast<int64_t>(b) * T + t) * C + c0 + c] = acc;
+      sum += acc;
+    }
+  }
+  // BatchNorm partials of this tile: sum, then the sum of squares centred at the tile mean (stable to combine)
+  const int n_tile = min(kCvT, T - t0);
+  red[tg][c] = sum;
+  __syncthreads();
+  const float tsum = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+  const float tmean = tsum / static_cast<float>(n_tile);
+  float m2 = 0.f;
+#pragma unroll
+  for (int o = 0; o < kCvPer; ++o)
+    if (t0 + tg * kCvPer + o < T) m2 = fmaf(out[o] - tmean, out[o] - tmean, m2);
+  __syncthreads();
+  red[tg][c] = m2;
+  __syncthreads();
+  if (tg == 0) {
+    float* p = part + static_cast<int64_t>(blockIdx.x) * 2 * C + c0 + c;
+    p[0] = tsum;
+    p[C] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+  }
+}
+
+// Chan's pairwise combination of the tile partials in fp64, fixed order: 16 thread groups each fold every 16th tile,
+// group 0 folds the 16 results.  grid: C / 64 blocks of 1024 threads.
+constexpr int kFinGroups = 16;
+
+__device__ __forceinline__ void chan_merge(double& n, double& mu, double& m2, double nb, double mb, double m2b) {
+  if (nb == 0.0) return;
+  const double delta = mb - mu, nn = n + nb;
+  m2 += m2b + delta * delta * n * nb / nn;
+  mu += delta * nb / nn;
+  n = nn;
+}
+
+__global__ void __launch_bounds__(64 * kFinGroups) bn_stats_finalize_kernel(const float* __restrict__ part, int B, int T, int C,
+                                                                          float eps, float* __restrict__ mean,
+                                                                          float* __restrict__ rstd) {
+  __shared__ double sh[3][kFinGroups][64];
+  const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  const int tblocks = (T + kCvT - 1) / kCvT;
+  double n = 0.0, mu = 0.0, m2 = 0.0;
+  for (int blk = grp; blk < B * tblocks; blk += kFinGroups) {
+    const int tb = blk % tblocks;
+    const double nb = static_cast<double>(min(kCvT, T - tb * kCvT));
+    const double sb = part[static_cast<int64_t>(blk) * 2 * C + c], m2b = part[static_cast<int64_t>(blk) * 2 * C + C + c];
+    chan_merge(n, mu, m2, nb, sb / nb, m2b);
+  }
+  sh[0][grp][cl] = n, sh[1][grp][cl] = mu, sh[2][grp][cl] = m2;
+  __syncthreads();
+  if (grp == 0) {
+    for (int g = 1; g < kFinGroups; ++g) chan_merge(n, mu, m2, sh[0][g][cl], sh[1][g][cl], sh[2][g][cl]);
+    mean[c] = static_cast<float>(mu);
+    rstd[c] = static_cast<float>(1.0 / sqrt(m2 / n + static_cast<double>(eps)));
+  }
+}
+
+// out[i] = sum over blocks of part[blk * stride + i] for 64 consecutive items per CTA, fp64, fixed order (same grouping)
+__device__ __forceinline__ double grouped_block_sum(const float* __restrict__ part, int nblocks, int64_t stride, int item,
+                                                    double (*sh)[64]) {
+  const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int blk = grp; blk < nblocks; blk += kFinGroups) acc += part[static_cast<int64_t>(blk) * stride + item];
+  sh[grp][cl] = acc;
+  __syncthreads();
+  if (grp == 0)
+    for (int g = 1; g < kFinGroups; ++g) acc += sh[g][cl];
+  return acc;
+}
+
+// s = swish(gamma * (d - mean) * rstd + beta);  C % 4 == 0
+__global__ void __launch_bounds__(256) bn_swish_fwd_kernel(const float* __restrict__ d, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, int64_t n4, int C4,
+                                                           float* __restrict__ s) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const int c4 = static_cast<int>(i % C4);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(d) + i);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 y;
+    y.x = fmaf((x.x - mu.x) * rs.x, ga.x, be.x);
+    y.y = fmaf((x.y - mu.y) * rs.y, ga.y, be.y);
+    y.z = fmaf((x.z - mu.z) * rs.z, ga.z, be.z);
+    y.w = fmaf((x.w - mu.w) * rs.w, ga.w, be.w);
+    reinterpret_cast<float4*>(s)[i] = make_float4(y.x * sigmoid_f(y.x), y.y * sigmoid_f(y.y), y.z * sigmoid_f(y.z),
+                                                  y.w * sigmoid_f(y.w));
+  }
+}
+
+__device__ __forceinline__ float swish_grad(float y) {
+  const float sg = sigmoid_f(y);
+  return sg + y * sg * (1.0f - sg);
+}
+
+constexpr int kBnRows = 128;              // rows per reduction block
+
+// partial sums over a block of rows: part[blk][0][c] = sum g_y, part[blk][1][c] = sum g_y * xhat
+__global__ void __launch_bounds__(256) bn_swish_bwd_reduce_kernel(const float* __restrict__ gs, const float* __restrict__ d,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  int64_t M, int C, float* __restrict__ part) {
+  __shared__ float red[2][4][kCvC];
+  const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int cc = blockIdx.y * kCvC + c;
+  const float mu = __ldg(mean + cc), rs = __ldg(rstd + cc), ga = __ldg(gamma + cc), be = __ldg(beta + cc);
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kBnRows;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+  for (int r = rg; r < kBnRows; r += 4) {
+    const int64_t row = r0 + r;
+    if (row < M) {
+      const float xh = (__ldg(d + row * C + cc) - mu) * rs;
+      const float gy = __ldg(gs + row * C + cc) * swish_grad(fmaf(xh, ga, be));
+      s1 += gy;
+      s2 = fmaf(gy, xh, s2);
+    }
+  }
+  red[0][rg][c] = s1;
+  red[1][rg][c] = s2;
+  __syncthreads();
+  if (rg < 2) {
+    float* p = part + (static_cast<int64_t>(blockIdx.x) * 2 + rg) * C + cc;
+    *p = red[rg][0][c] + red[rg][1][c] + red[rg][2][c] + red[rg][3][c];
+  }
+}
+
+// sums[0][c] = sum g_y (= g_beta), sums[1][c] = sum g_y * xhat (= g_gamma).  grid: 2C / 64 blocks of 1024 threads
+__global__ void __launch_bounds__(64 * kFinGroups) bn_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int C,
+                                                                        float* __restrict__ sums) {
+  __shared__ double sh[kFinGroups][64];
+  const int item = blockIdx.x * 64 + (threadIdx.x & 63);
+  const double acc = grouped_block_sum(part, nblocks, 2 * static_cast<int64_t>(C), item, sh);
+  if (threadIdx.x < 64) sums[item] = static_cast<float>(acc);
+}
+
+// g_d = gamma * rstd * (g_y - sum(g_y) / M - xhat * sum(g_y * xhat) / M)
+__global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __restrict__ gs, const float* __restrict__ d,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ sums, float inv_m, int64_t n4, int C4,
+                                                                 float* __restrict__ gd) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const int c4 = static_cast<int>(i % C4);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(d) + i), g = __ldg(reinterpret_cast<const float4*>(gs) + i);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4), rs = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sums) + c4), s2 = __ldg(reinterpret_cast<const float4*>(sums) + C4 + c4);
+    const float xs[4] = {x.x, x.y, x.z, x.w}, gv[4] = {g.x, g.y, g.z, g.w}, mus[4] = {mu.x, mu.y, mu.z, mu.w};
+    const float rss[4] = {rs.x, rs.y, rs.z, rs.w}, gas[4] = {ga.x, ga.y, ga.z, ga.w}, bes[4] = {be.x, be.y, be.z, be.w};
+    const float s1s[4] = {s1.x, s1.y, s1.z, s1.w}, s2s[4] = {s2.x, s2.y, s2.z, s2.w};
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float xh = (xs[u] - mus[u]) * rss[u];
+      const float gy = gv[u] * swish_grad(fmaf(xh, gas[u], bes[u]));
+      o[u] = gas[u] * rss[u] * (gy - s1s[u] * inv_m - xh * s2s[u] * inv_m);
+    }
+    reinterpret_cast<float4*>(gd)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// g_g = transposed depthwise convolution of g_d, then the GLU backward into both halves of g_a
+__global__ void __launch_bounds__(256) dwconv_bwd_data_glu_kernel(const float* __restrict__ gd, const float* __restrict__ a,
+                                                                  const float* __restrict__ w, int B, int T, int C, int ks,
+                                                                  float* __restrict__ ga) {
+  __shared__ float tile[kCvRows * kCvC];
+  const int tblocks = (T + kCvT - 1) / kCvT;
+  const int b = blockIdx.x / tblocks, tb = blockIdx.x % tblocks;
+  const int t0 = tb * kCvT, c0 = blockIdx.y * kCvC;
+  const int c = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  load_plain_tile(gd, b, T, C, t0, c0, tile);
+  float wr[kCvTaps];
+  load_taps(w, c0 + c, ks, true, wr);
+  __syncthreads();
+  float win[kCvWin];
+#pragma unroll
+  for (int i = 0; i < kCvWin; ++i) win[i] = tile[(tg * kCvPer + i) * kCvC + c];
+#pragma unroll
+  for (int o = 0; o < kCvPer; ++o) {
+    const int t = t0 + tg * kCvPer + o;
+    if (t >= T) break;
+    float gg = 0.f;
+#pragma unroll
+    for (int j = 0; j < kCvTaps; ++j) gg = fmaf(wr[j], win[o + j], gg);
+    const int64_t idx = (static_cast<int64_t>(b) * T + t) * (2 * C) + c0 + c;
+    const float a1 = __ldg(a + idx), sg = sigmoid_f(__ldg(a + idx + C));
+    ga[idx] = gg * sg;
+    ga[idx + C] = gg * a1 * sg * (1.0f - sg);
+  }
+}
+
+// per-utterance partials of g_w[c][j] = sum_t g_d[t] * g[t + j - 15] and g_bias[c] = sum_t g_d[t]:
+// part: [B][32][C], slot 31 = bias.  grid: x = utterance, y = channel tile; the CTA walks the utterance tile by tile.
+__global__ void __launch_bounds__(256) dwconv_bwd_weight_kernel(const float* __restrict__ gd, const float* __restrict__ a, int B,
+                                                                int T, int C, float* __restrict__ part) {
+  __shared__ float buf[4 * 32 * kCvC];               // the GLU tile (94 x 64) in the loop, then the cross-group reduction
+  const int tblocks = (T + kCvT - 1) / kCvT;
+  const int b = blockIdx.x, c0 = blockIdx.y * kCvC;
+  const int c = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int tb = 0; tb < tblocks; ++tb) {
+    const int t0 = tb * kCvT;
+    __syncthreads();                                 // the previous tile's windows are in registers
+    load_glu_tile(a, b, T, C, t0, c0, buf);
+    __syncthreads();
+    float win[kCvWin];
+#pragma unroll
+    for (int i = 0; i < kCvWin; ++i) win[i] = buf[(tg * kCvPer + i) * kCvC + c];
+#pragma unroll
+    for (int o = 0; o < kCvPer; ++o) {
+      const int t = t0 + tg * kCvPer + o;
+      const float g = t < T ? __ldg(gd + (static_cast<int64_t>(b) * T + t) * C + c0 + c) : 0.f;
+#pragma unroll
+      for (int j = 0; j < kCvTaps; ++j) acc[j] = fmaf(g, win[o + j], acc[j]);
+      acc[31] += g;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) buf[(tg * 32 + j) * kCvC + c] = acc[j];
+  __syncthreads();
+  for (int j = tg; j < 32; j += 4) {
+    const float v = buf[(0 * 32 + j) * kCvC + c] + buf[(1 * 32 + j) * kCvC + c] + buf[(2 * 32 + j) * kCvC + c] +
+                    buf[(3 * 32 + j) * kCvC + c];
+    part[(static_cast<int64_t>(b) * 32 + j) * C + c0 + c] = v;
+  }
+}
+
+// g_w[c][j] (ks centred taps) and g_bias[c] from the per-utterance partials.  grid: 32 * C / 64 blocks of 1024 threads
+__global__ void __launch_bounds__(64 * kFinGroups) dwconv_bwd_weight_finalize_kernel(const float* __restrict__ part, int nblocks,
+                                                                                   int C, int ks, float* __restrict__ gw,
+                                                                                   float* __restrict__ gbias) {
+  __shared__ double sh[kFinGroups][64];
+  const int item = blockIdx.x * 64 + (threadIdx.x & 63);      // slot * C + c
+  const double acc = grouped_block_sum(part, nblocks, 32 * static_cast<int64_t>(C), item, sh);
+  if (threadIdx.x >= 64) return;
+  const int slot = item / C, c = item % C;
+  const int off = (kCvTaps - ks) / 2;
+  if (slot == 31) {
+    if (gbias != nullptr) gbias[c] = static_cast<float>(acc);
+  } else if (slot >= off && slot < off + ks) {
+    gw[c * ks + slot - off] = static_cast<float>(acc);
+  }
+}
+
+static int conv_tblocks(int T) { return (T + kCvT - 1) / kCvT; }
+static int ew_blocks(int64_t n4) {
+  const int64_t want = (n4 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  return static_cast<int>(want < cap ? want : cap);
+}
+
+}  // namespace ob
+
+using namespace ob;
+
+#define OB_CONV_SHAPE(name)                                                                                            \
+  OB_REQUIRE(B > 0 && T > 0 && C > 0 && C % 64 == 0, name ": need B, T > 0 and C a positive multiple of 64 (C=%d)", C); \
+  OB_REQUIRE(ks >= 1 && ks <= 31 && (ks & 1), name ": kernel size must be odd and <= 31 (ks=%d)", ks)
+
+extern "C" size_t ob_convmod_workspace_bytes(int B, int T, int C) {
+  if (B <= 0 || T <= 0 || C <= 0) return 0;
+  const size_t tiles = static_cast<size_t>(B) * conv_tblocks(T);
+  const size_t rows = (static_cast<size_t>(B) * T + kBnRows - 1) / kBnRows;
+  const size_t a = (tiles * 2 > static_cast<size_t>(B) * 32 ? tiles * 2 : static_cast<size_t>(B) * 32) * C * sizeof(float);
+  const size_t b = rows * 2 * C * sizeof(float);
+  return (a > b ? a : b) + 256;
+}
+
+extern "C" int ob_glu_dwconv_bn_fwd(const float* a, const float* w, const float* bias, int B, int T, int C, int ks, float eps,
+                                    float* d, float* mean, float* rstd, void* ws, ob_stream_t stream) {
+  OB_REQUIRE(a && w && d && mean && rstd && ws, "ob_glu_dwconv_bn_fwd: null pointer");
+  OB_CONV_SHAPE("ob_glu_dwconv_bn_fwd");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* part = static_cast<float*>(ws);
+  dim3 grid(B * conv_tblocks(T), C / kCvC);
+  glu_dwconv_fwd_kernel<<<grid, 256, 0, st>>>(a, w, bias, B, T, C, ks, d, part);
+  OB_LAUNCH_CHECK("glu_dwconv_fwd_kernel");
+  bn_stats_finalize_kernel<<<C / 64, 64 * kFinGroups, 0, st>>>(part, B, T, C, eps, mean, rstd);
+  OB_LAUNCH_CHECK("bn_stats_finalize_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_bn_swish_fwd(const float* d, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                               int64_t M, int C, float* s, ob_stream_t stream) {
+  OB_REQUIRE(d && mean && rstd && gamma && beta && s, "ob_bn_swish_fwd: null pointer");
+  OB_REQUIRE(M > 0 && C > 0 && C % 64 == 0, "ob_bn_swish_fwd: need M > 0 and C a positive multiple of 64 (C=%d)", C);
+  const int64_t n4 = M * C / 4;
+  bn_swish_fwd_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, mean, rstd, gamma, beta, n4, C / 4, s);
+  OB_LAUNCH_CHECK("bn_swish_fwd_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_bn_swish_bwd(const float* gs, const float* d, const float* mean, const float* rstd, const float* gamma,
+                               const float* beta, int64_t M, int C, float* gd, float* g_gamma_beta, void* ws,
+                               ob_stream_t stream) {
+  OB_REQUIRE(gs && d && mean && rstd && gamma && beta && gd && g_gamma_beta && ws, "ob_bn_swish_bwd: null pointer");
+  OB_REQUIRE(M > 0 && C > 0 && C % 64 == 0, "ob_bn_swish_bwd: need M > 0 and C a positive multiple of 64 (C=%d)", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* part = static_cast<float*>(ws);
+  const int rblocks = static_cast<int>((M + kBnRows - 1) / kBnRows);
+  bn_swish_bwd_reduce_kernel<<<dim3(rblocks, C / kCvC), 256, 0, st>>>(gs, d, mean, rstd, gamma, beta, M, C, part);
+  OB_LAUNCH_CHECK("bn_swish_bwd_reduce_kernel");
+  // g_gamma_beta: [2][C] = (sum g_y = g_beta, sum g_y * xhat = g_gamma)
+  bn_bwd_finalize_kernel<<<2 * C / 64, 64 * kFinGroups, 0, st>>>(part, rblocks, C, g_gamma_beta);
+  OB_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  const int64_t n4 = M * C / 4;
+  bn_swish_bwd_apply_kernel<<<ew_blocks(n4), 256, 0, st>>>(gs, d, mean, rstd, gamma, beta, g_gamma_beta,
+                                                          1.0f / static_cast<float>(M), n4, C / 4, gd);
+  OB_LAUNCH_CHECK("bn_swish_bwd_apply_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_glu_dwconv_bwd(const float* gd, const float* a, const float* w, int B, int T, int C, int ks, float* ga,
+                                 float* gw, float* gbias, void* ws, ob_stream_t stream) {
+  OB_REQUIRE(gd && a && w && ga && gw && ws, "ob_glu_dwconv_bwd: null pointer");
+  OB_CONV_SHAPE("ob_glu_dwconv_bwd");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* part = static_cast<float*>(ws);
+  dim3 grid(B * conv_tblocks(T), C / kCvC);
+  dwconv_bwd_data_glu_kernel<<<grid, 256, 0, st>>>(gd, a, w, B, T, C, ks, ga);
+  OB_LAUNCH_CHECK("dwconv_bwd_data_glu_kernel");
+  dwconv_bwd_weight_kernel<<<dim3(B, C / kCvC), 256, 0, st>>>(gd, a, B, T, C, part);
+  OB_LAUNCH_CHECK("dwconv_bwd_weight_kernel");
+  dwconv_bwd_weight_finalize_kernel<<<32 * C / 64, 64 * kFinGroups, 0, st>>>(part, B, C, ks, gw, gbias);
+  OB_LAUNCH_CHECK("dwconv_bwd_weight_finalize_kernel");
+  return OB_OK;
+}

@@ -194,6 +194,25 @@ int ob_gemm_f32(const float* A, int a_mn_major, int64_t lda, int64_t a_bs0, int6
                 int64_t d_bs1, const float* bias, float scale, int accumulate, int M, int N, int K, int nb0, int nb1,
                 int passes, ob_stream_t stream);
 
+/* Middle of the convolution module (conformer.py:141-167) in the [B, T, C] layout: GLU -> depthwise conv1d (ks odd <= 31
+ * taps, zero padding ks/2, per utterance) -> BatchNorm with batch statistics over all B*T frames (biased variance, as
+ * nn.BatchNorm1d(track_running_stats=False)) -> swish.  The 1x1 convolutions on either side are ob_gemm_f32 products.
+ *   ob_glu_dwconv_bn_fwd: a [B,T,2C] (output of the first 1x1 conv) -> d [B,T,C] = dwconv(a[..,:C] * sigmoid(a[..,C:])) + bias,
+ *                         mean[C], rstd[C] of d (Chan-combined tile partials, fp64);  w [C, ks], bias [C] or NULL
+ *   ob_bn_swish_fwd:      s = swish(gamma * (d - mean) * rstd + beta)
+ *   ob_bn_swish_bwd:      g_s -> g_d; g_gamma_beta [2][C] = (g_beta, g_gamma)
+ *   ob_glu_dwconv_bwd:    g_d -> g_a [B,T,2C], g_w [C, ks], g_bias [C] (or NULL)
+ * C a multiple of 64.  ws: at least ob_convmod_workspace_bytes(B, T, C) bytes; all reductions have a fixed order. */
+size_t ob_convmod_workspace_bytes(int B, int T, int C);
+int ob_glu_dwconv_bn_fwd(const float* a, const float* w, const float* bias, int B, int T, int C, int ks, float eps,
+                         float* d, float* mean, float* rstd, void* ws, ob_stream_t stream);
+int ob_bn_swish_fwd(const float* d, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                    int64_t M, int C, float* s, ob_stream_t stream);
+int ob_bn_swish_bwd(const float* gs, const float* d, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, int64_t M, int C, float* gd, float* g_gamma_beta, void* ws, ob_stream_t stream);
+int ob_glu_dwconv_bwd(const float* gd, const float* a, const float* w, int B, int T, int C, int ks, float* ga,
+                      float* gw, float* gbias, void* ws, ob_stream_t stream);
+
 /* Debug/tuning knob (tests and profiling only): key/value pairs, see csrc/ob_gemm.cu. */
 int ob_debug_set(int key, int value);
 

@@ -157,3 +157,60 @@ def test_linear_matches_torch_fp32(ob, shape, n_out):
         assert a.shape == b.shape and a.is_contiguous()
         err = ((a - b).abs().max() / b.abs().max()).item()
         assert err < TOL, (name, err)
+
+
+@pytest.mark.parametrize("B,T,C,ks", [(3, 130, 64, 31), (2, 399, 256, 31), (4, 17, 128, 7), (1, 64, 64, 15)])
+def test_conv_module_middle_matches_torch(ob, B, T, C, ks):
+    """swish(BatchNorm(depthwise(GLU(a)))) and every gradient against torch's own ops (conformer.py:141-167)."""
+    import torch.nn.functional as F
+    from onebit_b200.convmod import glu_dwconv_bn_swish
+    a0 = R(B, T, 2 * C)
+    w0, b0 = R(C, 1, ks, seed=1) * 0.3, R(C, seed=2) * 0.1
+    ga0, be0 = R(C, seed=3) * 0.5 + 1.0, R(C, seed=4) * 0.2
+    gy = R(B, T, C, seed=5)
+
+    def reference(a, w, b, gamma, beta):
+        t = F.glu(a.transpose(1, 2), dim=1)
+        t = F.conv1d(t, w, b, padding=ks // 2, groups=C)
+        t = F.batch_norm(t, None, None, gamma, beta, True, 0.1, 1e-5)
+        return (t * torch.sigmoid(t)).transpose(1, 2)
+
+    outs = []
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for fn in (lambda *t: glu_dwconv_bn_swish(*t, 1e-5), reference):
+            leaves = [t.clone().requires_grad_(True) for t in (a0, w0, b0, ga0, be0)]
+            y = fn(*leaves)
+            y.backward(gy)
+            outs.append([y.detach()] + [t.grad for t in leaves])
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    for name, x, y in zip(("s", "g_a", "g_w", "g_bias", "g_gamma", "g_beta"), *outs):
+        assert x.shape == y.shape, name
+        # a bias in front of BatchNorm has no gradient (the mean is removed): both sides are round-off of a zero sum, so
+        # it is compared on the scale of the other per-channel sums
+        scale = outs[1][5].abs().max() if name == "g_bias" else y.abs().max().clamp_min(1e-30)
+        err = ((x - y).abs().max() / scale).item()
+        assert err < (2e-4 if name.startswith("g_") else 2e-5), (name, err)
+
+
+def test_conv_module_channel_last_equals_torch_path(ob):
+    """The whole ConvModule: B200 channel-last path (CUDA) against the module's torch path on a float64 CPU copy."""
+    from onebit_b200.conformer import ConvModule
+    torch.manual_seed(3)
+    mod = ConvModule(256, 31, 0.0).cuda()
+    ref = ConvModule(256, 31, 0.0).double()
+    ref.load_state_dict({k: v.double().cpu() for k, v in mod.state_dict().items()})
+    x0 = R(2, 150, 256)
+    gy = R(2, 150, 256, seed=1)
+    x = x0.clone().requires_grad_(True)
+    y = mod(x)
+    y.backward(gy)
+    xr = x0.double().cpu().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy.double().cpu())
+    assert (y.detach().cpu().double() - yr.detach()).abs().max().item() < 2e-5 * yr.abs().max().item()
+    assert (x.grad.cpu().double() - xr.grad).abs().max().item() < 2e-4 * xr.grad.abs().max().item()
+    for (n, p), (_, pr) in zip(mod.named_parameters(), ref.named_parameters()):
+        assert (p.grad.cpu().double() - pr.grad).abs().max().item() < 2e-4 * pr.grad.abs().max().clamp_min(1e-30).item(), n
