@@ -146,17 +146,18 @@ class _RelAttentionFn(torch.autograd.Function):
         bmm_nt(d_ac, _heads(k, H).transpose(-1, -2), out=_heads(g_qu, H))                      # dS_ac . k
         bmm_nt(d_ac.transpose(-1, -2), _heads(qu, H).transpose(-1, -2), out=_heads(g_k, H))    # dS_ac^T . (q+u)
         bmm_nt(d_bd, _heads(pos, H).transpose(-1, -2), out=_heads(g_qw, H))                    # dS_bd . pos
-        g_pos = torch.zeros_like(pos)                                                          # sum over the batch: atomic adds
-        bmm_nt(d_bd.transpose(-1, -2), _heads(qw, H).transpose(-1, -2), out=_heads(g_pos, H).expand(B, H, T, W // H),
-               accumulate=True)
+        g_pos_b = torch.empty_like(qw)                                                         # per utterance, then summed
+        bmm_nt(d_bd.transpose(-1, -2), _heads(qw, H).transpose(-1, -2), out=_heads(g_pos_b, H))
+        g_pos = g_pos_b.sum(dim=0, keepdim=True)
         g_u = g_qu.sum(dim=(0, 1)).view(H, W // H)
         g_w = g_qw.sum(dim=(0, 1)).view(H, W // H)
         return g_qu + g_qw, g_k, g_v, g_pos, g_u, g_w, None, None, None, None, None, None
 
 
 def rel_attention_usable(q: torch.Tensor, mask, n_heads: int) -> bool:
+    from .matmul import DISABLED
     return (q.is_cuda and q.dtype == torch.float32 and mask is not None and q.dim() == 3 and q.shape[1] <= MAX_T
-            and q.shape[2] % (4 * n_heads) == 0)
+            and q.shape[2] % (4 * n_heads) == 0 and "attn" not in DISABLED)
 
 
 def rel_attention(q, k, v, pos, u, w, mask, n_heads: int, p: float = 0.0, training: bool = False, keep=None):

@@ -16,7 +16,9 @@ MAX_TAPS = 31
 
 
 def usable(x: torch.Tensor, channels: int, taps: int) -> bool:
-    return x.is_cuda and x.dtype == torch.float32 and channels % 64 == 0 and taps <= MAX_TAPS and taps % 2 == 1
+    from .matmul import DISABLED
+    return (x.is_cuda and x.dtype == torch.float32 and channels % 64 == 0 and taps <= MAX_TAPS and taps % 2 == 1
+            and "conv" not in DISABLED)
 
 
 def _workspace(B, T, C, device):

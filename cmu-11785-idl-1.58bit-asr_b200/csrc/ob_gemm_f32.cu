@@ -52,7 +52,9 @@ struct F32Params {
   int nb0, nb1;           // batch = nb0 * nb1 (outer, inner)
   int a_b0, a_b1, b_b0, b_b1;   // 1 = the operand has this batch axis, 0 = broadcast (coordinate 0)
   int split_mode;         // 0: hi = rna(x) rewritten in place; 1: hi tile left raw (tensor core truncates), lo = x - trunc(x)
-  int k_splits, kb_per_split;   // split-K (batch == 1 only): each split adds its partial product into a zeroed D
+  int k_splits, kb_per_split;   // split-K (batch == 1 only): split s stores its partial product in part[s] (pitch ldp),
+  float* part;                  // summed in fixed order by splitk_reduce_kernel
+  int64_t ldp;
   float* D;                     // output, row pitch ldd, batch strides in elements
   int64_t ldd, d_bs0, d_bs1;
 };
@@ -246,9 +248,11 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int b0 = batch / p.nb1, b1 = batch - b0 * p.nb1;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int row0 = m0 + e * 32;
-      const float* bias = split == 0 ? p.bias : nullptr;      // warp-uniform broadcast loads below (L1-resident)
-      float* d_tile = p.D + b0 * p.d_bs0 + b1 * p.d_bs1;
-      const bool add = p.accumulate || p.k_splits > 1;
+      const bool to_part = p.k_splits > 1;                    // partial product of one K chunk: bias and D come later
+      const float* bias = to_part ? nullptr : p.bias;         // warp-uniform broadcast loads below (L1-resident)
+      float* d_tile = to_part ? p.part + static_cast<int64_t>(split) * p.M * p.ldp : p.D + b0 * p.d_bs0 + b1 * p.d_bs1;
+      const int64_t ldd = to_part ? p.ldp : p.ldd;
+      const bool add = p.accumulate && !to_part;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       constexpr int kChunks = BLOCK_N / 32;
@@ -289,7 +293,7 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const float4 v = lds128f(obuf + rr * 128 + ((rd_c ^ (rr & 7)) << 4));
           const int row = row0 + rr;
           if (row < p.M && col < p.N) {
-            float* dst = d_tile + static_cast<int64_t>(row) * p.ldd + col;
+            float* dst = d_tile + static_cast<int64_t>(row) * ldd + col;
             if (col + 3 < p.N) {
               if (add) atomicAdd(reinterpret_cast<float4*>(dst), v);
               else     *reinterpret_cast<float4*>(dst) = v;
@@ -319,9 +323,59 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
+// D = (accumulate ? D : 0) + bias + sum_s part[s], fixed order; one thread per 4 columns
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, int64_t ldp,
+                                                            const float* __restrict__ bias, int accumulate, float* __restrict__ D,
+                                                            int64_t ldd) {
+  const int n4 = static_cast<int>(ldp / 4);
+  const int64_t total = static_cast<int64_t>(M) * n4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const int row = static_cast<int>(i / n4), col = static_cast<int>(i % n4) * 4;
+    if (col >= N) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + (static_cast<int64_t>(s) * M + row) * ldp + col));
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    float* dst = D + static_cast<int64_t>(row) * ldd + col;
+    const float vs[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (col + u < N) {
+        float v = vs[u] + (bias != nullptr ? __ldg(bias + col + u) : 0.f);
+        if (accumulate) v += dst[u];
+        dst[u] = v;
+      }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+struct F32Plan {
+  int block_n, stages, k_splits, kb_per_split;
+};
+constexpr int kSplitKChunk = 1024;
+
+// Tile configuration and split-K decision.  Split-K: deep contractions with few output tiles (weight gradients, the
+// front-end projection).  Chunks of <= kSplitKChunk keep the in-tensor-core accumulation chains short (the fp32
+// accumulator truncates, which biases long chains) and fill the SMs; the chunk products are summed in fixed order.
+static F32Plan plan_f32(int M, int N, int K, int batch) {
+  F32Plan pl;
+  if (N <= 64) pl.block_n = 64, pl.stages = 4;
+  else if (N > 128 && K > 128) pl.block_n = 256, pl.stages = 2;
+  else pl.block_n = 128, pl.stages = 3;
+  const int64_t tiles_mn = (int64_t)((M + kFTileM - 1) / kFTileM) * ((N + pl.block_n - 1) / pl.block_n);
+  const int total_kb = (K + kFKBlock - 1) / kFKBlock;
+  pl.k_splits = 1, pl.kb_per_split = total_kb;
+  if (batch == 1 && K >= 2 * kSplitKChunk && tiles_mn * 2 <= sm_count() * 4) {
+    pl.kb_per_split = kSplitKChunk / kFKBlock;
+    pl.k_splits = (total_kb + pl.kb_per_split - 1) / pl.kb_per_split;
+  }
+  return pl;
+}
+static int64_t part_pitch(int N) { return (N + 3) / 4 * 4; }
+
 struct F32Operand {
   const void* ptr;
   int mn_major;
@@ -355,12 +409,11 @@ static int make_map4(CUtensorMap* map, const void* base, uint64_t inner, uint64_
 }
 
 static int g_f32_split_mode = 1;     // the tensor core truncates fp32 -> tf32 (measured), so the raw tile is the hi part
-constexpr int kSplitKChunk = 1024;
 void f32_gemm_debug(int split_mode) { g_f32_split_mode = split_mode; }
 
 template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES>
 static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_t ldd, int64_t d_bs0, int64_t d_bs1,
-                      F32Params p, cudaStream_t st) {
+                      F32Params p, const F32Plan& pl, cudaStream_t st) {
   using L = F32Smem<BLOCK_N, STAGES, PASSES>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
   auto kern = f32_gemm_kernel<A_MN, B_MN, BLOCK_N, STAGES, PASSES>;
@@ -382,39 +435,38 @@ static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_
   p.b_b0 = (p.nb0 > 1 && B.bs0 != 0), p.b_b1 = (p.nb1 > 1 && B.bs1 != 0);
   p.D = D, p.ldd = ldd, p.d_bs0 = p.nb0 > 1 ? d_bs0 : 0, p.d_bs1 = p.nb1 > 1 ? d_bs1 : 0;
   p.split_mode = g_f32_split_mode;
-  // split-K: deep contractions with few output tiles (weight gradients).  Chunks of <= kSplitKChunk keep the in-tensor-core
-  // accumulation chains short (the fp32 accumulator truncates, which biases long chains) and fill the SMs.
   const int64_t tiles_mn = (int64_t)((p.M + kFTileM - 1) / kFTileM) * ((p.N + BLOCK_N - 1) / BLOCK_N);
-  const int total_kb = (p.K + kFKBlock - 1) / kFKBlock;
-  p.k_splits = 1, p.kb_per_split = total_kb;
-  if (p.nb0 * p.nb1 == 1 && p.K >= 2 * kSplitKChunk && tiles_mn * 2 <= sm_count() * 4) {
-    p.kb_per_split = kSplitKChunk / kFKBlock;
-    p.k_splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-    if (!p.accumulate) OB_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)p.N * 4, (size_t)p.M, st));
-  }
+  p.k_splits = pl.k_splits, p.kb_per_split = pl.kb_per_split;
   const int64_t tiles = tiles_mn * p.k_splits * p.nb0 * p.nb1;
   int ctas = sm_count();
   if (tiles < ctas) ctas = (int)tiles;
   kern<<<ctas, kFThreads, L::kDynBytes, st>>>(map_a, map_b, p);
   OB_LAUNCH_CHECK("f32_gemm_kernel");
+  if (p.k_splits > 1) {
+    const int64_t work = (int64_t)p.M * (p.ldp / 4);
+    const int64_t want = (work + 255) / 256, cap = (int64_t)sm_count() * 16;
+    splitk_reduce_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(p.part, p.k_splits, p.M, p.N, p.ldp, p.bias,
+                                                                         p.accumulate, D, ldd);
+    OB_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
   return OB_OK;
 }
 
 template <int A_MN, int B_MN, int PASSES>
 static int dispatch_f32_cfg(const F32Operand& A, const F32Operand& B, float* D, int64_t ldd, int64_t d_bs0, int64_t d_bs1,
-                            const F32Params& p, cudaStream_t st) {
-  if (p.N <= 64) return launch_f32<A_MN, B_MN, 64, 4, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, st);
-  if (p.N > 128 && p.K > 128) return launch_f32<A_MN, B_MN, 256, 2, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, st);
-  return launch_f32<A_MN, B_MN, 128, 3, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, st);
+                            const F32Params& p, const F32Plan& pl, cudaStream_t st) {
+  if (pl.block_n == 64) return launch_f32<A_MN, B_MN, 64, 4, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
+  if (pl.block_n == 256) return launch_f32<A_MN, B_MN, 256, 2, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
+  return launch_f32<A_MN, B_MN, 128, 3, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
 }
 
 template <int PASSES>
 static int dispatch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_t ldd, int64_t d_bs0, int64_t d_bs1,
-                        const F32Params& p, cudaStream_t st) {
-  if (!A.mn_major && !B.mn_major) return dispatch_f32_cfg<0, 0, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, st);
-  if (!A.mn_major && B.mn_major) return dispatch_f32_cfg<0, 1, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, st);
-  if (A.mn_major && !B.mn_major) return dispatch_f32_cfg<1, 0, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, st);
-  return dispatch_f32_cfg<1, 1, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, st);
+                        const F32Params& p, const F32Plan& pl, cudaStream_t st) {
+  if (!A.mn_major && !B.mn_major) return dispatch_f32_cfg<0, 0, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
+  if (!A.mn_major && B.mn_major) return dispatch_f32_cfg<0, 1, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
+  if (A.mn_major && !B.mn_major) return dispatch_f32_cfg<1, 0, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
+  return dispatch_f32_cfg<1, 1, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
 }
 
 }  // namespace ob
@@ -426,10 +478,16 @@ static bool f32_ok(const void* ptr, int64_t ld, int64_t bs0, int64_t bs1) {
          bs1 >= 0;
 }
 
+extern "C" size_t ob_gemm_f32_workspace_bytes(int M, int N, int K, int nb0, int nb1) {
+  if (M <= 0 || N <= 0 || K <= 0 || nb0 <= 0 || nb1 <= 0) return 0;
+  const F32Plan pl = plan_f32(M, N, K, nb0 * nb1);
+  return pl.k_splits > 1 ? static_cast<size_t>(pl.k_splits) * M * part_pitch(N) * sizeof(float) : 0;
+}
+
 extern "C" int ob_gemm_f32(const float* A, int a_mn_major, int64_t lda, int64_t a_bs0, int64_t a_bs1, const float* B,
                            int b_mn_major, int64_t ldb, int64_t b_bs0, int64_t b_bs1, float* D, int64_t ldd, int64_t d_bs0,
                            int64_t d_bs1, const float* bias, float scale, int accumulate, int M, int N, int K, int nb0,
-                           int nb1, int passes, ob_stream_t stream) {
+                           int nb1, int passes, void* ws, size_t ws_bytes, ob_stream_t stream) {
   OB_REQUIRE(A && B && D, "ob_gemm_f32: null pointer");
   OB_REQUIRE(M > 0 && N > 0 && K > 0 && nb0 > 0 && nb1 > 0, "ob_gemm_f32: M, N, K and the batch counts must be positive");
   OB_REQUIRE(passes == 1 || passes == 3, "ob_gemm_f32: passes must be 1 (tf32) or 3 (fp32-level split)");
@@ -446,6 +504,17 @@ extern "C" int ob_gemm_f32(const float* A, int a_mn_major, int64_t lda, int64_t 
   F32Params p = {};
   p.bias = bias, p.scale = scale, p.accumulate = accumulate != 0;
   p.M = M, p.N = N, p.K = K, p.nb0 = nb0, p.nb1 = nb1;
+  const F32Plan pl = plan_f32(M, N, K, nb0 * nb1);
+  if (pl.k_splits > 1) {
+    const size_t need = static_cast<size_t>(pl.k_splits) * M * part_pitch(N) * sizeof(float);
+    if (ws == nullptr || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) {
+      set_error("ob_gemm_f32: this shape splits K %d ways and needs a 16-byte aligned workspace of %zu bytes (got %zu)",
+                pl.k_splits, need, ws_bytes);
+      return OB_ERR_WORKSPACE;
+    }
+    p.part = static_cast<float*>(ws), p.ldp = part_pitch(N);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return passes == 3 ? dispatch_f32<3>(a, b, D, ldd, d_bs0, d_bs1, p, st) : dispatch_f32<1>(a, b, D, ldd, d_bs0, d_bs1, p, st);
+  return passes == 3 ? dispatch_f32<3>(a, b, D, ldd, d_bs0, d_bs1, p, pl, st)
+                     : dispatch_f32<1>(a, b, D, ldd, d_bs0, d_bs1, p, pl, st);
 }

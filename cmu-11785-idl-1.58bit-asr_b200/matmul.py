@@ -7,6 +7,8 @@ views (``[B, T, H, d]`` projections, transposed operands, broadcast batches) are
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from ._cabi import check, lib
@@ -84,9 +86,11 @@ def bmm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None, bias: tor
     d_bs1 = so[1] if nb1 > 1 else 0
     if bias is not None and (bias.dtype != torch.float32 or not bias.is_cuda or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("bmm_nt: bias must be a contiguous float32 CUDA vector of N elements")
+    ws_bytes = lib.ob_gemm_f32_workspace_bytes(M, N, K, nb0, nb1) if K >= 2048 and nb0 * nb1 == 1 else 0
+    ws = torch.empty(ws_bytes, device=a.device, dtype=torch.uint8) if ws_bytes else None      # split-K partial products
     check(lib.ob_gemm_f32(a4.data_ptr(), a_mn, lda, a_bs0, a_bs1, b4.data_ptr(), b_mn, ldb, b_bs0, b_bs1, out4.data_ptr(), ldd,
                           d_bs0, d_bs1, None if bias is None else bias.data_ptr(), float(scale), int(accumulate), M, N, K, nb0,
-                          nb1, passes, _stream()))
+                          nb1, passes, None if ws is None else ws.data_ptr(), ws_bytes, _stream()))
     return result
 
 
@@ -121,8 +125,14 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb
 
 
+# A/B switches for measurements (bench.py --torch-nonrouted): "attn", "conv", "linear" in OB_TORCH_NONROUTED route that part of
+# the non-routed stack back to torch's own fp32 kernels
+DISABLED = set(filter(None, os.environ.get("OB_TORCH_NONROUTED", "").split(",")))
+
+
 def linear_usable(x: torch.Tensor, weight: torch.Tensor) -> bool:
-    return x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.numel() > 0
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.numel() > 0
+            and "linear" not in DISABLED)
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None) -> torch.Tensor:

@@ -185,14 +185,17 @@ int ob_ctc_greedy_decode(const void* logits, int dtype, int B, int T, int V, con
  * A + b0*a_bs0 + b1*a_bs1 + m*lda + k (K-major) or ... + k*lda + m (a_mn_major = 1); B likewise with (n, k) (K-major
  * B is an [N, K] weight; MN-major B is a [K, N] matrix); D is row-major [M, N] with pitch ldd.  A batch stride of 0
  * broadcasts an input over that batch axis.  All pointers 16-byte aligned, leading dimensions and batch strides
- * multiples of 4 elements; M, N, K arbitrary (> 0).  accumulate = 1 adds into D with vector atomics; a D batch stride of
- * 0 then sums the products of that batch axis (order of the fp32 additions not fixed).  Contractions of K >= 2048 with
- * few output tiles are split over K in chunks of 1024 (atomic adds into the zeroed D): this fills the SMs and keeps the
- * truncating in-tensor-core accumulation chains short.  Measured error vs fp64: <= 1e-5 of max|D| (passes = 3). */
+ * multiples of 4 elements; M, N, K arbitrary (> 0).  accumulate = 1 adds into D (one atomic vector add per element, so
+ * the result is deterministic unless a D batch stride of 0 makes several batch items share an output).  Unbatched
+ * contractions of K >= 2048 with few output tiles are split over K in chunks of 1024 whose products go to the workspace
+ * and are summed in fixed order: this fills the SMs and keeps the truncating in-tensor-core accumulation chains short.
+ * ws: at least ob_gemm_f32_workspace_bytes(M, N, K, nb0, nb1) bytes (0 for most shapes; ws may then be NULL).
+ * Measured error vs fp64: <= 1e-5 of max|D| (passes = 3). */
+size_t ob_gemm_f32_workspace_bytes(int M, int N, int K, int nb0, int nb1);
 int ob_gemm_f32(const float* A, int a_mn_major, int64_t lda, int64_t a_bs0, int64_t a_bs1, const float* B,
                 int b_mn_major, int64_t ldb, int64_t b_bs0, int64_t b_bs1, float* D, int64_t ldd, int64_t d_bs0,
                 int64_t d_bs1, const float* bias, float scale, int accumulate, int M, int N, int K, int nb0, int nb1,
-                int passes, ob_stream_t stream);
+                int passes, void* ws, size_t ws_bytes, ob_stream_t stream);
 
 /* Middle of the convolution module (conformer.py:141-167) in the [B, T, C] layout: GLU -> depthwise conv1d (ks odd <= 31
  * taps, zero padding ks/2, per utterance) -> BatchNorm with batch statistics over all B*T frames (biased variance, as

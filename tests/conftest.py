@@ -28,6 +28,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(autouse=True)
+def _restore_backend_flags():
+    """Tests that pin torch's own kernels to true fp32 must not leak that choice into later tests."""
+    import torch
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic)
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic = saved
+
+
 def bits_to_f32(s: str) -> np.float32:
     return np.float32(struct.unpack("<f", struct.pack("<I", int(s, 16)))[0])
 

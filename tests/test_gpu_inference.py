@@ -61,6 +61,7 @@ def test_packed_model_roundtrip_and_transcribe(ob):
     from onebit_b200.inference import load_packed_state_dict, packed_state_dict, transcribe_greedy
     cfg = dict(input_dim=80, vocab_size=64, enc_layers=2, dec_layers=1, enc_dropout=0.0, dec_dropout=0.0)
     torch.manual_seed(4)
+    torch.backends.cudnn.deterministic = True         # torch's front-end convolutions: same algorithm on every call
     model = ob.ConformerASR(**cfg).cuda().eval()
     batch = {"feats": torch.randn(3, 200, 80, device="cuda"), "feat_lens": torch.tensor([200, 150, 90], device="cuda")}
     toks_ref, n_ref = transcribe_greedy(model, batch, precision=2)
