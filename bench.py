@@ -57,6 +57,11 @@ def parse():
                    help="recompute the (bitwidth-independent, dropout-free) conv subsampling in each of the three passes, as the "
                         "reference does; by default it is computed once per step and shared - identical loss and gradients")
     p.add_argument("--sweep", action="store_true", help="gemm workload: also run the configs[1] K/N sweep")
+    p.add_argument("--torch-nonrouted", default="",
+                   help="A/B switch: comma list of {attn,conv,linear} to run on torch's own fp32 kernels instead of the "
+                        "library's (sets OB_TORCH_NONROUTED before the package is imported)")
+    p.add_argument("--foreach-adamw", action="store_true",
+                   help="use torch's default multi-tensor AdamW instead of the fused single-kernel one (same update rule)")
     p.add_argument("--tf32-nonrouted", action="store_true",
                    help="NOT the reference's numerics: let the non-routed fp32 matmuls (attention, vocabulary projections) use "
                         "TF32 tensor cores; reported with this flag in `config`, never the default")
@@ -350,6 +355,57 @@ def hot_kernel_rooflines(peaks, M):
         "weight_quant_pack": (lambda j: lib.ob_weight_quant_pack(layer.weight.data_ptr(), a.data_ptr(), 1, N, K, 2, pk2.data_ptr(),
                                                                  pkt2.data_ptr(), st), 4.5 * N * K, 0.0),
     })
+    # fp32 tensor-core GEMM (3 x tf32 split) at the shapes the model uses it on, and the convolution-module kernels
+    from onebit_b200.matmul import bmm_nt
+    dh = 64
+    Tp = (Tt + 3) // 4 * 4
+    qh = [torch.randn(Bq, Tt, Hh * dh, device=dev) for _ in range(2)]
+    heads = lambda t: t.view(Bq, Tt, Hh, dh).permute(0, 2, 1, 3)  # noqa: E731
+    sc = [torch.empty(Bq, Hh, Tt, Tp, device=dev)[..., :Tt] for _ in range(2)]
+    pr = [torch.rand(Bq, Hh, Tt, Tp, device=dev)[..., :Tt] for _ in range(2)]
+    mix = torch.empty(Bq, Tt, Hh * dh, device=dev)
+    V = TRAIN["vocab"]
+    w_voc, b_voc = torch.randn(V, K, device=dev) * 0.05, torch.zeros(V, device=dev)
+    logits = torch.empty(M, V, device=dev)
+    gvoc = torch.empty(V, K, device=dev)
+    w_pw, y_pw = torch.randn(2 * K, K, device=dev) * 0.05, torch.empty(M, 2 * K, device=dev)
+    nsc = float(Bq * Hh * Tt * Tt)
+    fns.update({
+        "f32gemm_scores_qk": (lambda j: bmm_nt(heads(qh[j % 2]), heads(qh[1 - j % 2]), out=sc[j % 2]),
+                              4.0 * nsc + 8.0 * Bq * Tt * Hh * dh, 2.0 * nsc * dh),
+        "f32gemm_probs_v": (lambda j: bmm_nt(pr[j % 2], heads(qh[j % 2]).transpose(-1, -2), out=heads(mix)),
+                            4.0 * nsc + 8.0 * Bq * Tt * Hh * dh, 2.0 * nsc * dh),
+        "f32gemm_probsT_do": (lambda j: bmm_nt(pr[j % 2].transpose(-1, -2), heads(qh[j % 2]).transpose(-1, -2), out=heads(mix)),
+                              4.0 * nsc + 8.0 * Bq * Tt * Hh * dh, 2.0 * nsc * dh),
+        "f32gemm_vocab_fwd": (lambda j: bmm_nt(xs[j], w_voc, out=logits, bias=b_voc),
+                              4.0 * M * K + 4.0 * V * K + 4.0 * M * V, 2.0 * M * V * K),
+        "f32gemm_vocab_dw": (lambda j: bmm_nt(logits.t(), xs[j].t(), out=gvoc),
+                             4.0 * M * K + 4.0 * V * K + 4.0 * M * V, 2.0 * M * V * K),
+        "f32gemm_pw1_fwd": (lambda j: bmm_nt(xs[j], w_pw, out=y_pw), 4.0 * M * K + 8.0 * K * K + 8.0 * M * K, 4.0 * M * K * K),
+    })
+    Bc, Tc = Bq, Tt
+    Mc = Bc * Tc
+    cv_a = [torch.randn(Bc, Tc, 2 * K, device=dev) for _ in range(2)]
+    cv_w, cv_b = torch.randn(K, 31, device=dev) * 0.1, torch.zeros(K, device=dev)
+    cv_d = [torch.randn(Bc, Tc, K, device=dev) for _ in range(2)]
+    cv_s, cv_gd, cv_ga = torch.empty(Bc, Tc, K, device=dev), torch.empty(Bc, Tc, K, device=dev), torch.empty(Bc, Tc, 2 * K, device=dev)
+    cv_stats, cv_ggb = torch.zeros(2, K, device=dev), torch.empty(2, K, device=dev)
+    cv_stats[1].fill_(1.0)
+    cv_gw, cv_gb = torch.empty(K, 31, device=dev), torch.empty(K, device=dev)
+    cv_ws = torch.empty(lib.ob_convmod_workspace_bytes(Bc, Tc, K), device=dev, dtype=torch.uint8)
+    fns.update({
+        "glu_dwconv_bn_fwd": (lambda j: lib.ob_glu_dwconv_bn_fwd(cv_a[j % 2].data_ptr(), cv_w.data_ptr(), cv_b.data_ptr(), Bc, Tc, K, 31,
+                                                                 1e-5, cv_s.data_ptr(), cv_stats[0].data_ptr(), cv_stats[1].data_ptr(),
+                                                                 cv_ws.data_ptr(), st), 12.0 * Mc * K, 0.0),
+        "bn_swish_fwd": (lambda j: lib.ob_bn_swish_fwd(cv_d[j % 2].data_ptr(), cv_stats[0].data_ptr(), cv_stats[1].data_ptr(), ln_w.data_ptr(),
+                                                       ln_b.data_ptr(), Mc, K, cv_s.data_ptr(), st), 8.0 * Mc * K, 0.0),
+        "bn_swish_bwd": (lambda j: lib.ob_bn_swish_bwd(cv_d[1 - j % 2].data_ptr(), cv_d[j % 2].data_ptr(), cv_stats[0].data_ptr(),
+                                                       cv_stats[1].data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), Mc, K, cv_gd.data_ptr(),
+                                                       cv_ggb.data_ptr(), cv_ws.data_ptr(), st), 20.0 * Mc * K, 0.0),
+        "glu_dwconv_bwd": (lambda j: lib.ob_glu_dwconv_bwd(cv_d[j % 2].data_ptr(), cv_a[j % 2].data_ptr(), cv_w.data_ptr(), Bc, Tc, K, 31,
+                                                           cv_ga.data_ptr(), cv_gw.data_ptr(), cv_gb.data_ptr(), cv_ws.data_ptr(), st),
+                           32.0 * Mc * K, 0.0),
+    })
     out = {}
     for name, (fn, nbytes_alg, flops) in fns.items():
         for _ in range(3):
@@ -376,7 +432,8 @@ def cpu_reference_train(args, sample_batch, steps):
                                 linear_cls=OracleQuantizedLinear).train()
     finally:
         OracleQuantizedLinear.act_bits_default = 8
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2,
+                            fused=not getattr(args, "foreach_adamw", False))
     batch = make_batch(sample_batch, args.frames, 1)
     cfg = StepConfig()
     train_step(model, batch, opt, cfg)
@@ -399,7 +456,8 @@ def run_train(args, world, rank):
         torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(0)                                   # same weights and precision masks on every rank
     model = ob.ConformerASR(TRAIN["mel"], TRAIN["vocab"], enc_dropout=args.dropout, dec_dropout=args.dropout).train().to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2,
+                            fused=not getattr(args, "foreach_adamw", False))
     sync = GradAllReducer(model.parameters()) if world > 1 else None
     cfg = StepConfig(share_frontend=args.share_frontend)
     batch = make_batch(B, T, 1000 + rank, device=dev)
@@ -458,13 +516,17 @@ def run_train(args, world, rank):
     out = {"metric": "conformer_train_audio_sec_per_sec", "value": round(value, 1), "unit": "audio-s/s", "n_gpus": world,
            "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None,
-           "dtype": "int8 x ternary fwd (int32 accum), bf16 bwd (fp32 accum); non-routed ops fp32 as in the reference",
+           "dtype": "int8 x ternary fwd (int32 accum), bf16 bwd (fp32 accum); non-routed matmuls fp32 via 3 x tf32 split "
+                    "on tcgen05 (error <= 1e-5 of max, fp32 accumulate), other non-routed ops fp32",
            "data": "synthetic", "impl": "ours",
            "config": {"workload": "Conformer BitLinear co-training step (BASELINE configs[2]; configs[3] at 8 GPUs): 12 blocks, "
                                   "d_model 256, d_ff 1024, 4 heads, V=5004, 3 passes (2-bit, 1-bit, stochastic precision) + "
                                   "CTC/attention/KL losses + clip + AdamW",
                       "batch_per_gpu": B, "global_batch": B * world, "frames": T, "mel": TRAIN["mel"], "dropout": args.dropout,
                       "audio_s_per_step": audio_s, "tf32_nonrouted": bool(args.tf32_nonrouted),
+                      "torch_nonrouted": args.torch_nonrouted or None,
+                      "optimizer": "torch.optim.AdamW(lr 5e-4, betas (0.9, 0.98), wd 1e-2" +
+                                   (")" if args.foreach_adamw else ", fused=True) - the reference's update rule, single-kernel form"),
                       "share_frontend": bool(args.share_frontend),
                       "share_frontend_note": "conv subsampling (no dropout, no bitwidth) evaluated once per step for the three passes: "
                                              "common-subexpression sharing inside the step, same loss and gradients "
@@ -668,6 +730,8 @@ def run_reference(args, world, rank):
 
 def main():
     args = parse()
+    if args.torch_nonrouted:
+        os.environ["OB_TORCH_NONROUTED"] = args.torch_nonrouted      # read when the package is imported
     # exactly ONE line on stdout: anything libraries print to fd 1 meanwhile (e.g. NCCL's version banner) goes to stderr
     sys.stdout.flush()
     real_stdout = os.dup(1)

@@ -30,7 +30,15 @@ _DTYPE_TAG = {torch.float32: OB_F32, torch.bfloat16: OB_BF16}
 _BITWIDTH_ERROR = "bitwidth must be one of {1,2,32}"
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device.  Called once per kernel launch, so it goes through
+    torch's raw C accessors (0.2 us) instead of building a ``torch.cuda.Stream`` object (10 us) when they exist."""
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 
