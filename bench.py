@@ -378,9 +378,9 @@ def hot_kernel_rooflines(peaks, M):
         "f32gemm_probsT_do": (lambda j: bmm_nt(pr[j % 2].transpose(-1, -2), heads(qh[j % 2]).transpose(-1, -2), out=heads(mix)),
                               4.0 * nsc + 8.0 * Bq * Tt * Hh * dh, 2.0 * nsc * dh),
         "f32gemm_vocab_fwd": (lambda j: bmm_nt(xs[j], w_voc, out=logits, bias=b_voc),
-                              4.0 * M * K + 4.0 * V * K + 4.0 * M * V, 2.0 * M * V * K),
+                              4.0 * M * K + 4.0 * V * K + 4.0 * M * V, 2.0 * M * V * K, "tensor"),
         "f32gemm_vocab_dw": (lambda j: bmm_nt(logits.t(), xs[j].t(), out=gvoc),
-                             4.0 * M * K + 4.0 * V * K + 4.0 * M * V, 2.0 * M * V * K),
+                             4.0 * M * K + 4.0 * V * K + 4.0 * M * V, 2.0 * M * V * K, "tensor"),
         "f32gemm_pw1_fwd": (lambda j: bmm_nt(xs[j], w_pw, out=y_pw), 4.0 * M * K + 8.0 * K * K + 8.0 * M * K, 4.0 * M * K * K),
     })
     Bc, Tc = Bq, Tt
@@ -407,7 +407,8 @@ def hot_kernel_rooflines(peaks, M):
                            32.0 * Mc * K, 0.0),
     })
     out = {}
-    for name, (fn, nbytes_alg, flops) in fns.items():
+    for name, spec in fns.items():
+        fn, nbytes_alg, flops = spec[:3]
         for _ in range(3):
             fn(nxt())
         ms = timed_region(1, lambda: fn(nxt()), 20) / 20
@@ -415,6 +416,13 @@ def hot_kernel_rooflines(peaks, M):
         out[name] = {"ms": round(ms, 4), "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": round(gbs / peaks["hbm_gbs"], 4), "algorithmic_bytes": int(nbytes_alg),
                      "tflops": round(flops / (ms * 1e-3) / 1e12, 1) if flops else None}
+        if len(spec) > 3 and spec[3] == "tensor":
+            # compute-bound shapes of the 3 x tf32 GEMM: three tf32 MMAs per algorithmic multiply-add; tf32 peak = half the
+            # measured dense bf16 rate (no tf32 figure in MEASURED_PEAKS.json)
+            tf32 = 3.0 * flops / (ms * 1e-3) / 1e12
+            peak = 0.5 * peaks["bf16_tflops"]
+            out[name].update({"bound": "tensor", "achieved": round(tf32, 1), "peak": round(peak, 1), "unit": "TFLOP/s (tf32 MMAs issued)",
+                              "frac": round(tf32 / peak, 4), "fp32_equivalent_tflops": round(tf32 / 3.0, 1)})
     return {"shape": {"M": M, "K": K, "N": N, "attention": [Bq, Hh, Tt, Tt]}, "kernels": out}
 
 

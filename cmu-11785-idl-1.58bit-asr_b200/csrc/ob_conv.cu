@@ -8,7 +8,7 @@
 //   bn_swish_bwd_reduce g_s, d -> per-row-block sums of g_y and g_y * xhat        (g_y = g_s * swish'(y))
 //   bn_swish_bwd_apply  g_s, d -> g_d
 //   dwconv_bwd_data_glu g_d, a -> g_a (depthwise transposed convolution + GLU backward)
-//   dwconv_bwd_weight   g_d, a -> per-utterance partials of g_w and g_bias, reduced in fixed order
+//   dwconv_bwd_weight   g_d, a -> per-tile partials of g_w and g_bias, reduced in fixed order
 //
 // BatchNorm uses batch statistics over all B*T frames including padding, biased variance, exactly as
 // nn.BatchNorm1d(track_running_stats=False) does in the reference (conformer.py:148), in training and in eval mode.
@@ -37,25 +37,45 @@ __device__ __forceinline__ void load_taps(const float* __restrict__ w, int c, in
   }
 }
 
-// tile of g = GLU(a) with halo into shared memory: rows t0-15 .. t0+78, zero outside the utterance
+// tile of g = GLU(a) with halo into shared memory: rows t0-15 .. t0+78, zero outside the utterance.  128-bit loads: a
+// thread owns 4 channels of a row (16 threads per 256-byte row half), all loads of a pass are issued before they are used
 __device__ __forceinline__ void load_glu_tile(const float* __restrict__ a, int b, int T, int C, int t0, int c0, float* tile) {
-  const int c = threadIdx.x & 63;
-  for (int r = threadIdx.x >> 6; r < kCvRows; r += 4) {
-    const int t = t0 - kCvHalo + r;
-    float v = 0.f;
-    if (t >= 0 && t < T) {
-      const float* row = a + (static_cast<int64_t>(b) * T + t) * (2 * C) + c0 + c;
-      v = __ldg(row) * sigmoid_f(__ldg(row + C));
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;          // 16 rows per pass
+  constexpr int kPasses = (kCvRows + 15) / 16;
+  float4 v1[kPasses], v2[kPasses];
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    const int r = r0 + 16 * p, t = t0 - kCvHalo + r;
+    v1[p] = v2[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < kCvRows && t >= 0 && t < T) {
+      const float* row = a + (static_cast<int64_t>(b) * T + t) * (2 * C) + c0 + c4;
+      v1[p] = __ldg(reinterpret_cast<const float4*>(row));
+      v2[p] = __ldg(reinterpret_cast<const float4*>(row + C));
     }
-    tile[r * kCvC + c] = v;
+  }
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    const int r = r0 + 16 * p;
+    if (r < kCvRows)
+      *reinterpret_cast<float4*>(tile + r * kCvC + c4) = make_float4(v1[p].x * sigmoid_f(v2[p].x), v1[p].y * sigmoid_f(v2[p].y),
+                                                                     v1[p].z * sigmoid_f(v2[p].z), v1[p].w * sigmoid_f(v2[p].w));
   }
 }
 
 __device__ __forceinline__ void load_plain_tile(const float* __restrict__ x, int b, int T, int C, int t0, int c0, float* tile) {
-  const int c = threadIdx.x & 63;
-  for (int r = threadIdx.x >> 6; r < kCvRows; r += 4) {
-    const int t = t0 - kCvHalo + r;
-    tile[r * kCvC + c] = (t >= 0 && t < T) ? __ldg(x + (static_cast<int64_t>(b) * T + t) * C + c0 + c) : 0.f;
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
+  constexpr int kPasses = (kCvRows + 15) / 16;
+  float4 v[kPasses];
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    const int r = r0 + 16 * p, t = t0 - kCvHalo + r;
+    v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < kCvRows && t >= 0 && t < T) v[p] = __ldg(reinterpret_cast<const float4*>(x + (static_cast<int64_t>(b) * T + t) * C + c0 + c4));
+  }
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    const int r = r0 + 16 * p;
+    if (r < kCvRows) *reinterpret_cast<float4*>(tile + r * kCvC + c4) = v[p];
   }
 }
 
@@ -63,7 +83,7 @@ __device__ __forceinline__ void load_plain_tile(const float* __restrict__ x, int
 __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w,
                                                              const float* __restrict__ bias, int B, int T, int C, int ks,
                                                              float* __restrict__ d, float* __restrict__ part) {
-  __shared__ float tile[kCvRows * kCvC];
+  __shared__ __align__(16) float tile[kCvRows * kCvC];
   __shared__ float red[4][kCvC];
   const int tblocks = (T + kCvT - 1) / kCvT;
   const int b = blockIdx.x / tblocks, tb = blockIdx.x % tblocks;
@@ -111,38 +131,43 @@ __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __rest
   }
 }
 
-// Chan's pairwise combination of the tile partials in fp64, fixed order: 16 thread groups each fold every 16th tile,
-// group 0 folds the 16 results.  grid: C / 64 blocks of 1024 threads.
+// Combination of the tile partials (sum, centred sum of squares) in fp64, fixed order: 16 thread groups each fold every
+// 16th tile, then the 16 results are folded.  grid: C / 64 blocks of 1024 threads.
 constexpr int kFinGroups = 16;
-
-__device__ __forceinline__ void chan_merge(double& n, double& mu, double& m2, double nb, double mb, double m2b) {
-  if (nb == 0.0) return;
-  const double delta = mb - mu, nn = n + nb;
-  m2 += m2b + delta * delta * n * nb / nn;
-  mu += delta * nb / nn;
-  n = nn;
-}
 
 __global__ void __launch_bounds__(64 * kFinGroups) bn_stats_finalize_kernel(const float* __restrict__ part, int B, int T, int C,
                                                                           float eps, float* __restrict__ mean,
                                                                           float* __restrict__ rstd) {
-  __shared__ double sh[3][kFinGroups][64];
+  // total M2 = sum_tiles [ M2_tile + n_tile * (mean_tile - mean)^2 ]  (the pairwise Chan update, summed in closed form)
+  __shared__ double sh[kFinGroups][64];
   const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int c = blockIdx.x * 64 + cl;
-  const int tblocks = (T + kCvT - 1) / kCvT;
-  double n = 0.0, mu = 0.0, m2 = 0.0;
-  for (int blk = grp; blk < B * tblocks; blk += kFinGroups) {
-    const int tb = blk % tblocks;
-    const double nb = static_cast<double>(min(kCvT, T - tb * kCvT));
-    const double sb = part[static_cast<int64_t>(blk) * 2 * C + c], m2b = part[static_cast<int64_t>(blk) * 2 * C + C + c];
-    chan_merge(n, mu, m2, nb, sb / nb, m2b);
+  const int tblocks = (T + kCvT - 1) / kCvT, nblk = B * tblocks;
+  const double n_tail = static_cast<double>(T - (tblocks - 1) * kCvT);
+  double s = 0.0;
+#pragma unroll 4
+  for (int blk = grp; blk < nblk; blk += kFinGroups) s += part[static_cast<int64_t>(blk) * 2 * C + c];
+  sh[grp][cl] = s;
+  __syncthreads();
+  double tot = 0.0;
+  for (int g = 0; g < kFinGroups; ++g) tot += sh[g][cl];
+  const double n = static_cast<double>(B) * T, mu = tot / n;
+  __syncthreads();
+  double m2 = 0.0;
+#pragma unroll 4
+  for (int blk = grp; blk < nblk; blk += kFinGroups) {
+    const bool tail = (blk % tblocks) == tblocks - 1;
+    const double nb = tail ? n_tail : static_cast<double>(kCvT);
+    const double dm = part[static_cast<int64_t>(blk) * 2 * C + c] * (tail ? 1.0 / n_tail : 1.0 / kCvT) - mu;
+    m2 += part[static_cast<int64_t>(blk) * 2 * C + C + c] + nb * dm * dm;
   }
-  sh[0][grp][cl] = n, sh[1][grp][cl] = mu, sh[2][grp][cl] = m2;
+  sh[grp][cl] = m2;
   __syncthreads();
   if (grp == 0) {
-    for (int g = 1; g < kFinGroups; ++g) chan_merge(n, mu, m2, sh[0][g][cl], sh[1][g][cl], sh[2][g][cl]);
+    double v = 0.0;
+    for (int g = 0; g < kFinGroups; ++g) v += sh[g][cl];
     mean[c] = static_cast<float>(mu);
-    rstd[c] = static_cast<float>(1.0 / sqrt(m2 / n + static_cast<double>(eps)));
+    rstd[c] = static_cast<float>(1.0 / sqrt(v / n + static_cast<double>(eps)));
   }
 }
 
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
 __global__ void __launch_bounds__(256) dwconv_bwd_data_glu_kernel(const float* __restrict__ gd, const float* __restrict__ a,
                                                                   const float* __restrict__ w, int B, int T, int C, int ks,
                                                                   float* __restrict__ ga) {
-  __shared__ float tile[kCvRows * kCvC];
+  __shared__ __align__(16) float tile[kCvRows * kCvC];
   const int tblocks = (T + kCvT - 1) / kCvT;
   const int b = blockIdx.x / tblocks, tb = blockIdx.x % tblocks;
   const int t0 = tb * kCvT, c0 = blockIdx.y * kCvC;
@@ -282,46 +307,47 @@ __global__ void __launch_bounds__(256) dwconv_bwd_data_glu_kernel(const float* _
   }
 }
 
-// per-utterance partials of g_w[c][j] = sum_t g_d[t] * g[t + j - 15] and g_bias[c] = sum_t g_d[t]:
-// part: [B][32][C], slot 31 = bias.  grid: x = utterance, y = channel tile; the CTA walks the utterance tile by tile.
+// per-tile partials of g_w[c][j] = sum_t g_d[t] * g[t + j - 15] and g_bias[c] = sum_t g_d[t]:
+// part: [B * tblocks][32][C], slot 31 = bias.  grid: x = b * tblocks + tb, y = channel tile.
 __global__ void __launch_bounds__(256) dwconv_bwd_weight_kernel(const float* __restrict__ gd, const float* __restrict__ a, int B,
                                                                 int T, int C, float* __restrict__ part) {
-  __shared__ float buf[4 * 32 * kCvC];               // the GLU tile (94 x 64) in the loop, then the cross-group reduction
+  __shared__ __align__(16) float buf[4 * 32 * kCvC];               // the GLU tile (94 x 64) first, then the cross-group reduction
   const int tblocks = (T + kCvT - 1) / kCvT;
-  const int b = blockIdx.x, c0 = blockIdx.y * kCvC;
+  const int b = blockIdx.x / tblocks, tb = blockIdx.x % tblocks;
+  const int t0 = tb * kCvT, c0 = blockIdx.y * kCvC;
   const int c = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  float gv[kCvPer];
+#pragma unroll
+  for (int o = 0; o < kCvPer; ++o) {
+    const int t = t0 + tg * kCvPer + o;
+    gv[o] = t < T ? __ldg(gd + (static_cast<int64_t>(b) * T + t) * C + c0 + c) : 0.f;
+  }
+  load_glu_tile(a, b, T, C, t0, c0, buf);
+  __syncthreads();
+  float win[kCvWin];
+#pragma unroll
+  for (int i = 0; i < kCvWin; ++i) win[i] = buf[(tg * kCvPer + i) * kCvC + c];
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-  for (int tb = 0; tb < tblocks; ++tb) {
-    const int t0 = tb * kCvT;
-    __syncthreads();                                 // the previous tile's windows are in registers
-    load_glu_tile(a, b, T, C, t0, c0, buf);
-    __syncthreads();
-    float win[kCvWin];
 #pragma unroll
-    for (int i = 0; i < kCvWin; ++i) win[i] = buf[(tg * kCvPer + i) * kCvC + c];
+  for (int o = 0; o < kCvPer; ++o) {
 #pragma unroll
-    for (int o = 0; o < kCvPer; ++o) {
-      const int t = t0 + tg * kCvPer + o;
-      const float g = t < T ? __ldg(gd + (static_cast<int64_t>(b) * T + t) * C + c0 + c) : 0.f;
-#pragma unroll
-      for (int j = 0; j < kCvTaps; ++j) acc[j] = fmaf(g, win[o + j], acc[j]);
-      acc[31] += g;
-    }
+    for (int j = 0; j < kCvTaps; ++j) acc[j] = fmaf(gv[o], win[o + j], acc[j]);
+    acc[31] += gv[o];
   }
-  __syncthreads();
+  __syncthreads();                                   // everyone has its window: the tile memory is free
 #pragma unroll
   for (int j = 0; j < 32; ++j) buf[(tg * 32 + j) * kCvC + c] = acc[j];
   __syncthreads();
   for (int j = tg; j < 32; j += 4) {
     const float v = buf[(0 * 32 + j) * kCvC + c] + buf[(1 * 32 + j) * kCvC + c] + buf[(2 * 32 + j) * kCvC + c] +
                     buf[(3 * 32 + j) * kCvC + c];
-    part[(static_cast<int64_t>(b) * 32 + j) * C + c0 + c] = v;
+    part[(static_cast<int64_t>(blockIdx.x) * 32 + j) * C + c0 + c] = v;
   }
 }
 
-// g_w[c][j] (ks centred taps) and g_bias[c] from the per-utterance partials.  grid: 32 * C / 64 blocks of 1024 threads
+// g_w[c][j] (ks centred taps) and g_bias[c] from the per-tile partials.  grid: 32 * C / 64 blocks of 1024 threads
 __global__ void __launch_bounds__(64 * kFinGroups) dwconv_bwd_weight_finalize_kernel(const float* __restrict__ part, int nblocks,
                                                                                    int C, int ks, float* __restrict__ gw,
                                                                                    float* __restrict__ gbias) {
@@ -357,7 +383,7 @@ extern "C" size_t ob_convmod_workspace_bytes(int B, int T, int C) {
   if (B <= 0 || T <= 0 || C <= 0) return 0;
   const size_t tiles = static_cast<size_t>(B) * conv_tblocks(T);
   const size_t rows = (static_cast<size_t>(B) * T + kBnRows - 1) / kBnRows;
-  const size_t a = (tiles * 2 > static_cast<size_t>(B) * 32 ? tiles * 2 : static_cast<size_t>(B) * 32) * C * sizeof(float);
+  const size_t a = tiles * 32 * C * sizeof(float);             // weight-gradient partials (largest user)
   const size_t b = rows * 2 * C * sizeof(float);
   return (a > b ? a : b) + 256;
 }
@@ -415,9 +441,9 @@ extern "C" int ob_glu_dwconv_bwd(const float* gd, const float* a, const float* w
   dim3 grid(B * conv_tblocks(T), C / kCvC);
   dwconv_bwd_data_glu_kernel<<<grid, 256, 0, st>>>(gd, a, w, B, T, C, ks, ga);
   OB_LAUNCH_CHECK("dwconv_bwd_data_glu_kernel");
-  dwconv_bwd_weight_kernel<<<dim3(B, C / kCvC), 256, 0, st>>>(gd, a, B, T, C, part);
+  dwconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(gd, a, B, T, C, part);
   OB_LAUNCH_CHECK("dwconv_bwd_weight_kernel");
-  dwconv_bwd_weight_finalize_kernel<<<32 * C / 64, 64 * kFinGroups, 0, st>>>(part, B, C, ks, gw, gbias);
+  dwconv_bwd_weight_finalize_kernel<<<32 * C / 64, 64 * kFinGroups, 0, st>>>(part, B * conv_tblocks(T), C, ks, gw, gbias);
   OB_LAUNCH_CHECK("dwconv_bwd_weight_finalize_kernel");
   return OB_OK;
 }
