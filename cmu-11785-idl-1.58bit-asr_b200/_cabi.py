@@ -58,6 +58,9 @@ SIGNATURES = {
     "ob_bn_swish_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _p]),
     "ob_bn_swish_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "ob_glu_dwconv_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ob_add_bias2": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p]),
+    "ob_add_colsum2_workspace_bytes": (_sz, [_i64, _i]),
+    "ob_add_colsum2": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p]),
     "ob_debug_set": (_i, [_i, _i]),
 }
 

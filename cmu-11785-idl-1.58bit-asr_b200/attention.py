@@ -118,8 +118,12 @@ class _RelAttentionFn(torch.autograd.Function):
         B, T, W = q.shape
         H = n_heads
         q, k, v, pos = q.contiguous(), k.contiguous(), v.contiguous(), pos.contiguous()
-        qu = q + u.reshape(1, 1, W)
-        qw = q + w.reshape(1, 1, W)
+        if W % 64 == 0:
+            qu, qw = torch.empty_like(q), torch.empty_like(q)
+            check(lib.ob_add_bias2(q.data_ptr(), u.contiguous().data_ptr(), w.contiguous().data_ptr(), B * T, W, qu.data_ptr(),
+                                   qw.data_ptr(), _stream()))
+        else:
+            qu, qw = q + u.reshape(1, 1, W), q + w.reshape(1, 1, W)
         ac = bmm_nt(_heads(qu, H), _heads(k, H), out=_scores_like(B, H, T, q.device))
         bd = bmm_nt(_heads(qw, H), _heads(pos, H), out=_scores_like(B, H, T, q.device))
         y, attn_d = _softmax_fwd(ac, bd, mask, keep, inv_keep, scale, rng)
@@ -149,9 +153,16 @@ class _RelAttentionFn(torch.autograd.Function):
         g_pos_b = torch.empty_like(qw)                                                         # per utterance, then summed
         bmm_nt(d_bd.transpose(-1, -2), _heads(qw, H).transpose(-1, -2), out=_heads(g_pos_b, H))
         g_pos = g_pos_b.sum(dim=0, keepdim=True)
-        g_u = g_qu.sum(dim=(0, 1)).view(H, W // H)
-        g_w = g_qw.sum(dim=(0, 1)).view(H, W // H)
-        return g_qu + g_qw, g_k, g_v, g_pos, g_u, g_w, None, None, None, None, None, None
+        if W % 64 == 0:
+            g_q, sums = torch.empty_like(qu), torch.empty(2, W, device=g.device, dtype=torch.float32)
+            ws = torch.empty(lib.ob_add_colsum2_workspace_bytes(B * T, W), device=g.device, dtype=torch.uint8)
+            check(lib.ob_add_colsum2(g_qu.data_ptr(), g_qw.data_ptr(), B * T, W, g_q.data_ptr(), sums.data_ptr(), ws.data_ptr(),
+                                     _stream()))
+            g_u, g_w = sums[0].view(H, W // H), sums[1].view(H, W // H)
+        else:
+            g_q = g_qu + g_qw
+            g_u, g_w = g_qu.sum(dim=(0, 1)).view(H, W // H), g_qw.sum(dim=(0, 1)).view(H, W // H)
+        return g_q, g_k, g_v, g_pos, g_u, g_w, None, None, None, None, None, None
 
 
 def rel_attention_usable(q: torch.Tensor, mask, n_heads: int) -> bool:

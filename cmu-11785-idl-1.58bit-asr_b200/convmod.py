@@ -7,6 +7,8 @@ of cuDNN's depthwise convolutions plus GLU / BatchNorm / swish / transposes; the
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 
 from ._cabi import check, lib
@@ -21,8 +23,13 @@ def usable(x: torch.Tensor, channels: int, taps: int) -> bool:
             and "conv" not in DISABLED)
 
 
+@functools.lru_cache(maxsize=None)
+def _ws_bytes(B: int, T: int, C: int) -> int:
+    return lib.ob_convmod_workspace_bytes(B, T, C)
+
+
 def _workspace(B, T, C, device):
-    return torch.empty(lib.ob_convmod_workspace_bytes(B, T, C), device=device, dtype=torch.uint8)
+    return torch.empty(_ws_bytes(B, T, C), device=device, dtype=torch.uint8)
 
 
 class _GluDwBnSwishFn(torch.autograd.Function):
@@ -38,11 +45,11 @@ class _GluDwBnSwishFn(torch.autograd.Function):
         stats = torch.empty(2, C, device=a.device, dtype=a.dtype)
         ws = _workspace(B, T, C, a.device)
         st = _stream()
+        sp = stats.data_ptr()                                  # mean row, rstd row
         check(lib.ob_glu_dwconv_bn_fwd(a.data_ptr(), w.data_ptr(), None if dw_bias is None else dw_bias.data_ptr(), B, T, C, ks,
-                                       float(eps), d.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), ws.data_ptr(), st))
+                                       float(eps), d.data_ptr(), sp, sp + 4 * C, ws.data_ptr(), st))
         s = torch.empty_like(d)
-        check(lib.ob_bn_swish_fwd(d.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                  B * T, C, s.data_ptr(), st))
+        check(lib.ob_bn_swish_fwd(d.data_ptr(), sp, sp + 4 * C, gamma.data_ptr(), beta.data_ptr(), B * T, C, s.data_ptr(), st))
         ctx.save_for_backward(a, w, d, stats, gamma, beta)
         ctx.has_bias, ctx.w_shape = dw_bias is not None, dw_weight.shape
         return s
@@ -57,8 +64,9 @@ class _GluDwBnSwishFn(torch.autograd.Function):
         st = _stream()
         gd = torch.empty_like(d)
         ggb = torch.empty(2, C, device=a.device, dtype=a.dtype)              # (g_beta, g_gamma)
-        check(lib.ob_bn_swish_bwd(gs.data_ptr(), d.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), gamma.data_ptr(),
-                                  beta.data_ptr(), B * T, C, gd.data_ptr(), ggb.data_ptr(), ws.data_ptr(), st))
+        sp = stats.data_ptr()
+        check(lib.ob_bn_swish_bwd(gs.data_ptr(), d.data_ptr(), sp, sp + 4 * C, gamma.data_ptr(), beta.data_ptr(), B * T, C,
+                                  gd.data_ptr(), ggb.data_ptr(), ws.data_ptr(), st))
         ga = torch.empty_like(a)
         gw = torch.empty_like(w)
         gb = torch.empty(C, device=a.device, dtype=a.dtype) if ctx.has_bias else None

@@ -364,6 +364,44 @@ __global__ void __launch_bounds__(64 * kFinGroups) dwconv_bwd_weight_finalize_ke
   }
 }
 
+// ---- glue of the attention core (conformer.py:113-117): q + pos_bias_u and q + pos_bias_v in one pass, and in the
+// backward g_q = g_qu + g_qw together with the column sums that are the gradients of the two biases ----
+__global__ void __launch_bounds__(256) add_bias2_kernel(const float* __restrict__ q, const float* __restrict__ u,
+                                                        const float* __restrict__ w, int64_t n4, int W4, float* __restrict__ qu,
+                                                        float* __restrict__ qw) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const int c4 = static_cast<int>(i % W4);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(q) + i);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(u) + c4), b = __ldg(reinterpret_cast<const float4*>(w) + c4);
+    reinterpret_cast<float4*>(qu)[i] = make_float4(x.x + a.x, x.y + a.y, x.z + a.z, x.w + a.w);
+    reinterpret_cast<float4*>(qw)[i] = make_float4(x.x + b.x, x.y + b.y, x.z + b.z, x.w + b.w);
+  }
+}
+
+// g = ga + gb; part[blk][0][c] = sum of ga, part[blk][1][c] = sum of gb over the block's rows
+__global__ void __launch_bounds__(256) add_colsum2_kernel(const float* __restrict__ ga, const float* __restrict__ gb, int64_t M,
+                                                          int W, float* __restrict__ g, float* __restrict__ part) {
+  __shared__ float red[2][4][kCvC];
+  const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int cc = blockIdx.y * kCvC + c;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kBnRows;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+  for (int r = rg; r < kBnRows; r += 4) {
+    const int64_t row = r0 + r;
+    if (row < M) {
+      const float a = __ldg(ga + row * W + cc), b = __ldg(gb + row * W + cc);
+      g[row * W + cc] = a + b;
+      s1 += a;
+      s2 += b;
+    }
+  }
+  red[0][rg][c] = s1;
+  red[1][rg][c] = s2;
+  __syncthreads();
+  if (rg < 2) part[(static_cast<int64_t>(blockIdx.x) * 2 + rg) * W + cc] = red[rg][0][c] + red[rg][1][c] + red[rg][2][c] + red[rg][3][c];
+}
+
 static int conv_tblocks(int T) { return (T + kCvT - 1) / kCvT; }
 static int ew_blocks(int64_t n4) {
   const int64_t want = (n4 + 255) / 256;
@@ -445,5 +483,34 @@ extern "C" int ob_glu_dwconv_bwd(const float* gd, const float* a, const float* w
   OB_LAUNCH_CHECK("dwconv_bwd_weight_kernel");
   dwconv_bwd_weight_finalize_kernel<<<32 * C / 64, 64 * kFinGroups, 0, st>>>(part, B * conv_tblocks(T), C, ks, gw, gbias);
   OB_LAUNCH_CHECK("dwconv_bwd_weight_finalize_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_add_bias2(const float* q, const float* u, const float* w, int64_t M, int W, float* qu, float* qw,
+                            ob_stream_t stream) {
+  OB_REQUIRE(q && u && w && qu && qw, "ob_add_bias2: null pointer");
+  OB_REQUIRE(M > 0 && W > 0 && W % 4 == 0, "ob_add_bias2: need M > 0 and W a positive multiple of 4 (W=%d)", W);
+  const int64_t n4 = M * W / 4;
+  add_bias2_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, u, w, n4, W / 4, qu, qw);
+  OB_LAUNCH_CHECK("add_bias2_kernel");
+  return OB_OK;
+}
+
+extern "C" size_t ob_add_colsum2_workspace_bytes(int64_t M, int W) {
+  if (M <= 0 || W <= 0) return 0;
+  return static_cast<size_t>((M + kBnRows - 1) / kBnRows) * 2 * W * sizeof(float) + 256;
+}
+
+extern "C" int ob_add_colsum2(const float* ga, const float* gb, int64_t M, int W, float* g, float* sums, void* ws,
+                              ob_stream_t stream) {
+  OB_REQUIRE(ga && gb && g && sums && ws, "ob_add_colsum2: null pointer");
+  OB_REQUIRE(M > 0 && W > 0 && W % 64 == 0, "ob_add_colsum2: need M > 0 and W a positive multiple of 64 (W=%d)", W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* part = static_cast<float*>(ws);
+  const int rblocks = static_cast<int>((M + kBnRows - 1) / kBnRows);
+  add_colsum2_kernel<<<dim3(rblocks, W / kCvC), 256, 0, st>>>(ga, gb, M, W, g, part);
+  OB_LAUNCH_CHECK("add_colsum2_kernel");
+  bn_bwd_finalize_kernel<<<2 * W / 64, 64 * kFinGroups, 0, st>>>(part, rblocks, W, sums);   // sums[0] = colsum(ga), [1] = colsum(gb)
+  OB_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   return OB_OK;
 }

@@ -25,8 +25,9 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
 // debug / tuning knobs (ob_debug_set)
 // ---------------------------------------------------------------------------------------------
 enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5,
-                kDbgF32SplitMode = 6 };
+                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7 };
 void f32_gemm_debug(int split_mode);   // ob_gemm_f32.cu
+void f32_gemm_debug_epilogue(int mode);
 static int g_dbg_kernel_flags = 0;   // bit0 skip TMA stores, bit1 skip epilogue math/STS, bit2 skip expansion (timing experiments)
 static int g_dbg_swap_lbo_sbo = 0;
 static int g_dbg_force_block_n = 0;
@@ -73,6 +74,11 @@ static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+    cudaFree(nullptr);      // thread without a current context (no runtime call yet): bind the primary context, retry
+    r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with %d (inner=%llu outer=%llu pitch=%llu box=%ux%u)", (int)r,
               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_bytes, box_inner, box_outer);
@@ -728,6 +734,7 @@ extern "C" int ob_debug_set(int key, int value) {
     case kDbgMaxCtas: g_dbg_max_ctas = value; return OB_OK;
     case kDbgKernelFlags: g_dbg_kernel_flags = value; return OB_OK;
     case kDbgF32SplitMode: f32_gemm_debug(value); return OB_OK;
+    case kDbgF32Epilogue: f32_gemm_debug_epilogue(value); return OB_OK;
     default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;
   }
 }

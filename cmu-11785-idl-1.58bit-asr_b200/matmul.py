@@ -15,38 +15,48 @@ from ._cabi import check, lib
 from .quant import _stream
 
 
-def _as4(t: torch.Tensor) -> torch.Tensor:
-    while t.dim() < 4:
-        t = t.unsqueeze(0)
-    if t.dim() != 4:
-        raise ValueError(f"expected at most 4 dimensions, got {tuple(t.shape)}")
-    return t
+def _describe(shape, stride):
+    """Pure shape/stride arithmetic (no tensors touched): a ``[.., rows, K]`` view with up to two leading batch axes ->
+    ``(nb0, nb1, rows, K, mn_major, ld, bs0, bs1)`` as ``ob_gemm_f32`` wants them, or None if the view has no contiguous
+    matrix axis / an unaligned pitch (the caller then packs a copy).  K-major: the contraction axis is contiguous."""
+    nd = len(shape)
+    if nd < 2 or nd > 4:
+        raise ValueError(f"bmm_nt: expected 2 to 4 dimensions, got shape {tuple(shape)}")
+    rows, K = shape[-2], shape[-1]
+    sr, sk = stride[-2], stride[-1]
+    nb1, bs1 = (shape[-3], stride[-3]) if nd >= 3 else (1, 0)
+    nb0, bs0 = (shape[-4], stride[-4]) if nd == 4 else (1, 0)
+    if nb1 == 1:
+        bs1 = 0
+    if nb0 == 1:
+        bs0 = 0
+    if (sk == 1 or K == 1) and (rows == 1 or sr >= K):
+        mn, ld = 0, (sr if rows > 1 else max((K + 3) // 4 * 4, 4))
+    elif (sr == 1 or rows == 1) and (K == 1 or sk >= rows):
+        mn, ld = 1, (sk if K > 1 else max((rows + 3) // 4 * 4, 4))
+    else:
+        return None
+    if ld % 4 or bs0 % 4 or bs1 % 4 or bs0 < 0 or bs1 < 0:
+        return None
+    return nb0, nb1, rows, K, mn, ld, bs0, bs1
 
 
-def _operand(t: torch.Tensor, what: str):
-    """(tensor, mn_major, ld, bs0, bs1) of a [nb0, nb1, rows, K] view; copies only if no axis is contiguous."""
+def _input(t: torch.Tensor, what: str):
+    """(tensor kept alive, data_ptr, descriptor) of an input operand; packs one copy (rows padded to 4 floats) only when the
+    view cannot be described or is not 16-byte aligned."""
     if t.dtype != torch.float32 or not t.is_cuda:
         raise RuntimeError(f"bmm_nt: {what} must be a CUDA float32 tensor (got {t.dtype} on {t.device}); there is no fallback")
-    for attempt in range(2):
-        s = t.stride()
-        rows, K = t.shape[2], t.shape[3]
-        if (s[3] == 1 or K == 1) and (rows == 1 or s[2] >= K):
-            mn, ld = 0, (s[2] if rows > 1 else max(K, 4))
-        elif (s[2] == 1 or rows == 1) and (K == 1 or s[3] >= rows):
-            mn, ld = 1, (s[3] if K > 1 else max(rows, 4))
-        else:
-            mn, ld = -1, 0
-        bs0 = s[0] if t.shape[0] > 1 else 0
-        bs1 = s[1] if t.shape[1] > 1 else 0
-        ok = mn >= 0 and ld % 4 == 0 and bs0 % 4 == 0 and bs1 % 4 == 0 and t.data_ptr() % 16 == 0 and bs0 >= 0 and bs1 >= 0
-        if ok:
-            return t, mn, ld, bs0, bs1
-        if attempt == 0:                                   # unaligned / fully strided view: one packed copy, rows padded to 4
-            rows_, K_ = t.shape[2], t.shape[3]
-            buf = torch.empty(t.shape[0], t.shape[1], rows_, (K_ + 3) // 4 * 4, device=t.device, dtype=t.dtype)
-            buf[..., :K_].copy_(t)
-            t = buf[..., :K_]
-    raise RuntimeError(f"bmm_nt: cannot describe {what} with strides {t.stride()}")
+    d = _describe(t.shape, t.stride())
+    ptr = t.data_ptr()
+    if d is None or ptr % 16:
+        K = t.shape[-1]
+        buf = torch.empty(*t.shape[:-1], (K + 3) // 4 * 4, device=t.device, dtype=t.dtype)
+        packed = buf[..., :K]
+        packed.copy_(t)
+        t, ptr, d = packed, packed.data_ptr(), _describe(packed.shape, packed.stride())
+        if d is None:
+            raise RuntimeError(f"bmm_nt: cannot describe {what} of shape {tuple(t.shape)}")
+    return t, ptr, d
 
 
 def bmm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None, bias: torch.Tensor = None, scale: float = 1.0,
@@ -56,41 +66,46 @@ def bmm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None, bias: tor
     a: ``[.., M, K]`` and b: ``[.., N, K]`` views with up to two leading batch axes (size-1 axes of ``b`` or ``a``
     broadcast); either of the last two axes may be the contiguous one, so ``x @ y`` is ``bmm_nt(x, y.transpose(-1, -2))``
     without a copy.  out: ``[.., M, N]`` with a contiguous last axis whose pitch is a multiple of 4 (allocated if None)."""
-    a4, b4 = _as4(a), _as4(b)
-    nb0, nb1 = max(a4.shape[0], b4.shape[0]), max(a4.shape[1], b4.shape[1])
-    M, K, N = a4.shape[2], a4.shape[3], b4.shape[2]
-    if b4.shape[3] != K:
-        raise ValueError(f"bmm_nt: contraction sizes differ ({K} vs {b4.shape[3]})")
-    for t, name in ((a4, "a"), (b4, "b")):
-        if t.shape[0] not in (1, nb0) or t.shape[1] not in (1, nb1):
-            raise ValueError(f"bmm_nt: batch axes of {name} {tuple(t.shape[:2])} do not broadcast to {(nb0, nb1)}")
-    a4, a_mn, lda, a_bs0, a_bs1 = _operand(a4, "a")
-    b4, b_mn, ldb, b_bs0, b_bs1 = _operand(b4, "b")
+    a, a_ptr, (a_nb0, a_nb1, M, K, a_mn, lda, a_bs0, a_bs1) = _input(a, "a")
+    b, b_ptr, (b_nb0, b_nb1, N, Kb, b_mn, ldb, b_bs0, b_bs1) = _input(b, "b")
+    if Kb != K:
+        raise ValueError(f"bmm_nt: contraction sizes differ ({K} vs {Kb})")
+    nb0, nb1 = max(a_nb0, b_nb0), max(a_nb1, b_nb1)
+    if a_nb0 not in (1, nb0) or a_nb1 not in (1, nb1) or b_nb0 not in (1, nb0) or b_nb1 not in (1, nb1):
+        raise ValueError(f"bmm_nt: batch axes {(a_nb0, a_nb1)} and {(b_nb0, b_nb1)} do not broadcast")
     if out is None:
         if accumulate:
             raise ValueError("bmm_nt: accumulate needs an output tensor")
         pitch = (N + 3) // 4 * 4
-        out4 = torch.empty(nb0, nb1, M, pitch, device=a.device, dtype=torch.float32)[..., :N]
-        lead = len(torch.broadcast_shapes(a.shape[:-2], b.shape[:-2]))
-        result = out4 if lead == 2 else (out4[0] if lead == 1 else out4[0, 0])
+        lead = max(a.dim(), b.dim()) - 2
+        full = torch.empty((nb0, nb1, M, pitch)[2 - lead:], device=a.device, dtype=torch.float32)
+        result = full if pitch == N else full[..., :N]
+        d_ptr, ldd, d_bs1, d_bs0 = full.data_ptr(), pitch, M * pitch, nb1 * M * pitch
     else:
-        out4 = _as4(out)
+        if out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError("bmm_nt: out must be a CUDA float32 tensor")
+        d = _describe(out.shape, out.stride())
+        d_ptr = out.data_ptr()
+        if d is None or d[4] != 0 or d_ptr % 16:
+            raise ValueError("bmm_nt: out needs a contiguous last axis, a row pitch that is a multiple of 4 and 16-byte alignment")
+        o_nb0, o_nb1, o_m, o_n, _, ldd, d_bs0, d_bs1 = d
+        if (o_nb0, o_nb1, o_m, o_n) != (nb0, nb1, M, N):
+            raise ValueError(f"bmm_nt: out must have shape {(nb0, nb1, M, N)} (leading 1s optional), got {tuple(out.shape)}")
         result = out
-        if out4.shape != (nb0, nb1, M, N) or out4.dtype != torch.float32 or not out4.is_cuda:
-            raise ValueError(f"bmm_nt: out must be float32 CUDA of shape {(nb0, nb1, M, N)}, got {tuple(out4.shape)}")
-    so = out4.stride()
-    if (so[3] != 1 and N > 1) or (M > 1 and so[2] % 4 != 0) or out4.data_ptr() % 16 != 0:
-        raise ValueError("bmm_nt: out needs a contiguous last axis, a row pitch that is a multiple of 4 and 16-byte alignment")
-    ldd = so[2] if M > 1 else (N + 3) // 4 * 4
-    d_bs0 = so[0] if nb0 > 1 else 0
-    d_bs1 = so[1] if nb1 > 1 else 0
-    if bias is not None and (bias.dtype != torch.float32 or not bias.is_cuda or bias.numel() != N or not bias.is_contiguous()):
-        raise ValueError("bmm_nt: bias must be a contiguous float32 CUDA vector of N elements")
+    if nb0 == 1:
+        d_bs0 = 0
+    if nb1 == 1:
+        d_bs1 = 0
+    bias_ptr = None
+    if bias is not None:
+        if bias.dtype != torch.float32 or not bias.is_cuda or bias.numel() != N or not bias.is_contiguous():
+            raise ValueError("bmm_nt: bias must be a contiguous float32 CUDA vector of N elements")
+        bias_ptr = bias.data_ptr()
     ws_bytes = lib.ob_gemm_f32_workspace_bytes(M, N, K, nb0, nb1) if K >= 2048 and nb0 * nb1 == 1 else 0
     ws = torch.empty(ws_bytes, device=a.device, dtype=torch.uint8) if ws_bytes else None      # split-K partial products
-    check(lib.ob_gemm_f32(a4.data_ptr(), a_mn, lda, a_bs0, a_bs1, b4.data_ptr(), b_mn, ldb, b_bs0, b_bs1, out4.data_ptr(), ldd,
-                          d_bs0, d_bs1, None if bias is None else bias.data_ptr(), float(scale), int(accumulate), M, N, K, nb0,
-                          nb1, passes, None if ws is None else ws.data_ptr(), ws_bytes, _stream()))
+    check(lib.ob_gemm_f32(a_ptr, a_mn, lda, a_bs0, a_bs1, b_ptr, b_mn, ldb, b_bs0, b_bs1, d_ptr, ldd, d_bs0, d_bs1, bias_ptr,
+                          scale, accumulate, M, N, K, nb0, nb1, passes, None if ws is None else ws.data_ptr(), ws_bytes,
+                          _stream()))
     return result
 
 

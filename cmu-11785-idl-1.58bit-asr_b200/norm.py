@@ -6,12 +6,19 @@ kernel takes ~130 us on a [25536, 256] input; this one is bandwidth-bound).
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 
 from ._cabi import check, lib
 from .quant import _stream
 
 SUPPORTED_WIDTHS = (128, 256, 512, 1024)
+
+
+@functools.lru_cache(maxsize=None)
+def _bwd_ws_bytes(C: int) -> int:
+    return lib.ob_layernorm_bwd_workspace_bytes(C)
 
 
 class _LayerNormFn(torch.autograd.Function):
@@ -24,8 +31,9 @@ class _LayerNormFn(torch.autograd.Function):
         M = x2.shape[0]
         y = torch.empty_like(x2)
         stats = torch.empty((2, M), device=x.device, dtype=torch.float32)
-        check(lib.ob_layernorm_fwd(x2.data_ptr(), weight.data_ptr(), bias.data_ptr(), eps, M, C, y.data_ptr(),
-                                   stats[0].data_ptr(), stats[1].data_ptr(), _stream()))
+        sp = stats.data_ptr()                                  # mean row, rstd row (pointer arithmetic: no view objects)
+        check(lib.ob_layernorm_fwd(x2.data_ptr(), weight.data_ptr(), bias.data_ptr(), eps, M, C, y.data_ptr(), sp, sp + 4 * M,
+                                   _stream()))
         ctx.save_for_backward(x2, stats, weight)
         ctx.x_shape = x.shape
         return y.view(x.shape)
@@ -39,10 +47,10 @@ class _LayerNormFn(torch.autograd.Function):
             g2 = g2.contiguous()
         dx = torch.empty_like(x2)
         dparams = torch.empty((2, C), device=x2.device, dtype=torch.float32)
-        ws = torch.empty(lib.ob_layernorm_bwd_workspace_bytes(C), device=x2.device, dtype=torch.uint8)
-        check(lib.ob_layernorm_bwd(g2.data_ptr(), x2.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
-                                   weight.data_ptr(), M, C, dx.data_ptr(), dparams[0].data_ptr(), dparams[1].data_ptr(),
-                                   ws.data_ptr(), _stream()))
+        ws = torch.empty(_bwd_ws_bytes(C), device=x2.device, dtype=torch.uint8)
+        sp, dp = stats.data_ptr(), dparams.data_ptr()
+        check(lib.ob_layernorm_bwd(g2.data_ptr(), x2.data_ptr(), sp, sp + 4 * M, weight.data_ptr(), M, C, dx.data_ptr(), dp,
+                                   dp + 4 * C, ws.data_ptr(), _stream()))
         return dx.view(ctx.x_shape), dparams[0], dparams[1], None
 
 

@@ -16,6 +16,7 @@ Everything executes in libonebit.so; tensors on the CPU are rejected - there is 
 """
 from __future__ import annotations
 
+import functools
 import math
 import sys
 
@@ -169,6 +170,16 @@ class _QuantLinearFn(torch.autograd.Function):
         return gx, gw, ga, gb, None, None, None
 
 
+@functools.lru_cache(maxsize=None)
+def _colsum_blocks(M: int) -> int:
+    return lib.ob_bwd_colsum_blocks(M)
+
+
+@functools.lru_cache(maxsize=None)
+def _dw_ws_bytes(M: int, N: int, K: int) -> int:
+    return lib.ob_bwd_dw_workspace_bytes(M, N, K)
+
+
 def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w, need_b):
     """Shared backward of the quantised linear: prep (bf16 casts + column sums), grad_x GEMM, grad_W GEMM + fused
     STE / alpha / bias reductions.  Returns (grad_x [M,K] | None, grad_W | None, grad_alpha | None, grad_bias | None)."""
@@ -180,7 +191,7 @@ def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w
     dev, st = g2.device, _stream()
     dys = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
     qb = torch.empty((M, K), device=dev, dtype=torch.bfloat16) if need_w else None
-    colsum = torch.empty((lib.ob_bwd_colsum_blocks(M), N), device=dev, dtype=torch.float32) if need_b else None
+    colsum = torch.empty((_colsum_blocks(M), N), device=dev, dtype=torch.float32) if need_b else None
     check(lib.ob_bwd_prep(g2.data_ptr(), _tag(g2), s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(),
                           None if qb is None else qb.data_ptr(), None if colsum is None else colsum.data_ptr(), st))
     gx = gw = ga = gb = None
@@ -192,7 +203,7 @@ def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w
         gw = torch.empty((N, K), device=dev, dtype=torch.float32)
         ga = torch.empty((), device=dev, dtype=torch.float32)
         gb = torch.empty((N,), device=dev, dtype=torch.float32) if need_b else None
-        nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
+        nbytes = _dw_ws_bytes(M, N, K)
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         check(lib.ob_bwd_dw(dys.data_ptr(), qb.data_ptr(), None if colsum is None else colsum.data_ptr(),
                             weight.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW, bitwidth, M, N, K,

@@ -169,6 +169,16 @@ int ob_relattn_softmax_bwd(const float* gd, const float* y, const uint8_t* keep,
                            uint64_t offset, uint32_t drop_threshold, float scale, int B, int H, int T, int ld,
                            float* d_ac, float* d_bd, ob_stream_t stream);
 
+/* Glue of the attention core (conformer.py:113-117): qu = q + u and qw = q + w in one pass over q [M, W] (u, w: [W], the
+ * flattened pos_bias_u / pos_bias_v), and for the backward g = ga + gb with sums[0] = column sums of ga (gradient of u),
+ * sums[1] = column sums of gb (gradient of w); fixed-order reduction, ws >= ob_add_colsum2_workspace_bytes(M, W).
+ * W a multiple of 4 (ob_add_bias2) / of 64 (ob_add_colsum2). */
+int ob_add_bias2(const float* q, const float* u, const float* w, int64_t M, int W, float* qu, float* qw,
+                 ob_stream_t stream);
+size_t ob_add_colsum2_workspace_bytes(int64_t M, int W);
+int ob_add_colsum2(const float* ga, const float* gb, int64_t M, int W, float* g, float* sums, void* ws,
+                   ob_stream_t stream);
+
 /* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
  * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded
  * with -1), out_lens [B].  ws: at least ob_ctc_decode_workspace_bytes(B, T) bytes. */

@@ -99,3 +99,25 @@ def test_swaps_into_unmodified_reference_conformer():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_gemm_operand_descriptors():
+    """Shape/stride -> ob_gemm_f32 operand description (host logic of matmul.bmm_nt), on CPU tensors."""
+    import onebit_b200  # noqa: F401
+    from onebit_b200.matmul import _describe
+    proj = torch.empty(3, 399, 256)
+    heads = proj.view(3, 399, 4, 64).permute(0, 2, 1, 3)                       # [B, H, T, d] view of [B, T, H*d]
+    assert _describe(heads.shape, heads.stride()) == (3, 4, 399, 64, 0, 256, 399 * 256, 64)
+    t = heads.transpose(-1, -2)                                                # MN-major: the row axis is contiguous
+    assert _describe(t.shape, t.stride()) == (3, 4, 64, 399, 1, 256, 399 * 256, 64)
+    scores = torch.empty(3, 4, 399, 400)[..., :399]                            # padded pitch
+    assert _describe(scores.shape, scores.stride())[4:6] == (0, 400)
+    w = torch.empty(5004, 256)
+    assert _describe(w.shape, w.stride()) == (1, 1, 5004, 256, 0, 256, 0, 0)
+    assert _describe(w.t().shape, w.t().stride()) == (1, 1, 256, 5004, 1, 256, 0, 0)
+    pos = torch.empty(1, 399, 256).view(1, 399, 4, 64).permute(0, 2, 1, 3)
+    assert _describe(pos.shape, pos.stride())[6:] == (0, 64)                   # size-1 batch axis -> broadcast
+    assert _describe((77, 45), (45, 1)) is None                                # pitch not a multiple of 4: packed copy
+    assert _describe((8, 8, 8), (1, 8, 64)) is None or _describe((8, 8, 8), (1, 8, 64))[4] in (0, 1)
+    with pytest.raises(ValueError):
+        _describe((4,), (1,))

@@ -94,12 +94,16 @@ if what in ("all", "time"):
     y = torch.empty(25536, 5004, device=dev)
     w2 = R(512, 256)
     y2 = torch.empty(25536, 512, device=dev)
-    for passes in (3, 1):
-        print(f"passes={passes}")
-        print(f"  scores q.k^T  ours {timeit(lambda: bmm_nt(q, k, out=sc, passes=passes)):8.1f} us   torch {timeit(lambda: torch.matmul(q, k.transpose(-1, -2))):8.1f} us")
-        print(f"  attn.v        ours {timeit(lambda: bmm_nt(att, v.transpose(-1, -2), out=o, passes=passes)):8.1f} us   torch {timeit(lambda: torch.matmul(att, v)):8.1f} us")
-        print(f"  attn^T.do     ours {timeit(lambda: bmm_nt(att.transpose(-1, -2), v.transpose(-1, -2), out=o, passes=passes)):8.1f} us   torch {timeit(lambda: torch.matmul(att.transpose(-1, -2), v)):8.1f} us")
-        print(f"  vocab fwd     ours {timeit(lambda: bmm_nt(x, w, out=y, passes=passes)):8.1f} us   torch {timeit(lambda: torch.nn.functional.linear(x, w)):8.1f} us")
-        print(f"  vocab dx      ours {timeit(lambda: bmm_nt(y, w.t(), out=x, passes=passes)):8.1f} us   torch {timeit(lambda: torch.matmul(y, w)):8.1f} us")
-        print(f"  vocab dw      ours {timeit(lambda: bmm_nt(y.t(), x.t(), out=w, passes=passes)):8.1f} us   torch {timeit(lambda: torch.matmul(y.t(), x)):8.1f} us")
-        print(f"  pw1 fwd       ours {timeit(lambda: bmm_nt(x, w2, out=y2, passes=passes)):8.1f} us   torch {timeit(lambda: torch.nn.functional.linear(x, w2)):8.1f} us", flush=True)
+    for epi, name in ((1, "direct row stores"), (2, "TMA box stores"), (0, "auto")):
+        lib.ob_debug_set(7, epi)
+        print(f"passes=3, epilogue: {name}")
+        print(f"  scores q.k^T  ours {timeit(lambda: bmm_nt(q, k, out=sc)):8.1f} us")
+        print(f"  dO.v^T        ours {timeit(lambda: bmm_nt(v, k, out=sc)):8.1f} us")
+        print(f"  attn.v        ours {timeit(lambda: bmm_nt(att, v.transpose(-1, -2), out=o)):8.1f} us")
+        print(f"  attn^T.do     ours {timeit(lambda: bmm_nt(att.transpose(-1, -2), v.transpose(-1, -2), out=o)):8.1f} us")
+        print(f"  vocab fwd     ours {timeit(lambda: bmm_nt(x, w, out=y)):8.1f} us")
+        print(f"  vocab dx      ours {timeit(lambda: bmm_nt(y, w.t(), out=x)):8.1f} us")
+        print(f"  pw1 fwd       ours {timeit(lambda: bmm_nt(x, w2, out=y2)):8.1f} us", flush=True)
+    lib.ob_debug_set(7, 0)
+    print(f"torch: scores {timeit(lambda: torch.matmul(q, k.transpose(-1, -2))):8.1f} us, attn.v {timeit(lambda: torch.matmul(att, v)):8.1f} us, "
+          f"vocab fwd {timeit(lambda: torch.nn.functional.linear(x, w)):8.1f} us")
