@@ -61,6 +61,8 @@ SIGNATURES = {
     "ob_add_bias2": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p]),
     "ob_add_colsum2_workspace_bytes": (_sz, [_i64, _i]),
     "ob_add_colsum2": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p]),
+    "ob_residual_dropout_fwd": (_i, [_p, _p, _p, ctypes.c_float, ctypes.c_float, _u64, _u64, _u32, _i64, _i, _p, _p]),
+    "ob_residual_dropout_bwd": (_i, [_p, _p, ctypes.c_float, ctypes.c_float, _u64, _u64, _u32, _i64, _i, _p, _p]),
     "ob_debug_set": (_i, [_i, _i]),
 }
 

@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import attention, convmod, matmul
+from . import attention, convmod, matmul, residual
 from .norm import layer_norm
 from .quant import QuantizedLinear
 
@@ -52,6 +52,18 @@ def swish(t: torch.Tensor) -> torch.Tensor:
 def _frame_mask(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     """[B,T,T] attention mask -> [B,T,1] validity of each query frame (conformer.py:42-44, 134-137)."""
     return None if mask is None else mask[:, :, 0].unsqueeze(-1)
+
+
+def _module_tail(x, y, mask, scale: float, dropout: nn.Dropout, training: bool):
+    """``x + scale * dropout(y) * frame_validity`` - the tail of every encoder module (conformer.py:41-45, 133-138, 163-167);
+    one B200 kernel each way when the tensors qualify, the reference's op sequence otherwise."""
+    if residual.usable(x):
+        return residual.residual_dropout(x, y, _frame_mask(mask), scale, dropout.p, training)
+    y = dropout(y)
+    keep = _frame_mask(mask)
+    if keep is not None:
+        y = y * keep
+    return x + y if scale == 1.0 else x + scale * y
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -118,11 +130,7 @@ class FeedForwardModule(nn.Module):
             out = fused(hidden, bitwidth, self.dropout.p, self.training)
         else:
             out = self.lin2(self.dropout(swish(hidden)), bitwidth)
-        out = self.dropout(out)
-        keep = _frame_mask(mask)
-        if keep is not None:
-            out = out * keep
-        return x + 0.5 * out
+        return _module_tail(x, out, mask, 0.5, self.dropout, self.training)
 
 
 class MHSA(nn.Module):
@@ -188,11 +196,7 @@ class MHSA(nn.Module):
         return self._finish(x, mixed, mask, bitwidth)
 
     def _finish(self, x, mixed, mask, bitwidth):
-        mixed = self.dropout(self.out_proj(mixed, bitwidth))
-        keep = _frame_mask(mask)
-        if keep is not None:
-            mixed = mixed * keep
-        return x + mixed
+        return _module_tail(x, self.out_proj(mixed, bitwidth), mask, 1.0, self.dropout, self.training)
 
 
 class ConvModule(nn.Module):
@@ -215,15 +219,12 @@ class ConvModule(nn.Module):
             # channel-last path: 1x1 convolutions as matrix products over the channel axis, B200 kernels in between
             a = matmul.linear(self.ln(x), self.pw1.weight.squeeze(-1), self.pw1.bias)
             s = convmod.glu_dwconv_bn_swish(a, self.dw.weight, self.dw.bias, self.bn.weight, self.bn.bias, self.bn.eps)
-            t = self.dropout(matmul.linear(s, self.pw2.weight.squeeze(-1), self.pw2.bias))
+            t = matmul.linear(s, self.pw2.weight.squeeze(-1), self.pw2.bias)
         else:
             t = self.ln(x).transpose(1, 2)                # channels first for torch's convolutions
             t = self.bn(self.dw(self.glu(self.pw1(t))))
-            t = self.dropout(self.pw2(swish(t))).transpose(1, 2)
-        keep = _frame_mask(mask)
-        if keep is not None:
-            t = t * keep
-        return x + t
+            t = self.pw2(swish(t)).transpose(1, 2)
+        return _module_tail(x, t, mask, 1.0, self.dropout, self.training)
 
 
 class Conv2dSubsampling(nn.Module):

@@ -402,6 +402,33 @@ __global__ void __launch_bounds__(256) add_colsum2_kernel(const float* __restric
   if (rg < 2) part[(static_cast<int64_t>(blockIdx.x) * 2 + rg) * W + cc] = red[rg][0][c] + red[rg][1][c] + red[rg][2][c] + red[rg][3][c];
 }
 
+// ---- module tail (conformer.py:45, 133-138, 163-167): out = x + scale * dropout(y) * rowmask, one pass; the dropout bits
+// come from the Philox stream (8 consecutive elements = the 8 lanes of block e / 8) and are regenerated in the backward ----
+template <bool BWD>
+__global__ void __launch_bounds__(256) residual_dropout_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                               const float* __restrict__ rowmask, float scale, float inv_keep,
+                                                               DropRng rng, int64_t n8, int C8, float* __restrict__ out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float rm = rowmask != nullptr ? __ldg(rowmask + i / C8) : 1.0f;
+    const uint32_t kb = rng.threshold != 0u ? philox_keep8(static_cast<unsigned long long>(i), rng) : 0xFFu;
+    const float f = scale * rm * (rng.threshold != 0u ? inv_keep : 1.0f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(y) + 2 * i + h);
+      float4 o;
+      o.x = (kb >> (4 * h + 0)) & 1u ? v.x * f : 0.f;
+      o.y = (kb >> (4 * h + 1)) & 1u ? v.y * f : 0.f;
+      o.z = (kb >> (4 * h + 2)) & 1u ? v.z * f : 0.f;
+      o.w = (kb >> (4 * h + 3)) & 1u ? v.w * f : 0.f;
+      if (!BWD) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + h);
+        o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+      }
+      reinterpret_cast<float4*>(out)[2 * i + h] = o;
+    }
+  }
+}
+
 static int conv_tblocks(int T) { return (T + kCvT - 1) / kCvT; }
 static int ew_blocks(int64_t n4) {
   const int64_t want = (n4 + 255) / 256;
@@ -512,5 +539,33 @@ extern "C" int ob_add_colsum2(const float* ga, const float* gb, int64_t M, int W
   OB_LAUNCH_CHECK("add_colsum2_kernel");
   bn_bwd_finalize_kernel<<<2 * W / 64, 64 * kFinGroups, 0, st>>>(part, rblocks, W, sums);   // sums[0] = colsum(ga), [1] = colsum(gb)
   OB_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_residual_dropout_fwd(const float* x, const float* y, const float* rowmask, float scale, float inv_keep,
+                                       uint64_t seed, uint64_t offset, uint32_t drop_threshold, int64_t M, int C, float* out,
+                                       ob_stream_t stream) {
+  OB_REQUIRE(x && y && out, "ob_residual_dropout_fwd: null pointer");
+  OB_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "ob_residual_dropout_fwd: need M > 0 and C a positive multiple of 8 (C=%d)", C);
+  OB_REQUIRE(drop_threshold < 65536u, "ob_residual_dropout_fwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
+  const DropRng rng = {seed, offset, drop_threshold};
+  const int64_t n8 = M * C / 8;
+  residual_dropout_kernel<false><<<ew_blocks(n8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rowmask, scale, inv_keep, rng,
+                                                                                                n8, C / 8, out);
+  OB_LAUNCH_CHECK("residual_dropout_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_residual_dropout_bwd(const float* g, const float* rowmask, float scale, float inv_keep, uint64_t seed,
+                                       uint64_t offset, uint32_t drop_threshold, int64_t M, int C, float* gy,
+                                       ob_stream_t stream) {
+  OB_REQUIRE(g && gy, "ob_residual_dropout_bwd: null pointer");
+  OB_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "ob_residual_dropout_bwd: need M > 0 and C a positive multiple of 8 (C=%d)", C);
+  OB_REQUIRE(drop_threshold < 65536u, "ob_residual_dropout_bwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
+  const DropRng rng = {seed, offset, drop_threshold};
+  const int64_t n8 = M * C / 8;
+  residual_dropout_kernel<true><<<ew_blocks(n8), 256, 0, static_cast<cudaStream_t>(stream)>>>(nullptr, g, rowmask, scale, inv_keep,
+                                                                                               rng, n8, C / 8, gy);
+  OB_LAUNCH_CHECK("residual_dropout_kernel");
   return OB_OK;
 }

@@ -179,6 +179,16 @@ size_t ob_add_colsum2_workspace_bytes(int64_t M, int W);
 int ob_add_colsum2(const float* ga, const float* gb, int64_t M, int W, float* g, float* sums, void* ws,
                    ob_stream_t stream);
 
+/* Tail of every encoder module (conformer.py:45, 133-138, 163-167): out = x + scale * dropout(y) * rowmask in one pass
+ * ([M, C] fp32, rowmask [M] of 0/1 or NULL, C a multiple of 8).  Dropout as in ob_swish_drop_quant (drop_threshold = 0: none);
+ * element e is 16-bit lane e % 8 of the Philox block with counter (e / 8, offset).  Backward: g_y = scale * dropmask *
+ * rowmask * g (the gradient w.r.t. x is g itself). */
+int ob_residual_dropout_fwd(const float* x, const float* y, const float* rowmask, float scale, float inv_keep,
+                            uint64_t seed, uint64_t offset, uint32_t drop_threshold, int64_t M, int C, float* out,
+                            ob_stream_t stream);
+int ob_residual_dropout_bwd(const float* g, const float* rowmask, float scale, float inv_keep, uint64_t seed,
+                            uint64_t offset, uint32_t drop_threshold, int64_t M, int C, float* gy, ob_stream_t stream);
+
 /* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
  * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded
  * with -1), out_lens [B].  ws: at least ob_ctc_decode_workspace_bytes(B, T) bytes. */

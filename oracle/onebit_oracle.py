@@ -309,6 +309,13 @@ def dropout_keep_flat(n: int, seed: int, offset: int, threshold: int) -> np.ndar
     return lanes[(f & ~np.uint64(32)).astype(np.int64), pick] >= threshold
 
 
+def dropout_keep_groups8(n: int, seed: int, offset: int, threshold: int) -> np.ndarray:
+    """Keep mask of the module-tail kernel (ob_residual_dropout_fwd): element e is lane e % 8 of the block with counter
+    (e // 8, offset)."""
+    assert n % 8 == 0 and 0 <= threshold < 65536
+    return (_philox_lanes16(np.arange(n // 8, dtype=np.uint64), offset, seed) >= threshold).reshape(n)
+
+
 def dropout_keep_relattn(B: int, H: int, T: int, seed: int, offset: int, threshold: int) -> np.ndarray:
     """Keep mask [B,H,T,T] of the fused attention chain: column j = lane + 32 u of row r = (b*H + h)*T + i is 16-bit lane
     u % 8 of the block with counter ((r * 32 + lane) * 8 + u // 8, offset)."""

@@ -426,6 +426,37 @@ def test_rel_attention_rng_path_equals_explicit_mask(ob, B, H, T):
     assert 0.70 < keep.float().mean().item() < 0.80
 
 
+@pytest.mark.parametrize("M,C,with_mask", [(37, 256, True), (1000, 64, False), (5, 8, True)])
+def test_residual_dropout_tail(ob, M, C, with_mask):
+    """x + scale * dropout(y) * rowmask: the in-kernel Philox mask equals the oracle's, forward and backward."""
+    from onebit_b200._cabi import lib, check
+    seed, offset, thr = 77, 40, int(round(0.1 * 2 ** 16))
+    inv_keep = 65536.0 / (65536 - thr)
+    keep = torch.from_numpy(orc.dropout_keep_groups8(M * C, seed, offset, thr).reshape(M, C)).cuda().float()
+    g = torch.Generator().manual_seed(M + C)
+    x, y, gr = (torch.randn(M, C, generator=g).cuda() for _ in range(3))
+    rm = (torch.rand(M, generator=g) > 0.3).float().cuda() if with_mask else None
+    rmv = rm[:, None] if with_mask else 1.0
+    out, gy = torch.empty_like(x), torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    rp = None if rm is None else rm.data_ptr()
+    check(lib.ob_residual_dropout_fwd(x.data_ptr(), y.data_ptr(), rp, 0.5, inv_keep, seed, offset, thr, M, C, out.data_ptr(), st))
+    check(lib.ob_residual_dropout_bwd(gr.data_ptr(), rp, 0.5, inv_keep, seed, offset, thr, M, C, gy.data_ptr(), st))
+    assert torch.allclose(out, x + 0.5 * inv_keep * keep * y * rmv, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(gy, 0.5 * inv_keep * keep * gr * rmv, rtol=1e-6, atol=1e-6)
+    # no dropout: plain residual
+    check(lib.ob_residual_dropout_fwd(x.data_ptr(), y.data_ptr(), rp, 1.0, 1.0, 0, 0, 0, M, C, out.data_ptr(), st))
+    assert torch.allclose(out, x + y * rmv, rtol=1e-6, atol=1e-6)
+    # autograd wrapper
+    from onebit_b200.residual import residual_dropout
+    xa, ya = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    fm = None if rm is None else rm.bool().view(M, 1)
+    o = residual_dropout(xa, ya, fm, 0.5, 0.0, True)
+    o.backward(gr)
+    assert torch.allclose(o, x + 0.5 * y * rmv, atol=1e-6) and torch.equal(xa.grad, gr)
+    assert torch.allclose(ya.grad, 0.5 * gr * rmv, atol=1e-6)
+
+
 def test_layer_dropout_is_seeded_and_advances(ob):
     """forward_swish_dropout / rel_attention_probs draw their stream from the device generator: same seed -> same result,
     consecutive calls -> different masks, and the backward drops exactly what the forward dropped."""

@@ -33,10 +33,16 @@ dt = (time.perf_counter() - t0) / n
 print(f"B={B} T={T} share_frontend={share}: {dt * 1e3:.1f} ms/step, {B * T * 0.01 / dt:.1f} audio-s/s, loss {loss.item():.4f}, "
       f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     train_step(model, batch, opt, cfg)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=60))
+# where the copies / strided adds / reductions come from: by op and input shape
+by_shape = prof.key_averages(group_by_input_shape=True)
+rows = [e for e in by_shape if e.key in ("aten::copy_", "aten::add", "aten::add_", "aten::sum", "aten::mul", "aten::clone", "aten::contiguous")]
+rows.sort(key=lambda e: -e.device_time_total)
+for e in rows[:24]:
+    print(f"{e.device_time_total / 1e3:8.2f} ms {e.count:5d} x  {e.key:18s} {str(e.input_shapes)[:110]}")
 # device kernels only, by name
 kern = {}
 for ev in prof.events():
