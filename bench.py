@@ -60,6 +60,9 @@ def parse():
     p.add_argument("--torch-nonrouted", default="",
                    help="A/B switch: comma list of {attn,conv,linear,tail} to run on torch's own fp32 kernels instead of the "
                         "library's (sets OB_TORCH_NONROUTED before the package is imported)")
+    p.add_argument("--no-stack-passes", action="store_true",
+                   help="run the three co-training encoder passes one after the other (as train.py does) instead of side by "
+                        "side on one stacked batch - same loss and gradients (tests), 3x the launches")
     p.add_argument("--foreach-adamw", action="store_true",
                    help="use torch's default multi-tensor AdamW instead of the fused single-kernel one (same update rule)")
     p.add_argument("--tf32-nonrouted", action="store_true",
@@ -395,12 +398,12 @@ def hot_kernel_rooflines(peaks, M):
     cv_ws = torch.empty(lib.ob_convmod_workspace_bytes(Bc, Tc, K), device=dev, dtype=torch.uint8)
     fns.update({
         "glu_dwconv_bn_fwd": (lambda j: lib.ob_glu_dwconv_bn_fwd(cv_a[j % 2].data_ptr(), cv_w.data_ptr(), cv_b.data_ptr(), Bc, Tc, K, 31,
-                                                                 1e-5, cv_s.data_ptr(), cv_stats[0].data_ptr(), cv_stats[1].data_ptr(),
+                                                                 1e-5, 1, cv_s.data_ptr(), cv_stats[0].data_ptr(), cv_stats[1].data_ptr(),
                                                                  cv_ws.data_ptr(), st), 12.0 * Mc * K, 0.0),
         "bn_swish_fwd": (lambda j: lib.ob_bn_swish_fwd(cv_d[j % 2].data_ptr(), cv_stats[0].data_ptr(), cv_stats[1].data_ptr(), ln_w.data_ptr(),
-                                                       ln_b.data_ptr(), Mc, K, cv_s.data_ptr(), st), 8.0 * Mc * K, 0.0),
+                                                       ln_b.data_ptr(), Mc, K, 1, cv_s.data_ptr(), st), 8.0 * Mc * K, 0.0),
         "bn_swish_bwd": (lambda j: lib.ob_bn_swish_bwd(cv_d[1 - j % 2].data_ptr(), cv_d[j % 2].data_ptr(), cv_stats[0].data_ptr(),
-                                                       cv_stats[1].data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), Mc, K, cv_gd.data_ptr(),
+                                                       cv_stats[1].data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), Mc, K, 1, cv_gd.data_ptr(),
                                                        cv_ggb.data_ptr(), cv_ws.data_ptr(), st), 20.0 * Mc * K, 0.0),
         "glu_dwconv_bwd": (lambda j: lib.ob_glu_dwconv_bwd(cv_d[j % 2].data_ptr(), cv_a[j % 2].data_ptr(), cv_w.data_ptr(), Bc, Tc, K, 31,
                                                            cv_ga.data_ptr(), cv_gw.data_ptr(), cv_gb.data_ptr(), cv_ws.data_ptr(), st),
@@ -467,7 +470,7 @@ def run_train(args, world, rank):
     opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2,
                             fused=not getattr(args, "foreach_adamw", False))
     sync = GradAllReducer(model.parameters()) if world > 1 else None
-    cfg = StepConfig(share_frontend=args.share_frontend)
+    cfg = StepConfig(share_frontend=args.share_frontend, stack_passes=args.share_frontend and not args.no_stack_passes)
     batch = make_batch(B, T, 1000 + rank, device=dev)
     warm = max(args.warmup, 3)
 
@@ -536,6 +539,11 @@ def run_train(args, world, rank):
                       "optimizer": "torch.optim.AdamW(lr 5e-4, betas (0.9, 0.98), wd 1e-2" +
                                    (")" if args.foreach_adamw else ", fused=True) - the reference's update rule, single-kernel form"),
                       "share_frontend": bool(args.share_frontend),
+                      "stack_passes": bool(cfg.stack_passes),
+                      "stack_passes_note": "the teacher / student / stochastic-precision encoder passes share every weight and are "
+                                           "evaluated side by side on one stacked batch: each routed layer runs once per bitwidth "
+                                           "group, BatchNorm statistics stay per pass; same loss and gradients as three separate "
+                                           "passes (tests/test_conformer_cpu.py, tests/test_gpu_conformer.py)",
                       "share_frontend_note": "conv subsampling (no dropout, no bitwidth) evaluated once per step for the three passes: "
                                              "common-subexpression sharing inside the step, same loss and gradients "
                                              "(tests/test_conformer_cpu.py); --no-share-frontend restores the 3x evaluation",

@@ -54,9 +54,9 @@ SIGNATURES = {
     "ob_gemm_f32": (_i, [_p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, ctypes.c_float, _i,
                          _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "ob_convmod_workspace_bytes": (_sz, [_i, _i, _i]),
-    "ob_glu_dwconv_bn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, ctypes.c_float, _p, _p, _p, _p, _p]),
-    "ob_bn_swish_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _p]),
-    "ob_bn_swish_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
+    "ob_glu_dwconv_bn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, ctypes.c_float, _i, _p, _p, _p, _p, _p]),
+    "ob_bn_swish_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _p]),
+    "ob_bn_swish_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
     "ob_glu_dwconv_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ob_add_bias2": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p]),
     "ob_add_colsum2_workspace_bytes": (_sz, [_i64, _i]),

@@ -45,8 +45,46 @@ class ModelDims:
     p_drop: float = 0.1
 
 
+@dataclass(frozen=True)
+class StackedBits:
+    """Bitwidths of several passes evaluated side by side on one stacked batch (the three co-training passes of
+    train.py:83-103 share every weight and differ only in the bitwidth): the first ``utt2`` utterances of the stack go
+    through a routed layer at 2 bits, the others at 1 bit.  ``groups`` = number of stacked passes (BatchNorm statistics stay
+    per pass)."""
+    utt2: int
+    groups: int
+
+
 def swish(t: torch.Tensor) -> torch.Tensor:
     return t * torch.sigmoid(t)
+
+
+def _routed_one(layer, x, bitwidth: int, swish_dropout):
+    if swish_dropout is None:
+        return layer(x, bitwidth)
+    dropout, training = swish_dropout
+    fused = getattr(layer, "forward_swish_dropout", None)
+    if fused is not None:           # B200 layer: activation, dropout and the layer's quantiser in one kernel, then the GEMM
+        return fused(x, bitwidth, dropout.p, training)
+    return layer(dropout(swish(x)), bitwidth)
+
+
+def _routed(layer, x, bits, swish_dropout=None):
+    """``layer(x, bits)`` for an int bitwidth or a ``StackedBits``; ``swish_dropout = (nn.Dropout, training)`` puts the FFN
+    mid-section ``dropout(swish(.))`` (conformer.py:37-38) in front of the layer."""
+    if not isinstance(bits, StackedBits):
+        return _routed_one(layer, x, bits, swish_dropout)
+    utt2, total = bits.utt2, x.shape[0]
+    grouped = getattr(layer, "forward_grouped", None)
+    if grouped is not None and layer.grouped_usable(x, swish=swish_dropout is not None):
+        sd = None if swish_dropout is None else (swish_dropout[0].p, swish_dropout[1])
+        return grouped(x, utt2 * (x.numel() // (total * x.shape[-1])), sd)
+    parts = []
+    if utt2 > 0:
+        parts.append(_routed_one(layer, x[:utt2], 2, swish_dropout))
+    if utt2 < total:
+        parts.append(_routed_one(layer, x[utt2:], 1, swish_dropout))
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
 
 
 def _frame_mask(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -124,12 +162,8 @@ class FeedForwardModule(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x, bitwidth: int, mask=None):
-        hidden = self.lin1(self.ln(x), bitwidth)
-        fused = getattr(self.lin2, "forward_swish_dropout", None)
-        if fused is not None:       # B200 layer: activation, dropout and lin2's quantiser in one kernel, then the GEMM
-            out = fused(hidden, bitwidth, self.dropout.p, self.training)
-        else:
-            out = self.lin2(self.dropout(swish(hidden)), bitwidth)
+        hidden = _routed(self.lin1, self.ln(x), bitwidth)
+        out = _routed(self.lin2, hidden, bitwidth, swish_dropout=(self.dropout, self.training))
         return _module_tail(x, out, mask, 0.5, self.dropout, self.training)
 
 
@@ -179,24 +213,34 @@ class MHSA(nn.Module):
         if width != self.d_model:
             raise AssertionError(f"Expected {self.d_model}, got {width}")
         normed = self.ln(x)
+        q_flat, k_flat, v_flat = (_routed(p, normed, bitwidth) for p in (self.q_proj, self.k_proj, self.v_proj))
+        pos_flat = self._positions(pos_emb, bitwidth, batch)
         if attention.rel_attention_usable(normed, mask, self.n_heads) and pos_emb.shape[:2] == (1, frames):
             # tensor-core path: the projections are consumed in their [B, T, H*d] layout, no head transposes
-            mixed = attention.rel_attention(self.q_proj(normed, bitwidth), self.k_proj(normed, bitwidth),
-                                            self.v_proj(normed, bitwidth), self.pos_proj(pos_emb, bitwidth), self.pos_bias_u,
-                                            self.pos_bias_v, mask, self.n_heads, self.dropout.p, self.training)
+            mixed = attention.rel_attention(q_flat, k_flat, v_flat, pos_flat, self.pos_bias_u, self.pos_bias_v, mask,
+                                            self.n_heads, self.dropout.p, self.training)
             return self._finish(x, mixed, mask, bitwidth)
-        q = self._split(self.q_proj(normed, bitwidth), batch)
-        k = self._split(self.k_proj(normed, bitwidth), batch)
-        v = self._split(self.v_proj(normed, bitwidth), batch)
-        pos = self._split(self.pos_proj(pos_emb, bitwidth), 1)
+        q, k, v = self._split(q_flat, batch), self._split(k_flat, batch), self._split(v_flat, batch)
+        pos = self._split(pos_flat, pos_flat.shape[0])
         u = self.pos_bias_u.view(1, self.n_heads, 1, self.d_head)
         w = self.pos_bias_v.view(1, self.n_heads, 1, self.d_head)
         probs = self._probabilities(torch.matmul(q + u, k.transpose(-2, -1)), torch.matmul(q + w, pos.transpose(-2, -1)), mask)
         mixed = (probs @ v).transpose(1, 2).contiguous().view(batch, frames, width)
         return self._finish(x, mixed, mask, bitwidth)
 
+    def _positions(self, pos_emb, bitwidth, batch):
+        """Projected positional table: ``[1, T, W]``, or per utterance ``[batch, T, W]`` when stacked passes use two bitwidths."""
+        if not isinstance(bitwidth, StackedBits):
+            return self.pos_proj(pos_emb, bitwidth)
+        if bitwidth.utt2 >= batch:
+            return self.pos_proj(pos_emb, 2)
+        if bitwidth.utt2 <= 0:
+            return self.pos_proj(pos_emb, 1)
+        two, one = self.pos_proj(pos_emb, 2), self.pos_proj(pos_emb, 1)
+        return torch.cat([two.expand(bitwidth.utt2, -1, -1), one.expand(batch - bitwidth.utt2, -1, -1)], dim=0)
+
     def _finish(self, x, mixed, mask, bitwidth):
-        return _module_tail(x, self.out_proj(mixed, bitwidth), mask, 1.0, self.dropout, self.training)
+        return _module_tail(x, _routed(self.out_proj, mixed, bitwidth), mask, 1.0, self.dropout, self.training)
 
 
 class ConvModule(nn.Module):
@@ -213,16 +257,18 @@ class ConvModule(nn.Module):
         self.pw2 = nn.Conv1d(d_model, d_model, 1)
         self.dropout = nn.Dropout(dropout)
 
-    def forward(self, x, mask=None):
+    def forward(self, x, mask=None, groups: int = 1):
+        """``groups`` > 1: x stacks that many passes; BatchNorm uses each pass's own batch statistics."""
         taps = self.dw.kernel_size[0]
         if convmod.usable(x, x.shape[-1], taps) and self.bn.affine and self.dw.padding[0] == taps // 2:
             # channel-last path: 1x1 convolutions as matrix products over the channel axis, B200 kernels in between
             a = matmul.linear(self.ln(x), self.pw1.weight.squeeze(-1), self.pw1.bias)
-            s = convmod.glu_dwconv_bn_swish(a, self.dw.weight, self.dw.bias, self.bn.weight, self.bn.bias, self.bn.eps)
+            s = convmod.glu_dwconv_bn_swish(a, self.dw.weight, self.dw.bias, self.bn.weight, self.bn.bias, self.bn.eps, groups)
             t = matmul.linear(s, self.pw2.weight.squeeze(-1), self.pw2.bias)
         else:
             t = self.ln(x).transpose(1, 2)                # channels first for torch's convolutions
-            t = self.bn(self.dw(self.glu(self.pw1(t))))
+            t = self.dw(self.glu(self.pw1(t)))
+            t = self.bn(t) if groups == 1 else torch.cat([self.bn(c) for c in t.chunk(groups, dim=0)], dim=0)
             t = self.pw2(swish(t)).transpose(1, 2)
         return _module_tail(x, t, mask, 1.0, self.dropout, self.training)
 
@@ -259,8 +305,9 @@ class ConformerBlock(nn.Module):
         self.ln = LayerNorm(d_model)
 
     def forward(self, x, src_mask, bitwidth_linear: int, pos_emb):
+        groups = bitwidth_linear.groups if isinstance(bitwidth_linear, StackedBits) else 1
         x = self.mhsa(self.ff1(x, bitwidth_linear), src_mask, bitwidth_linear, pos_emb)
-        return self.ln(self.ff2(self.conv(x), bitwidth_linear))
+        return self.ln(self.ff2(self.conv(x, groups=groups), bitwidth_linear))
 
 
 class ConformerEncoder(nn.Module):
@@ -294,6 +341,40 @@ class ConformerEncoder(nn.Module):
         for i, block in enumerate(self.blocks):
             x = block(x, pair_mask, self._bitwidth(i, precision, sp_mask), pos_emb)
         return self.ln_out(x), valid
+
+
+    @staticmethod
+    def stack_plan(passes):
+        """Order in which ``passes`` = [(precision, sp_mask), ...] can be stacked so that the 2-bit utterances of every block are
+        a prefix of the stack: all-2-bit passes, then the (single) stochastic-precision pass, then all-1-bit passes.  Returns
+        None when the combination cannot be stacked (full precision passes, several stochastic ones)."""
+        two = [i for i, (prec, m) in enumerate(passes) if m is None and prec == 2]
+        one = [i for i, (prec, m) in enumerate(passes) if m is None and prec == 1]
+        sp = [i for i, (_, m) in enumerate(passes) if m is not None]
+        if len(two) + len(one) + len(sp) != len(passes) or len(sp) > 1 or len(passes) < 2:
+            return None
+        return two + sp + one, len(two), (passes[sp[0]][1] if sp else None)
+
+    def forward_stacked(self, feats, feat_lens, passes, frontend_out=None):
+        """Several passes over the same batch side by side (see ``StackedBits``): returns [(memory, valid), ...] in the order of
+        ``passes``, equal to ``[self(feats, feat_lens, prec, mask) for prec, mask in passes]`` up to summation order."""
+        plan = self.stack_plan(passes)
+        if plan is None:
+            return [self(feats, feat_lens, prec, m, frontend_out) for prec, m in passes]
+        order, n_two, sp_mask = plan
+        x = frontend_out if frontend_out is not None else self.frontend(feats)
+        n_pass, batch, frames = len(passes), x.size(0), x.size(1)
+        valid = torch.arange(frames, device=x.device)[None, :] < (feat_lens // 4)[:, None]
+        pair_mask = (valid[:, :, None] & valid[:, None, :]).repeat(n_pass, 1, 1)
+        x, pos_emb = self.pos_enc(x.repeat(n_pass, 1, 1))
+        for i, block in enumerate(self.blocks):
+            sp_two = sp_mask is not None and sp_mask[i] != 1
+            x = block(x, pair_mask, StackedBits((n_two + int(sp_two)) * batch, n_pass), pos_emb)
+        y = self.ln_out(x)
+        outs = [None] * n_pass
+        for slot, i in enumerate(order):
+            outs[i] = (y[slot * batch:(slot + 1) * batch], valid)
+        return outs
 
 
 class TransformerDecoder(nn.Module):
@@ -334,6 +415,11 @@ class ConformerASR(nn.Module):
         """batch: dict with ``feats [B,T,F]`` and ``feat_lens [B]`` -> (encoder output, frame validity, CTC logits)."""
         memory, valid = self.encoder(batch["feats"], batch["feat_lens"], precision, sp_mask, frontend_out)
         return memory, valid, matmul.linear(memory, self.ctc_head.weight, self.ctc_head.bias)
+
+    def forward_passes(self, batch, passes, frontend_out=None):
+        """``[self(batch, prec, mask, frontend_out) for prec, mask in passes]`` with the encoder passes stacked side by side."""
+        outs = self.encoder.forward_stacked(batch["feats"], batch["feat_lens"], passes, frontend_out)
+        return [(mem, valid, matmul.linear(mem, self.ctc_head.weight, self.ctc_head.bias)) for mem, valid in outs]
 
     def decode_logits(self, enc_out, enc_mask, tgt_inp, tgt_pad_mask):
         return self.decoder(tgt_inp, enc_out, enc_mask, tgt_pad_mask)

@@ -152,7 +152,7 @@ class _RelAttentionFn(torch.autograd.Function):
         bmm_nt(d_bd, _heads(pos, H).transpose(-1, -2), out=_heads(g_qw, H))                    # dS_bd . pos
         g_pos_b = torch.empty_like(qw)                                                         # per utterance, then summed
         bmm_nt(d_bd.transpose(-1, -2), _heads(qw, H).transpose(-1, -2), out=_heads(g_pos_b, H))
-        g_pos = g_pos_b.sum(dim=0, keepdim=True)
+        g_pos = g_pos_b.sum(dim=0, keepdim=True) if pos.shape[0] == 1 else g_pos_b        # shared table: sum over the batch
         if W % 64 == 0:
             g_q, sums = torch.empty_like(qu), torch.empty(2, W, device=g.device, dtype=torch.float32)
             ws = torch.empty(lib.ob_add_colsum2_workspace_bytes(B * T, W), device=g.device, dtype=torch.uint8)
@@ -174,7 +174,7 @@ def rel_attention_usable(q: torch.Tensor, mask, n_heads: int) -> bool:
 def rel_attention(q, k, v, pos, u, w, mask, n_heads: int, p: float = 0.0, training: bool = False, keep=None):
     """The attention core of ``MHSA.forward`` (conformer.py:113-129) without the projections.
 
-    q, k, v: ``[B, T, H*d]``; pos: ``[1, T, H*d]`` (projected positional encoding); u, w: ``[H, d]`` (``pos_bias_u``,
+    q, k, v: ``[B, T, H*d]``; pos: ``[1, T, H*d]`` (projected positional encoding) or ``[B, T, H*d]``; u, w: ``[H, d]`` (``pos_bias_u``,
     ``pos_bias_v``); mask: ``[B, T, T]`` bool.  Returns ``[B, T, H*d]``."""
     d = q.shape[2] // n_heads
     keep, inv_keep, rng = _dropout_args(q.device, p, training, keep)

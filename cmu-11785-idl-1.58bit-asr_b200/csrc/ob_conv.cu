@@ -453,47 +453,64 @@ extern "C" size_t ob_convmod_workspace_bytes(int B, int T, int C) {
   return (a > b ? a : b) + 256;
 }
 
+// `groups` > 1: the batch is a stack of `groups` independent passes (B / groups utterances each, contiguous): BatchNorm
+// statistics - and therefore the two-pass backward - are per pass; the stencil kernels do not care.
 extern "C" int ob_glu_dwconv_bn_fwd(const float* a, const float* w, const float* bias, int B, int T, int C, int ks, float eps,
-                                    float* d, float* mean, float* rstd, void* ws, ob_stream_t stream) {
+                                    int groups, float* d, float* mean, float* rstd, void* ws, ob_stream_t stream) {
   OB_REQUIRE(a && w && d && mean && rstd && ws, "ob_glu_dwconv_bn_fwd: null pointer");
   OB_CONV_SHAPE("ob_glu_dwconv_bn_fwd");
+  OB_REQUIRE(groups >= 1 && B % groups == 0, "ob_glu_dwconv_bn_fwd: B (%d) must be a multiple of groups (%d)", B, groups);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* part = static_cast<float*>(ws);
   dim3 grid(B * conv_tblocks(T), C / kCvC);
   glu_dwconv_fwd_kernel<<<grid, 256, 0, st>>>(a, w, bias, B, T, C, ks, d, part);
   OB_LAUNCH_CHECK("glu_dwconv_fwd_kernel");
-  bn_stats_finalize_kernel<<<C / 64, 64 * kFinGroups, 0, st>>>(part, B, T, C, eps, mean, rstd);
-  OB_LAUNCH_CHECK("bn_stats_finalize_kernel");
+  const int Bg = B / groups;
+  for (int g = 0; g < groups; ++g) {                     // mean, rstd: [groups][C]
+    bn_stats_finalize_kernel<<<C / 64, 64 * kFinGroups, 0, st>>>(part + static_cast<size_t>(g) * Bg * conv_tblocks(T) * 2 * C, Bg, T,
+                                                               C, eps, mean + g * C, rstd + g * C);
+    OB_LAUNCH_CHECK("bn_stats_finalize_kernel");
+  }
   return OB_OK;
 }
 
 extern "C" int ob_bn_swish_fwd(const float* d, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                               int64_t M, int C, float* s, ob_stream_t stream) {
+                               int64_t M, int C, int groups, float* s, ob_stream_t stream) {
   OB_REQUIRE(d && mean && rstd && gamma && beta && s, "ob_bn_swish_fwd: null pointer");
   OB_REQUIRE(M > 0 && C > 0 && C % 64 == 0, "ob_bn_swish_fwd: need M > 0 and C a positive multiple of 64 (C=%d)", C);
-  const int64_t n4 = M * C / 4;
-  bn_swish_fwd_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, mean, rstd, gamma, beta, n4, C / 4, s);
-  OB_LAUNCH_CHECK("bn_swish_fwd_kernel");
+  OB_REQUIRE(groups >= 1 && M % groups == 0, "ob_bn_swish_fwd: M must be a multiple of groups (%d)", groups);
+  const int64_t Mg = M / groups, n4 = Mg * C / 4;
+  for (int g = 0; g < groups; ++g) {
+    bn_swish_fwd_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(d + g * Mg * C, mean + g * C, rstd + g * C,
+                                                                                      gamma, beta, n4, C / 4, s + g * Mg * C);
+    OB_LAUNCH_CHECK("bn_swish_fwd_kernel");
+  }
   return OB_OK;
 }
 
+// g_gamma_beta: [groups][2][C], per group (sum g_y = g_beta, sum g_y * xhat = g_gamma); the parameter gradients are the
+// sums over the groups
 extern "C" int ob_bn_swish_bwd(const float* gs, const float* d, const float* mean, const float* rstd, const float* gamma,
-                               const float* beta, int64_t M, int C, float* gd, float* g_gamma_beta, void* ws,
+                               const float* beta, int64_t M, int C, int groups, float* gd, float* g_gamma_beta, void* ws,
                                ob_stream_t stream) {
   OB_REQUIRE(gs && d && mean && rstd && gamma && beta && gd && g_gamma_beta && ws, "ob_bn_swish_bwd: null pointer");
   OB_REQUIRE(M > 0 && C > 0 && C % 64 == 0, "ob_bn_swish_bwd: need M > 0 and C a positive multiple of 64 (C=%d)", C);
+  OB_REQUIRE(groups >= 1 && M % groups == 0, "ob_bn_swish_bwd: M must be a multiple of groups (%d)", groups);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* part = static_cast<float*>(ws);
-  const int rblocks = static_cast<int>((M + kBnRows - 1) / kBnRows);
-  bn_swish_bwd_reduce_kernel<<<dim3(rblocks, C / kCvC), 256, 0, st>>>(gs, d, mean, rstd, gamma, beta, M, C, part);
-  OB_LAUNCH_CHECK("bn_swish_bwd_reduce_kernel");
-  // g_gamma_beta: [2][C] = (sum g_y = g_beta, sum g_y * xhat = g_gamma)
-  bn_bwd_finalize_kernel<<<2 * C / 64, 64 * kFinGroups, 0, st>>>(part, rblocks, C, g_gamma_beta);
-  OB_LAUNCH_CHECK("bn_bwd_finalize_kernel");
-  const int64_t n4 = M * C / 4;
-  bn_swish_bwd_apply_kernel<<<ew_blocks(n4), 256, 0, st>>>(gs, d, mean, rstd, gamma, beta, g_gamma_beta,
-                                                          1.0f / static_cast<float>(M), n4, C / 4, gd);
-  OB_LAUNCH_CHECK("bn_swish_bwd_apply_kernel");
+  const int64_t Mg = M / groups, n4 = Mg * C / 4;
+  const int rblocks = static_cast<int>((Mg + kBnRows - 1) / kBnRows);
+  for (int g = 0; g < groups; ++g) {
+    const float *gs_g = gs + g * Mg * C, *d_g = d + g * Mg * C, *mean_g = mean + g * C, *rstd_g = rstd + g * C;
+    float* sums_g = g_gamma_beta + static_cast<size_t>(g) * 2 * C;
+    bn_swish_bwd_reduce_kernel<<<dim3(rblocks, C / kCvC), 256, 0, st>>>(gs_g, d_g, mean_g, rstd_g, gamma, beta, Mg, C, part);
+    OB_LAUNCH_CHECK("bn_swish_bwd_reduce_kernel");
+    bn_bwd_finalize_kernel<<<2 * C / 64, 64 * kFinGroups, 0, st>>>(part, rblocks, C, sums_g);
+    OB_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+    bn_swish_bwd_apply_kernel<<<ew_blocks(n4), 256, 0, st>>>(gs_g, d_g, mean_g, rstd_g, gamma, beta, sums_g,
+                                                            1.0f / static_cast<float>(Mg), n4, C / 4, gd + g * Mg * C);
+    OB_LAUNCH_CHECK("bn_swish_bwd_apply_kernel");
+  }
   return OB_OK;
 }
 

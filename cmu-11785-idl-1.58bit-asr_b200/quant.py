@@ -180,7 +180,7 @@ def _dw_ws_bytes(M: int, N: int, K: int) -> int:
     return lib.ob_bwd_dw_workspace_bytes(M, N, K)
 
 
-def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w, need_b):
+def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w, need_b, gx_out=None):
     """Shared backward of the quantised linear: prep (bf16 casts + column sums), grad_x GEMM, grad_W GEMM + fused
     STE / alpha / bias reductions.  Returns (grad_x [M,K] | None, grad_W | None, grad_alpha | None, grad_bias | None)."""
     M, K = q.shape
@@ -196,7 +196,7 @@ def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w
                           None if qb is None else qb.data_ptr(), None if colsum is None else colsum.data_ptr(), st))
     gx = gw = ga = gb = None
     if need_x:
-        gx = torch.empty((M, K), device=dev, dtype=gy.dtype)
+        gx = gx_out if gx_out is not None else torch.empty((M, K), device=dev, dtype=gy.dtype)
         check(lib.ob_bwd_dx(dys.data_ptr(), s.data_ptr(), packed_t.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW,
                             M, N, K, gx.data_ptr(), _tag(gx), st))
     if need_w:
@@ -276,6 +276,70 @@ class _SwishDropQuantLinearFn(torch.autograd.Function):
                                         ctx.inv_keep, *ctx.rng, h2.numel(), gh.data_ptr(), _stream()))
             gh = gh.view(ctx.h_shape)
         return gh, gw, ga, gb, None, None, None, None, None, None
+
+
+class _GroupedQuantLinearFn(torch.autograd.Function):
+    """One layer applied to a stack of passes that differ in bitwidth: token rows ``[0, rows2)`` use the 2-bit codes,
+    rows ``[rows2, M)`` the 1-bit codes (the co-training passes of train.py:83-103 evaluated side by side).  One
+    activation quantiser over all rows, one GEMM per group; the backward runs the layer backward per group and adds the
+    parameter gradients here instead of through three separate autograd accumulations.  ``pre`` = None, or
+    ``(inv_keep, rng)`` to apply swish + dropout in front of the quantiser (FFN mid-section)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, alpha, bias, rows2, pk2, pkt2, pk1, pkt1, pre):
+        K = x.shape[-1]
+        N = weight.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        st = _stream()
+        if pre is None:
+            q, s = _ActQuantCache.get(x2)
+        else:
+            q = torch.empty((M, K), device=x.device, dtype=torch.int8)
+            s = torch.empty((M,), device=x.device, dtype=torch.float32)
+            check(lib.ob_swish_drop_quant(x2.data_ptr(), None, pre[0], *pre[1], M, K, q.data_ptr(), s.data_ptr(), st))
+        y = torch.empty((M, N), device=x.device, dtype=x.dtype)
+        bias_ptr = None if bias is None else bias.data_ptr()
+        esz = y.element_size()
+        for r0, r1, pk in ((0, rows2, pk2), (rows2, M, pk1)):
+            if r1 > r0:
+                check(lib.ob_gemm_tern_i8_fwd(q.data_ptr() + r0 * K, s.data_ptr() + 4 * r0, pk.data_ptr(), alpha.data_ptr(),
+                                              OB_ALPHA_RAW, bias_ptr, r1 - r0, N, K, y.data_ptr() + r0 * N * esz, _tag(y), st))
+        ctx.save_for_backward(q, s, weight, alpha, pkt2, pkt1, *(() if pre is None else (x2,)))
+        ctx.rows2, ctx.has_bias, ctx.x_shape, ctx.pre = rows2, bias is not None, x.shape, pre
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        q, s, weight, alpha, pkt2, pkt1 = ctx.saved_tensors[:6]
+        M, K = q.shape
+        N = weight.shape[0]
+        need_x, need_w, need_a, need_b = ctx.needs_input_grad[:4]
+        g2 = gy.reshape(M, N)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        gx = torch.empty((M, K), device=g2.device, dtype=gy.dtype) if need_x else None
+        gw = ga = gb = None
+        for r0, r1, pkt, bw in ((0, ctx.rows2, pkt2, 2), (ctx.rows2, M, pkt1, 1)):
+            if r1 <= r0:
+                continue
+            _, gw_g, ga_g, gb_g = _linear_backward(g2[r0:r1], q[r0:r1], s[r0:r1], weight, alpha, pkt, bw, need_x,
+                                                   need_w or need_a, need_b and ctx.has_bias,
+                                                   gx_out=None if gx is None else gx[r0:r1])
+            gw = gw_g if gw is None or gw_g is None else gw.add_(gw_g)
+            ga = ga_g if ga is None or ga_g is None else ga.add_(ga_g)
+            gb = gb_g if gb is None or gb_g is None else gb.add_(gb_g)
+        if need_x and ctx.pre is not None:                # back through dropout and swish
+            h2 = ctx.saved_tensors[6]
+            gh = torch.empty_like(h2)
+            check(lib.ob_swish_drop_bwd(gx.data_ptr(), h2.data_ptr(), None, ctx.pre[0], *ctx.pre[1], h2.numel(), gh.data_ptr(),
+                                        _stream()))
+            gx = gh
+        if gx is not None:
+            gx = gx.view(ctx.x_shape)
+        return gx, gw, ga, gb, None, None, None, None, None, None
 
 
 class _QuantizeWeightFn(torch.autograd.Function):
@@ -384,6 +448,27 @@ class QuantizedLinear(nn.Module):
         y = _QuantLinearFn.apply(xp, w, self.alpha, b, bitwidth, packed, packed_t)
         return y[..., :N]
 
+
+    def grouped_usable(self, x: torch.Tensor, swish: bool = False) -> bool:
+        return (x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32 and x.numel() > 0
+                and self.in_features % 64 == 0 and self.out_features % 64 == 0
+                and (not swish or self.in_features in _FUSED_SWISH_K))
+
+    def forward_grouped(self, x: torch.Tensor, rows2: int, swish_dropout=None) -> torch.Tensor:
+        """``forward`` over stacked passes: the first ``rows2`` token rows at 2 bits, the others at 1 bit (see
+        ``_GroupedQuantLinearFn``).  ``swish_dropout = (p, training)`` applies the FFN mid-section in front."""
+        M = x.numel() // self.in_features
+        if not 0 <= rows2 <= M:
+            raise ValueError(f"onebit_b200: rows2 = {rows2} outside [0, {M}]")
+        pk2, pkt2 = self.packed_weight(2) if rows2 > 0 else (None, None)
+        pk1, pkt1 = self.packed_weight(1) if rows2 < M else (None, None)
+        pk2, pkt2 = (pk1, pkt1) if pk2 is None else (pk2, pkt2)      # unused group: any valid tensor
+        pk1, pkt1 = (pk2, pkt2) if pk1 is None else (pk1, pkt1)
+        pre = None
+        if swish_dropout is not None:
+            p, training = swish_dropout
+            pre = draw_dropout_stream(x.device, p) if (training and p > 0.0) else (1.0, _NO_RNG)
+        return _GroupedQuantLinearFn.apply(x, self.weight, self.alpha, self.bias, rows2, pk2, pkt2, pk1, pkt1, pre)
 
     def forward_swish_dropout(self, h: torch.Tensor, bitwidth: int, p: float = 0.0, training: bool = False,
                               keep: torch.Tensor = None) -> torch.Tensor:

@@ -34,6 +34,7 @@ class StepConfig:
     pad_id: int = 0
     blank_id: int = 3
     share_frontend: bool = False
+    stack_passes: bool = False      # evaluate the three encoder passes side by side on one stacked batch (same math)
 
 
 # ---------------------------------------------------------------------------------------------- losses (losses.py)
@@ -117,8 +118,17 @@ def cotraining_loss(model, batch: Dict[str, torch.Tensor], cfg: StepConfig, sp_m
     tok_lens_host = batch.get("token_lens_cpu", token_lens)
     shared = model.encoder.frontend(batch["feats"]) if cfg.share_frontend else None
 
+    stacked = None
+    if cfg.stack_passes and hasattr(model, "forward_passes"):
+        # the teacher, student and stochastic-precision encoder passes share every weight: one stacked batch, each layer
+        # applied once per bitwidth group (same values as three separate passes)
+        stacked = dict(zip(((2, None), (1, None), (2, "sp")), model.forward_passes(batch, [(2, None), (1, None), (2, sp_mask)],
+                                                                                    frontend_out=shared)))
+
     def one_pass(precision, mask_list=None):
-        if shared is not None:
+        if stacked is not None:
+            enc, mask, ctc = stacked[(precision, None if mask_list is None else "sp")]
+        elif shared is not None:
             enc, mask, ctc = model(batch, precision, mask_list, frontend_out=shared)
         else:
             enc, mask, ctc = model(batch, precision, mask_list)

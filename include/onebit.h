@@ -225,14 +225,18 @@ int ob_gemm_f32(const float* A, int a_mn_major, int64_t lda, int64_t a_bs0, int6
  *   ob_bn_swish_fwd:      s = swish(gamma * (d - mean) * rstd + beta)
  *   ob_bn_swish_bwd:      g_s -> g_d; g_gamma_beta [2][C] = (g_beta, g_gamma)
  *   ob_glu_dwconv_bwd:    g_d -> g_a [B,T,2C], g_w [C, ks], g_bias [C] (or NULL)
- * C a multiple of 64.  ws: at least ob_convmod_workspace_bytes(B, T, C) bytes; all reductions have a fixed order. */
+ * C a multiple of 64.  ws: at least ob_convmod_workspace_bytes(B, T, C) bytes; all reductions have a fixed order.
+ * groups > 1: the batch is a stack of `groups` independent passes (B / groups utterances each, contiguous) whose
+ * BatchNorm statistics are separate: mean, rstd are [groups][C] and g_gamma_beta is [groups][2][C] (sum over the groups
+ * = the parameter gradients). */
 size_t ob_convmod_workspace_bytes(int B, int T, int C);
 int ob_glu_dwconv_bn_fwd(const float* a, const float* w, const float* bias, int B, int T, int C, int ks, float eps,
-                         float* d, float* mean, float* rstd, void* ws, ob_stream_t stream);
+                         int groups, float* d, float* mean, float* rstd, void* ws, ob_stream_t stream);
 int ob_bn_swish_fwd(const float* d, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                    int64_t M, int C, float* s, ob_stream_t stream);
+                    int64_t M, int C, int groups, float* s, ob_stream_t stream);
 int ob_bn_swish_bwd(const float* gs, const float* d, const float* mean, const float* rstd, const float* gamma,
-                    const float* beta, int64_t M, int C, float* gd, float* g_gamma_beta, void* ws, ob_stream_t stream);
+                    const float* beta, int64_t M, int C, int groups, float* gd, float* g_gamma_beta, void* ws,
+                    ob_stream_t stream);
 int ob_glu_dwconv_bwd(const float* gd, const float* a, const float* w, int B, int T, int C, int ks, float* ga,
                       float* gw, float* gbias, void* ws, ob_stream_t stream);
 

@@ -75,6 +75,40 @@ def test_host_lengths_and_shared_frontend_do_not_change_the_loss(fx):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/onebit_asr"), reason="reference tree not mounted")
+@pytest.mark.parametrize("sp_mask", [[1, 0, 1], [0, 0, 0], [1, 1, 1]])
+def test_stacked_passes_equal_sequential_passes(fx, sp_mask):
+    """The three co-training passes evaluated side by side on one stacked batch (StepConfig.stack_passes) give the loss and
+    the gradients of three separate passes: per-bitwidth row groups in the routed layers, per-pass BatchNorm statistics."""
+    torch.set_num_threads(1)
+    batch = load_batch(fx)
+    m = build(8, 3)
+    results = []
+    for cfg in (StepConfig(share_frontend=True), StepConfig(share_frontend=True, stack_passes=True)):
+        m.zero_grad(set_to_none=True)
+        loss, parts = cotraining_loss(m, batch, cfg, sp_mask)
+        loss.backward()
+        results.append((loss.item(), {k: v.item() for k, v in parts.items()},
+                        {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    (l_seq, p_seq, g_seq), (l_stk, p_stk, g_stk) = results
+    assert abs(l_seq - l_stk) < 1e-5 * abs(l_seq)
+    for k in p_seq:
+        assert abs(p_seq[k] - p_stk[k]) < 1e-5 * max(1.0, abs(p_seq[k])), k
+    assert g_seq.keys() == g_stk.keys()
+    for n in g_seq:
+        scale = g_seq[n].abs().max().item() + 1e-12
+        assert (g_seq[n] - g_stk[n]).abs().max().item() < 2e-4 * scale + 1e-7, n
+
+
+def test_stack_plan():
+    from onebit_b200.conformer import ConformerEncoder
+    plan = ConformerEncoder.stack_plan
+    assert plan([(2, None), (1, None), (2, [1, 0])]) == ([0, 2, 1], 1, [1, 0])
+    assert plan([(1, None), (2, None)]) == ([1, 0], 1, None)
+    assert plan([(2, None), (32, None)]) is None                      # full precision passes are not stacked
+    assert plan([(2, [0]), (2, [1])]) is None                        # two stochastic passes: 2-bit rows would not be a prefix
+    assert plan([(2, None)]) is None
+
+
 def test_module_tree_matches_reference_state_dict():
     saved = {k: sys.modules.get(k) for k in ("quant", "conformer")}
     sys.path.insert(0, "/root/reference/onebit_asr")

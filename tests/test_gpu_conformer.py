@@ -84,3 +84,60 @@ def test_packed_weights_are_requantised_once_per_step(fx):
     finally:
         obq.pack_weight = orig
     assert calls["n"] == 2 * 27
+
+
+def _batch_on_device(fx):
+    b = {k: torch.from_numpy(fx[k]).cuda() for k in ("feats", "feat_lens", "tokens", "token_lens")}
+    b["feat_lens_cpu"] = torch.from_numpy(fx["feat_lens"])
+    b["token_lens_cpu"] = torch.from_numpy(fx["token_lens"])
+    return b
+
+
+def test_grouped_layer_equals_two_calls(fx):
+    """QuantizedLinear.forward_grouped (rows [0, rows2) at 2 bits, the rest at 1 bit) == the two plain calls, forward and
+    every gradient; same for the fused swish front."""
+    import onebit_b200 as ob
+    torch.manual_seed(5)
+    for K, N, swish in ((256, 1024, False), (1024, 256, True)):
+        layer = ob.QuantizedLinear(K, N).cuda()
+        with torch.no_grad():
+            layer.bias.normal_(0, 0.1)
+        x0 = torch.randn(6, 50, K, device="cuda")
+        gy = torch.randn(6, 50, N, device="cuda")
+        outs = []
+        for grouped in (True, False):
+            layer.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_(True)
+            if grouped:
+                y = layer.forward_grouped(x, 4 * 50, (0.0, True) if swish else None)
+            else:
+                f = (lambda t, bw: layer.forward_swish_dropout(t, bw, 0.0, True)) if swish else layer
+                y = torch.cat([f(x[:4], 2), f(x[4:], 1)], dim=0)
+            y.backward(gy)
+            outs.append((y.detach(), x.grad, layer.weight.grad.clone(), layer.alpha.grad.clone(), layer.bias.grad.clone()))
+        for name, a, b in zip(("y", "g_x", "g_w", "g_alpha", "g_bias"), *outs):
+            tol = 0.0 if name in ("y", "g_x") else 1e-5
+            assert (a - b).abs().max().item() <= tol * b.abs().max().item() + (0.0 if tol == 0.0 else 1e-6), (K, N, name)
+
+
+def test_stacked_passes_equal_sequential_passes_on_device(fx):
+    """StepConfig.stack_passes on the B200 kernels: same loss and gradients as three separate encoder passes (dropout 0)."""
+    import onebit_b200 as ob
+    from onebit_b200.training import StepConfig, cotraining_loss
+    batch = _batch_on_device(fx)
+    torch.manual_seed(3)
+    m = ob.ConformerASR(**CFG).cuda().train()
+    res = []
+    for cfg in (StepConfig(share_frontend=True), StepConfig(share_frontend=True, stack_passes=True)):
+        m.zero_grad(set_to_none=True)
+        loss, parts = cotraining_loss(m, batch, cfg, [1, 0, 1])
+        loss.backward()
+        res.append((loss.item(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    (l_seq, g_seq), (l_stk, g_stk) = res
+    assert abs(l_seq - l_stk) < 1e-5 * abs(l_seq)
+    assert g_seq.keys() == g_stk.keys()
+    total = sum(float(g.double().pow(2).sum()) for g in g_seq.values()) ** 0.5
+    for n in g_seq:
+        err = (g_seq[n] - g_stk[n]).abs().max().item()
+        # same bound as the layer's backward (bf16 operands): stacking changes which sums are rounded to bf16 first
+        assert err < 1e-2 * g_seq[n].abs().max().item() + 1e-6 * total, (n, err)

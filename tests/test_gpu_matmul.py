@@ -217,3 +217,24 @@ def test_conv_module_channel_last_equals_torch_path(ob):
         # the depthwise bias sits in front of BatchNorm: its gradient is a zero sum, compared on the scale of g_beta
         scale = bn_scale if n == "dw.bias" else pr.grad.abs().max().clamp_min(1e-30).item()
         assert (p.grad.cpu().double() - pr.grad).abs().max().item() < 2e-4 * scale, n
+
+
+def test_conv_module_middle_groups(ob):
+    """groups = 3: a stack of three passes, BatchNorm statistics per pass == three separate calls."""
+    from onebit_b200.convmod import glu_dwconv_bn_swish
+    B, T, C, ks = 6, 77, 64, 31
+    a0, w0, b0 = R(B, T, 2 * C), R(C, 1, ks, seed=1) * 0.3, R(C, seed=2) * 0.1
+    ga0, be0, gy = R(C, seed=3) * 0.5 + 1.0, R(C, seed=4) * 0.2, R(B, T, C, seed=5)
+    outs = []
+    for stacked in (True, False):
+        leaves = [t.clone().requires_grad_(True) for t in (a0, w0, b0, ga0, be0)]
+        a, rest = leaves[0], leaves[1:]
+        if stacked:
+            y = glu_dwconv_bn_swish(a, *rest, 1e-5, 3)
+        else:
+            y = torch.cat([glu_dwconv_bn_swish(a[2 * g:2 * g + 2], *rest, 1e-5, 1) for g in range(3)], dim=0)
+        y.backward(gy)
+        outs.append([y.detach()] + [t.grad for t in leaves])
+    for name, x, y in zip(("s", "g_a", "g_w", "g_bias", "g_gamma", "g_beta"), *outs):
+        scale = outs[1][5].abs().max() if name == "g_bias" else y.abs().max().clamp_min(1e-30)
+        assert ((x - y).abs().max() / scale).item() < 1e-5, name
