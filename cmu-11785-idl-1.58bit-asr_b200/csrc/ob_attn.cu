@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
       const int t = c0 + j;
       const int wrapped = t >= T + 1;
       const uint32_t mk = __ldg(m_r + j);
-      const uint32_t kp = __ldg(k_r + j);
+      const uint32_t kp = keep != nullptr ? __ldg(k_r + j) : 1u;  // no explicit mask: the bits come from the RNG below
       av[u] = __ldg(ac_r + j);
       bv[u] = __ldg(bd_r0 + max(t - 1 + (wrapped ? wrap_off : 0), 0));
       zbits |= static_cast<bits_t>(t == 0 || t == T + 1) << u;   // the zero column of [0 | bd]

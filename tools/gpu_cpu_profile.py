@@ -21,7 +21,7 @@ g = torch.Generator().manual_seed(1)
 batch = {"feats": torch.randn(B, T, 80, generator=g).cuda(), "feat_lens": torch.full((B,), T).cuda(),
          "tokens": torch.randint(4, 5004, (B, 64), generator=g).cuda(), "token_lens": torch.full((B,), 64).cuda(),
          "feat_lens_cpu": torch.full((B,), T), "token_lens_cpu": torch.full((B,), 64)}
-cfg = StepConfig(share_frontend=True)
+cfg = StepConfig(share_frontend=True, stack_passes=os.environ.get("OB_STACK", "1") == "1")
 for _ in range(3):
     train_step(model, batch, opt, cfg)
 torch.cuda.synchronize()
