@@ -4,8 +4,9 @@ The reference has no distributed code; the only ex
 the gradients.  Every parameter's AccumulateGrad fires exactly once per ``loss.backward()`` even though the latent
 weights are used by three passes, so a post-accumulate-grad hook per parameter is enough: gradients are copied into
 flat fp32 buckets (~25 MB, filled in reverse-autograd order) and each full bucket is all-reduced asynchronously on
-a side stream while the rest of backward runs.  ``finish()`` joins the side stream, averages and scatters the
-buckets back before ``clip_grad_norm_`` needs the global gradients (train.py:117).
+a side stream while the rest of backward runs (one multi-tensor copy per completed bucket).  ``finish()`` joins the side
+stream, averages, and makes every ``.grad`` a view of its bucket before ``clip_grad_norm_`` needs the global gradients
+(train.py:117); gradients must be reset with ``zero_grad(set_to_none=True)`` between steps (``train_step`` does).
 """
 from __future__ import annotations
 
@@ -48,7 +49,8 @@ class GradAllReducer:
             offsets.append(n)
             n += p.numel()
         flat = torch.zeros(n, dtype=torch.float32, device=plist[0].device)
-        self.buckets.append({"params": plist, "offsets": offsets, "flat": flat, "numel": n})
+        views = [flat[off:off + p.numel()] for p, off in zip(plist, offsets)]
+        self.buckets.append({"params": plist, "offsets": offsets, "flat": flat, "numel": n, "views": views})
 
     def _reset(self):
         self._pending = [len(b["params"]) for b in self.buckets]
@@ -58,11 +60,11 @@ class GradAllReducer:
     def _on_grad(self, p: torch.nn.Parameter):
         if self.world == 1:
             return
-        bi, off = self._where[p]
-        b = self.buckets[bi]
-        b["flat"][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        bi, _ = self._where[p]
         self._pending[bi] -= 1
-        if self._pending[bi] == 0:
+        if self._pending[bi] == 0:                       # the bucket is complete: one multi-tensor copy, then the all-reduce
+            b = self.buckets[bi]
+            torch._foreach_copy_(b["views"], [q.grad.reshape(-1) for q in b["params"]])
             self._launch(bi)
 
     def _launch(self, bi: int):
@@ -82,9 +84,11 @@ class GradAllReducer:
             return
         for bi, b in enumerate(self.buckets):           # parameters without a gradient this step (e.g. alpha at 32 bit)
             if not self._launched[bi]:
-                for p, off in zip(b["params"], b["offsets"]):
+                for p, v in zip(b["params"], b["views"]):
                     if p.grad is None:
-                        b["flat"][off:off + p.numel()].zero_()
+                        v.zero_()
+                    else:
+                        v.copy_(p.grad.reshape(-1))
                 self._launch(bi)
         for h in self._handles:
             h.wait()
@@ -93,12 +97,10 @@ class GradAllReducer:
         inv = 1.0 / self.world
         for b in self.buckets:
             b["flat"].mul_(inv)
-            for p, off in zip(b["params"], b["offsets"]):
-                g = b["flat"][off:off + p.numel()].view_as(p)
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
+            for p, v in zip(b["params"], b["views"]):
+                # the averaged gradient lives in the bucket: .grad becomes a view of it (no copy back).  The next backward
+                # starts from zero_grad(set_to_none=True) - as train_step does - and refills the bucket from fresh gradients.
+                p.grad = v.view_as(p)
         self._reset()
 
     def remove(self):
