@@ -217,28 +217,38 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_reduce_kernel(const float* _
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   int64_t M, int C, float* __restrict__ part) {
-  __shared__ float red[2][4][kCvC];
-  const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
-  const int cc = blockIdx.y * kCvC + c;
-  const float mu = __ldg(mean + cc), rs = __ldg(rstd + cc), ga = __ldg(gamma + cc), be = __ldg(beta + cc);
+  // a thread owns 4 channels (128-bit loads) of every 16th row of the block; fixed-order fold over the 16 row groups
+  __shared__ float4 red[2][16][16];
+  const int c4 = threadIdx.x & 15, rg = threadIdx.x >> 4;
+  const int cc = blockIdx.y * kCvC + c4 * 4;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + cc)), rs = __ldg(reinterpret_cast<const float4*>(rstd + cc));
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + cc)), be = __ldg(reinterpret_cast<const float4*>(beta + cc));
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kBnRows;
-  float s1 = 0.f, s2 = 0.f;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-  for (int r = rg; r < kBnRows; r += 4) {
+  for (int r = rg; r < kBnRows; r += 16) {
     const int64_t row = r0 + r;
     if (row < M) {
-      const float xh = (__ldg(d + row * C + cc) - mu) * rs;
-      const float gy = __ldg(gs + row * C + cc) * swish_grad(fmaf(xh, ga, be));
-      s1 += gy;
-      s2 = fmaf(gy, xh, s2);
+      const float4 x = __ldg(reinterpret_cast<const float4*>(d + row * C + cc));
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gs + row * C + cc));
+      float xh, gy;
+      xh = (x.x - mu.x) * rs.x, gy = g.x * swish_grad(fmaf(xh, ga.x, be.x)), s1.x += gy, s2.x = fmaf(gy, xh, s2.x);
+      xh = (x.y - mu.y) * rs.y, gy = g.y * swish_grad(fmaf(xh, ga.y, be.y)), s1.y += gy, s2.y = fmaf(gy, xh, s2.y);
+      xh = (x.z - mu.z) * rs.z, gy = g.z * swish_grad(fmaf(xh, ga.z, be.z)), s1.z += gy, s2.z = fmaf(gy, xh, s2.z);
+      xh = (x.w - mu.w) * rs.w, gy = g.w * swish_grad(fmaf(xh, ga.w, be.w)), s1.w += gy, s2.w = fmaf(gy, xh, s2.w);
     }
   }
-  red[0][rg][c] = s1;
-  red[1][rg][c] = s2;
+  red[0][rg][c4] = s1;
+  red[1][rg][c4] = s2;
   __syncthreads();
-  if (rg < 2) {
-    float* p = part + (static_cast<int64_t>(blockIdx.x) * 2 + rg) * C + cc;
-    *p = red[rg][0][c] + red[rg][1][c] + red[rg][2][c] + red[rg][3][c];
+  if (threadIdx.x < 32) {
+    const int which = threadIdx.x >> 4;
+    float4 acc = red[which][0][c4];
+    for (int g = 1; g < 16; ++g) {
+      const float4 v = red[which][g][c4];
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(part + (static_cast<int64_t>(blockIdx.x) * 2 + which) * C + cc) = acc;
   }
 }
 
