@@ -58,7 +58,7 @@ def parse():
                         "reference does; by default it is computed once per step and shared - identical loss and gradients")
     p.add_argument("--sweep", action="store_true", help="gemm workload: also run the configs[1] K/N sweep")
     p.add_argument("--torch-nonrouted", default="",
-                   help="A/B switch: comma list of {attn,conv,linear,tail} to run on torch's own fp32 kernels instead of the "
+                   help="A/B switch: comma list of {attn,conv,linear,tail,decoder} to run on torch's own fp32 kernels instead of the "
                         "library's (sets OB_TORCH_NONROUTED before the package is imported)")
     p.add_argument("--no-stack-passes", action="store_true",
                    help="run the three co-training encoder passes one after the other (as train.py does) instead of side by "

@@ -393,9 +393,53 @@ class TransformerDecoder(nn.Module):
         steps = tgt_inp.size(1)
         ahead = torch.ones(steps, steps, device=tgt_inp.device).triu(1).bool()
         causal = ahead.float().masked_fill(ahead, float("-inf"))
-        hidden = self.dec(self.emb(tgt_inp), memory, tgt_mask=causal, memory_key_padding_mask=(memory_mask == 0),
-                          tgt_key_padding_mask=tgt_key_padding_mask)
+        if matmul.linear_usable(memory, self.out.weight) and "decoder" not in matmul.DISABLED and not self.dec.layers[0].norm_first:
+            hidden = self._layers_on_library(self.emb(tgt_inp), memory, causal, memory_mask == 0, tgt_key_padding_mask)
+        else:
+            hidden = self.dec(self.emb(tgt_inp), memory, tgt_mask=causal, memory_key_padding_mask=(memory_mask == 0),
+                              tgt_key_padding_mask=tgt_key_padding_mask)
         return matmul.linear(self.ln(hidden), self.out.weight, self.out.bias)
+
+    # The same computation as nn.TransformerDecoder(post-norm layers, batch_first) with its parameters, written out so that
+    # every projection goes through ``matmul.linear`` (fp32-accurate tensor-core GEMM) - in particular the key/value
+    # projection of the encoder memory, the one large matmul of the decoder.  Attention itself stays torch's fused SDPA.
+    @staticmethod
+    def _attend(mha: nn.MultiheadAttention, query, source, additive_mask, key_padding, training: bool, self_attention: bool):
+        width, heads = mha.embed_dim, mha.num_heads
+        w, b = mha.in_proj_weight, mha.in_proj_bias
+        if self_attention:
+            q, k, v = matmul.linear(query, w, b).split(width, dim=-1)
+        else:
+            q = matmul.linear(query, w[:width], None if b is None else b[:width])
+            k, v = matmul.linear(source, w[width:], None if b is None else b[width:]).split(width, dim=-1)
+        batch, q_len, k_len = query.shape[0], query.shape[1], source.shape[1]
+
+        def heads_first(t, length):
+            return t.reshape(batch, length, heads, width // heads).transpose(1, 2)
+
+        mask = None
+        if key_padding is not None:
+            mask = torch.zeros(batch, 1, 1, k_len, device=query.device, dtype=query.dtype)
+            mask = mask.masked_fill(key_padding[:, None, None, :], float("-inf"))
+        if additive_mask is not None:
+            mask = additive_mask[None, None] if mask is None else mask + additive_mask[None, None]
+        if mask is not None:
+            mask = mask.expand(batch, heads, q_len, k_len)
+        out = F.scaled_dot_product_attention(heads_first(q, q_len), heads_first(k, k_len), heads_first(v, k_len), attn_mask=mask,
+                                             dropout_p=mha.dropout if training else 0.0)
+        out = out.transpose(1, 2).reshape(batch, q_len, width)
+        return matmul.linear(out, mha.out_proj.weight, mha.out_proj.bias)
+
+    def _layers_on_library(self, x, memory, causal, memory_padding, tgt_padding):
+        for layer in self.dec.layers:
+            attn = self._attend(layer.self_attn, x, x, causal, tgt_padding, self.training, True)
+            x = layer.norm1(x + layer.dropout1(attn))
+            attn = self._attend(layer.multihead_attn, x, memory, None, memory_padding, self.training, False)
+            x = layer.norm2(x + layer.dropout2(attn))
+            ff = matmul.linear(layer.dropout(layer.activation(matmul.linear(x, layer.linear1.weight, layer.linear1.bias))),
+                               layer.linear2.weight, layer.linear2.bias)
+            x = layer.norm3(x + layer.dropout3(ff))
+        return x if self.dec.norm is None else self.dec.norm(x)
 
 
 class ConformerASR(nn.Module):

@@ -109,6 +109,38 @@ def test_stack_plan():
     assert plan([(2, None)]) is None
 
 
+def test_written_out_decoder_equals_torch_decoder(monkeypatch):
+    """TransformerDecoder._layers_on_library (every projection through matmul.linear) is nn.TransformerDecoder's computation:
+    forced onto CPU with F.linear standing in for the GEMM, outputs and gradients must agree with the torch module."""
+    from onebit_b200 import matmul
+    from onebit_b200.conformer import TransformerDecoder
+    torch.manual_seed(0)
+    dec = TransformerDecoder(64, 256, 2, 4, 1024, 0.0, 0).train()
+    tgt = torch.randint(1, 64, (3, 9))
+    tgt[1, 6:] = 0
+    tgt[2, 4:] = 0
+    mem = torch.randn(3, 21, 256)
+    mem_mask = torch.ones(3, 21, dtype=torch.bool)
+    mem_mask[1, 15:] = False
+    mem_mask[2, 5:] = False
+
+    def run():
+        dec.zero_grad()
+        m = mem.clone().requires_grad_(True)
+        y = dec(tgt, m, mem_mask, tgt == 0)
+        y.square().sum().backward()
+        return y.detach(), m.grad, {n: p.grad.clone() for n, p in dec.named_parameters()}
+
+    y_ref, gm_ref, gp_ref = run()
+    monkeypatch.setattr(matmul, "linear_usable", lambda x, w: True)
+    monkeypatch.setattr(matmul, "linear", lambda x, w, b=None: torch.nn.functional.linear(x, w, b))
+    y_lib, gm_lib, gp_lib = run()
+    assert (y_ref - y_lib).abs().max().item() < 1e-6
+    assert (gm_ref - gm_lib).abs().max().item() < 1e-5 * gm_ref.abs().max().item()
+    for n in gp_ref:
+        assert (gp_ref[n] - gp_lib[n]).abs().max().item() < 1e-5 * gp_ref[n].abs().max().item() + 1e-9, n
+
+
 def test_module_tree_matches_reference_state_dict():
     saved = {k: sys.modules.get(k) for k in ("quant", "conformer")}
     sys.path.insert(0, "/root/reference/onebit_asr")
