@@ -63,6 +63,9 @@ SIGNATURES = {
     "ob_add_colsum2": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p]),
     "ob_residual_dropout_fwd": (_i, [_p, _p, _p, ctypes.c_float, ctypes.c_float, _u64, _u64, _u32, _i64, _i, _p, _p]),
     "ob_residual_dropout_bwd": (_i, [_p, _p, ctypes.c_float, ctypes.c_float, _u64, _u64, _u32, _i64, _i, _p, _p]),
+    "ob_conv1_relu_workspace_bytes": (_sz, []),
+    "ob_conv1_relu_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "ob_conv1_relu_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ob_debug_set": (_i, [_i, _i]),
 }
 

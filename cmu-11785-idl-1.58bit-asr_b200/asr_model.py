@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import attention, convmod, matmul, residual
+from . import attention, convmod, frontend, matmul, residual
 from .norm import layer_norm
 from .quant import QuantizedLinear
 
@@ -287,7 +287,11 @@ class Conv2dSubsampling(nn.Module):
         self.out = nn.Linear(d_model * bins, d_model)
 
     def forward(self, feats):
-        maps = self.conv(feats.unsqueeze(1))              # [B, C, T', F']
+        if frontend.usable(feats, self.conv[0]):
+            # first convolution + bias + ReLU in one write-bound pass, channels-last for cuDNN's second convolution
+            maps = self.conv[3](self.conv[2](frontend.conv1_relu(feats, self.conv[0].weight, self.conv[0].bias)))
+        else:
+            maps = self.conv(feats.unsqueeze(1))          # [B, C, T', F']
         b, c, t, f = maps.shape
         return matmul.linear(maps.transpose(1, 2).contiguous().view(b, t, c * f), self.out.weight, self.out.bias)
 

@@ -189,6 +189,16 @@ int ob_residual_dropout_fwd(const float* x, const float* y, const float* rowmask
 int ob_residual_dropout_bwd(const float* g, const float* rowmask, float scale, float inv_keep, uint64_t seed,
                             uint64_t offset, uint32_t drop_threshold, int64_t M, int C, float* gy, ob_stream_t stream);
 
+/* First layer of the subsampling front-end (conformer.py:177-181): y = relu(conv2d(x, w, bias, stride 2)) with one input
+ * channel, 3 x 3 taps and C = 256 output channels.  x [B, T, F] fp32, w [C, 9] (the [C,1,3,3] weight), bias [C] or NULL;
+ * y [B, T1, F1, C] channels-last, T1 = (T-3)/2+1, F1 = (F-3)/2+1.  Backward: g [B, T1, F1, C] -> gw [C, 9], gb [C] (the
+ * ReLU mask is recomputed from x; the input needs no gradient); ws >= ob_conv1_relu_workspace_bytes(), fixed-order sums. */
+size_t ob_conv1_relu_workspace_bytes(void);
+int ob_conv1_relu_fwd(const float* x, const float* w, const float* bias, int B, int T, int F, int C, float* y,
+                      ob_stream_t stream);
+int ob_conv1_relu_bwd(const float* g, const float* x, const float* w, const float* bias, int B, int T, int F, int C,
+                      float* gw, float* gb, void* ws, ob_stream_t stream);
+
 /* Greedy CTC decoding (onebit_asr/metrics.py:51-60): per-frame argmax over V (first maximal index), blanks dropped,
  * repeats collapsed.  logits [B, T, V] (dtype tag), lens [B] valid frames; out_tokens [B, T] int32 (compacted, padded
  * with -1), out_lens [B].  ws: at least ob_ctc_decode_workspace_bytes(B, T) bytes. */

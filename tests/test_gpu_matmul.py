@@ -238,3 +238,28 @@ def test_conv_module_middle_groups(ob):
     for name, x, y in zip(("s", "g_a", "g_w", "g_bias", "g_gamma", "g_beta"), *outs):
         scale = outs[1][5].abs().max() if name == "g_bias" else y.abs().max().clamp_min(1e-30)
         assert ((x - y).abs().max() / scale).item() < 1e-5, name
+
+
+@pytest.mark.parametrize("B,T,F", [(3, 200, 80), (2, 37, 23), (1, 3, 3)])
+def test_frontend_conv1_relu_matches_torch(ob, B, T, F):
+    """relu(conv2d(x, w, b, stride 2)) of the one-channel first front-end layer, forward and parameter gradients."""
+    from onebit_b200.frontend import conv1_relu
+    x = R(B, T, F)
+    w0, b0 = R(256, 1, 3, 3, seed=1) * 0.3, R(256, seed=2) * 0.1
+    outs = []
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for ours in (True, False):
+            w, b = w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            y = conv1_relu(x, w, b) if ours else torch.relu(torch.nn.functional.conv2d(x[:, None], w, b, stride=2))
+            gy = R(*y.shape, seed=3)
+            y.backward(gy)
+            outs.append((y.detach(), w.grad, b.grad))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    for name, a, b in zip(("y", "g_w", "g_b"), *outs):
+        assert a.shape == b.shape, name
+        err = ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+        assert err < (1e-5 if name == "y" else 2e-4), (name, err)
+    assert outs[0][0].is_contiguous(memory_format=torch.channels_last)
