@@ -560,7 +560,10 @@ def run_train(args, world, rank):
         out["roofline"] = dict(kernel=dom[0], shape=hk["shape"],
                                traffic=ncu_traffic(f"{dom[0]}_{M}x{hk['shape']['K']}x{hk['shape']['N']}_f32"),
                                **{k: dom[1][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
-                               peak_source=f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)")
+                               peak_source=f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)",
+                               note="dominant kernel of the BitLinear layer (the north_star path) at the model's widest routed "
+                                    "shape; every kernel of the step, incl. the fp32 tensor-core GEMM of the non-routed matmuls "
+                                    "(the largest single family of the step), is in layer_kernels")
         out["layer_kernels"] = hk
         if world == 1:
             # SURVEY.md section 8(d) also asks for ONE precision-2 pass (forward + backward + AdamW), next to the full step
