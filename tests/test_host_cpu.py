@@ -47,6 +47,22 @@ def test_argument_validation_without_gpu():
     assert lib.ob_debug_set(999, 1) == _cabi.OB_ERR_ARG
     assert lib.ob_bwd_dw_workspace_bytes(1000, 256, 256) >= 256 * 256 * 4
     assert lib.ob_bwd_colsum_blocks(129) == (129 + 31) // 32
+    # entry points around the layer: shapes and strides are checked before anything touches the device
+    E = _cabi.OB_ERR_ARG
+    gemm = lambda **kw: lib.ob_gemm_f32(16, 0, kw.get("lda", 64), 0, 0, 32, 0, 64, 0, 0, 48, kw.get("ldd", 64), 0, 0, None, 1.0, 0,  # noqa: E731
+                                        8, 8, kw.get("K", 64), 1, 1, kw.get("passes", 3), None, 0, None)
+    assert gemm(passes=2) == E and "passes" in _cabi.last_error()
+    assert gemm(lda=62) == E and gemm(K=0) == E and gemm(ldd=4) == E
+    assert lib.ob_gemm_f32_workspace_bytes(5004, 256, 25536, 1, 1) == 25 * 5004 * 256 * 4     # 25 K-chunks of 1024
+    assert lib.ob_gemm_f32_workspace_bytes(25536, 5004, 256, 1, 1) == 0 and lib.ob_gemm_f32_workspace_bytes(399, 399, 64, 64, 4) == 0
+    assert lib.ob_glu_dwconv_bn_fwd(16, 16, None, 6, 50, 64, 33, 1e-5, 1, 16, 16, 16, 16, None) == E         # 33 taps
+    assert lib.ob_glu_dwconv_bn_fwd(16, 16, None, 6, 50, 64, 31, 1e-5, 4, 16, 16, 16, 16, None) == E         # 6 % 4 groups
+    assert lib.ob_bn_swish_fwd(16, 16, 16, 16, 16, 100, 60, 1, 16, None) == E                                # C % 64
+    assert lib.ob_residual_dropout_fwd(16, 16, None, 1.0, 1.0, 0, 0, 70000, 8, 64, 16, None) == E             # 16-bit threshold
+    assert lib.ob_swish_drop_quant(16, None, 1.0, 0, 0, 0, 8, 300, 16, 16, None) == E                        # K not supported
+    assert lib.ob_relattn_softmax_fwd(16, 16, 16, None, 1.0, 0, 0, 0, 0.125, 1, 1, 40, 39, 16, None, None) == E   # ld < T
+    assert lib.ob_conv1_relu_fwd(16, 16, None, 2, 50, 80, 128, 16, None) == E                                 # C != 256
+    assert lib.ob_convmod_workspace_bytes(64, 399, 256) >= 64 * 7 * 32 * 256 * 4
 
 
 def test_constructor_matches_reference_fixtures(kat_seeded):
