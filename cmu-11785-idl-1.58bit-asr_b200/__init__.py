@@ -5,7 +5,7 @@ name is not a Python identifier).  ``install_as_reference_quant()`` registers th
 the reference's ``conformer.py`` (which does ``from quant import QuantizedLinear``, conformer.py:12)
 picks this layer up unchanged.
 """
-from . import _cabi, asr_model, attention, conformer, dp, inference, norm, training
+from . import _cabi, asr_model, attention, conformer, dp, inference, norm, routes, training
 from .asr_model import ConformerASR
 from .inference import PackedQuantizedLinear, ctc_greedy_decode, pack_model_for_inference
 from .quant import BitLinear, QuantizedLinear, act_quant_int8, install_as_reference_quant, quantize_weight

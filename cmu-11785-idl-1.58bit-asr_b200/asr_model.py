@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import attention, convmod, frontend, matmul, residual
+from . import attention, convmod, frontend, matmul, residual, routes
 from .norm import layer_norm
 from .quant import QuantizedLinear
 
@@ -95,7 +95,7 @@ def _frame_mask(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 def _module_tail(x, y, mask, scale: float, dropout: nn.Dropout, training: bool):
     """``x + scale * dropout(y) * frame_validity`` - the tail of every encoder module (conformer.py:41-45, 133-138, 163-167);
     one B200 kernel each way when the tensors qualify, the reference's op sequence otherwise."""
-    if residual.usable(x):
+    if routes.taken("module_tail", residual.usable(x), x, "tail" in matmul.DISABLED):
         return residual.residual_dropout(x, y, _frame_mask(mask), scale, dropout.p, training)
     y = dropout(y)
     keep = _frame_mask(mask)
@@ -200,7 +200,7 @@ class MHSA(nn.Module):
     def _probabilities(self, content, position, mask):
         """``content`` = (q+u) k^T, ``position`` = (q+v) p^T before the shift -> attention weights after dropout."""
         inv_sqrt = 1.0 / math.sqrt(self.d_head)
-        if attention.usable(content, mask):
+        if routes.taken("attention_chain", attention.usable(content, mask), content):
             return attention.rel_attention_probs(content, position, mask, inv_sqrt, self.dropout.p, self.training)
         logits = (content + self.rel_shift(position)) / math.sqrt(self.d_head)
         if mask is not None:
@@ -215,7 +215,8 @@ class MHSA(nn.Module):
         normed = self.ln(x)
         q_flat, k_flat, v_flat = (_routed(p, normed, bitwidth) for p in (self.q_proj, self.k_proj, self.v_proj))
         pos_flat = self._positions(pos_emb, bitwidth, batch)
-        if attention.rel_attention_usable(normed, mask, self.n_heads) and pos_emb.shape[:2] == (1, frames):
+        on_library = attention.rel_attention_usable(normed, mask, self.n_heads) and pos_emb.shape[:2] == (1, frames)
+        if routes.taken("attention", on_library, normed, "attn" in matmul.DISABLED):
             # tensor-core path: the projections are consumed in their [B, T, H*d] layout, no head transposes
             mixed = attention.rel_attention(q_flat, k_flat, v_flat, pos_flat, self.pos_bias_u, self.pos_bias_v, mask,
                                             self.n_heads, self.dropout.p, self.training)
@@ -260,7 +261,8 @@ class ConvModule(nn.Module):
     def forward(self, x, mask=None, groups: int = 1):
         """``groups`` > 1: x stacks that many passes; BatchNorm uses each pass's own batch statistics."""
         taps = self.dw.kernel_size[0]
-        if convmod.usable(x, x.shape[-1], taps) and self.bn.affine and self.dw.padding[0] == taps // 2:
+        on_library = convmod.usable(x, x.shape[-1], taps) and self.bn.affine and self.dw.padding[0] == taps // 2
+        if routes.taken("conv_module", on_library, x, "conv" in matmul.DISABLED):
             # channel-last path: 1x1 convolutions as matrix products over the channel axis, B200 kernels in between
             a = matmul.linear(self.ln(x), self.pw1.weight.squeeze(-1), self.pw1.bias)
             s = convmod.glu_dwconv_bn_swish(a, self.dw.weight, self.dw.bias, self.bn.weight, self.bn.bias, self.bn.eps, groups)
@@ -287,7 +289,7 @@ class Conv2dSubsampling(nn.Module):
         self.out = nn.Linear(d_model * bins, d_model)
 
     def forward(self, feats):
-        if frontend.usable(feats, self.conv[0]):
+        if routes.taken("frontend_conv1", frontend.usable(feats, self.conv[0]), feats, "frontend" in matmul.DISABLED):
             # first convolution + bias + ReLU in one write-bound pass, channels-last for cuDNN's second convolution
             maps = self.conv[3](self.conv[2](frontend.conv1_relu(feats, self.conv[0].weight, self.conv[0].bias)))
         else:
@@ -397,7 +399,9 @@ class TransformerDecoder(nn.Module):
         steps = tgt_inp.size(1)
         ahead = torch.ones(steps, steps, device=tgt_inp.device).triu(1).bool()
         causal = ahead.float().masked_fill(ahead, float("-inf"))
-        if matmul.linear_usable(memory, self.out.weight) and "decoder" not in matmul.DISABLED and not self.dec.layers[0].norm_first:
+        on_library = (matmul.linear_usable(memory, self.out.weight) and "decoder" not in matmul.DISABLED
+                      and not self.dec.layers[0].norm_first)
+        if routes.taken("decoder_layers", on_library, memory, bool({"decoder", "linear"} & matmul.DISABLED)):
             hidden = self._layers_on_library(self.emb(tgt_inp), memory, causal, memory_mask == 0, tgt_key_padding_mask)
         else:
             hidden = self.dec(self.emb(tgt_inp), memory, tgt_mask=causal, memory_key_padding_mask=(memory_mask == 0),

@@ -25,9 +25,10 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
 // debug / tuning knobs (ob_debug_set)
 // ---------------------------------------------------------------------------------------------
 enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5,
-                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7 };
+                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8 };
 void f32_gemm_debug(int split_mode);   // ob_gemm_f32.cu
 void f32_gemm_debug_epilogue(int mode);
+void f32_gemm_debug_pair(int on);
 static int g_dbg_kernel_flags = 0;   // bit0 skip TMA stores, bit1 skip epilogue math/STS, bit2 skip expansion (timing experiments)
 static int g_dbg_swap_lbo_sbo = 0;
 static int g_dbg_force_block_n = 0;
@@ -735,6 +736,7 @@ extern "C" int ob_debug_set(int key, int value) {
     case kDbgKernelFlags: g_dbg_kernel_flags = value; return OB_OK;
     case kDbgF32SplitMode: f32_gemm_debug(value); return OB_OK;
     case kDbgF32Epilogue: f32_gemm_debug_epilogue(value); return OB_OK;
+    case kDbgF32Pair: f32_gemm_debug_pair(value); return OB_OK;
     default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;
   }
 }

@@ -31,9 +31,13 @@ constexpr int kFEpiWarps = 8;
 constexpr int kFThreads = (kFEpiWarp0 + kFEpiWarps) * 32;
 constexpr int kFStageOutBytes = 32 * 128;          // one epilogue chunk: 32 rows x 32 fp32
 
-template <int BLOCK_N, int STAGES, int PASSES>
+// CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a [256 x BLOCK_N] tile.  Each CTA loads and splits its own
+// 128 rows of A and its own half (BLOCK_N / 2 rows) of B, so per output element the splitter traffic and the tensor
+// core's operand reads of B are halved - the shared-memory pipe is what limits the deep shapes.
+template <int BLOCK_N, int STAGES, int PASSES, int CTAS = 1>
 struct F32Smem {
-  static constexpr int kBTileBytes = BLOCK_N * 128;
+  static constexpr int kRowsB = BLOCK_N / CTAS;                        // B rows held by this CTA
+  static constexpr int kBTileBytes = kRowsB * 128;
   static constexpr int kHiBytes = kFATileBytes + kBTileBytes;          // [A_hi | B_hi], then [A_lo | B_lo] behind it
   static constexpr int kStageBytes = (PASSES == 3 ? 2 : 1) * kHiBytes;
   static constexpr int kOffOut = STAGES * kStageBytes;                 // 8 epilogue warps x 4 KB
@@ -61,32 +65,36 @@ struct F32Params {
   int d_b0, d_b1;               // batch coordinates of the output map
 };
 
-template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES>
+template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES, int CTAS = 1>
 __global__ void __launch_bounds__(kFThreads, 1)
 f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_d, const F32Params p) {
-  using L = F32Smem<BLOCK_N, STAGES, PASSES>;
+  using L = F32Smem<BLOCK_N, STAGES, PASSES, CTAS>;
+  static_assert(CTAS == 1 || (CTAS == 2 && PASSES == 3), "the CTA-pair variant is built for the split product only");
+  constexpr int kTileM = kFTileM * CTAS;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtTF32, kFmtTF32, A_MN, B_MN, kFTileM, BLOCK_N);
+  constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtTF32, kFmtTF32, A_MN, B_MN, kTileM, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-  uint64_t* full_bar = bars;                      // operand tiles landed (TMA)
-  uint64_t* ready_bar = bars + STAGES;            // splitters wrote hi / lo
-  uint64_t* empty_bar = bars + 2 * STAGES;        // MMAs that read the stage retired
+  uint64_t* full_bar = bars;                      // this CTA's operand tiles landed (TMA)
+  uint64_t* ready_bar = bars + STAGES;            // splitters wrote hi / lo (pair: both CTAs' splitters, leader's barrier)
+  uint64_t* empty_bar = bars + 2 * STAGES;        // MMAs that read the stage retired (pair: multicast to both CTAs)
   uint64_t* tmem_full_bar = bars + 3 * STAGES;    // [2]
-  uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;
+  uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;   // (pair: both CTAs' epilogue warps, leader's barrier)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + kFTileM - 1) / kFTileM;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int m_tiles = (p.M + kTileM - 1) / kTileM;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles_mn = m_tiles * n_tiles;
   const int tiles_per_batch = tiles_mn * p.k_splits;               // split index outermost within a batch item
   const int num_tiles = tiles_per_batch * p.nb0 * p.nb1;
   const int total_kb = (p.K + kFKBlock - 1) / kFKBlock;
+  const int first_tile = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;   // the CTAs of a pair walk the same tiles
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -96,21 +104,21 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], kFSplitWarps);
+      mbar_init(&ready_bar[s], kFSplitWarps * CTAS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kFEpiWarps);
+      mbar_init(&tmem_empty_bar[s], kFEpiWarps * CTAS);
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(tmem_slot, kTmemCols); tmem_relinquish_pair(); }
+    else           { tmem_alloc(tmem_slot, kTmemCols);      tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -118,10 +126,10 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int batch = tile / tiles_per_batch, ts = tile - batch * tiles_per_batch;
         const int split = ts / tiles_mn, t = ts - split * tiles_mn;
-        const int m0 = (t / n_tiles) * kFTileM, n0 = (t % n_tiles) * BLOCK_N;
+        const int m0 = (t / n_tiles) * kTileM + rank * kFTileM, n0 = (t % n_tiles) * BLOCK_N + rank * L::kRowsB;
         const int b0 = batch / p.nb1, b1 = batch - b0 * p.nb1;
         const int kb0 = split * p.kb_per_split, num_kb = min(p.kb_per_split, total_kb - kb0);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -139,7 +147,7 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 32; ++j)
+            for (int j = 0; j < L::kRowsB / 32; ++j)
               tma_load_4d(b + j * 4096, &map_b, &full_bar[stage], n0 + 32 * j, k0, b1 * p.b_b1, b0 * p.b_b0);
           } else {
             tma_load_4d(b, &map_b, &full_bar[stage], k0, n0, b1 * p.b_b1, b0 * p.b_b0);
@@ -150,7 +158,7 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {                 // pair: one thread of the leader CTA issues for both
       uint32_t stage = 0, phase = 0;
       int it = 0;
       // K-major: SWIZZLE_128B, 8-row groups 1024 B apart.  MN-major fp32: SWIZZLE_128B_BASE32B, LBO = stride between the
@@ -159,15 +167,17 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       constexpr uint32_t kSboA = A_MN ? 512 : 1024, kSboB = B_MN ? 512 : 1024;
       constexpr uint32_t kLayA = A_MN ? 1 : 2, kLayB = B_MN ? 1 : 2;
       constexpr uint32_t kStepA = A_MN ? 64 : 2, kStepB = B_MN ? 64 : 2;   // 8 contraction elements, in 16-byte units
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        if (CTAS == 2) mbar_wait_cluster(&tmem_empty_bar[as], aphase ^ 1); else mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         const int split = (tile % tiles_per_batch) / tiles_mn;
         const int num_kb = min(p.kb_per_split, total_kb - split * p.kb_per_split);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(PASSES == 3 ? &ready_bar[stage] : &full_bar[stage], phase);
+          // pair: the peer's TMA-written hi tile is covered by its splitters, which waited for it before arriving here
+          if (CTAS == 2) mbar_wait_cluster(&ready_bar[stage], phase);
+          else           mbar_wait(PASSES == 3 ? &ready_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = sbase + stage * L::kStageBytes, b_addr = a_addr + kFATileBytes;
           const uint64_t a_hi = make_smem_desc(a_addr, kLboA, kSboA, kLayA);
@@ -177,7 +187,11 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kFKBlock / 8; ++k) {
             const uint32_t acc = (kb | k) != 0;
-            if (PASSES == 3) {
+            if (CTAS == 2) {
+              umma_tf32_pair(d_tmem, a_lo + kStepA * k, b_hi + kStepB * k, kIdesc, acc);
+              umma_tf32_pair(d_tmem, a_hi + kStepA * k, b_lo + kStepB * k, kIdesc, 1);
+              umma_tf32_pair(d_tmem, a_hi + kStepA * k, b_hi + kStepB * k, kIdesc, 1);
+            } else if (PASSES == 3) {
               umma_tf32(d_tmem, a_lo + kStepA * k, b_hi + kStepB * k, kIdesc, acc);
               umma_tf32(d_tmem, a_hi + kStepA * k, b_lo + kStepB * k, kIdesc, 1);
               umma_tf32(d_tmem, a_hi + kStepA * k, b_hi + kStepB * k, kIdesc, 1);
@@ -185,8 +199,13 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               umma_tf32(d_tmem, a_hi + kStepA * k, b_hi + kStepB * k, kIdesc, acc);
             }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+          if (CTAS == 2) {
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -199,7 +218,8 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       constexpr int kChunks = L::kHiBytes / 16;
       constexpr int kIters = kChunks / kFSplitThreads;
       static_assert(kChunks % (2 * kFSplitThreads) == 0, "tile bytes must divide over the splitter threads");
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint32_t ready_addr0 = CTAS == 2 ? mapa_u32(smem_u32(&ready_bar[0]), 0) : smem_u32(&ready_bar[0]);
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int split = (tile % tiles_per_batch) / tiles_mn;
         const int num_kb = min(p.kb_per_split, total_kb - split * p.kb_per_split);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -229,7 +249,9 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ready_bar[stage]);
+          if (lane == 0) {
+            if (CTAS == 2) mbar_arrive_cluster(ready_addr0 + stage * 8); else mbar_arrive(&ready_bar[stage]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -244,11 +266,12 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t obuf = sbase + L::kOffOut + ew * kFStageOutBytes;
     const uint32_t wr_row = lane * 128, wr_swz = (lane & 7) << 4;
     const int rd_r = lane >> 3, rd_c = lane & 7;
+    const uint32_t tmem_empty_addr0 = CTAS == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int batch = tile / tiles_per_batch, ts = tile - batch * tiles_per_batch;
       const int split = ts / tiles_mn, t = ts - split * tiles_mn;
-      const int m0 = (t / n_tiles) * kFTileM, n0 = (t % n_tiles) * BLOCK_N;
+      const int m0 = (t / n_tiles) * kTileM + rank * kFTileM, n0 = (t % n_tiles) * BLOCK_N;
       const int b0 = batch / p.nb1, b1 = batch - b0 * p.nb1;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int row0 = m0 + e * 32;
@@ -329,16 +352,18 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(tmem_empty_addr0 + as * 8); else mbar_arrive(&tmem_empty_bar[as]);
+      }
     }
     if (p.tma_out && lane == 0) tma_store_wait_all<0>();          // global writes complete before the CTA retires
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();     // pair: the peer's shared memory is read until the last MMA retires
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -373,7 +398,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 struct F32Plan {
   int block_n, stages, k_splits, kb_per_split;
+  int pair;                 // 1: CTA pairs on [256 x 256] tiles (cta_group::2)
 };
+static int g_f32_pair = 0;           // opt-in (ob_debug_set key 8) until it has been measured on the device
 constexpr int kSplitKChunk = 1024;
 
 // Tile configuration and split-K decision.  Split-K: deep contractions with few output tiles (weight gradients, the
@@ -384,10 +411,13 @@ static F32Plan plan_f32(int M, int N, int K, int batch) {
   if (N <= 64) pl.block_n = 64, pl.stages = 4;
   else if (N > 128 && K > 128) pl.block_n = 256, pl.stages = 2;
   else pl.block_n = 128, pl.stages = 3;
-  const int64_t tiles_mn = (int64_t)((M + kFTileM - 1) / kFTileM) * ((N + pl.block_n - 1) / pl.block_n);
+  // pairs pay where the kernel is shared-memory bound (deep contraction, wide output) and M fills the 256-row tiles
+  pl.pair = g_f32_pair && pl.block_n == 256 && M >= 2 * kFTileM;
+  const int tile_m = pl.pair ? 2 * kFTileM : kFTileM;
+  const int64_t tiles_mn = (int64_t)((M + tile_m - 1) / tile_m) * ((N + pl.block_n - 1) / pl.block_n);
   const int total_kb = (K + kFKBlock - 1) / kFKBlock;
   pl.k_splits = 1, pl.kb_per_split = total_kb;
-  if (batch == 1 && K >= 2 * kSplitKChunk && tiles_mn * 2 <= sm_count() * 4) {
+  if (batch == 1 && K >= 2 * kSplitKChunk && tiles_mn * (pl.pair ? 4 : 2) <= sm_count() * 4) {
     pl.kb_per_split = kSplitKChunk / kFKBlock;
     pl.k_splits = (total_kb + pl.kb_per_split - 1) / pl.kb_per_split;
   }
@@ -437,14 +467,15 @@ static int make_map4(CUtensorMap* map, const void* base, uint64_t inner, uint64_
 static int g_f32_split_mode = 1;     // the tensor core truncates fp32 -> tf32 (measured), so the raw tile is the hi part
 static int g_f32_epilogue = 0;       // 0 auto, 1 direct row stores, 2 TMA box stores
 void f32_gemm_debug_epilogue(int mode) { g_f32_epilogue = mode; }
+void f32_gemm_debug_pair(int on) { g_f32_pair = on; }
 void f32_gemm_debug(int split_mode) { g_f32_split_mode = split_mode; }
 
-template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES>
+template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES, int CTAS = 1>
 static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_t ldd, int64_t d_bs0, int64_t d_bs1,
                       F32Params p, const F32Plan& pl, cudaStream_t st) {
-  using L = F32Smem<BLOCK_N, STAGES, PASSES>;
+  using L = F32Smem<BLOCK_N, STAGES, PASSES, CTAS>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
-  auto kern = f32_gemm_kernel<A_MN, B_MN, BLOCK_N, STAGES, PASSES>;
+  auto kern = f32_gemm_kernel<A_MN, B_MN, BLOCK_N, STAGES, PASSES, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
@@ -457,7 +488,7 @@ static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_
   else      rc = make_map4(&map_a, A.ptr, p.K, p.M, A.ld, p.nb1, A.bs1, p.nb0, A.bs0, 32, kFTileM, kSwK);
   if (rc != OB_OK) return rc;
   if (B_MN) rc = make_map4(&map_b, B.ptr, p.N, p.K, B.ld, p.nb1, B.bs1, p.nb0, B.bs0, 32, 32, kSwMN);
-  else      rc = make_map4(&map_b, B.ptr, p.K, p.N, B.ld, p.nb1, B.bs1, p.nb0, B.bs0, 32, BLOCK_N, kSwK);
+  else      rc = make_map4(&map_b, B.ptr, p.K, p.N, B.ld, p.nb1, B.bs1, p.nb0, B.bs0, 32, L::kRowsB, kSwK);
   if (rc != OB_OK) return rc;
   rc = make_map4(&map_d, D, p.N, p.M, ldd, p.nb1, d_bs1, p.nb0, d_bs0, 32, 32, kSwK);
   if (rc != OB_OK) return rc;
@@ -469,12 +500,23 @@ static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_
   p.b_b0 = (p.nb0 > 1 && B.bs0 != 0), p.b_b1 = (p.nb1 > 1 && B.bs1 != 0);
   p.D = D, p.ldd = ldd, p.d_bs0 = p.nb0 > 1 ? d_bs0 : 0, p.d_bs1 = p.nb1 > 1 ? d_bs1 : 0;
   p.split_mode = g_f32_split_mode;
-  const int64_t tiles_mn = (int64_t)((p.M + kFTileM - 1) / kFTileM) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  constexpr int kTileM = kFTileM * CTAS;
+  const int64_t tiles_mn = (int64_t)((p.M + kTileM - 1) / kTileM) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   p.k_splits = pl.k_splits, p.kb_per_split = pl.kb_per_split;
   const int64_t tiles = tiles_mn * p.k_splits * p.nb0 * p.nb1;
-  int ctas = sm_count();
-  if (tiles < ctas) ctas = (int)tiles;
-  kern<<<ctas, kFThreads, L::kDynBytes, st>>>(map_a, map_b, map_d, p);
+  int groups = sm_count() / CTAS;                  // persistent: one CTA (or CTA pair) per SM (pair of SMs)
+  if (tiles < groups) groups = (int)tiles;
+  if (CTAS == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups * 2), cfg.blockDim = dim3(kFThreads), cfg.dynamicSmemBytes = L::kDynBytes, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_d, p));
+  } else {
+    kern<<<groups, kFThreads, L::kDynBytes, st>>>(map_a, map_b, map_d, p);
+  }
   OB_LAUNCH_CHECK("f32_gemm_kernel");
   if (p.k_splits > 1) {
     const int64_t work = (int64_t)p.M * (p.ldp / 4);
@@ -489,6 +531,7 @@ static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_
 template <int A_MN, int B_MN, int PASSES>
 static int dispatch_f32_cfg(const F32Operand& A, const F32Operand& B, float* D, int64_t ldd, int64_t d_bs0, int64_t d_bs1,
                             const F32Params& p, const F32Plan& pl, cudaStream_t st) {
+  if (PASSES == 3 && pl.pair) return launch_f32<A_MN, B_MN, 256, 3, 3, 2>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
   if (pl.block_n == 64) return launch_f32<A_MN, B_MN, 64, 4, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
   if (pl.block_n == 256) return launch_f32<A_MN, B_MN, 256, 2, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
   return launch_f32<A_MN, B_MN, 128, 3, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);

@@ -11,6 +11,7 @@ import os
 
 import torch
 
+from . import routes
 from ._cabi import check, lib
 from .quant import _stream
 
@@ -152,6 +153,6 @@ def linear_usable(x: torch.Tensor, weight: torch.Tensor) -> bool:
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None) -> torch.Tensor:
     """``x @ weight.T + bias`` in fp32 on the tensor cores (3 x tf32 split); ``torch.nn.functional.linear`` elsewhere."""
-    if not linear_usable(x, weight):
+    if not routes.taken("linear", linear_usable(x, weight), x, "linear" in DISABLED):
         return torch.nn.functional.linear(x, weight, bias)
     return _LinearFn.apply(x, weight, bias)

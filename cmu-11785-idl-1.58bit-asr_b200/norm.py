@@ -10,6 +10,7 @@ import functools
 
 import torch
 
+from . import routes
 from ._cabi import check, lib
 from .quant import _stream
 
@@ -56,7 +57,8 @@ class _LayerNormFn(torch.autograd.Function):
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """LayerNorm over the last axis; uses the library for CUDA fp32 inputs of a supported width, torch otherwise."""
-    if (x.is_cuda and x.dtype == torch.float32 and x.shape[-1] in SUPPORTED_WIDTHS and x.numel() > 0
-            and weight is not None and bias is not None and weight.dtype == torch.float32):
+    on_library = (x.is_cuda and x.dtype == torch.float32 and x.shape[-1] in SUPPORTED_WIDTHS and x.numel() > 0
+                  and weight is not None and bias is not None and weight.dtype == torch.float32)
+    if routes.taken("layer_norm", on_library, x):
         return _LayerNormFn.apply(x, weight, bias, eps)
     return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
