@@ -52,6 +52,10 @@ cases = [
     ("NT ragged 1000x500x300 bias", lambda: (R(1000, 300), R(500, 300), R(500))),
     ("NN (B mn-major) 700x256x516", lambda: (R(700, 516), R(516, 256).t(), None)),
     ("TN (A,B mn-major, split-K) 5004x256x9000", lambda: (R(9000, 5004).t(), R(9000, 256).t(), None)),
+    ("extra TK (A mn-major, B k-major) 3000x512x700", lambda: (R(700, 3000).t(), R(512, 700), None)),
+    ("extra NT batch 2x3 600x300x200 bias", lambda: (R(2, 3, 600, 200), R(2, 3, 300, 200), R(300))),
+    ("extra NT broadcast B over batch 2x3 600x300x200", lambda: (R(2, 3, 600, 200), R(1, 3, 300, 200), None)),
+    ("extra NT tails 257x129x129", lambda: (R(257, 132)[:, :129], R(129, 132)[:, :129], None)),
     ("NT vocabulary fwd 25536x5004x256 bias", lambda: (R(25536, 256), R(5004, 256), R(5004))),
     ("NN vocabulary dx 25536x256x5004", lambda: (R(25536, 5004), R(5004, 256).t(), None)),
     ("TN vocabulary dW 5004x256x25536", lambda: (R(25536, 5004).t(), R(25536, 256).t(), None)),
@@ -62,7 +66,7 @@ for name, make in cases:
     if only and not any(o in name for o in only):
         continue
     a, b, bias = make()
-    lib.ob_debug_set(KEY_PAIR, 0)
+    lib.ob_debug_set(KEY_PAIR, 0)             # the script restores the library default (pairs on) only by exiting
     single = bmm_nt(a, b, bias=bias)
     torch.cuda.synchronize()
     lib.ob_debug_set(KEY_PAIR, 1)
@@ -82,6 +86,15 @@ for name, make in cases:
     row["us_single"] = round(timeit(lambda: bmm_nt(a, b, bias=bias)), 1)
     lib.ob_debug_set(KEY_PAIR, 1)
     row["us_pair"] = round(timeit(lambda: bmm_nt(a, b, bias=bias)), 1)
+    if "batch 2x3 600" in name and bias is not None:          # accumulation into an existing output (vector atomic adds)
+        outs = []
+        for on in (0, 1):
+            lib.ob_debug_set(KEY_PAIR, on)
+            acc = torch.ones(2, 3, 600, 300, device=dev)
+            bmm_nt(a, b, out=acc, accumulate=True)
+            outs.append(acc)
+        torch.cuda.synchronize()
+        row["accumulate_equal"] = bool(torch.equal(outs[0], outs[1]))
     lib.ob_debug_set(KEY_PAIR, 0)
     emit(**row)
     del a, b, bias, single, pair
