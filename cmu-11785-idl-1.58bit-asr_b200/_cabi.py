@@ -66,6 +66,9 @@ SIGNATURES = {
     "ob_conv1_relu_workspace_bytes": (_sz, []),
     "ob_conv1_relu_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "ob_conv1_relu_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "ob_ctc_state_pitch": (_i, [_i]),
+    "ob_ctc_loss_fwd": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "ob_ctc_loss_bwd": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ob_debug_set": (_i, [_i, _i]),
 }
 

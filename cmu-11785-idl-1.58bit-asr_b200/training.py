@@ -61,7 +61,11 @@ def att_ce_loss(logits: torch.Tensor, targets: torch.Tensor, pad_id: int, label_
 
 
 def ctc_loss_from_logits(ctc_logits, feat_lens, tokens, token_lens, blank_id: int):
-    """nn.CTCLoss(blank, zero_infinity=True) on log-softmaxed [T,B,V] (losses.py:41-47)."""
+    """nn.CTCLoss(blank, zero_infinity=True) on log-softmaxed [T,B,V] (losses.py:41-47); on the device the same value and
+    gradient come from the library's kernels straight from the [B,T,V] logits (ctc.py)."""
+    from . import ctc, matmul, routes
+    if routes.taken("ctc_loss", ctc.usable(ctc_logits, tokens), ctc_logits, "ctc" in matmul.DISABLED or not ctc.ENABLED):
+        return ctc.ctc_loss(ctc_logits, feat_lens, tokens, token_lens, blank_id)
     logp = F.log_softmax(ctc_logits, dim=-1).transpose(0, 1)
     return F.ctc_loss(logp, tokens, feat_lens, token_lens, blank=blank_id, reduction="mean", zero_infinity=True)
 
@@ -117,6 +121,10 @@ def cotraining_loss(model, batch: Dict[str, torch.Tensor], cfg: StepConfig, sp_m
     lens_host = batch.get("feat_lens_cpu")
     tok_lens_host = batch.get("token_lens_cpu", token_lens)
     shared = model.encoder.frontend(batch["feats"]) if cfg.share_frontend else None
+    # device copies of the CTC lengths for the library's CTC kernels (which clamp to the number of frames themselves)
+    from . import ctc as ctc_kernels
+    feat_lens_dev = batch.get("feat_lens")
+    lens_dev = feat_lens_dev // 4 if (feat_lens_dev is not None and feat_lens_dev.is_cuda and token_lens.is_cuda) else None
 
     stacked = None
     if cfg.stack_passes and hasattr(model, "forward_passes"):
@@ -138,7 +146,10 @@ def cotraining_loss(model, batch: Dict[str, torch.Tensor], cfg: StepConfig, sp_m
             ctc_lens = torch.clamp(lens_host // 4, max=enc.size(1))
         else:
             ctc_lens = mask.sum(dim=1).long()
-        l_ctc = ctc_loss_from_logits(ctc, ctc_lens, tokens, tok_lens_host, cfg.blank_id)
+        if lens_dev is not None and ctc_kernels.usable(ctc, tokens):
+            l_ctc = ctc_loss_from_logits(ctc, lens_dev, tokens, token_lens, cfg.blank_id)
+        else:
+            l_ctc = ctc_loss_from_logits(ctc, ctc_lens, tokens, tok_lens_host, cfg.blank_id)
         return (1 - cfg.gamma_ctc) * l_att + cfg.gamma_ctc * l_ctc, logits
 
     l2, logits2 = one_pass(2)                                  # teacher

@@ -207,6 +207,22 @@ int ob_ctc_greedy_decode(const void* logits, int dtype, int B, int T, int V, con
                          int blank_id, int32_t* out_tokens, int32_t* out_lens, void* ws,
                          ob_stream_t stream);
 
+/* CTC loss of the training step from the logits (onebit_asr/losses.py:41-47: log_softmax, transpose, nn.CTCLoss(blank,
+ * zero_infinity=True), reduction 'mean'): loss[0] = mean_b(nll_b / max(L_b, 1)), an infinite nll_b counts as 0 and gets a
+ * zero gradient.  logits [B, T, V] fp32 with row pitch ld (elements); in_lens [B], tgt_lens [B] int64 on the device;
+ * targets [B, Lmax] int64, row pitch tgt_ld, Lmax <= 511.  The caller owns lse [B*T], alpha and beta [B, T, Sp] with
+ * Sp = ob_ctc_state_pitch(Lmax), nll [B] and loss [1]; the backward reads them again together with grad_out [1] (the
+ * upstream gradient of the loss, on the device) and writes grad_logits [B, T, V] (row pitch ldg): g_b (softmax - state
+ * occupancy per label), zero beyond in_lens[b].  Fixed-order reductions (deterministic). */
+int ob_ctc_state_pitch(int Lmax);
+int ob_ctc_loss_fwd(const float* logits, int64_t ld, const int64_t* in_lens, const int64_t* targets, int64_t tgt_ld,
+                    const int64_t* tgt_lens, int B, int T, int V, int Lmax, int blank, float* lse, float* alpha,
+                    float* beta, float* nll, float* loss, ob_stream_t stream);
+int ob_ctc_loss_bwd(const float* logits, int64_t ld, const int64_t* in_lens, const int64_t* targets, int64_t tgt_ld,
+                    const int64_t* tgt_lens, int B, int T, int V, int Lmax, int blank, const float* lse,
+                    const float* alpha, const float* beta, const float* nll, const float* grad_out, float* grad_logits,
+                    int64_t ldg, ob_stream_t stream);
+
 /* Batched fp32 GEMM on the tensor cores for the non-routed matmuls of the model (attention products conformer.py:113-129,
  * vocabulary projections, 1x1 convolutions - fp32 torch.matmul / nn.Linear / nn.Conv1d in the reference):
  *   D[b0,b1](m, n) (+)= scale * sum_k A[b0,b1](m, k) * B[b0,b1](n, k) + bias[n]

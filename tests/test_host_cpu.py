@@ -63,6 +63,10 @@ def test_argument_validation_without_gpu():
     assert lib.ob_relattn_softmax_fwd(16, 16, 16, None, 1.0, 0, 0, 0, 0.125, 1, 1, 40, 39, 16, None, None) == E   # ld < T
     assert lib.ob_conv1_relu_fwd(16, 16, None, 2, 50, 80, 128, 16, None) == E                                 # C != 256
     assert lib.ob_convmod_workspace_bytes(64, 399, 256) >= 64 * 7 * 32 * 256 * 4
+    assert lib.ob_ctc_state_pitch(64) == 132 and lib.ob_ctc_state_pitch(0) == 4
+    ctc_fwd = lambda **kw: lib.ob_ctc_loss_fwd(16, kw.get("ld", 8), 16, 16, 3, 16, 2, 4, 8, kw.get("L", 3), kw.get("blank", 0),  # noqa: E731
+                                               16, 16, 16, 16, 16, None)
+    assert ctc_fwd(blank=8) == E and ctc_fwd(ld=7) == E and ctc_fwd(L=512) == E                              # blank >= V, pitch < V, L > 511
 
 
 def test_constructor_matches_reference_fixtures(kat_seeded):

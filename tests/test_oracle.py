@@ -157,3 +157,23 @@ def test_dropout_masks_are_bernoulli_and_keyed():
     k = ob.dropout_keep_relattn(2, 3, 70, seed=7, offset=0, threshold=thr)
     assert k.shape == (2, 3, 70, 70) and abs(k.mean() - 0.9) < 1e-2
     assert ob.dropout_keep_flat(256, 1, 0, 0).all()            # threshold 0 keeps everything
+
+
+@pytest.mark.parametrize("case", ["ragged", "repeats", "empty_and_infeasible", "longer"])
+def test_ctc_oracle_matches_reference_fixture(case):
+    """oracle/ctc_oracle.py against the reference's own ctc_loss_from_logits (tests/golden/make_golden_ctc.py)."""
+    import os
+
+    from conftest import GOLDEN
+    from oracle import ctc_oracle
+
+    fx = np.load(os.path.join(GOLDEN, "kat_ctc.npz"))
+    get = lambda k: fx[f"{case}.{k}"]  # noqa: E731
+    loss, grad, nll = ctc_oracle.ctc_loss_and_grad(get("logits"), get("in_lens"), get("targets"), get("tgt_lens"), int(get("blank")),
+                                                   float(get("grad_out")))
+    assert abs(loss - float(get("loss"))) <= 1e-6 * abs(float(get("loss")))          # fp32 reference vs fp64 restatement
+    assert np.abs(grad - get("grad")).max() <= 2e-5
+    if case == "empty_and_infeasible":                                             # zero_infinity: no loss, no gradient
+        assert np.isinf(nll[1]) and not np.any(get("grad")[1]) and not np.any(grad[1])
+    beyond = get("in_lens")[:, None] <= np.arange(get("logits").shape[1])[None, :]
+    assert not np.any(grad[beyond])                                                # frames past the input length
