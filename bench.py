@@ -58,8 +58,11 @@ def parse():
                         "reference does; by default it is computed once per step and shared - identical loss and gradients")
     p.add_argument("--sweep", action="store_true", help="gemm workload: also run the configs[1] K/N sweep")
     p.add_argument("--torch-nonrouted", default="",
-                   help="A/B switch: comma list of {attn,conv,linear,tail,decoder} to run on torch's own fp32 kernels instead of the "
+                   help="A/B switch: comma list of {attn,conv,linear,tail,decoder,frontend,ctc} to run on torch's own fp32 kernels instead of the "
                         "library's (sets OB_TORCH_NONROUTED before the package is imported)")
+    p.add_argument("--allocator-headroom-gib", type=float, default=6.0,
+                   help="train: free block kept in torch's caching allocator after the first warm-up step so that a shifted request "
+                        "size never reaches cudaMalloc inside the timed steps (training.reserve_allocator_headroom); 0 disables")
     p.add_argument("--no-stack-passes", action="store_true",
                    help="run the three co-training encoder passes one after the other (as train.py does) instead of side by "
                         "side on one stacked batch - same loss and gradients (tests), 3x the launches")
@@ -459,7 +462,8 @@ def run_train(args, world, rank):
     import onebit_b200 as ob
     from onebit_b200 import _cabi
     from onebit_b200.dp import GradAllReducer
-    from onebit_b200.training import StepConfig, train_step
+    from onebit_b200 import routes
+    from onebit_b200.training import StepConfig, reserve_allocator_headroom, train_step
     peaks = load_peaks()
     dev = torch.device("cuda", torch.cuda.current_device())
     B, T = args.batch, args.frames
@@ -476,8 +480,13 @@ def run_train(args, world, rank):
 
     def step():
         return train_step(model, batch, opt, cfg, grad_sync=sync)[0]
-    for _ in range(warm):
+    headroom = 0
+    for i in range(warm):
         step()
+        if i == 0:                                          # the steady allocations exist now: add the slack block
+            headroom = reserve_allocator_headroom(dev, args.allocator_headroom_gib)
+    mallocs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
+    routes.reset()
     l0 = _cabi.lib.ob_launch_count()
     sampler = ClockSampler(torch.cuda.current_device()).start()
     window = os.environ.get("OB_NCU_WINDOW") == "1"     # `ncu --profile-from-start off` then sees only the timed steps
@@ -488,6 +497,8 @@ def run_train(args, world, rank):
         torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = _cabi.lib.ob_launch_count() - l0
+    timed_mallocs = torch.cuda.memory_stats().get("num_device_alloc", 0) - mallocs0     # cudaMallocs inside the timed steps
+    taken = routes.counts()                                 # which implementation every op around the layer took (CUDA tensors)
     ms_per_step = ms / args.steps
     audio_s = world * B * T * FRAME_S
     value = audio_s / (ms_per_step * 1e-3)
@@ -548,8 +559,10 @@ def run_train(args, world, rank):
                                              "common-subexpression sharing inside the step, same loss and gradients "
                                              "(tests/test_conformer_cpu.py); --no-share-frontend restores the 3x evaluation",
                       "l2": "per-step activations (tens of GB) exceed the 126 MB L2; no explicit flush",
+                      "allocator_headroom_gib": round(headroom / 2 ** 30, 1),
+                      "cuda_mallocs_in_timed_steps": int(timed_mallocs),
                       "parallelism": f"dp{world}"},
-           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "routes": taken,
            "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
     if rank == 0:
         M = B * (((T - 1) // 2 - 1) // 2)

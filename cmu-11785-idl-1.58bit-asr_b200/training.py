@@ -161,6 +161,24 @@ def cotraining_loss(model, batch: Dict[str, torch.Tensor], cfg: StepConfig, sp_m
     return loss, {"Lint2": l2, "Lint1": l1, "Lint_sp": ls, "KL1": kl1, "KL_sp": kls}
 
 
+def reserve_allocator_headroom(device, gib: float = 6.0) -> int:
+    """Grow torch's caching allocator by one free, splittable block of ``gib`` GiB on ``device``; returns the bytes reserved.
+
+    Why: the stochastic-precision mask (train.py:56-59) changes the row split of every grouped layer from step to step, so
+    the sizes the allocator is asked for keep shifting a little.  With the reserved pool only ~2 GiB above the peak of live
+    tensors a request can miss the cached blocks several steps into a run, and the ``cudaMalloc`` it falls back to stalls the
+    enqueueing thread until the device has drained - measured as one 207 ms step among 122 ms steps
+    (profiles/r01_step_times.json).  A cached block with room to split absorbs those requests.  Call it once after the first
+    step; a no-op for CPU devices or ``gib <= 0``."""
+    device = torch.device(device)
+    if device.type != "cuda" or gib <= 0:
+        return 0
+    n = int(gib * 2 ** 30)
+    block = torch.empty(n, dtype=torch.uint8, device=device)      # released at once: stays in the allocator's large pool
+    del block
+    return n
+
+
 def train_step(model, batch, optimizer, cfg: StepConfig, sched=None, sp_mask=None, grad_sync=None):
     """zero_grad -> 3-pass loss -> backward -> (DP all-reduce) -> clip -> AdamW -> schedule (train.py:114-120).
 

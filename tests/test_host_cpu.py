@@ -141,3 +141,28 @@ def test_gemm_operand_descriptors():
     assert _describe((8, 8, 8), (1, 8, 64)) is None or _describe((8, 8, 8), (1, 8, 64))[4] in (0, 1)
     with pytest.raises(ValueError):
         _describe((4,), (1,))
+
+
+def test_route_audit_counts_and_strict_mode():
+    """routes.py: torch routes are only counted (and, in strict mode, refused) for CUDA tensors; switched-off ops may pass."""
+    import torch
+    from onebit_b200 import routes
+    from onebit_b200.training import reserve_allocator_headroom
+
+    class OnDevice:                     # what the audit looks at
+        is_cuda, dtype, shape = True, torch.float16, (2, 3)
+
+    routes.reset()
+    assert routes.taken("attention", False, torch.zeros(2)) is False            # CPU tensor (oracle-driven runs): not an event
+    assert routes.taken("attention", True, OnDevice()) is True
+    assert routes.taken("layer_norm", False, OnDevice()) is False
+    assert routes.counts() == {"library": {"attention": 1}, "torch": {"layer_norm": 1}}
+    routes.strict(True)
+    try:
+        with pytest.raises(RuntimeError, match="OB_STRICT_ROUTES"):
+            routes.taken("layer_norm", False, OnDevice())
+        assert routes.taken("conv_module", False, OnDevice(), switched_off=True) is False     # A/B switch: allowed
+    finally:
+        routes.strict(False)
+        routes.reset()
+    assert reserve_allocator_headroom("cpu", 6.0) == 0                           # nothing to reserve off the device
