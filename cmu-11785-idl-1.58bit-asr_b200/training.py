@@ -175,8 +175,10 @@ def reserve_allocator_headroom(device, gib: float = 6.0) -> int:
         return 0
     n = int(gib * 2 ** 30)
     block = torch.empty(n, dtype=torch.uint8, device=device)      # released at once: stays in the allocator's large pool
-    del block
-    return n
+    # requests below 1 MiB come from a separate pool of 2 MiB segments: 64 spare segments for those
+    small = [torch.empty(512 * 1024, dtype=torch.uint8, device=device) for _ in range(256)]
+    del block, small
+    return n + 256 * 512 * 1024
 
 
 def train_step(model, batch, optimizer, cfg: StepConfig, sched=None, sp_mask=None, grad_sync=None):
