@@ -432,6 +432,49 @@ def hot_kernel_rooflines(peaks, M):
     return {"shape": {"M": M, "K": K, "N": N, "attention": [Bq, Hh, Tt, Tt]}, "kernels": out}
 
 
+def ctc_kernel_rooflines(peaks, B, T, V, L, blank=3):
+    """The CTC loss kernels (csrc/ob_ctc.cu) at the step's shape through the C ABI: forward (row log-sum-exp + alpha/beta recursion
+    + mean) and backward (gradient pass); the 0.5 GB logits exceed L2 by themselves."""
+    from onebit_b200 import _cabi
+    lib = _cabi.lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(0)
+    x = torch.randn(B, T, V, device=dev)
+    dx = torch.empty(B, T, V, device=dev)
+    targets = torch.randint(4, V, (B, L), device=dev)
+    in_lens = torch.full((B,), T, dtype=torch.long, device=dev)
+    tgt_lens = torch.full((B,), L, dtype=torch.long, device=dev)
+    Sp = lib.ob_ctc_state_pitch(L)
+    lse, ab = torch.empty(B * T, device=dev), torch.empty(2, B, T, Sp, device=dev)
+    nll, loss, gout = torch.empty(B, device=dev), torch.empty((), device=dev), torch.ones((), device=dev)
+
+    def fwd():
+        rc = lib.ob_ctc_loss_fwd(x.data_ptr(), V, in_lens.data_ptr(), targets.data_ptr(), L, tgt_lens.data_ptr(), B, T, V, L, blank,
+                                 lse.data_ptr(), ab[0].data_ptr(), ab[1].data_ptr(), nll.data_ptr(), loss.data_ptr(), st)
+        if rc != 0:
+            raise RuntimeError(_cabi.last_error())
+
+    def bwd():
+        rc = lib.ob_ctc_loss_bwd(x.data_ptr(), V, in_lens.data_ptr(), targets.data_ptr(), L, tgt_lens.data_ptr(), B, T, V, L, blank,
+                                 lse.data_ptr(), ab[0].data_ptr(), ab[1].data_ptr(), nll.data_ptr(), gout.data_ptr(), dx.data_ptr(), V, st)
+        if rc != 0:
+            raise RuntimeError(_cabi.last_error())
+    out = {}
+    for name, fn, nbytes_alg in (("ctc_loss_fwd", fwd, 4.0 * B * T * V + 8.0 * B * T * Sp + 4.0 * B * T),
+                                 ("ctc_loss_bwd", bwd, 8.0 * B * T * V + 8.0 * B * T * Sp)):
+        for _ in range(3):
+            fn()
+        ms = timed_region(1, fn, 10) / 10
+        gbs = nbytes_alg / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": round(gbs / peaks["hbm_gbs"], 4), "algorithmic_bytes": int(nbytes_alg), "tflops": None}
+    out["ctc_loss_fwd"]["note"] = ("three launches: row log-sum-exp (HBM-bound), the alpha/beta recursion (T serial frames per "
+                                   "utterance: latency-bound), the mean")
+    out["ctc_loss_fwd"]["shape"] = out["ctc_loss_bwd"]["shape"] = [B, T, V, L]
+    return out
+
+
 def cpu_reference_train(args, sample_batch, steps):
     """The reference's training step on the host: the same module tree with the reference's fp32 layer (Oracle-A),
     all host threads; a bounded sample (sample_batch utterances of the same length)."""
@@ -578,6 +621,10 @@ def run_train(args, world, rank):
                                     "shape; every kernel of the step, incl. the fp32 tensor-core GEMM of the non-routed matmuls "
                                     "(the largest single family of the step), is in layer_kernels")
         out["layer_kernels"] = hk
+        try:                                                # added late in round 1: a failure here must not cost the bench line
+            hk["kernels"].update(ctc_kernel_rooflines(peaks, B, ((T - 1) // 2 - 1) // 2, TRAIN["vocab"], TRAIN["tokens"]))
+        except Exception as e:  # noqa: BLE001
+            hk["kernels"]["ctc_loss"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1:
             # SURVEY.md section 8(d) also asks for ONE precision-2 pass (forward + backward + AdamW), next to the full step
             from onebit_b200.training import att_ce_loss, ctc_loss_from_logits, make_att_targets
