@@ -79,6 +79,25 @@ def test_bmm_nt_strided_views_bias_scale_accumulate(ob):
     assert rel(acc[0, 0], torch.matmul(a.double(), b.double().transpose(-1, -2)).sum(0)[0]) < TOL
 
 
+@pytest.mark.parametrize("name", ["nt_wide_n", "tk_a_mn_major", "deep_k_split", "nn_wide_k"])
+def test_cta_pair_tiles_equal_single_cta_tiles(ob, name):
+    """The 256-wide tiles run on CTA pairs (cta_group::2) by default; ob_debug_set(8, 0) selects single CTAs.  Same MMA
+    sequence per output element, so the results are bitwise equal (tools/gpu_f32pair.py measures the same on more shapes)."""
+    from onebit_b200._cabi import lib
+    from onebit_b200.matmul import bmm_nt
+    a, b = CASES[name]() if name in CASES else (R(700, 516), R(516, 256, seed=1).t())
+    try:
+        assert lib.ob_debug_set(8, 0) == 0
+        single = bmm_nt(a, b)
+        assert lib.ob_debug_set(8, 1) == 0
+        pair = bmm_nt(a, b)
+        torch.cuda.synchronize()
+    finally:
+        lib.ob_debug_set(8, 1)
+    assert torch.equal(single, pair)
+    assert rel(pair, a.double() @ b.double().transpose(-1, -2)) <= TOL
+
+
 def test_bmm_nt_rejects_bad_arguments(ob):
     from onebit_b200.matmul import bmm_nt
     with pytest.raises(RuntimeError):
