@@ -7,6 +7,12 @@ flat fp32 buckets (~25 MB, filled in reverse-autograd order) and each full bucke
 a side stream while the rest of backward runs (one multi-tensor copy per completed bucket).  ``finish()`` joins the side
 stream, averages, and makes every ``.grad`` a view of its bucket before ``clip_grad_norm_`` needs the global gradients
 (train.py:117); gradients must be reset with ``zero_grad(set_to_none=True)`` between steps (``train_step`` does).
+
+Replica consistency: the constructor broadcasts every parameter (and the given buffers) from rank 0, as DDP does, so a
+rank that was seeded or restored differently cannot diverge silently.  Buckets are all-reduced strictly in bucket-index
+order on every rank - a bucket that completes early waits for its predecessors, the rest are flushed in order by
+``finish()`` - so the sequence of NCCL calls is identical on all ranks even when the set of parameters that received a
+gradient differs between them.
 """
 from __future__ import annotations
 
@@ -17,10 +23,16 @@ import torch.distributed as dist
 
 
 class GradAllReducer:
-    def __init__(self, params, bucket_bytes: int = 25 << 20, process_group=None):
+    def __init__(self, params, bucket_bytes: int = 25 << 20, process_group=None, buffers=(), broadcast: bool = True):
+        params = list(params)
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        if broadcast and self.world > 1:
+            with torch.no_grad():
+                for t in list(params) + list(buffers):
+                    dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
         self.cuda = bool(self.params) and self.params[0].is_cuda
         self.stream = torch.cuda.Stream() if self.cuda else None
         # buckets in reverse parameter order ~ the order gradients become ready
@@ -55,6 +67,8 @@ class GradAllReducer:
     def _reset(self):
         self._pending = [len(b["params"]) for b in self.buckets]
         self._launched = [False] * len(self.buckets)
+        self._ready = [False] * len(self.buckets)
+        self._next = 0                                   # next bucket index to all-reduce (same order on every rank)
         self._handles = []
 
     def _on_grad(self, p: torch.nn.Parameter):
@@ -65,7 +79,10 @@ class GradAllReducer:
         if self._pending[bi] == 0:                       # the bucket is complete: one multi-tensor copy, then the all-reduce
             b = self.buckets[bi]
             torch._foreach_copy_(b["views"], [q.grad.reshape(-1) for q in b["params"]])
-            self._launch(bi)
+            self._ready[bi] = True
+            while self._next < len(self.buckets) and self._ready[self._next]:
+                self._launch(self._next)
+                self._next += 1
 
     def _launch(self, bi: int):
         b = self.buckets[bi]
@@ -82,14 +99,16 @@ class GradAllReducer:
         """Wait for every bucket, divide by the world size and write the averaged gradients back."""
         if self.world == 1:
             return
-        for bi, b in enumerate(self.buckets):           # parameters without a gradient this step (e.g. alpha at 32 bit)
-            if not self._launched[bi]:
+        for bi in range(self._next, len(self.buckets)):  # the rest, in index order
+            b = self.buckets[bi]
+            if not self._ready[bi]:                      # holds parameters without a gradient this step (e.g. alpha at 32 bit)
                 for p, v in zip(b["params"], b["views"]):
                     if p.grad is None:
                         v.zero_()
                     else:
                         v.copy_(p.grad.reshape(-1))
-                self._launch(bi)
+            self._launch(bi)
+        self._next = len(self.buckets)
         for h in self._handles:
             h.wait()
         if self.cuda:

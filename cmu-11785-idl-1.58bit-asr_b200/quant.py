@@ -30,6 +30,32 @@ from ._cabi import OB_ALPHA_EFF, OB_ALPHA_RAW, OB_BF16, OB_F32, check, lib
 _DTYPE_TAG = {torch.float32: OB_F32, torch.bfloat16: OB_BF16}
 _BITWIDTH_ERROR = "bitwidth must be one of {1,2,32}"
 
+# ----------------------------------------------------------------------------------------------
+# validity of the cached 2-bit codes
+# ----------------------------------------------------------------------------------------------
+# A layer keeps the packed codes of its latent weights between forwards (three passes per step use them).  A tensor's
+# ``_version`` alone does not tell when they go stale: ``torch.optim.AdamW(fused=True)`` (and any ``.data`` edit) writes the
+# parameters without bumping it.  The cache key therefore also carries a process-wide *weight epoch* that moves on
+#   * after every ``optimizer.step()`` of any torch optimiser (global post-step hook, registered below),
+#   * whenever a backward of the layer has run (gradients exist -> the next forward most likely follows an update),
+#   * on ``invalidate_packed_weights()`` - the explicit call for raw ``.data`` / pointer writes outside an optimiser.
+# The cost of a spurious bump is one re-quantisation per layer and bitwidth (what the reference does on every forward).
+_weight_epoch = [0]
+
+
+def invalidate_packed_weights() -> None:
+    """Declare every cached packed code stale (call after writing latent weights or alpha behind autograd's back)."""
+    _weight_epoch[0] += 1
+
+
+def _optimizer_step_hook(optimizer, args, kwargs) -> None:
+    _weight_epoch[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook  # noqa: E402
+
+_register_step_hook(_optimizer_step_hook)
+
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 _raw_device = getattr(torch._C, "_cuda_getDevice", None)
@@ -162,6 +188,7 @@ class _QuantLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         q, s, weight, alpha, packed_t = ctx.saved_tensors
+        _weight_epoch[0] += 1
         need_x, need_w, need_a, need_b = ctx.needs_input_grad[:4]
         gx, gw, ga, gb = _linear_backward(gy, q, s, weight, alpha, packed_t, ctx.bitwidth, need_x, need_w or need_a,
                                           need_b and ctx.has_bias)
@@ -264,6 +291,7 @@ class _SwishDropQuantLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         saved = ctx.saved_tensors
+        _weight_epoch[0] += 1
         h2, q, s, weight, alpha, packed_t = saved[:6]
         keep = saved[6] if len(saved) > 6 else None
         need_h, need_w, need_a, need_b = ctx.needs_input_grad[:4]
@@ -314,6 +342,7 @@ class _GroupedQuantLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         q, s, weight, alpha, pkt2, pkt1 = ctx.saved_tensors[:6]
+        _weight_epoch[0] += 1
         M, K = q.shape
         N = weight.shape[0]
         need_x, need_w, need_a, need_b = ctx.needs_input_grad[:4]
@@ -402,10 +431,11 @@ class QuantizedLinear(nn.Module):
             self.alpha.copy_(weight_absmean(self.weight))
 
     def packed_weight(self, bitwidth: int):
-        """2-bit packed codes for ``bitwidth`` (cached per weight/alpha version: one quantiser launch per
-        optimiser step and bitwidth, instead of one per forward as in quant.py:124)."""
+        """2-bit packed codes for ``bitwidth``, cached while the latent weights are known to be unchanged (tensor versions
+        and the weight epoch above): one quantiser launch per optimiser step and bitwidth, instead of one per forward as
+        in quant.py:124."""
         w, a = self.weight, self.alpha
-        key = (w._version, a._version, w.data_ptr(), a.data_ptr())
+        key = (_weight_epoch[0], w._version, a._version, w.data_ptr(), a.data_ptr())
         hit = self._packed.get(bitwidth)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]

@@ -25,7 +25,10 @@ def fx():
     return dict(np.load(os.path.join(GOLDEN, "conformer_step.npz")))
 
 
-def test_cotraining_run_matches_reference(fx):
+@pytest.mark.parametrize("fused_adamw", [False, True])
+def test_cotraining_run_matches_reference(fx, fused_adamw):
+    """``fused_adamw``: torch's single-kernel AdamW (what bench.py uses) updates parameters without bumping their
+    ``_version``; the packed codes must still follow the weights (losses of steps 1..3 depend on it)."""
     import onebit_b200 as ob
     from onebit_b200.training import StepConfig, cotraining_loss
     torch.backends.cudnn.allow_tf32 = False           # the non-routed convolutions stay true fp32 for the comparison
@@ -36,7 +39,8 @@ def test_cotraining_run_matches_reference(fx):
     batch = {k: torch.from_numpy(fx[k]).cuda() for k in ("feats", "feat_lens", "tokens", "token_lens")}
     batch["feat_lens_cpu"] = torch.from_numpy(fx["feat_lens"])
     batch["token_lens_cpu"] = torch.from_numpy(fx["token_lens"])
-    opt = torch.optim.AdamW(model.parameters(), lr=float(fx["lr"]), betas=(0.9, 0.98), weight_decay=1e-2)
+    opt = torch.optim.AdamW(model.parameters(), lr=float(fx["lr"]), betas=(0.9, 0.98), weight_decay=1e-2,
+                            fused=fused_adamw)
     cfg = StepConfig()
     losses, norms = [], {}
     for step, spm in enumerate(fx["sp_masks"]):

@@ -64,10 +64,48 @@ def test_weight_codes_seeded_layers(ob, kat_seeded):
             assert sha16(codes) == ref[f"sha_q{bw}"], (key, bw)
             assert np.array_equal(orc.unpack_codes(packed.cpu().numpy(), "i8"), codes)
             assert np.array_equal(orc.unpack_codes(packed_t.cpu().numpy(), "bf16"), codes.T)
-        assert layer.packed_weight(2)[0] is layer.packed_weight(2)[0]        # cached per weight version
+        assert layer.packed_weight(2)[0] is layer.packed_weight(2)[0]        # cached while the weights are unchanged
+
+
+def _fresh_codes(obq, layer, bw):
+    packed, _ = obq.pack_weight(layer.weight, layer.alpha, bw)
+    return obq.unpack_codes(packed, 0).cpu().numpy()
+
+
+@pytest.mark.parametrize("update", ["mul_", "data_mul_", "adamw_foreach", "adamw_fused", "sgd_after_backward"])
+def test_packed_cache_follows_every_kind_of_weight_update(ob, update):
+    """The cached 2-bit codes must be re-quantised after ANY update of the latent weights - including the ones that do not
+    bump ``Tensor._version`` (fused AdamW, ``.data`` edits): quant.py:124 re-quantises on every forward."""
+    from onebit_b200 import quant as obq
+    torch.manual_seed(7)
+    layer = ob.QuantizedLinear(256, 128).cuda()
+    x = torch.randn(40, 256, device="cuda")
+    before = obq.unpack_codes(layer.packed_weight(2)[0], 0).cpu().numpy()
+    assert layer.packed_weight(2)[0] is layer.packed_weight(2)[0]
+    if update == "mul_":
         with torch.no_grad():
-            layer.weight.mul_(1.0)
-        assert layer.packed_weight(2)[0] is not packed or True
+            layer.weight.mul_(-1.0)
+    elif update == "data_mul_":
+        layer.weight.data.mul_(-1.0)
+        obq.invalidate_packed_weights()              # raw .data writes are invisible to autograd: the documented call
+    elif update == "sgd_after_backward":
+        layer(x, 2).square().mean().backward()
+        layer.weight.data.add_(layer.weight.grad, alpha=-50.0)   # manual update, no optimiser, no version bump
+    else:
+        opt = torch.optim.AdamW(layer.parameters(), lr=0.05, fused=(update == "adamw_fused"))
+        for _ in range(2):
+            opt.zero_grad()
+            layer(x, 2).square().mean().backward()
+            opt.step()
+    packed_now = layer.packed_weight(2)[0]
+    after = obq.unpack_codes(packed_now, 0).cpu().numpy()
+    assert np.array_equal(after, _fresh_codes(obq, layer, 2)), update
+    assert not np.array_equal(after, before), update
+    # and the forward really uses them
+    y = layer(x, 2)
+    ref = orc.linear_forward(x.cpu().numpy(), layer.weight.detach().cpu().numpy(), layer.alpha.detach().cpu().numpy(),
+                             layer.bias.detach().cpu().numpy(), 2, act_bits=8)
+    assert rel_err(y.detach().cpu().numpy(), ref) < 1e-4
 
 
 def test_absmean(ob):
@@ -218,6 +256,42 @@ def test_layer_vs_oracle(ob, M, K, N, bw):
     # (bf16 operand rounding, 2^-9 per element), not with its own value -> absolute bound of 1e-2 of that norm
     g_hat_norm = float(np.linalg.norm(g_ref["weight"].astype(np.float64))) * 2 ** 0.5      # ~half the entries are masked
     assert math.isclose(layer.alpha.grad.item(), float(g_ref["alpha"]), rel_tol=1e-2, abs_tol=1e-2 * g_hat_norm)
+
+
+@pytest.mark.parametrize("M,rows2,K,N", [(25536, None, 256, 1024), (25536, None, 1024, 256),
+                                         (76608, 25536 + 7 * 399, 256, 1024), (76608, 2 * 25536 + 399, 256, 256)])
+def test_backward_at_bench_token_counts(ob, M, rows2, K, N):
+    """Backward GEMMs at the token counts the bench runs (M = 25 536 = 64 x 399 per pass; 76 608 rows when the three co-training
+    passes are stacked, with a ragged 2-bit / 1-bit split as the stochastic-precision pass produces): grad_x, grad_W (token
+    splits + finaliser), grad_alpha, grad_bias against float64 numpy of the same math (oracle, seconds on the host)."""
+    torch.manual_seed(K + N + 1)
+    layer = ob.QuantizedLinear(K, N)
+    with torch.no_grad():
+        layer.bias.normal_(0, 0.1)
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, K, generator=g)
+    gy = torch.randn(M, N, generator=g) * (1.0 / 64.0)
+    W, a, b = (t.detach().numpy().copy() for t in (layer.weight, layer.alpha, layer.bias))
+    layer = layer.cuda()
+    xd = x.cuda().requires_grad_(True)
+    y = layer(xd, 2) if rows2 is None else layer.forward_grouped(xd, rows2)
+    y.backward(gy.cuda())
+    groups = [(0, M, 2)] if rows2 is None else [(0, rows2, 2), (rows2, M, 1)]
+    gw_ref, ga_ref, gb_ref = np.zeros((N, K)), 0.0, np.zeros(N)
+    for r0, r1, bw in groups:
+        y_ref = orc.linear_forward(x[r0:r1].numpy(), W, a, b, bw, 8)
+        g_ref = orc.linear_backward(gy[r0:r1].numpy(), x[r0:r1].numpy(), W, a, b, bw, 8)
+        assert rel_err(y[r0:r1].detach().cpu().numpy(), y_ref) < 1e-4
+        assert rel_err(xd.grad[r0:r1].cpu().numpy(), g_ref["x"]) < 1e-2
+        gw_ref += g_ref["weight"].astype(np.float64)
+        ga_ref += float(g_ref["alpha"])
+        gb_ref += g_ref["bias"].astype(np.float64)
+    gw = layer.weight.grad.cpu().numpy()
+    assert rel_err(gw, gw_ref) < 1e-2
+    assert np.array_equal(gw != 0, gw_ref != 0)                      # STE mask
+    assert rel_err(layer.bias.grad.cpu().numpy(), gb_ref) < 1e-4
+    g_hat_norm = float(np.linalg.norm(gw_ref)) * 2 ** 0.5
+    assert math.isclose(layer.alpha.grad.item(), ga_ref, rel_tol=1e-2, abs_tol=1e-2 * g_hat_norm)
 
 
 def test_size_independent_properties_at_bench_size(ob):

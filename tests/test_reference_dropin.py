@@ -1,0 +1,189 @@
+"""The drop-in seam exercised with the reference's OWN modules, byte-compiled into ``baseline/_ref``
+(oracle/build_ref.py): the unmodified ``conformer.ConformerASR`` with its flat ``from quant import QuantizedLinear``
+(conformer.py:12) resolved to
+
+  * the reference's own ``quant.py``            -> pins ``baseline/_ref`` itself to the committed golden vectors (CPU),
+  * ``oracle/torch_oracle.py``'s layer          -> Oracle-A / Oracle-B model on the CPU,
+  * ``onebit_b200.quant`` on a B200             -> the product, compared with Oracle-B (``-m gpu``).
+
+tolerances (GPU): encoder output / CTC logits rel <= 2e-3 of max (fp32 model around an exact integer GEMM; LayerNorms amplify
+                  the last-bit differences of the dequantisation), gradient norms rel <= 2e-2 (bf16 tensor-core backward),
+                  config-1 loss rel <= 3e-3 vs Oracle-B and 1e-2 vs the pure reference.
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import ref_loader
+
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason="baseline/_ref not built (python oracle/build_ref.py)")
+
+
+def _oracle_quant_module(act_bits):
+    from oracle.torch_oracle import OracleQuantizedLinear
+
+    class Layer(OracleQuantizedLinear):
+        act_bits_default = act_bits
+    mod = types.ModuleType("quant")
+    mod.QuantizedLinear = Layer
+    return mod
+
+
+_ORACLE_B = _oracle_quant_module(8)
+_ORACLE_A = _oracle_quant_module(32)
+
+
+def _small_batch():
+    g = torch.Generator().manual_seed(77)
+    return {"feats": torch.randn(3, 131, 80, generator=g), "feat_lens": torch.tensor([131, 100, 64])}
+
+
+# ---------------------------------------------------------------------------------------------- CPU: pin baseline/_ref
+@needs_ref
+def test_ref_build_is_the_reference(kat_edges):
+    """The byte-compiled modules reproduce the committed known answers of the reference's quant.py (KAT-1)."""
+    ref = ref_loader.load()
+    for bw in (1, 2):
+        W = torch.tensor(kat_edges["W"], requires_grad=True)
+        a = torch.tensor(kat_edges["alpha"], requires_grad=True)
+        what = ref.quant.quantize_weight(W, a, bw)
+        what.backward(torch.tensor(kat_edges["g"]))
+        assert what.detach().tolist() == kat_edges[f"bw{bw}"]["W_hat"]
+        assert W.grad.tolist() == kat_edges[f"bw{bw}"]["grad_W"]
+        assert abs(a.grad.item() - kat_edges[f"bw{bw}"]["grad_alpha"]) < 1e-6
+
+
+@needs_ref
+def test_oracle_layer_inside_the_unmodified_conformer_equals_the_reference():
+    """Oracle-A served through the flat-import seam gives the pure reference's numbers (forward and every gradient)."""
+    ref, swapped = ref_loader.load(), ref_loader.load(quant_module=_ORACLE_A)
+    batch = _small_batch()
+    outs = []
+    for ns in (ref, swapped):
+        torch.manual_seed(3)
+        m = ns.conformer.ConformerASR(80, 48, enc_layers=2, dec_layers=1, enc_dropout=0.0, dec_dropout=0.0).train()
+        enc, _, ctc = m(batch, precision=2, sp_mask=[1, 0])
+        (enc.square().mean() + ctc.square().mean()).backward()
+        outs.append((enc.detach(), ctc.detach(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    assert torch.allclose(outs[0][0], outs[1][0], atol=1e-6) and torch.allclose(outs[0][1], outs[1][1], atol=1e-6)
+    assert outs[0][2].keys() == outs[1][2].keys()
+    for n in outs[0][2]:
+        assert torch.allclose(outs[0][2][n], outs[1][2][n], rtol=1e-4, atol=1e-7), n
+
+
+@needs_ref
+def test_reference_run_epoch_runs_unmodified():
+    """bench.py's reference arm drives train.py:run_epoch itself; one tiny step here."""
+    ref = ref_loader.load(with_train=True)
+    torch.manual_seed(0)
+    m = ref.conformer.ConformerASR(80, 40, enc_layers=2, dec_layers=1)
+    g = torch.Generator().manual_seed(1)
+    batch = {"feats": torch.randn(2, 200, 80, generator=g), "feat_lens": torch.tensor([200, 160]),
+             "tokens": torch.randint(4, 40, (2, 6), generator=g), "token_lens": torch.tensor([6, 6])}
+
+    class DM:
+        def train_dataloader(self):
+            return [batch]
+
+        def special_ids(self):
+            return dict(bos_id=1, eos_id=2, pad_id=0, blank_id=3)
+    opt = torch.optim.AdamW(m.parameters(), lr=5e-4)
+    loss = ref.train.run_epoch(m, DM(), opt, None, "cpu", types.SimpleNamespace(enc_layers=2), True, 0.5, 1.0, 0.2)[0]
+    assert np.isfinite(loss) and loss > 0
+
+
+# ---------------------------------------------------------------------------------------------- GPU: the product in the seam
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("precision,sp_mask", [(2, None), (1, None), (2, [1, 0, 1])])
+def test_unmodified_reference_conformer_on_the_cuda_layer(precision, sp_mask):
+    """conformer.py's own FeedForwardModule / MHSA forward (conformer.py:34-45, 105-138) calling the B200 layer at 2 and 1 bits,
+    forward and backward, against the same code calling the Oracle-B layer on the CPU."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import onebit_b200 as ob
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    oracle, product = ref_loader.load(quant_module=_ORACLE_B), ref_loader.load(quant_module=ob.quant)
+    kw = dict(enc_layers=3, dec_layers=1, enc_dropout=0.0, dec_dropout=0.0)
+    torch.manual_seed(21)
+    m_cpu = oracle.conformer.ConformerASR(80, 64, **kw).train()
+    torch.manual_seed(21)
+    m_gpu = product.conformer.ConformerASR(80, 64, **kw).train()
+    routed = [m for m in m_gpu.modules() if isinstance(m, ob.QuantizedLinear)]
+    assert len(routed) == 27 and type(m_gpu).__module__.endswith(".conformer")      # the reference's class, our layer
+    assert all(torch.equal(v, m_gpu.state_dict()[k]) for k, v in m_cpu.state_dict().items())
+    m_gpu = m_gpu.cuda()
+    batch = _small_batch()
+    batch_gpu = {k: v.cuda() for k, v in batch.items()}
+    g = torch.Generator().manual_seed(5)
+    w_enc, w_ctc = torch.randn(3, 31, 256, generator=g), torch.randn(3, 31, 64, generator=g)
+
+    enc_c, mask_c, ctc_c = m_cpu(batch, precision=precision, sp_mask=sp_mask)
+    ((enc_c * w_enc).sum() + (ctc_c * w_ctc).sum()).backward()
+    enc_g, mask_g, ctc_g = m_gpu(batch_gpu, precision=precision, sp_mask=sp_mask)
+    ((enc_g * w_enc.cuda()).sum() + (ctc_g * w_ctc.cuda()).sum()).backward()
+    assert torch.equal(mask_c, mask_g.cpu())
+    assert _rel(enc_g.detach().cpu(), enc_c.detach()) < 2e-3
+    assert _rel(ctc_g.detach().cpu(), ctc_c.detach()) < 2e-3
+    grads_c = dict(m_cpu.named_parameters())
+    total = float(torch.sqrt(sum(p.grad.double().pow(2).sum() for p in m_cpu.parameters() if p.grad is not None)))
+    for n, p in m_gpu.named_parameters():
+        ref = grads_c[n].grad
+        assert (p.grad is None) == (ref is None), n
+        if ref is None:
+            continue
+        # alpha gradients cancel heavily (sum over N*K terms): absolute bound relative to the total gradient norm
+        atol = 1e-3 * total if n.endswith(".alpha") else 1e-5 * total
+        got, want = p.grad.double().norm().item(), ref.double().norm().item()
+        assert abs(got - want) <= 2e-2 * want + atol, (n, got, want)
+
+
+@pytest.mark.gpu
+def test_config1_default_dims_step_matches_reference():
+    """BASELINE configs[0]: default dims (12 blocks, V = 5004), batch 4 x 1000 frames, one co-training step (dropout 0, fixed
+    precision mask) on the B200 kernels vs the fixture the executed reference produced (tests/golden/make_golden_config1.py)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import onebit_b200 as ob
+    from onebit_b200.training import StepConfig, cotraining_loss
+    fx = dict(np.load(os.path.join(GOLDEN, "conformer_config1.npz")))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, T, U, V = (int(v) for v in fx["shape"])
+    g = torch.Generator().manual_seed(int(fx["seed_batch"]))
+    feats = torch.randn(B, T, 80, generator=g)
+    tokens = torch.randint(4, V, (B, U), generator=g)
+    assert abs(float(feats.double().sum()) - float(fx["feats_sum"])) < 1e-6 and int(tokens.sum()) == int(fx["tokens_sum"])
+    host = {"feats": feats, "feat_lens": torch.from_numpy(fx["feat_lens"]), "tokens": tokens,
+            "token_lens": torch.full((B,), U, dtype=torch.long)}
+    batch = {k: v.cuda() for k, v in host.items()}
+    batch["feat_lens_cpu"], batch["token_lens_cpu"] = host["feat_lens"], host["token_lens"]
+    sp_mask = [int(v) for v in fx["sp_mask"]]
+    for cfg in (StepConfig(), StepConfig(share_frontend=True, stack_passes=True)):       # sequential passes, and the bench's stacked form
+        torch.manual_seed(int(fx["seed_model"]))
+        model = ob.ConformerASR(80, V, enc_dropout=0.0, dec_dropout=0.0).train().cuda()
+        assert len(model.quantized_layers()) == 108
+        loss, _ = cotraining_loss(model, batch, cfg, sp_mask)
+        loss.backward()
+        assert abs(loss.item() - float(fx["loss_B"])) <= 3e-3 * float(fx["loss_B"]), (loss.item(), float(fx["loss_B"]))
+        assert abs(loss.item() - float(fx["loss_A"])) <= 1e-2 * float(fx["loss_A"]), (loss.item(), float(fx["loss_A"]))
+        params = dict(model.named_parameters())
+        total_ref = float(fx["norms_B"][list(fx["norm_names"]).index("__total__")])
+        total = float(torch.sqrt(sum(p.grad.double().pow(2).sum() for p in model.parameters() if p.grad is not None)))
+        assert abs(total - total_ref) <= 2e-2 * total_ref, (total, total_ref)
+        for name, ref in zip(fx["norm_names"], fx["norms_B"]):
+            name = str(name)
+            if name == "__total__":
+                continue
+            atol = 1e-3 * total_ref if name.endswith(".alpha") else 1e-5 * total_ref
+            got = params[name].grad.double().norm().item()
+            assert abs(got - ref) <= 2e-2 * ref + atol, (name, got, ref)
