@@ -16,9 +16,10 @@ Workloads (one "step" = one pass of the hot path over one batch of synthetic inp
   gemm   BASELINE.json configs[1] alone: act-quant + ternary x int8 tcgen05 GEMM at M = 65536, K = N = 2048;
          metric = BitLinear int8 TOPS.  `--sweep` adds the whole K/N sweep.
 
-`--impl reference` times the reference's own path restated on the CPU (oracle/: the reference's fp32 layer inside
-the same module tree) on the host cores, on a bounded sample of the same workload.
-Prints ONE JSON line on rank 0.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref: its modules byte-compiled by oracle/build_ref.py) on the host
+cores: train.py's own run_epoch on BASELINE configs[0] (batch 4 x 1000 frames, default dims) - a bounded sample of the step the
+GPU arm times; that process never imports the product package.  The GPU arm's `cpu_baseline` is the same thing run in a
+child process.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -52,6 +53,13 @@ def parse():
     p.add_argument("--out-features", type=int, default=2048)
     p.add_argument("--bitwidth", type=int, default=2)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--global-batch", type=int, default=0,
+                   help="train: fix the GLOBAL batch (BASELINE configs[3]: 512) instead of the per-GPU batch: each rank takes "
+                        "global/N utterances, in micro-batches of at most --max-micro-batch with gradient accumulation "
+                        "(strong scaling); 0 = weak scaling with --batch utterances per GPU")
+    p.add_argument("--max-micro-batch", type=int, default=128)
+    p.add_argument("--no-small-m", action="store_true", help="skip the small-batch (M <= 256) table inside the train line")
+    p.add_argument("--no-sweep-summary", action="store_true", help="skip the configs[1] K/N sweep summary inside the train line")
     p.add_argument("--no-gemm", action="store_true", help="skip the GEMM microbench inside the train line")
     p.add_argument("--no-share-frontend", dest="share_frontend", action="store_false",
                    help="recompute the (bitwidth-independent, dropout-free) conv subsampling in each of the three passes, as the "
@@ -263,7 +271,92 @@ def gemm_microbench(args, steps, sweep=False):
     return out
 
 
+def _graph_time_us(fn_of_i, n_per_graph, reps=5):
+    """Device time per call of fn_of_i(i), i = 0..n_per_graph-1, replayed from a CUDA graph (no host launch gaps)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        fn_of_i(0)
+        with torch.cuda.graph(g, stream=side):
+            for i in range(n_per_graph):
+                fn_of_i(i)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    return timed_region(1, g.replay, reps) / reps / n_per_graph * 1e3
+
+
+def sweep_summary(rows, peaks):
+    """configs[1] K/N sweep condensed: every shape against the roof that binds it (int8 ridge = int8 peak / measured HBM)."""
+    peak_i8, _ = int8_peak(peaks)
+    ridge = peak_i8 * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    out = {"ridge_op_per_byte": round(ridge, 1), "int8_peak_tops": round(peak_i8, 1), "hbm_peak_gbs": peaks["hbm_gbs"], "by_M": {}}
+    for Ms in sorted({r["M"] for r in rows}):
+        sel = [r for r in rows if r["M"] == Ms]
+        for r in sel:
+            ops = 2.0 * r["M"] * r["N"] * r["K"]
+            by = r["M"] * r["K"] + r["N"] * r["K"] / 4 + 2.0 * r["M"] * r["N"] + 4 * r["M"] + 4 * r["N"]
+            r["bound"] = "tensor" if ops / by >= ridge else "hbm"
+            r["frac"] = round(r["tops"] / peak_i8 if r["bound"] == "tensor" else r["gbs"] / peaks["hbm_gbs"], 4)
+        reg = {}
+        for bound in ("tensor", "hbm"):
+            fr = sorted(r["frac"] for r in sel if r["bound"] == bound)
+            if fr:
+                reg[bound] = {"shapes": len(fr), "min_frac": fr[0], "median_frac": fr[len(fr) // 2], "max_frac": fr[-1]}
+        out["by_M"][str(Ms)] = {"regimes": reg,
+                                "rows": [{k: r[k] for k in ("K", "N", "us", "tops", "gbs", "bound", "frac")} for r in sel]}
+    return out
+
+
+def small_batch_table(peaks):
+    """north_star: "at small batch, the packed-weight GEMV-like regime is also reported as achieved GB/s".  M token rows in
+    {1, 8, 64, 256} x the model's three routed shapes; M <= 64 runs the weight-streaming DP4A kernel (csrc/ob_gemv.cu), 256 the
+    tcgen05 kernel.  Device time per launch from a CUDA-graph replay over 8 rotating weight/activation sets (the layers of a
+    model are distinct: 8 x 64 KB..1 MB stays in L2, as it does in a real 108-layer forward at this batch); bytes = packed W
+    (N K / 4) + int8 activations (M K) + fp32 output (4 M N) + scales and bias."""
+    import onebit_b200 as ob
+    from onebit_b200 import quant as obq
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = []
+    for K, N in ((256, 256), (256, 1024), (1024, 256), (2048, 2048)):
+        torch.manual_seed(0)
+        layers = [ob.QuantizedLinear(K, N).to(dev) for _ in range(8)]
+        pks = [l.packed_weight(2)[0] for l in layers]
+        for M in (1, 8, 64, 256):
+            xs = [torch.randn(M, K, device=dev) for _ in range(8)]
+            qs = [ob.act_quant_int8(x) for x in xs]
+
+            def gemm(i):
+                j = i % 8
+                obq.gemm_fwd(qs[j][0], qs[j][1], pks[j], layers[j].alpha, layers[j].bias, N, torch.float32)
+
+            def layer_fwd(i):
+                j = i % 8
+                q, sc = ob.act_quant_int8(xs[j])
+                obq.gemm_fwd(q, sc, pks[j], layers[j].alpha, layers[j].bias, N, torch.float32)
+            us = _graph_time_us(gemm, 64)
+            us_layer = _graph_time_us(layer_fwd, 64)
+            by = N * K / 4 + M * K + 4.0 * M * N + 4 * M + 4 * N
+            rows.append({"M": M, "K": K, "N": N, "kernel": "gemv_tern_i8 (DP4A)" if M <= 64 else "gemm_expand (tcgen05)",
+                         "us": round(us, 2), "gbs": round(by / us / 1e3, 1), "frac_hbm": round(by / us / 1e3 / peaks["hbm_gbs"], 4),
+                         "weight_gbs": round(N * K / 4 / us / 1e3, 1), "layer_fwd_us": round(us_layer, 2),
+                         "algorithmic_bytes": int(by)})
+    return {"note": "packed-weight GEMV-like regime; at these sizes (16 KB - 1 MB of weights) a launch is latency-bound: "
+                    "the floor is the ~2 us launch + one dependent HBM/L2 round trip, not bandwidth", "rows": rows}
+
+
 # ------------------------------------------------------------------------------------------ train workload
+def train_workload_config(args, world):
+    """The workload both arms are quoted on (the reference arm runs a bounded sample of it, stated in its `cpu_baseline.sample`)."""
+    B = args.global_batch // world if args.global_batch else args.batch
+    return {"workload": "Conformer BitLinear co-training step (BASELINE configs[2]; configs[3] = global batch 512): 12 blocks, "
+                        "d_model 256, d_ff 1024, 4 heads, V=5004, 3 passes (2-bit, 1-bit, stochastic precision) + "
+                        "CTC/attention/KL losses + clip + AdamW",
+            "batch_per_gpu": B, "global_batch": B * world, "frames": args.frames, "mel": TRAIN["mel"], "dropout": args.dropout,
+            "l2": "no explicit flush: the activations one step streams (tens of GB) exceed the 126 MB L2 many times over",
+            "parallelism": f"dp{world}"}
+
+
 def make_batch(B, T, seed, device=None, pinned=False):
     g = torch.Generator().manual_seed(seed)
     feats = torch.randn(B, T, TRAIN["mel"], generator=g)
@@ -475,30 +568,18 @@ def ctc_kernel_rooflines(peaks, B, T, V, L, blank=3):
     return out
 
 
-def cpu_reference_train(args, sample_batch, steps):
-    """The reference's training step on the host: the same module tree with the reference's fp32 layer (Oracle-A),
-    all host threads; a bounded sample (sample_batch utterances of the same length)."""
-    import onebit_b200 as ob
-    from onebit_b200.training import StepConfig, train_step
-    from oracle.torch_oracle import OracleQuantizedLinear
-    torch.set_num_threads(os.cpu_count())
-    torch.manual_seed(0)
-    OracleQuantizedLinear.act_bits_default = 32
+def cpu_baseline_child(args):
+    """cpu_baseline of the GPU arm = the reference arm run in a CHILD process (this process holds the product and must not
+    import the reference; the child must not import the product).  Returns the child's `cpu_baseline` object."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--dropout", str(args.dropout), "--workload", "train"]
     try:
-        model = ob.ConformerASR(TRAIN["mel"], TRAIN["vocab"], enc_dropout=args.dropout, dec_dropout=args.dropout,
-                                linear_cls=OracleQuantizedLinear).train()
-    finally:
-        OracleQuantizedLinear.act_bits_default = 8
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2,
-                            fused=not getattr(args, "foreach_adamw", False))
-    batch = make_batch(sample_batch, args.frames, 1)
-    cfg = StepConfig()
-    train_step(model, batch, opt, cfg)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        train_step(model, batch, opt, cfg)
-    dt = (time.perf_counter() - t0) / steps
-    return sample_batch * args.frames * FRAME_S / dt, dt
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "reference",
+                "sample": f"child process failed: {type(e).__name__}: {e}"}
 
 
 def run_train(args, world, rank):
@@ -509,16 +590,30 @@ def run_train(args, world, rank):
     from onebit_b200.training import StepConfig, reserve_allocator_headroom, train_step
     peaks = load_peaks()
     dev = torch.device("cuda", torch.cuda.current_device())
-    B, T = args.batch, args.frames
+    T = args.frames
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world                      # strong scaling: the global batch is fixed (configs[3]: 512)
+    else:
+        B = args.batch                                      # weak scaling: the per-GPU batch is fixed
+    n_micro = -(-B // args.max_micro_batch)
+    if B % n_micro:
+        raise SystemExit(f"per-GPU batch {B} does not split into {n_micro} equal micro-batches")
+    Bm = B // n_micro
     if args.tf32_nonrouted:
         torch.backends.cuda.matmul.allow_tf32 = True
-    torch.manual_seed(0)                                   # same weights and precision masks on every rank
+    torch.manual_seed(0)                                   # same weights and (CPU RNG) precision masks on every rank
     model = ob.ConformerASR(TRAIN["mel"], TRAIN["vocab"], enc_dropout=args.dropout, dec_dropout=args.dropout).train().to(dev)
+    torch.cuda.manual_seed(1234 + rank)                    # dropout streams differ per replica (weights were drawn on the CPU)
     opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2,
                             fused=not getattr(args, "foreach_adamw", False))
-    sync = GradAllReducer(model.parameters()) if world > 1 else None
+    sync = GradAllReducer(model.parameters(), buffers=model.buffers()) if world > 1 else None
+    if sync is not None:
+        sync.timing = True
     cfg = StepConfig(share_frontend=args.share_frontend, stack_passes=args.share_frontend and not args.no_stack_passes)
-    batch = make_batch(B, T, 1000 + rank, device=dev)
+    batch = [make_batch(Bm, T, 1000 + rank * 16 + i, device=dev) for i in range(n_micro)]
+    batch = batch[0] if n_micro == 1 else batch
     warm = max(args.warmup, 3)
 
     def step():
@@ -530,6 +625,8 @@ def run_train(args, world, rank):
             headroom = reserve_allocator_headroom(dev, args.allocator_headroom_gib)
     mallocs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
     routes.reset()
+    if sync is not None:
+        sync.exposed_ms()                                   # drop the warm-up samples
     l0 = _cabi.lib.ob_launch_count()
     sampler = ClockSampler(torch.cuda.current_device()).start()
     window = os.environ.get("OB_NCU_WINDOW") == "1"     # `ncu --profile-from-start off` then sees only the timed steps
@@ -542,6 +639,9 @@ def run_train(args, world, rank):
     launches = _cabi.lib.ob_launch_count() - l0
     timed_mallocs = torch.cuda.memory_stats().get("num_device_alloc", 0) - mallocs0     # cudaMallocs inside the timed steps
     taken = routes.counts()                                 # which implementation every op around the layer took (CUDA tensors)
+    exposed = sync.exposed_ms() if sync is not None else None
+    if sync is not None:
+        sync.timing = False
     ms_per_step = ms / args.steps
     audio_s = world * B * T * FRAME_S
     value = audio_s / (ms_per_step * 1e-3)
@@ -550,12 +650,15 @@ def run_train(args, world, rank):
         return {"metric": "conformer_train_audio_sec_per_sec", "value": round(value, 1), "unit": "audio-s/s",
                 "ms_per_step": round(ms_per_step, 2), "gpu_launches": int(launches), "note": "OB_NCU_WINDOW run (profiling aid)"}
     # end to end through the public API: host (pinned) batch -> device each step, loss read back each step
-    host = make_batch(B, T, 2000 + rank, pinned=True)
+    hosts = [make_batch(Bm, T, 2000 + rank * 16 + i, pinned=True) for i in range(n_micro)]
 
     def e2e_step():
-        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        b["feat_lens_cpu"], b["token_lens_cpu"] = host["feat_lens"], host["token_lens"]
-        return train_step(model, b, opt, cfg, grad_sync=sync)[0].item()
+        mbs = []
+        for host in hosts:
+            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            b["feat_lens_cpu"], b["token_lens_cpu"] = host["feat_lens"], host["token_lens"]
+            mbs.append(b)
+        return train_step(model, mbs[0] if n_micro == 1 else mbs, opt, cfg, grad_sync=sync)[0].item()
     e2e_step()
     e2e_steps = max(2, min(args.steps, 5))
     if world > 1:
@@ -573,22 +676,20 @@ def run_train(args, world, rank):
         t = torch.tensor([e2e_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = t.item()
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = sum(v.numel() * v.element_size() for host in hosts for v in host.values())
     e2e = {"value": round(audio_s / (e2e_ms * 1e-3), 1), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 2), "last_loss": round(last, 4),
            "api": "onebit_b200.training.train_step(model, host_batch, AdamW) incl. H2D of the batch and loss.item()"}
 
     out = {"metric": "conformer_train_audio_sec_per_sec", "value": round(value, 1), "unit": "audio-s/s", "n_gpus": world,
            "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None,
+           "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
            "dtype": "int8 x ternary fwd (int32 accum), bf16 bwd (fp32 accum); non-routed matmuls fp32 via 3 x tf32 split "
                     "on tcgen05 (error <= 1e-5 of max, fp32 accumulate), other non-routed ops fp32",
            "data": "synthetic", "impl": "ours",
-           "config": {"workload": "Conformer BitLinear co-training step (BASELINE configs[2]; configs[3] at 8 GPUs): 12 blocks, "
-                                  "d_model 256, d_ff 1024, 4 heads, V=5004, 3 passes (2-bit, 1-bit, stochastic precision) + "
-                                  "CTC/attention/KL losses + clip + AdamW",
-                      "batch_per_gpu": B, "global_batch": B * world, "frames": T, "mel": TRAIN["mel"], "dropout": args.dropout,
-                      "audio_s_per_step": audio_s, "tf32_nonrouted": bool(args.tf32_nonrouted),
+           "config": train_workload_config(args, world),
+           "run_info": {"audio_s_per_step": audio_s, "micro_batches_per_step": n_micro, "micro_batch": Bm,
+                      "allreduce_exposed_ms": None if exposed is None else round(exposed, 3), "tf32_nonrouted": bool(args.tf32_nonrouted),
                       "torch_nonrouted": args.torch_nonrouted or None,
                       "optimizer": "torch.optim.AdamW(lr 5e-4, betas (0.9, 0.98), wd 1e-2" +
                                    (")" if args.foreach_adamw else ", fused=True) - the reference's update rule, single-kernel form"),
@@ -601,14 +702,12 @@ def run_train(args, world, rank):
                       "share_frontend_note": "conv subsampling (no dropout, no bitwidth) evaluated once per step for the three passes: "
                                              "common-subexpression sharing inside the step, same loss and gradients "
                                              "(tests/test_conformer_cpu.py); --no-share-frontend restores the 3x evaluation",
-                      "l2": "per-step activations (tens of GB) exceed the 126 MB L2; no explicit flush",
                       "allocator_headroom_gib": round(headroom / 2 ** 30, 1),
-                      "cuda_mallocs_in_timed_steps": int(timed_mallocs),
-                      "parallelism": f"dp{world}"},
+                      "cuda_mallocs_in_timed_steps": int(timed_mallocs)},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "routes": taken,
            "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
     if rank == 0:
-        M = B * (((T - 1) // 2 - 1) // 2)
+        M = Bm * (((T - 1) // 2 - 1) // 2)
         hk = hot_kernel_rooflines(peaks, M)
         # dominant kernel of the layer inside the step = the one with the largest per-layer time at this shape
         core = ("act_quant_i8", "gemm_fwd", "bwd_prep", "bwd_dx", "bwd_dw")
@@ -622,14 +721,16 @@ def run_train(args, world, rank):
                                     "(the largest single family of the step), is in layer_kernels")
         out["layer_kernels"] = hk
         try:                                                # added late in round 1: a failure here must not cost the bench line
-            hk["kernels"].update(ctc_kernel_rooflines(peaks, B, ((T - 1) // 2 - 1) // 2, TRAIN["vocab"], TRAIN["tokens"]))
+            hk["kernels"].update(ctc_kernel_rooflines(peaks, Bm, ((T - 1) // 2 - 1) // 2, TRAIN["vocab"], TRAIN["tokens"]))
         except Exception as e:  # noqa: BLE001
             hk["kernels"]["ctc_loss"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1:
             # SURVEY.md section 8(d) also asks for ONE precision-2 pass (forward + backward + AdamW), next to the full step
             from onebit_b200.training import att_ce_loss, ctc_loss_from_logits, make_att_targets
 
-            def one_pass():
+            batch0 = batch if n_micro == 1 else batch[0]
+
+            def one_pass(batch=batch0):
                 opt.zero_grad(set_to_none=True)
                 enc, mask, ctc = model(batch, 2)
                 t_inp, t_out, t_pad = make_att_targets(batch["tokens"], cfg.bos_id, cfg.eos_id, cfg.pad_id)
@@ -644,15 +745,18 @@ def run_train(args, world, rank):
                 one_pass()
             ms1 = timed_region(1, one_pass, 3) / 3
             out["variants"] = {"one_precision2_pass": {"ms_per_step": round(ms1, 2),
-                                                       "audio_s_per_s": round(B * T * FRAME_S / (ms1 * 1e-3), 1)}}
+                                                       "audio_s_per_s": round(Bm * T * FRAME_S / (ms1 * 1e-3), 1)}}
         if world == 1 and not args.no_gemm:
-            out["bitlinear_gemm"] = gemm_microbench(args, 20)
+            out["bitlinear_gemm"] = gemm_microbench(args, 20, sweep=not args.no_sweep_summary)
+            if "sweep" in out["bitlinear_gemm"]:
+                out["bitlinear_gemm"]["sweep_summary"] = sweep_summary(out["bitlinear_gemm"].pop("sweep"), peaks)
+        if world == 1 and not args.no_small_m:
+            try:
+                out["small_batch"] = small_batch_table(peaks)
+            except Exception as e:  # noqa: BLE001
+                out["small_batch"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
-            sample = 2
-            v, dt = cpu_reference_train(args, sample, 2)
-            out["cpu_baseline"] = {"value": round(v, 2), "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"{sample} utterances x {T} frames per step (of {B}), same model/step, reference fp32 "
-                                             f"layer (oracle/torch_oracle.py, Oracle-A) on torch-CPU, {dt:.2f} s/step"}
+            out["cpu_baseline"] = cpu_baseline_child(args)
     return out
 
 
@@ -767,43 +871,55 @@ def run_gemm(args, world, rank):
 
 
 def run_reference(args, world, rank):
-    """Reference arm: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    """Reference arm: the UNMODIFIED reference from baseline/_ref on the host cores (rank 0 only).  Never imports the product."""
     if rank != 0:
         return None
-    steps = max(1, min(args.steps, 3))
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return {"impl": "reference", "unavailable": "baseline/_ref not built (python oracle/build_ref.py needs /root/reference)"}
+    cores = os.cpu_count()
     if args.workload == "train":
-        sample = 2
-        v, dt = cpu_reference_train(args, sample, steps)
-        unit, metric = "audio-s/s", "conformer_train_audio_sec_per_sec"
-        cfg = {"workload": "Conformer BitLinear co-training step (BASELINE configs[2]; configs[3] at 8 GPUs): 12 blocks, "
-                           "d_model 256, d_ff 1024, 4 heads, V=5004, 3 passes (2-bit, 1-bit, stochastic precision) + "
-                           "CTC/attention/KL losses + clip + AdamW",
-               "batch_per_gpu": args.batch, "frames": args.frames, "mel": TRAIN["mel"], "dropout": args.dropout,
-               "parallelism": "cpu"}
-        sample_txt = (f"{sample} utterances x {args.frames} frames per step (bounded sample of batch {args.batch}), reference fp32 "
-                      "layer restated in oracle/torch_oracle.py (Oracle-A) inside the same module tree, torch-CPU")
+        from oracle import ref_bench
+        r = ref_bench.run(args.steps, args.warmup, args.dropout)
+        c1 = r["config"]
+        v, dt, unit, metric = r["audio_s_per_s"], r["s_per_step"], "audio-s/s", "conformer_train_audio_sec_per_sec"
+        cfg = train_workload_config(args, world)
+        steps_done, warm = r["steps_timed"], args.warmup
+        sample_txt = (f"bounded sample of that step = BASELINE configs[0]: {c1['batch']} utterances x {c1['frames']} frames, "
+                      f"{c1['tokens']} tokens, default dims, V={c1['vocab']}, dropout {args.dropout}, weights seed 0 / inputs seed 1; "
+                      f"the reference's own train.py:run_epoch (3 passes + losses + backward + clip + AdamW) from baseline/_ref, "
+                      f"torch-CPU fp32, {r['threads']} threads; {dt:.2f} s/step over {steps_done} steps"
+                      + (f"; one precision-2 pass fwd+bwd+AdamW {r['one_pass']['s_per_step']:.2f} s "
+                         f"= {r['one_pass']['audio_s_per_s']:.1f} audio-s/s" if "one_pass" in r else ""))
+        extra = {"one_precision2_pass": r.get("one_pass"), "full_step": {"s_per_step": round(dt, 3), "audio_s_per_s": round(v, 2)},
+                 "sample_config": c1, "last_loss": r["last_loss"]}
     else:
-        from oracle.torch_oracle import OracleQuantizedLinear
-        torch.set_num_threads(os.cpu_count())
+        ref = ref_loader.load()
+        torch.set_num_threads(cores)
         torch.manual_seed(0)
         rows = 2048
-        layer = OracleQuantizedLinear(args.in_features, args.out_features, act_bits=32)
+        layer = ref.quant.QuantizedLinear(args.in_features, args.out_features)
         x = torch.randn(rows, args.in_features)
+        steps_done, warm = max(1, args.steps), max(1, args.warmup)
         with torch.no_grad():
-            layer(x, args.bitwidth)
-            t0 = time.perf_counter()
-            for _ in range(steps):
+            for _ in range(warm):
                 layer(x, args.bitwidth)
-        dt = (time.perf_counter() - t0) / steps
+            t0 = time.perf_counter()
+            for _ in range(steps_done):
+                layer(x, args.bitwidth)
+        dt = (time.perf_counter() - t0) / steps_done
         v = 2.0 * rows * args.in_features * args.out_features / dt / 1e12
         unit, metric = "TOPS", "bitlinear_int8_tops"
-        cfg = {"workload": f"BitLinear fwd M={args.tokens} K={args.in_features} N={args.out_features} bitwidth={args.bitwidth} "
-                           "(BASELINE configs[1])", "parallelism": "cpu"}
-        sample_txt = f"{rows} of {args.tokens} tokens per step, reference fp32 layer (Oracle-A) on torch-CPU"
-    return {"metric": metric, "value": round(v, 4), "unit": unit, "n_gpus": world, "steps": steps, "warmup": 1,
+        cfg = {"workload": f"BitLinear fwd (act-quant + GEMM) M={args.tokens} K={args.in_features} N={args.out_features} "
+                           f"bitwidth={args.bitwidth} (BASELINE configs[1])",
+               "l2": "operands (q 134 MB, y 268 MB) exceed the 126 MB L2; no explicit flush", "parallelism": f"dp{world}"}
+        sample_txt = (f"{rows} of {args.tokens} token rows per step through the reference's own QuantizedLinear.forward "
+                      f"(quant.py:120-127: re-quantise W, fp32 F.linear) from baseline/_ref, torch-CPU, {cores} threads")
+        extra = {}
+    return {"metric": metric, "value": round(v, 4), "unit": unit, "n_gpus": world, "steps": steps_done, "warmup": warm,
             "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg,
-            "cpu_baseline": {"value": round(v, 4), "unit": unit, "cores": os.cpu_count(), "kind": "port", "sample": sample_txt},
+            "cpu_baseline": {"value": round(v, 4), "unit": unit, "cores": cores, "kind": "reference", "sample": sample_txt, **extra},
             "e2e": {"value": round(v, 4), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
 

@@ -16,6 +16,7 @@ OB_F32, OB_BF16 = 0, 1
 OB_ALPHA_EFF, OB_ALPHA_RAW = 0, 1
 OB_ORDER_I8, OB_ORDER_BF16 = 0, 1
 DBG_SWAP_LBO_SBO, DBG_FORCE_BLOCK_N, DBG_FORCE_SPLITS, DBG_MAX_CTAS = 1, 2, 3, 4
+DBG_SMALL_M = 9         # 1: keep M <= 64 on the tcgen05 kernel instead of the weight-streaming DP4A kernel
 
 _p, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
 _u64, _u32 = ctypes.c_uint64, ctypes.c_uint32

@@ -52,6 +52,9 @@ class GradAllReducer:
             for p, off in zip(b["params"], b["offsets"]):
                 self._where[p] = (bi, off)
         self._handles = []
+        self.enabled = True               # False: gradients only accumulate locally (all but the last micro-batch)
+        self.timing = False               # True: CUDA events around finish() -> exposed_ms()
+        self._events = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self._reset()
 
@@ -72,7 +75,7 @@ class GradAllReducer:
         self._handles = []
 
     def _on_grad(self, p: torch.nn.Parameter):
-        if self.world == 1:
+        if self.world == 1 or not self.enabled:
             return
         bi, _ = self._where[p]
         self._pending[bi] -= 1
@@ -99,6 +102,10 @@ class GradAllReducer:
         """Wait for every bucket, divide by the world size and write the averaged gradients back."""
         if self.world == 1:
             return
+        ev = None
+        if self.timing and self.cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         for bi in range(self._next, len(self.buckets)):  # the rest, in index order
             b = self.buckets[bi]
             if not self._ready[bi]:                      # holds parameters without a gradient this step (e.g. alpha at 32 bit)
@@ -120,7 +127,20 @@ class GradAllReducer:
                 # the averaged gradient lives in the bucket: .grad becomes a view of it (no copy back).  The next backward
                 # starts from zero_grad(set_to_none=True) - as train_step does - and refills the bucket from fresh gradients.
                 p.grad = v.view_as(p)
+        if ev is not None:
+            ev[1].record()
+            self._events.append(ev)
         self._reset()
+
+    def exposed_ms(self):
+        """Mean device time between the end of backward and the averaged gradients being ready (the part of the exchange
+        that did NOT overlap with backward), over the ``finish()`` calls made while ``timing`` was set; None if none."""
+        if not self._events:
+            return None
+        torch.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in self._events]
+        self._events = []
+        return sum(ms) / len(ms)
 
     def remove(self):
         for h in self._hooks:

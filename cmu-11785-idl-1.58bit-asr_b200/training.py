@@ -3,8 +3,9 @@
 One optimiser step = three encoder passes over the same batch with shared latent weights - 2-bit teacher, 1-bit
 student, stochastic-precision mix - each with attention-CE + CTC, two KL terms to the detached teacher, ONE
 backward, grad-norm clip 5.0, AdamW (train.py:83-120).  The math is restated here so that the workload runs where
-the reference tree is not mounted and under data parallelism (``dp.GradAllReducer``); tests/test_conformer_parity.py
-checks it against the reference's own ``run_epoch`` arithmetic.
+the reference tree is not mounted and under data parallelism (``dp.GradAllReducer``); tests/test_conformer_cpu.py and
+tests/test_gpu_conformer.py check it against fixtures produced by the reference's own ``run_epoch`` arithmetic
+(tests/golden/make_golden_conformer.py).
 
 Differences from the reference are host-side only: the CTC lengths are taken from the host copy of ``feat_lens``
 (no device->host sync inside the step; same values as ``mask.sum(1)``), and the conv subsampling front-end - which
@@ -184,15 +185,26 @@ def reserve_allocator_headroom(device, gib: float = 6.0) -> int:
 def train_step(model, batch, optimizer, cfg: StepConfig, sched=None, sp_mask=None, grad_sync=None):
     """zero_grad -> 3-pass loss -> backward -> (DP all-reduce) -> clip -> AdamW -> schedule (train.py:114-120).
 
-    ``grad_sync``: a ``dp.GradAllReducer`` whose hooks launch bucketed all-reduces during backward; ``finish()``
+    ``batch``: one batch dict, or a list of micro-batches whose gradients are accumulated before the one optimiser step
+    (loss = mean over the micro-batches: the same update as one batch holding all their utterances, except that BatchNorm
+    uses each micro-batch's own statistics - as under data parallelism, conformer.py:148).
+    ``grad_sync``: a ``dp.GradAllReducer`` whose hooks launch bucketed all-reduces during (the last) backward; ``finish()``
     waits for them before the global-norm clip."""
     optimizer.zero_grad(set_to_none=True)
-    loss, parts = cotraining_loss(model, batch, cfg, sp_mask)
-    loss.backward()
+    micro = batch if isinstance(batch, (list, tuple)) else [batch]
+    total, parts = None, None
+    for i, mb in enumerate(micro):
+        if grad_sync is not None:
+            grad_sync.enabled = i == len(micro) - 1          # all-reduce the accumulated gradients once
+        loss, parts = cotraining_loss(model, mb, cfg, sp_mask)
+        if len(micro) > 1:
+            loss = loss / len(micro)
+        loss.backward()
+        total = loss.detach() if total is None else total + loss.detach()
     if grad_sync is not None:
         grad_sync.finish()
     torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=cfg.max_grad_norm)
     optimizer.step()
     if sched is not None:
         sched.step()
-    return loss.detach(), parts
+    return total, parts

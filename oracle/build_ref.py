@@ -4,7 +4,7 @@ they lie (TEST / BASELINE INFRASTRUCTURE - never imported by the product package
     python oracle/build_ref.py            # build container only (needs /root/reference); also run by __graft_entry__.build()
 
 The reference is pure Python, so "compiling" it means ``py_compile``: every module below is compiled straight from
-``/root/reference/onebit_asr/<name>.py`` into ``baseline/_ref/onebit_asr/<name>.pyc`` (sourceless import).  No reference
+``/root/reference/onebit_asr/<name>.py`` into ``baseline/_ref/onebit_asr/<name>.bc`` (CPython bytecode, imported sourceless; not ``.pyc``: gpurun snapshots skip that suffix).  No reference
 source text is copied into the repository; ``baseline/_ref/`` is git-ignored (it stays out of the history) but not
 gpurun-ignored, so - like the built ``libonebit.so`` - it travels to the GPU box, where ``/root/reference`` does not exist.
 ``MANIFEST.json`` records the sha256 of each source file, the interpreter and the torch version it was built with.
@@ -39,7 +39,7 @@ def build_ref(reference: str = "/root/reference", out: str = OUT) -> bool:
         pass
     for name in MODULES:
         src = os.path.join(src_dir, name + ".py")
-        py_compile.compile(src, cfile=os.path.join(pkg, name + ".pyc"), dfile=f"<reference>/onebit_asr/{name}.py", doraise=True)
+        py_compile.compile(src, cfile=os.path.join(pkg, name + ".bc"), dfile=f"<reference>/onebit_asr/{name}.py", doraise=True)
         with open(src, "rb") as f:
             manifest["modules"][name] = hashlib.sha256(f.read()).hexdigest()
     with open(manifest_path, "w") as f:

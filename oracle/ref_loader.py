@@ -21,12 +21,12 @@ _cache = {}
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REF_DIR, "MANIFEST.json"))
+    return all(os.path.exists(os.path.join(REF_DIR, *p)) for p in (("MANIFEST.json",), ("onebit_asr", "quant.bc"), ("onebit_asr", "conformer.bc")))
 
 
 def _exec(name: str, as_name: str, visible: dict):
-    """Execute ``baseline/_ref/onebit_asr/<name>.pyc`` as module ``as_name`` with ``visible`` temporarily in sys.modules."""
-    path = os.path.join(REF_DIR, "onebit_asr", name + ".pyc")
+    """Execute ``baseline/_ref/onebit_asr/<name>.bc`` as module ``as_name`` with ``visible`` temporarily in sys.modules."""
+    path = os.path.join(REF_DIR, "onebit_asr", name + ".bc")
     loader = importlib.machinery.SourcelessFileLoader(as_name, path)
     spec = importlib.util.spec_from_loader(as_name, loader)
     mod = importlib.util.module_from_spec(spec)

@@ -166,6 +166,35 @@ def test_forward_gemm_exact_integer_dot(ob, M, N, K, block_n):
     assert rel_err(yb.float().cpu().numpy(), (ref - bias.double()).cpu().numpy()) < 1e-2
 
 
+@pytest.mark.parametrize("M", [1, 3, 8, 17, 64])
+@pytest.mark.parametrize("N,K", [(256, 256), (1024, 256), (256, 1024), (2048, 2048), (64, 64), (192, 320)])
+def test_small_batch_gemv_kernel(ob, M, N, K):
+    """M <= 64 token rows take the weight-streaming DP4A kernel (csrc/ob_gemv.cu): exact integer contraction, and the SAME
+    bits as the tcgen05 kernel it stands in for (fp32 and bf16 outputs, with and without bias)."""
+    from onebit_b200 import _cabi, quant as obq
+    g = torch.Generator().manual_seed(7 * M + N + K)
+    q = torch.randint(-128, 128, (M, K), generator=g, dtype=torch.int8).cuda()
+    scale = (torch.rand(M, generator=g) * 50 + 10).cuda()
+    codes = torch.randint(-1, 2, (N, K), generator=g, dtype=torch.int8)
+    packed = torch.from_numpy(orc.pack_codes(codes.numpy(), "i8")).cuda()
+    alpha = torch.tensor(-0.0625).cuda()                     # raw (negative) alpha: |alpha| + 1e-8 inside
+    bias = torch.randn(N, generator=g).cuda()
+    a_eff = np.float32(abs(np.float32(-0.0625))) + np.float32(1e-8)
+    ref = (q.double() @ codes.cuda().double().t()) * (float(a_eff) / scale.double())[:, None] + bias.double()
+    outs = {}
+    for mode in (0, 1):                                      # 0: GEMV kernel, 1: forced tcgen05 kernel
+        _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, mode)
+        try:
+            outs[mode] = (obq.gemm_fwd(q, scale, packed, alpha, bias, N, torch.float32),
+                          obq.gemm_fwd(q, scale, packed, alpha, None, N, torch.bfloat16))
+            torch.cuda.synchronize()
+        finally:
+            _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, 0)
+    assert rel_err(outs[0][0].cpu().numpy(), ref.cpu().numpy()) < 1e-6
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
 # ------------------------------------------------------------------ whole layer vs golden fixtures
 def _golden_layer(ob, k):
     layer = ob.QuantizedLinear(128, 192)
