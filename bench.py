@@ -315,7 +315,7 @@ def small_batch_table(peaks):
     model are distinct: 8 x 64 KB..1 MB stays in L2, as it does in a real 108-layer forward at this batch); bytes = packed W
     (N K / 4) + int8 activations (M K) + fp32 output (4 M N) + scales and bias."""
     import onebit_b200 as ob
-    from onebit_b200 import quant as obq
+    from onebit_b200 import _cabi, quant as obq
     dev = torch.device("cuda", torch.cuda.current_device())
     rows = []
     for K, N in ((256, 256), (256, 1024), (1024, 256), (2048, 2048)):
@@ -336,11 +336,18 @@ def small_batch_table(peaks):
                 obq.gemm_fwd(q, sc, pks[j], layers[j].alpha, layers[j].bias, N, torch.float32)
             us = _graph_time_us(gemm, 64)
             us_layer = _graph_time_us(layer_fwd, 64)
+            us_tc = None
+            if M <= 64:                                        # the same call forced onto the 128-row tcgen05 tile, for comparison
+                _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, 1)
+                try:
+                    us_tc = round(_graph_time_us(gemm, 64), 2)
+                finally:
+                    _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, 0)
             by = N * K / 4 + M * K + 4.0 * M * N + 4 * M + 4 * N
             rows.append({"M": M, "K": K, "N": N, "kernel": "gemv_tern_i8 (DP4A)" if M <= 64 else "gemm_expand (tcgen05)",
                          "us": round(us, 2), "gbs": round(by / us / 1e3, 1), "frac_hbm": round(by / us / 1e3 / peaks["hbm_gbs"], 4),
                          "weight_gbs": round(N * K / 4 / us / 1e3, 1), "layer_fwd_us": round(us_layer, 2),
-                         "algorithmic_bytes": int(by)})
+                         "tcgen05_tile_us": us_tc, "algorithmic_bytes": int(by)})
     return {"note": "packed-weight GEMV-like regime; at these sizes (16 KB - 1 MB of weights) a launch is latency-bound: "
                     "the floor is the ~2 us launch + one dependent HBM/L2 round trip, not bandwidth", "rows": rows}
 

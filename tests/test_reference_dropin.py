@@ -124,10 +124,9 @@ def test_unmodified_reference_conformer_on_the_cuda_layer(precision, sp_mask):
     m_gpu = m_gpu.cuda()
     batch = _small_batch()
     batch_gpu = {k: v.cuda() for k, v in batch.items()}
-    g = torch.Generator().manual_seed(5)
-    w_enc, w_ctc = torch.randn(3, 31, 256, generator=g), torch.randn(3, 31, 64, generator=g)
-
     enc_c, mask_c, ctc_c = m_cpu(batch, precision=precision, sp_mask=sp_mask)
+    g = torch.Generator().manual_seed(5)
+    w_enc, w_ctc = torch.randn(enc_c.shape, generator=g), torch.randn(ctc_c.shape, generator=g)
     ((enc_c * w_enc).sum() + (ctc_c * w_ctc).sum()).backward()
     enc_g, mask_g, ctc_g = m_gpu(batch_gpu, precision=precision, sp_mask=sp_mask)
     ((enc_g * w_enc.cuda()).sum() + (ctc_g * w_ctc.cuda()).sum()).backward()
