@@ -15,6 +15,7 @@ OB_OK, OB_ERR_ARG, OB_ERR_CUDA, OB_ERR_ARCH, OB_ERR_WORKSPACE = 0, 1, 2, 3, 4
 OB_F32, OB_BF16 = 0, 1
 OB_ALPHA_EFF, OB_ALPHA_RAW = 0, 1
 OB_ORDER_I8, OB_ORDER_BF16 = 0, 1
+OB_PREP_TAIL, OB_PREP_SWISH = 1, 2
 DBG_SWAP_LBO_SBO, DBG_FORCE_BLOCK_N, DBG_FORCE_SPLITS, DBG_MAX_CTAS = 1, 2, 3, 4
 DBG_SMALL_M = 9         # 1: keep M <= 64 on the tcgen05 kernel instead of the weight-streaming DP4A kernel
 
@@ -45,6 +46,11 @@ SIGNATURES = {
     "ob_layernorm_fwd": (_i, [_p, _p, _p, ctypes.c_float, _i64, _i, _p, _p, _p, _p]),
     "ob_layernorm_bwd_workspace_bytes": (_sz, [_i]),
     "ob_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p]),
+    "ob_layernorm_quant_fwd": (_i, [_p, _p, _p, ctypes.c_float, _i64, _i, _p, _p, _p, _p, _p]),
+    "ob_layernorm_bwd3": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p]),
+    "ob_gemm_tern_i8_fwd_tail": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _p, _p, ctypes.c_float, _u64, _u64, _u32, _i64, _p,
+                                      _p]),
+    "ob_bwd_prep_fused": (_i, [_p, _i, _p, _p, ctypes.c_float, _u64, _u64, _u32, _i64, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "ob_relattn_softmax_fwd": (_i, [_p, _p, _p, _p, ctypes.c_float, _u64, _u64, _u32, ctypes.c_float, _i, _i, _i, _i, _p, _p,
                                     _p]),
     "ob_relattn_softmax_bwd": (_i, [_p, _p, _p, ctypes.c_float, _u64, _u64, _u32, ctypes.c_float, _i, _i, _i, _i, _p, _p,

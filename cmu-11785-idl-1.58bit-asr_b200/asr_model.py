@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import attention, convmod, frontend, matmul, residual, routes
+from . import attention, convmod, frontend, fused, matmul, residual, routes
 from .norm import layer_norm
 from .quant import QuantizedLinear
 
@@ -85,6 +85,23 @@ def _routed(layer, x, bits, swish_dropout=None):
     if utt2 < total:
         parts.append(_routed_one(layer, x[utt2:], 1, swish_dropout))
     return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+
+
+def _rows2(bits, x) -> Optional[int]:
+    """Number of leading token rows of ``x [B, T, C]`` that use the 2-bit codes (the rest use the 1-bit codes), or None when the
+    call is not a 1-/2-bit one (full precision)."""
+    rows = x.numel() // x.shape[-1]
+    if isinstance(bits, StackedBits):
+        return bits.utt2 * (rows // x.shape[0])
+    return rows if bits == 2 else (0 if bits == 1 else None)
+
+
+def _b200_layers(*layers) -> bool:
+    return all(hasattr(l, "packed_weight") or hasattr(l, "packed") for l in layers) and "fuse" not in matmul.DISABLED
+
+
+def _row_mask(mask):
+    return None if mask is None else residual._RowMaskCache.get(_frame_mask(mask))
 
 
 def _frame_mask(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -162,6 +179,11 @@ class FeedForwardModule(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x, bitwidth: int, mask=None):
+        rows2 = _rows2(bitwidth, x)
+        if rows2 is not None and _b200_layers(self.lin1, self.lin2) and fused.ffn_usable(x, self.lin1, self.lin2):
+            # the whole module as one fused chain: LayerNorm inside lin1's quantiser, the tail inside lin2's GEMM epilogue
+            routes.taken("ffn_module_fused", True, x)
+            return fused.ffn_forward(x, self.ln.ln, self.lin1, self.lin2, rows2, _row_mask(mask), self.dropout.p, self.training)
         hidden = _routed(self.lin1, self.ln(x), bitwidth)
         out = _routed(self.lin2, hidden, bitwidth, swish_dropout=(self.dropout, self.training))
         return _module_tail(x, out, mask, 0.5, self.dropout, self.training)
@@ -212,10 +234,22 @@ class MHSA(nn.Module):
         batch, frames, width = x.shape
         if width != self.d_model:
             raise AssertionError(f"Expected {self.d_model}, got {width}")
+        rows2 = _rows2(bitwidth, x)
+        qkv = (self.q_proj, self.k_proj, self.v_proj)
+        on_library = attention.rel_attention_usable(x, mask, self.n_heads) and pos_emb.shape[:2] == (1, frames)
+        if (rows2 is not None and on_library and _b200_layers(*qkv, self.out_proj) and fused.ln_proj_usable(x, qkv)
+                and fused.proj_tail_usable(x, x, self.out_proj)):
+            # LayerNorm inside the shared q/k/v quantiser, the tail inside out_proj's GEMM epilogue
+            routes.taken("attention", True, x)
+            routes.taken("mhsa_module_fused", True, x)
+            x_res, (q_flat, k_flat, v_flat) = fused.ln_projections(x, self.ln.ln, qkv, rows2)
+            pos_flat = self._positions(pos_emb, bitwidth, batch)
+            mixed = attention.rel_attention(q_flat, k_flat, v_flat, pos_flat, self.pos_bias_u, self.pos_bias_v, mask,
+                                            self.n_heads, self.dropout.p, self.training)
+            return fused.proj_tail(mixed, x_res, self.out_proj, rows2, _row_mask(mask), self.dropout.p, self.training)
         normed = self.ln(x)
-        q_flat, k_flat, v_flat = (_routed(p, normed, bitwidth) for p in (self.q_proj, self.k_proj, self.v_proj))
+        q_flat, k_flat, v_flat = (_routed(p, normed, bitwidth) for p in qkv)
         pos_flat = self._positions(pos_emb, bitwidth, batch)
-        on_library = attention.rel_attention_usable(normed, mask, self.n_heads) and pos_emb.shape[:2] == (1, frames)
         if routes.taken("attention", on_library, normed, "attn" in matmul.DISABLED):
             # tensor-core path: the projections are consumed in their [B, T, H*d] layout, no head transposes
             mixed = attention.rel_attention(q_flat, k_flat, v_flat, pos_flat, self.pos_bias_u, self.pos_bias_v, mask,

@@ -144,6 +144,82 @@ __device__ __forceinline__ uint32_t philox_keep8(unsigned long long group, const
   return bits;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions, vector loads, the int8 activation quantiser's arithmetic, bf16 packing, swish
+// (shared by ob_quant.cu, ob_norm.cu and the fused prologue / epilogue kernels)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x), b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+
+// Row absmax accumulated on the BIT PATTERNS of |v| (unsigned integer max): order-preserving for non-negative floats, and
+// a NaN (pattern > 0x7f800000) or Inf in the row comes out on top instead of being dropped as fmaxf would.
+__device__ __forceinline__ uint32_t amax_bits4(uint32_t acc, float4 v) {
+  acc = max(acc, __float_as_uint(fabsf(v.x)));
+  acc = max(acc, __float_as_uint(fabsf(v.y)));
+  acc = max(acc, __float_as_uint(fabsf(v.z)));
+  return max(acc, __float_as_uint(fabsf(v.w)));
+}
+__device__ __forceinline__ uint32_t warp_max_bits(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float act_scale_from_amax(float amax) {
+  // torch evaluates `127.0 / t` as reciprocal(t) * 127 (two roundings); pinned bit-exactly by the oracle.
+  // A non-finite row (NaN or Inf absmax) gets a NaN scale, so the GEMM epilogue's alpha / s turns the whole output row
+  // into NaN: divergence stays visible instead of being clamped to -128 codes.
+  if (!(amax <= 3.402823466e38f)) return __int_as_float(0x7fc00000);
+  return __fmul_rn(__frcp_rn(fmaxf(amax, 1e-5f)), 127.0f);
+}
+// q = clamp(rint(v * s), -128, 127) for four values, packed little-endian.  Clamping to the (integer) bounds first and
+// then adding 1.5 * 2^23 rounds to the nearest integer, ties to even, exactly like rint() - the sum's low mantissa
+// byte IS the int8 two's-complement code - and it stays on the full-rate FP pipes (FRND and F2I run on the
+// quarter-rate XU pipe, which ncu showed ~50-60 % busy in these kernels).
+__device__ __forceinline__ uint32_t quant4(float4 v, float s) {
+  constexpr float kMagic = 12582912.0f;
+  const uint32_t a = __float_as_uint(fminf(fmaxf(__fmul_rn(v.x, s), -128.f), 127.f) + kMagic);
+  const uint32_t b = __float_as_uint(fminf(fmaxf(__fmul_rn(v.y, s), -128.f), 127.f) + kMagic);
+  const uint32_t c = __float_as_uint(fminf(fmaxf(__fmul_rn(v.z, s), -128.f), 127.f) + kMagic);
+  const uint32_t d = __float_as_uint(fminf(fmaxf(__fmul_rn(v.w, s), -128.f), 127.f) + kMagic);
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// swish with the SFU exponential (ex2.approx, ~2 ulp) and an IEEE reciprocal: the full-precision expf made this
+// kernel ALU-bound (26 M exponentials per launch at the FFN width); the result differs from torch's sigmoid*x in
+// the last bits only, which moves an int8 code by at most one step on a ~1e-5 fraction of elements
+// swish(h) = h * sigmoid(h) on the SFU (ex2 + rcp, ~2 ulp); exp(-h) = inf for h < -88 gives h * 0 = -0
+__device__ __forceinline__ float swish_f(float h) { return h * __fdividef(1.0f, 1.0f + __expf(-h)); }
+
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&lo);
+  r.y = *reinterpret_cast<uint32_t*>(&hi);
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
 // ---------------------------------------------------------------------------------------------

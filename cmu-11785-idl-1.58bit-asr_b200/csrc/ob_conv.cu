@@ -426,13 +426,13 @@ __global__ void __launch_bounds__(256) residual_dropout_kernel(const float* __re
     for (int h = 0; h < 2; ++h) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(y) + 2 * i + h);
       float4 o;
-      o.x = (kb >> (4 * h + 0)) & 1u ? v.x * f : 0.f;
-      o.y = (kb >> (4 * h + 1)) & 1u ? v.y * f : 0.f;
-      o.z = (kb >> (4 * h + 2)) & 1u ? v.z * f : 0.f;
-      o.w = (kb >> (4 * h + 3)) & 1u ? v.w * f : 0.f;
+      o.x = (kb >> (4 * h + 0)) & 1u ? __fmul_rn(v.x, f) : 0.f;      // explicit mul / add: same bits as the GEMM's fused tail
+      o.y = (kb >> (4 * h + 1)) & 1u ? __fmul_rn(v.y, f) : 0.f;
+      o.z = (kb >> (4 * h + 2)) & 1u ? __fmul_rn(v.z, f) : 0.f;
+      o.w = (kb >> (4 * h + 3)) & 1u ? __fmul_rn(v.w, f) : 0.f;
       if (!BWD) {
         const float4 r = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + h);
-        o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+        o.x = __fadd_rn(o.x, r.x), o.y = __fadd_rn(o.y, r.y), o.z = __fadd_rn(o.z, r.z), o.w = __fadd_rn(o.w, r.w);
       }
       reinterpret_cast<float4*>(out)[2 * i + h] = o;
     }

@@ -127,17 +127,30 @@ struct GemmSmem {
   static constexpr int kDynBytes = kBytes + 1024;                    // slack for the 1024-byte alignment
 };
 
+// Optional module tail fused into the forward epilogue (TAIL = 1, fp32 output only): the layer's output y never reaches HBM,
+//   out = resid + (keep ? y * factor * rowmask[row] : 0)      = x + scale * dropout(y) * frame_mask   (conformer.py:41-45, 133-138)
+// with the keep bits of the library's Philox stream (element index (row_base + row) * N + col, eight 16-bit lanes per
+// block of 8 elements - the same lanes residual_dropout_kernel and the backward prep use).
+struct TailArgs {
+  const float* resid;       // [M, N] fp32, laid out like the output
+  const float* rowmask;     // float validity per GLOBAL row (row_base + row), or nullptr
+  float factor;             // scale / (1 - p)  (scale when dropout is off)
+  DropRng rng;              // threshold 0 -> no dropout
+  long long row_base;
+};
+
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator, 3 = idle,
 // 4..11 = expanders, 12..19 = epilogue (warp % 4 selects the TMEM lane quarter, (warp-12)/4 the column half).
 // OUT_BF16: output element type (0 = fp32, 1 = bf16); the epilogue moves 128 bytes of a row per chunk.
 // OUT_BUFS: staging buffers per epilogue warp; the TMA stores of up to OUT_BUFS-1 earlier chunks stay in flight
 // (the store-read latency, not the instruction count, bounds the output rate with only two).
-template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS, int OUT_BUFS>
+template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS, int OUT_BUFS, int TAIL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bp,
                    const __grid_constant__ CUtensorMap map_out, const float* __restrict__ row_scale,
                    const float* __restrict__ alpha, int alpha_mode, const float* __restrict__ bias, int M, int NC,
-                   int KC, int dbg) {
+                   int KC, int dbg, const TailArgs tail) {
+  static_assert(TAIL == 0 || (MODE == kFwdI8 && OUT_BF16 == 0), "the fused module tail exists for the fp32 forward only");
   using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS, OUT_BUFS>;
   constexpr int kElemsPerKBlock = MODE == kFwdI8 ? 128 : 64;
   constexpr int kChunkCols = OUT_BF16 ? 64 : 32;          // output columns per 128-byte chunk
@@ -329,10 +342,11 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int row0 = m_blk * kTileM + rank * kBlockM + e * 32;
       const int row = row0 + lane;
-      float factor = 0.f;
+      float factor = 0.f, tail_f = 0.f;
       if (row < M) {
         const float s = __ldg(row_scale + row);
         factor = MODE == kFwdI8 ? __fdiv_rn(a_eff, s) : a_eff * s;
+        if (TAIL) tail_f = tail.rowmask != nullptr ? tail.factor * __ldg(tail.rowmask + tail.row_base + row) : tail.factor;
       }
       // bias slice of this tile -> smem (double-buffered by accumulator stage; the named barrier below orders it)
       float* bias_s = reinterpret_cast<float*>(smem + L::kOffBias) + as * BLOCK_N;
@@ -370,6 +384,40 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             tmem_ld_32x32(taddr + h * 32, r);
             tmem_ld_wait();
             if (dbg & 2) continue;
+            if (TAIL) {
+              // 32 columns = four Philox blocks of 8 elements; the residual row segment comes straight from global memory
+              const int64_t e0 = (tail.row_base + row) * static_cast<int64_t>(NC) + col0;
+              const float* rrow = tail.resid + static_cast<int64_t>(row) * NC + col0;
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+                if (row < M) {
+                  ra = __ldg(reinterpret_cast<const float4*>(rrow) + 2 * j8);
+                  rb = __ldg(reinterpret_cast<const float4*>(rrow) + 2 * j8 + 1);
+                }
+                const uint32_t kb = tail.rng.threshold != 0u
+                                        ? philox_keep8(static_cast<unsigned long long>((e0 >> 3) + j8), tail.rng) : 0xFFu;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int j4 = 2 * j8 + u;
+                  const float4 b = lds128f(bias_addr + (c * kChunkCols + j4 * 4) * 4);
+                  const float4 rr = u == 0 ? ra : rb;
+                  const uint32_t k4 = kb >> (4 * u);
+                  float v0 = fmaf(__uint_as_float(r[4 * j4 + 0] + 0x4B400000u) - 12582912.0f, factor, b.x);
+                  float v1 = fmaf(__uint_as_float(r[4 * j4 + 1] + 0x4B400000u) - 12582912.0f, factor, b.y);
+                  float v2 = fmaf(__uint_as_float(r[4 * j4 + 2] + 0x4B400000u) - 12582912.0f, factor, b.z);
+                  float v3 = fmaf(__uint_as_float(r[4 * j4 + 3] + 0x4B400000u) - 12582912.0f, factor, b.w);
+                  // explicit mul / add (no contraction): the same bits as residual_dropout_kernel on a stored y
+                  v0 = __fadd_rn((k4 & 1u) ? __fmul_rn(v0, tail_f) : 0.f, rr.x);
+                  v1 = __fadd_rn((k4 & 2u) ? __fmul_rn(v1, tail_f) : 0.f, rr.y);
+                  v2 = __fadd_rn((k4 & 4u) ? __fmul_rn(v2, tail_f) : 0.f, rr.z);
+                  v3 = __fadd_rn((k4 & 8u) ? __fmul_rn(v3, tail_f) : 0.f, rr.w);
+                  sts128(obuf + ((j4 << 4) ^ swz), make_uint4(__float_as_uint(v0), __float_as_uint(v1),
+                                                              __float_as_uint(v2), __float_as_uint(v3)));
+                }
+              }
+              continue;
+            }
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 b = lds128f(bias_addr + (c * kChunkCols + h * 32 + j4 * 4) * 4);
@@ -608,13 +656,13 @@ static GemmCfg pick_gemm_cfg(int M, int NC) {
   return best;
 }
 
-template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS, int OUT_BUFS>
+template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS, int OUT_BUFS, int TAIL>
 static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_bp, const CUtensorMap& map_out,
                               const float* row_scale, const float* alpha, int alpha_mode, const float* bias, int M,
-                              int NC, int KC, cudaStream_t st) {
+                              int NC, int KC, cudaStream_t st, const TailArgs& tail) {
   using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS, OUT_BUFS>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OUT_BF16, CTAS, OUT_BUFS>;
+  auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OUT_BF16, CTAS, OUT_BUFS, TAIL>;
   static bool attr_set = false;
   if (!attr_set) {
     OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
@@ -637,14 +685,17 @@ static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_b
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC,
-                             g_dbg_kernel_flags));
+                             g_dbg_kernel_flags, tail));
   count_launch();
   return OB_OK;
 }
 
-template <int MODE, int OUT_BF16>
+static const TailArgs kNoTail = {nullptr, nullptr, 1.0f, {0ull, 0ull, 0u}, 0ll};
+
+template <int MODE, int OUT_BF16, int TAIL = 0>
 static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const float* row_scale, const float* alpha,
-                                int alpha_mode, const float* bias, void* out, int M, int NC, int KC, cudaStream_t st) {
+                                int alpha_mode, const float* bias, void* out, int M, int NC, int KC, cudaStream_t st,
+                                const TailArgs& tail = kNoTail) {
   const GemmCfg cfg = pick_gemm_cfg(M, NC);
   const int bn = cfg.block_n;
   CUtensorMap map_a, map_bp, map_out;
@@ -668,19 +719,19 @@ static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const floa
   else
     rc = make_map(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, NC, M, (uint64_t)NC * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != OB_OK) return rc;
-#define OB_GEMM_ARGS map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st
+#define OB_GEMM_ARGS map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st, tail
   if (cfg.ctas == 2) {
     if (bn == 256) {
       // long contractions want the deeper operand ring; short ones are output-bound and want double-buffered staging
-      if (KC >= 1024) return launch_gemm_expand<MODE, 256, 5, OUT_BF16, 2, 1>(OB_GEMM_ARGS);
-      return launch_gemm_expand<MODE, 256, 4, OUT_BF16, 2, 2>(OB_GEMM_ARGS);
+      if (KC >= 1024) return launch_gemm_expand<MODE, 256, 5, OUT_BF16, 2, 1, TAIL>(OB_GEMM_ARGS);
+      return launch_gemm_expand<MODE, 256, 4, OUT_BF16, 2, 2, TAIL>(OB_GEMM_ARGS);
     }
-    return launch_gemm_expand<MODE, 128, 6, OUT_BF16, 2, 2>(OB_GEMM_ARGS);
+    return launch_gemm_expand<MODE, 128, 6, OUT_BF16, 2, 2, TAIL>(OB_GEMM_ARGS);
   }
   switch (bn) {
-    case 256: return launch_gemm_expand<MODE, 256, 3, OUT_BF16, 1, 1>(OB_GEMM_ARGS);
-    case 128: return launch_gemm_expand<MODE, 128, 4, OUT_BF16, 1, 2>(OB_GEMM_ARGS);
-    default:  return launch_gemm_expand<MODE, 64, 6, OUT_BF16, 1, 2>(OB_GEMM_ARGS);
+    case 256: return launch_gemm_expand<MODE, 256, 3, OUT_BF16, 1, 1, TAIL>(OB_GEMM_ARGS);
+    case 128: return launch_gemm_expand<MODE, 128, 4, OUT_BF16, 1, 2, TAIL>(OB_GEMM_ARGS);
+    default:  return launch_gemm_expand<MODE, 64, 6, OUT_BF16, 1, 2, TAIL>(OB_GEMM_ARGS);
   }
 #undef OB_GEMM_ARGS
 }
@@ -767,6 +818,23 @@ extern "C" int ob_gemm_tern_i8_fwd(const int8_t* q, const float* scale, const ui
   if (y_dtype == OB_BF16)
     return dispatch_gemm_expand<kFwdI8, 1>(q, packed_i8, scale, alpha, alpha_mode, bias, y, M, N, K, st);
   OB_REQUIRE(false, "ob_gemm_tern_i8_fwd: unknown dtype tag %d", y_dtype);
+}
+
+extern "C" int ob_gemm_tern_i8_fwd_tail(const int8_t* q, const float* scale, const uint8_t* packed_i8, const float* alpha,
+                                        int alpha_mode, const float* bias, int M, int N, int K, const float* resid,
+                                        const float* rowmask, float tail_factor, uint64_t seed, uint64_t offset,
+                                        uint32_t drop_threshold, int64_t row_base, float* out, ob_stream_t stream) {
+  OB_REQUIRE(q && scale && packed_i8 && alpha && resid && out, "ob_gemm_tern_i8_fwd_tail: null pointer");
+  OB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0 && K <= 32768 && row_base >= 0,
+             "ob_gemm_tern_i8_fwd_tail: need K %% 64 == 0, K <= 32768 and N %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  OB_REQUIRE(drop_threshold < 65536u, "ob_gemm_tern_i8_fwd_tail: drop_threshold (%u) is a 16-bit value", drop_threshold);
+  OB_REQUIRE(aligned16(q) && aligned16(packed_i8) && aligned16(out) && aligned16(resid),
+             "ob_gemm_tern_i8_fwd_tail: pointers must be 16-byte aligned");
+  int rc = check_device();
+  if (rc != OB_OK) return rc;
+  const TailArgs tail = {resid, rowmask, tail_factor, {seed, offset, drop_threshold}, static_cast<long long>(row_base)};
+  return dispatch_gemm_expand<kFwdI8, 0, 1>(q, packed_i8, scale, alpha, alpha_mode, bias, out, M, N, K,
+                                            static_cast<cudaStream_t>(stream), tail);
 }
 
 extern "C" int ob_bwd_dx(const void* dys_bf16, const float* scale, const uint8_t* packed_t, const float* alpha,

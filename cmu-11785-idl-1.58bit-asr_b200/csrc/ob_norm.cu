@@ -60,14 +60,77 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   }
 }
 
+// LayerNorm fused with the per-token absmax int8 quantiser of the routed projection(s) that consume it (conformer.py:35-36,
+// 109-112): the normalised row never leaves the registers - int8 codes, the scale and the
+// (mean, rstd) the backward needs are all that is written (5 bytes per element instead of 13 for LayerNorm + quantiser).
+// Same expressions as ln_fwd_kernel and act_quant_reg_kernel, so the codes equal act_quant(layer_norm(x)) bit for bit.
+template <int V>
+__global__ void __launch_bounds__(256) ln_quant_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, int64_t M, int C,
+                                                           int8_t* __restrict__ q, float* __restrict__ scale,
+                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 g[V], b[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    g[j] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+    b[j] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j] = __ldg(xr + lane + 32 * j);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = wsum(s) * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float a = v[j].x - mean, c = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+      ss += (a * a + c * c) + (d * d + e * e);
+    }
+    const float rstd = 1.0f / sqrtf(wsum(ss) * inv_c + eps);
+    uint32_t amax = 0u;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float4 o;
+      o.x = (v[j].x - mean) * rstd * g[j].x + b[j].x;
+      o.y = (v[j].y - mean) * rstd * g[j].y + b[j].y;
+      o.z = (v[j].z - mean) * rstd * g[j].z + b[j].z;
+      o.w = (v[j].w - mean) * rstd * g[j].w + b[j].w;
+      v[j] = o;
+      amax = amax_bits4(amax, o);
+    }
+    const float sc = act_scale_from_amax(__uint_as_float(warp_max_bits(amax)));
+    uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * C);
+#pragma unroll
+    for (int j = 0; j < V; ++j) qr[lane + 32 * j] = quant4(v[j], sc);
+    if (lane == 0) {
+      scale[row] = sc;
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
 constexpr int kLnBwdBlocks = 296;      // persistent grid (2 per SM); fixed so the parameter-gradient sum order is fixed
 
-// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  partial d-gamma += dy * xhat, d-beta += dy
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) [+ resid],  g = dy * gamma;  partial d-gamma += dy * xhat, d-beta += dy.
+// dy = dy0 (+ dy1 + dy2): the gradients of up to three projections that read the same normalised tensor (q, k, v) are
+// summed on load; `resid` is the gradient that reached the module's input along the residual path, added on store - both
+// spare a separate element-wise kernel over [M, C].
 template <int V>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy1,
+                                                     const float* __restrict__ dy2, const float* __restrict__ x,
                                                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                                                     const float* __restrict__ gamma, int64_t M, int C,
-                                                     float* __restrict__ dx, float* __restrict__ part /* [2][blocks][C] */) {
+                                                     const float* __restrict__ gamma, const float* __restrict__ resid, int64_t M,
+                                                     int C, float* __restrict__ dx, float* __restrict__ part /* [2][blocks][C] */) {
   __shared__ float4 red[8][32 * V];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -88,7 +151,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const float4 xv = __ldg(xr + lane + 32 * j), dv = __ldg(dr + lane + 32 * j);
+      const float4 xv = __ldg(xr + lane + 32 * j);
+      float4 dv = __ldg(dr + lane + 32 * j);
+      if (dy1 != nullptr) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(dy1 + row * C) + lane + 32 * j);
+        dv.x += t.x; dv.y += t.y; dv.z += t.z; dv.w += t.w;
+      }
+      if (dy2 != nullptr) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(dy2 + row * C) + lane + 32 * j);
+        dv.x += t.x; dv.y += t.y; dv.z += t.z; dv.w += t.w;
+      }
       xh[j] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
       gg[j] = make_float4(dv.x * g[j].x, dv.y * g[j].y, dv.z * g[j].z, dv.w * g[j].w);
       s1 += (gg[j].x + gg[j].y) + (gg[j].z + gg[j].w);
@@ -105,6 +177,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       o.y = rstd * (gg[j].y - m1 - xh[j].y * m2);
       o.z = rstd * (gg[j].z - m1 - xh[j].z * m2);
       o.w = rstd * (gg[j].w - m1 - xh[j].w * m2);
+      if (resid != nullptr) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(resid + row * C) + lane + 32 * j);
+        o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+      }
       oxr[lane + 32 * j] = o;
     }
   }
@@ -183,24 +259,56 @@ extern "C" int ob_layernorm_fwd(const float* x, const float* gamma, const float*
 
 extern "C" size_t ob_layernorm_bwd_workspace_bytes(int C) { return (size_t)2 * kLnBwdBlocks * C * sizeof(float); }
 
-extern "C" int ob_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                                int64_t M, int C, float* dx, float* dgamma, float* dbeta, void* ws, ob_stream_t stream) {
-  OB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws && M > 0,
-             "ob_layernorm_bwd: null pointer or M <= 0");
-  OB_REQUIRE(C == 128 || C == 256 || C == 512 || C == 1024, "ob_layernorm_bwd: C (%d) must be 128, 256, 512 or 1024", C);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int launch_ln_bwd(const float* dy, const float* dy1, const float* dy2, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, const float* resid, int64_t M, int C, float* dx, float* dgamma, float* dbeta, void* ws,
+                         cudaStream_t st) {
   const int64_t want = (M + 7) / 8;
   const int blocks = (int)(want < kLnBwdBlocks ? want : kLnBwdBlocks);
   float* part = static_cast<float*>(ws);
   switch (C) {
-    case 128:  ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, C, dx, part); break;
-    case 256:  ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, C, dx, part); break;
-    case 512:  ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, C, dx, part); break;
-    default:   ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, C, dx, part); break;
+    case 128:  ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); break;
+    case 256:  ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); break;
+    case 512:  ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); break;
+    default:   ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); break;
   }
   OB_LAUNCH_CHECK("ln_bwd_kernel");
   dim3 grid((C + 31) / 32, 2);
   ln_param_grad_kernel<<<grid, 256, 0, st>>>(part, blocks, C, dgamma, dbeta);
   OB_LAUNCH_CHECK("ln_param_grad_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                int64_t M, int C, float* dx, float* dgamma, float* dbeta, void* ws, ob_stream_t stream) {
+  OB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws && M > 0,
+             "ob_layernorm_bwd: null pointer or M <= 0");
+  OB_REQUIRE(C == 128 || C == 256 || C == 512 || C == 1024, "ob_layernorm_bwd: C (%d) must be 128, 256, 512 or 1024", C);
+  return launch_ln_bwd(dy, nullptr, nullptr, x, mean, rstd, gamma, nullptr, M, C, dx, dgamma, dbeta, ws,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ob_layernorm_bwd3(const float* dy0, const float* dy1, const float* dy2, const float* x, const float* mean,
+                                 const float* rstd, const float* gamma, const float* resid, int64_t M, int C, float* dx,
+                                 float* dgamma, float* dbeta, void* ws, ob_stream_t stream) {
+  OB_REQUIRE(dy0 && x && mean && rstd && gamma && dx && dgamma && dbeta && ws && M > 0,
+             "ob_layernorm_bwd3: null pointer or M <= 0");
+  OB_REQUIRE(dy1 != nullptr || dy2 == nullptr, "ob_layernorm_bwd3: dy2 given without dy1");
+  OB_REQUIRE(C == 128 || C == 256 || C == 512 || C == 1024, "ob_layernorm_bwd3: C (%d) must be 128, 256, 512 or 1024", C);
+  return launch_ln_bwd(dy0, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, dgamma, dbeta, ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ob_layernorm_quant_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int C,
+                                      int8_t* q, float* scale, float* mean, float* rstd, ob_stream_t stream) {
+  OB_REQUIRE(x && gamma && beta && q && scale && mean && rstd && M > 0, "ob_layernorm_quant_fwd: null pointer or M <= 0");
+  OB_REQUIRE(C == 128 || C == 256 || C == 512 || C == 1024, "ob_layernorm_quant_fwd: C (%d) must be 128, 256, 512 or 1024", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = ln_blocks(M);
+  switch (C) {
+    case 128:  ln_quant_fwd_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
+    case 256:  ln_quant_fwd_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
+    case 512:  ln_quant_fwd_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
+    default:   ln_quant_fwd_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
+  }
+  OB_LAUNCH_CHECK("ln_quant_fwd_kernel");
   return OB_OK;
 }

@@ -18,17 +18,6 @@ static int num_sms() {
   return g_num_sms;
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
 // Deterministic block sum (fixed tree); result valid in thread 0.
 template <int THREADS>
 __device__ __forceinline__ float block_sum(float v, float* smem /* THREADS/32 floats */) {
@@ -382,36 +371,6 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict_
 // per-token absmax int8 activation quantiser.  One warp per row; the row lives in registers
 // (V float4 per lane, K = 128*V) so x is read from HBM exactly once.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ float4 load4(const T* p);
-template <>
-__device__ __forceinline__ float4 load4<float>(const float* p) {
-  return __ldg(reinterpret_cast<const float4*>(p));
-}
-template <>
-__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
-  uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
-  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x), b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
-  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
-}
-
-__device__ __forceinline__ float act_scale_from_amax(float amax) {
-  // torch evaluates `127.0 / t` as reciprocal(t) * 127 (two roundings); pinned bit-exactly by the oracle
-  return __fmul_rn(__frcp_rn(fmaxf(amax, 1e-5f)), 127.0f);
-}
-// q = clamp(rint(v * s), -128, 127) for four values, packed little-endian.  Clamping to the (integer) bounds first and
-// then adding 1.5 * 2^23 rounds to the nearest integer, ties to even, exactly like rint() - the sum's low mantissa
-// byte IS the int8 two's-complement code - and it stays on the full-rate FP pipes (FRND and F2I run on the
-// quarter-rate XU pipe, which ncu showed ~50-60 % busy in these kernels).
-__device__ __forceinline__ uint32_t quant4(float4 v, float s) {
-  constexpr float kMagic = 12582912.0f;
-  const uint32_t a = __float_as_uint(fminf(fmaxf(__fmul_rn(v.x, s), -128.f), 127.f) + kMagic);
-  const uint32_t b = __float_as_uint(fminf(fmaxf(__fmul_rn(v.y, s), -128.f), 127.f) + kMagic);
-  const uint32_t c = __float_as_uint(fminf(fmaxf(__fmul_rn(v.z, s), -128.f), 127.f) + kMagic);
-  const uint32_t d = __float_as_uint(fminf(fmaxf(__fmul_rn(v.w, s), -128.f), 127.f) + kMagic);
-  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
-}
-
 // K == 128*V: lane l holds float4 index l + 32*j, j < V (coalesced 512-byte warp loads)
 template <typename T, int V>
 __global__ void __launch_bounds__(256) act_quant_reg_kernel(const T* __restrict__ x, int64_t M, int K,
@@ -422,14 +381,13 @@ __global__ void __launch_bounds__(256) act_quant_reg_kernel(const T* __restrict_
   for (int64_t row = warp0; row < M; row += nwarps) {
     const T* xr = x + row * K;
     float4 v[V];
-    float amax = 0.f;
+    uint32_t amax = 0u;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       v[j] = load4<T>(xr + (lane + 32 * j) * 4);
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+      amax = amax_bits4(amax, v[j]);
     }
-    amax = warp_max(amax);
-    const float s = act_scale_from_amax(amax);
+    const float s = act_scale_from_amax(__uint_as_float(warp_max_bits(amax)));
     uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * K);
 #pragma unroll
     for (int j = 0; j < V; ++j) qr[lane + 32 * j] = quant4(v[j], s);
@@ -447,13 +405,9 @@ __global__ void __launch_bounds__(256) act_quant_generic_kernel(const T* __restr
   const int k4 = K >> 2;
   for (int64_t row = warp0; row < M; row += nwarps) {
     const T* xr = x + row * K;
-    float amax = 0.f;
-    for (int i = lane; i < k4; i += 32) {
-      float4 v = load4<T>(xr + i * 4);
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-    }
-    amax = warp_max(amax);
-    const float s = act_scale_from_amax(amax);
+    uint32_t amax = 0u;
+    for (int i = lane; i < k4; i += 32) amax = amax_bits4(amax, load4<T>(xr + i * 4));
+    const float s = act_scale_from_amax(__uint_as_float(warp_max_bits(amax)));
     uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * K);
     for (int i = lane; i < k4; i += 32) qr[i] = quant4(load4<T>(xr + i * 4), s);
     if (lane == 0) scale[row] = s;
@@ -464,12 +418,6 @@ __global__ void __launch_bounds__(256) act_quant_generic_kernel(const T* __restr
 // fused FFN mid-section (conformer.py:36-39): z = dropout(swish(h)), then the activation quantiser of lin2.
 // One read of h (+ the keep mask), one write of int8 codes: replaces sigmoid, mul, dropout and act-quant kernels.
 // ---------------------------------------------------------------------------------------------
-// swish with the SFU exponential (ex2.approx, ~2 ulp) and an IEEE reciprocal: the full-precision expf made this
-// kernel ALU-bound (26 M exponentials per launch at the FFN width); the result differs from torch's sigmoid*x in
-// the last bits only, which moves an int8 code by at most one step on a ~1e-5 fraction of elements
-// swish(h) = h * sigmoid(h) on the SFU (ex2 + rcp, ~2 ulp); exp(-h) = inf for h < -88 gives h * 0 = -0
-__device__ __forceinline__ float swish_f(float h) { return h * __fdividef(1.0f, 1.0f + __expf(-h)); }
-
 template <int V>
 __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __restrict__ h, const uint8_t* __restrict__ keep,
                                                                float inv_keep, DropRng rng, int64_t M, int K,
@@ -481,7 +429,7 @@ __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __re
     const float* hr = h + row * K;
     float4 v[V];
     uint32_t kb[V];                                     // keep flags of float4 j in bits 0..3
-    float amax = 0.f;
+    uint32_t amax = 0u;
 #pragma unroll
     for (int j = 0; j < V; ++j) {                       // all loads of the row first (memory-level parallelism)
       const int e = (lane + 32 * j) * 4;
@@ -512,10 +460,9 @@ __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __re
       t.z = (kb[j] & 4u) ? swish_f(t.z) * ik : 0.f;
       t.w = (kb[j] & 8u) ? swish_f(t.w) * ik : 0.f;
       v[j] = t;
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+      amax = amax_bits4(amax, t);
     }
-    amax = warp_max(amax);
-    const float s = act_scale_from_amax(amax);
+    const float s = act_scale_from_amax(__uint_as_float(warp_max_bits(amax)));
     uint32_t* qr = reinterpret_cast<uint32_t*>(q + row * K);
 #pragma unroll
     for (int j = 0; j < V; ++j) qr[lane + 32 * j] = quant4(v[j], s);
@@ -560,69 +507,111 @@ __global__ void __launch_bounds__(256) swish_drop_bwd_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward prep: dys = bf16(dY / s_m), qb = bf16(q), column sums of dY per row block
+// backward prep: dys = bf16(g / s_m), qb = bf16(q), column sums of g per row block, where g is the layer's upstream
+// gradient - read as is (mode 0) or produced on the fly from the gradient of the op that FOLLOWS the layer in the module:
+//   mode 1  module tail  out = x + scale * dropout(y) * frame_mask  (conformer.py:41-45, 133-138):
+//           g = dOut * scale * frame_mask[row] * keep / (1 - p)         (same Philox lanes as the forward epilogue)
+//   mode 2  FFN mid-section  z = dropout(swish(h)) feeding lin2 (conformer.py:36-39), g is lin1's upstream gradient:
+//           g = dZ * keep / (1 - p) * swish'(h)                          (same lanes as swish_drop_quant_kernel)
+// so neither the tail's nor the activation's backward exists as a separate pass over [M, N] fp32.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPrepRows = 32;
+constexpr int kPrepChunk = 2048;            // columns per pass: 256 threads x 8 columns
 
-__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-  uint2 r;
-  r.x = *reinterpret_cast<uint32_t*>(&lo);
-  r.y = *reinterpret_cast<uint32_t*>(&hi);
-  return r;
-}
+struct PrepOp {
+  const float* rowmask;     // mode 1: float validity per row (global row index), or nullptr
+  const float* h;           // mode 2: pre-activation [M, N] fp32
+  float factor;             // mode 1: scale / (1 - p);  mode 2: 1 / (1 - p)   (p = 0 when the stream is off)
+  DropRng rng;              // threshold 0 -> no dropout
+  long long row_base;       // global index of row 0 of this call (rows of one tensor processed in several calls)
+};
 
-template <typename T>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ dY, const float* __restrict__ scale,
                                                        const int8_t* __restrict__ q, int M, int N, int K,
                                                        __nv_bfloat16* __restrict__ dys, __nv_bfloat16* __restrict__ qb,
-                                                       float* __restrict__ colsum) {
+                                                       float* __restrict__ colsum, PrepOp op) {
   __shared__ float inv_s[kPrepRows];
-  __shared__ float4 red[256];
+  __shared__ float rowf[kPrepRows];
+  __shared__ float4 red[2][256];
   const int r0 = blockIdx.x * kPrepRows;
   const int rows = min(kPrepRows, M - r0);
-  if (threadIdx.x < kPrepRows) inv_s[threadIdx.x] = threadIdx.x < rows ? __frcp_rn(__ldg(scale + r0 + threadIdx.x)) : 0.f;
+  if (threadIdx.x < kPrepRows) {
+    const bool ok = threadIdx.x < rows;
+    inv_s[threadIdx.x] = ok ? __frcp_rn(__ldg(scale + r0 + threadIdx.x)) : 0.f;
+    float f = op.factor;
+    if (MODE == 1 && ok && op.rowmask != nullptr) f *= __ldg(op.rowmask + op.row_base + r0 + threadIdx.x);
+    rowf[threadIdx.x] = f;
+  }
   __syncthreads();
-  // dY: a column chunk is min(N,1024) wide; tpr threads (4 columns each) cover a row of the chunk and
-  // rpi = 256/tpr row groups walk down the rows; the row groups' column sums are combined in fixed order.
-  for (int c0 = 0; c0 < N; c0 += 1024) {
-    const int cw = min(1024, N - c0);
-    const int tpr = cw >> 2;
+  // a thread owns two float4 of a row (8 columns); tpr threads cover a row of the chunk, rpi = 256 / tpr row groups walk
+  // down the rows and their column sums are combined in fixed order
+  for (int c0 = 0; c0 < N; c0 += kPrepChunk) {
+    const int cw = min(kPrepChunk, N - c0);
+    const int tpr = cw >> 3;
     const int rpi = 256 / tpr;
     const int rg = threadIdx.x / tpr;
-    const int c = c0 + (threadIdx.x - rg * tpr) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int j = threadIdx.x - rg * tpr;
+    int ca, cb;
+    if (MODE == 2) {            // float4 pair (f, f + 32): the two halves of one Philox block of the FFN mid-section's stream
+      ca = c0 + 4 * (((j >> 5) << 6) + (j & 31));
+      cb = ca + 128;
+    } else {
+      ca = c0 + 8 * j;
+      cb = ca + 4;
+    }
+    float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_a;
     if (rg < rpi) {
-      int r = rg;
-      for (; r + 7 * rpi < rows; r += 8 * rpi) {                 // 8 independent 16-byte loads in flight per thread
-        float4 v[8];
+#pragma unroll 2
+      for (int r = rg; r < rows; r += rpi) {
+        const int64_t off = (int64_t)(r0 + r) * N;
+        float4 va = load4<T>(dY + off + ca), vb = load4<T>(dY + off + cb);
+        if (MODE == 1) {
+          const float f = rowf[r];
+          uint32_t kb = 0xFFu;
+          if (op.rng.threshold != 0u)
+            kb = philox_keep8(static_cast<unsigned long long>(((op.row_base + r0 + r) * N + ca) >> 3), op.rng);
+          va.x = (kb & 1u) ? va.x * f : 0.f;   va.y = (kb & 2u) ? va.y * f : 0.f;
+          va.z = (kb & 4u) ? va.z * f : 0.f;   va.w = (kb & 8u) ? va.w * f : 0.f;
+          vb.x = (kb & 16u) ? vb.x * f : 0.f;  vb.y = (kb & 32u) ? vb.y * f : 0.f;
+          vb.z = (kb & 64u) ? vb.z * f : 0.f;  vb.w = (kb & 128u) ? vb.w * f : 0.f;
+        } else if (MODE == 2) {
+          const float4 ha = __ldg(reinterpret_cast<const float4*>(op.h + off + ca));
+          const float4 hb = __ldg(reinterpret_cast<const float4*>(op.h + off + cb));
+          uint32_t kb = 0xFFu;
+          if (op.rng.threshold != 0u)
+            kb = philox_keep8(static_cast<unsigned long long>(((op.row_base + r0 + r) * N + ca) >> 2), op.rng);
+          const float ik = op.factor;
+          const float hs[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+          const float gs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+          float o[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = load4<T>(dY + (int64_t)(r0 + r + u * rpi) * N + c);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-          const float is = inv_s[r + u * rpi];
-          *reinterpret_cast<uint2*>(dys + (int64_t)(r0 + r + u * rpi) * N + c) =
-              pack_bf16x4(v[u].x * is, v[u].y * is, v[u].z * is, v[u].w * is);
+          for (int u = 0; u < 8; ++u) {
+            const float sg = __fdividef(1.0f, 1.0f + __expf(-hs[u]));
+            o[u] = ((kb >> u) & 1u) ? gs[u] * ik * (sg + hs[u] * sg * (1.0f - sg)) : 0.f;
+          }
+          va = make_float4(o[0], o[1], o[2], o[3]);
+          vb = make_float4(o[4], o[5], o[6], o[7]);
         }
-      }
-      for (; r < rows; r += rpi) {
-        const int64_t off = (int64_t)(r0 + r) * N + c;
-        float4 v = load4<T>(dY + off);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        acc_a.x += va.x; acc_a.y += va.y; acc_a.z += va.z; acc_a.w += va.w;
+        acc_b.x += vb.x; acc_b.y += vb.y; acc_b.z += vb.z; acc_b.w += vb.w;
         const float is = inv_s[r];
-        *reinterpret_cast<uint2*>(dys + off) = pack_bf16x4(v.x * is, v.y * is, v.z * is, v.w * is);
+        *reinterpret_cast<uint2*>(dys + off + ca) = pack_bf16x4(va.x * is, va.y * is, va.z * is, va.w * is);
+        *reinterpret_cast<uint2*>(dys + off + cb) = pack_bf16x4(vb.x * is, vb.y * is, vb.z * is, vb.w * is);
       }
     }
     if (colsum != nullptr) {
-      red[threadIdx.x] = acc;
+      red[0][threadIdx.x] = acc_a;
+      red[1][threadIdx.x] = acc_b;
       __syncthreads();
       if (rg == 0) {
         for (int g = 1; g < rpi; ++g) {
-          float4 o = red[g * tpr + threadIdx.x];
-          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+          const float4 oa = red[0][g * tpr + threadIdx.x], ob2 = red[1][g * tpr + threadIdx.x];
+          acc_a.x += oa.x; acc_a.y += oa.y; acc_a.z += oa.z; acc_a.w += oa.w;
+          acc_b.x += ob2.x; acc_b.y += ob2.y; acc_b.z += ob2.z; acc_b.w += ob2.w;
         }
-        *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + c) = acc;
+        *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + ca) = acc_a;
+        *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + cb) = acc_b;
       }
       __syncthreads();
     }
@@ -793,20 +782,46 @@ extern "C" int ob_bwd_prep(const void* dY, int dy_dtype, const float* scale, con
                            void* dys_bf16, void* qb_bf16, float* colsum, ob_stream_t stream) {
   OB_REQUIRE(dY && scale && dys_bf16, "ob_bwd_prep: null pointer");
   OB_REQUIRE(qb_bf16 == nullptr || q != nullptr, "ob_bwd_prep: qb requested without q");
-  OB_REQUIRE(M > 0 && N > 0 && N % 4 == 0 && K % 8 == 0, "ob_bwd_prep: need N %% 4 == 0 and K %% 8 == 0 (N=%d K=%d)", N, K);
+  OB_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && K % 8 == 0, "ob_bwd_prep: need N %% 8 == 0 and K %% 8 == 0 (N=%d K=%d)", N, K);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = ob_bwd_colsum_blocks(M);
+  const PrepOp op = {nullptr, nullptr, 1.0f, {0ull, 0ull, 0u}, 0ll};
   if (dy_dtype == OB_F32)
-    bwd_prep_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(dY), scale, q, M, N, K,
-                                                   static_cast<__nv_bfloat16*>(dys_bf16),
-                                                   static_cast<__nv_bfloat16*>(qb_bf16), colsum);
+    bwd_prep_kernel<float, 0><<<blocks, 256, 0, st>>>(static_cast<const float*>(dY), scale, q, M, N, K,
+                                                      static_cast<__nv_bfloat16*>(dys_bf16),
+                                                      static_cast<__nv_bfloat16*>(qb_bf16), colsum, op);
   else if (dy_dtype == OB_BF16)
-    bwd_prep_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dY), scale, q, M, N, K,
-                                                           static_cast<__nv_bfloat16*>(dys_bf16),
-                                                           static_cast<__nv_bfloat16*>(qb_bf16), colsum);
+    bwd_prep_kernel<__nv_bfloat16, 0><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dY), scale, q, M, N, K,
+                                                              static_cast<__nv_bfloat16*>(dys_bf16),
+                                                              static_cast<__nv_bfloat16*>(qb_bf16), colsum, op);
   else
     OB_REQUIRE(false, "ob_bwd_prep: unknown dtype tag %d", dy_dtype);
   OB_LAUNCH_CHECK("bwd_prep_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_bwd_prep_fused(const float* g_next, int mode, const float* rowmask, const float* h, float factor,
+                                 uint64_t seed, uint64_t offset, uint32_t drop_threshold, int64_t row_base,
+                                 const float* scale, const int8_t* q, int M, int N, int K, void* dys_bf16, void* qb_bf16,
+                                 float* colsum, ob_stream_t stream) {
+  OB_REQUIRE(g_next && scale && dys_bf16, "ob_bwd_prep_fused: null pointer");
+  OB_REQUIRE(mode == OB_PREP_TAIL || mode == OB_PREP_SWISH, "ob_bwd_prep_fused: mode must be OB_PREP_TAIL or OB_PREP_SWISH (%d)", mode);
+  OB_REQUIRE(mode != OB_PREP_SWISH || h != nullptr, "ob_bwd_prep_fused: OB_PREP_SWISH needs the pre-activation h");
+  OB_REQUIRE(qb_bf16 == nullptr || q != nullptr, "ob_bwd_prep_fused: qb requested without q");
+  OB_REQUIRE(drop_threshold < 65536u, "ob_bwd_prep_fused: drop_threshold (%u) is a 16-bit value", drop_threshold);
+  OB_REQUIRE(M > 0 && N > 0 && K % 8 == 0 && row_base >= 0, "ob_bwd_prep_fused: bad sizes (M=%d N=%d K=%d)", M, N, K);
+  OB_REQUIRE(mode == OB_PREP_SWISH ? N % 256 == 0 : N % 8 == 0,
+             "ob_bwd_prep_fused: N (%d) must be a multiple of 8 (tail) / 256 (swish)", N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = ob_bwd_colsum_blocks(M);
+  const PrepOp op = {rowmask, h, factor, {seed, offset, drop_threshold}, static_cast<long long>(row_base)};
+  if (mode == OB_PREP_TAIL)
+    bwd_prep_kernel<float, 1><<<blocks, 256, 0, st>>>(g_next, scale, q, M, N, K, static_cast<__nv_bfloat16*>(dys_bf16),
+                                                      static_cast<__nv_bfloat16*>(qb_bf16), colsum, op);
+  else
+    bwd_prep_kernel<float, 2><<<blocks, 256, 0, st>>>(g_next, scale, q, M, N, K, static_cast<__nv_bfloat16*>(dys_bf16),
+                                                      static_cast<__nv_bfloat16*>(qb_bf16), colsum, op);
+  OB_LAUNCH_CHECK("bwd_prep_kernel(fused)");
   return OB_OK;
 }
 

@@ -154,6 +154,39 @@ int ob_layernorm_bwd(const float* dy, const float* x, const float* mean, const f
                      const float* gamma, int64_t M, int C, float* dx, float* dgamma, float* dbeta,
                      void* ws, ob_stream_t stream);
 
+/* Fusions around the layer inside the routed modules (conformer.py:35-45, 109-138).
+ *
+ * ob_layernorm_quant_fwd: LayerNorm and the per-token absmax int8 quantiser of the projection(s) that read it, in one
+ *   pass: writes only the int8 codes q [M, C], the scales [M] and mean / rstd [M] (the normalised fp32 tensor never
+ *   reaches HBM).  q and scale equal ob_act_quant_i8(ob_layernorm_fwd(x)) bit for bit.
+ * ob_layernorm_bwd3: ob_layernorm_bwd with the upstream gradient given as dy0 (+ dy1 (+ dy2)) - the gradients of up to
+ *   three projections that consumed the same normalised tensor (q, k, v) are summed on load - and, when `resid` is not
+ *   NULL, the gradient that reached the module input along the residual path added on store: dx = LN'(...) + resid.
+ * ob_gemm_tern_i8_fwd_tail: ob_gemm_tern_i8_fwd (fp32 output) with the module tail in the epilogue,
+ *     out[m,n] = resid[m,n] + (keep(m,n) ? y[m,n] * tail_factor * rowmask[row_base + m] : 0),
+ *   i.e. x + scale * dropout(y) * frame_mask with tail_factor = scale / (1 - p); keep = 16-bit Philox lane
+ *   ((row_base + m) * N + n) % 8 of block ((row_base + m) * N + n) / 8 >= drop_threshold (0 = no dropout), the stream of
+ *   ob_residual_dropout_fwd; rowmask (float per global row) may be NULL.  Same bits as the two separate calls.
+ * ob_bwd_prep_fused: ob_bwd_prep whose dY is produced on the fly from the gradient g_next of the op that follows the
+ *   layer: OB_PREP_TAIL  dY = g_next * factor * rowmask[row] * keep   (backward of the fused tail above),
+ *          OB_PREP_SWISH dY = g_next * factor * keep * swish'(h)     (backward of ob_swish_drop_quant in front of the NEXT
+ *                                                                      layer; h = this layer's fp32 output [M, N]). */
+#define OB_PREP_TAIL 1
+#define OB_PREP_SWISH 2
+int ob_layernorm_quant_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int C,
+                           int8_t* q, float* scale, float* mean, float* rstd, ob_stream_t stream);
+int ob_layernorm_bwd3(const float* dy0, const float* dy1, const float* dy2, const float* x, const float* mean,
+                      const float* rstd, const float* gamma, const float* resid, int64_t M, int C, float* dx,
+                      float* dgamma, float* dbeta, void* ws, ob_stream_t stream);
+int ob_gemm_tern_i8_fwd_tail(const int8_t* q, const float* scale, const uint8_t* packed_i8, const float* alpha,
+                             int alpha_mode, const float* bias, int M, int N, int K, const float* resid,
+                             const float* rowmask, float tail_factor, uint64_t seed, uint64_t offset,
+                             uint32_t drop_threshold, int64_t row_base, float* out, ob_stream_t stream);
+int ob_bwd_prep_fused(const float* g_next, int mode, const float* rowmask, const float* h, float factor,
+                      uint64_t seed, uint64_t offset, uint32_t drop_threshold, int64_t row_base,
+                      const float* scale, const int8_t* q, int M, int N, int K, void* dys_bf16, void* qb_bf16,
+                      float* colsum, ob_stream_t stream);
+
 /* Element-wise chain between the attention matmuls of the reference MHSA (conformer.py:118-128), fused:
  * y = nan_to_num(softmax(masked_fill((ac + rel_shift(bd)) * scale))), attn_d = dropout(y).  ac, bd [B,H,T,T] fp32 (bd
  * BEFORE the relative shift), mask [B,T,T] bytes (0 = masked), T <= 2048.  Dropout as in ob_swish_drop_quant: explicit
