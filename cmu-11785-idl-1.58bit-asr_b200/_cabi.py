@@ -17,7 +17,6 @@ OB_ALPHA_EFF, OB_ALPHA_RAW = 0, 1
 OB_ORDER_I8, OB_ORDER_BF16 = 0, 1
 OB_PREP_TAIL, OB_PREP_SWISH = 1, 2
 DBG_SWAP_LBO_SBO, DBG_FORCE_BLOCK_N, DBG_FORCE_SPLITS, DBG_MAX_CTAS = 1, 2, 3, 4
-DBG_DW_CLUSTER = 10     # 1: grad_W through the split kernel + finaliser instead of the cluster-reduced kernel
 DBG_SMALL_M = 9         # 1: keep M <= 64 on the tcgen05 kernel instead of the weight-streaming DP4A kernel
 
 _p, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t

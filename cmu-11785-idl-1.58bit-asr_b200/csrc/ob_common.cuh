@@ -220,41 +220,6 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
   return r;
 }
 
-// Deterministic block sum (fixed tree); result valid in thread 0.
-template <int THREADS>
-__device__ __forceinline__ float block_sum(float v, float* smem /* THREADS/32 floats */) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) smem[wid] = v;
-  __syncthreads();
-  float r = 0.f;
-  if (wid == 0) {
-    r = lane < THREADS / 32 ? smem[lane] : 0.f;
-    r = warp_sum(r);
-  }
-  __syncthreads();
-  return r;
-}
-
-// ---------------------------------------------------------------------------------------------
-// STE backward pieces (quant.py:80-92), shared by the dense path and the grad_W finalizer
-// ---------------------------------------------------------------------------------------------
-// returns masked gradient; adds g*term to acc
-__device__ __forceinline__ float ste_elem(float g, float w, float a_eff, int bitwidth, float& acc) {
-  const float wa = __fdiv_rn(w, a_eff);
-  const float mag = fabsf(wa);
-  const float sgn = wa > 0.f ? 1.f : (wa < 0.f ? -1.f : 0.f);
-  float term;
-  if (mag < 1.0f) {                                                     // strict, quant.py:87
-    const float proj = (bitwidth == 2) ? (mag >= 0.5f ? sgn : 0.f) : sgn;   // quant.py:88
-    term = __fadd_rn(-wa, proj);
-  } else {
-    term = sgn;                                                         // quant.py:89
-  }
-  acc = __fmaf_rn(g, term, acc);
-  return mag <= 1.0f ? g : 0.f;                                         // quant.py:81-82
-}
-
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
 // ---------------------------------------------------------------------------------------------

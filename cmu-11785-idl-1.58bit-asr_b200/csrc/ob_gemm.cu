@@ -25,11 +25,10 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
 // debug / tuning knobs (ob_debug_set)
 // ---------------------------------------------------------------------------------------------
 enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5,
-                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9, kDbgDwCluster = 10 };
+                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9 };
 int small_m_limit(int K);              // ob_gemv.cu
 int launch_gemv_tern_i8(const int8_t* q, const float* scale, const uint8_t* packed, const float* alpha, int alpha_mode,
                         const float* bias, int M, int N, int K, void* y, int out_bf16, cudaStream_t st);
-static int g_dbg_dw_cluster = 0;       // 1: grad_W always through the split kernel + finaliser (no cluster reduction)
 static int g_dbg_small_m = 0;          // 0: M <= 64 takes the DP4A kernel (ob_gemv.cu), 1: always the tcgen05 kernel
 void f32_gemm_debug(int split_mode);   // ob_gemm_f32.cu
 void f32_gemm_debug_epilogue(int mode);
@@ -623,214 +622,6 @@ dw_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ C
   }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// grad_W with the token-split reduction done on chip (clusters + distributed shared memory)
-// ---------------------------------------------------------------------------------------------
-// dw_kernel above leaves `splits` (18-74) fp32 partials of the whole [N, K] gradient in HBM for a finaliser launch - for
-// the model's shapes more bytes than the operands themselves.  Here the CTAs that split the tokens of one output tile form
-// a thread-block cluster of CL: each accumulates its token range in TMEM as before, parks the [128 x BLOCK_N] fp32 tile in
-// its own shared memory (the operand ring is free by then), and after a cluster barrier every CTA reduces one column slice
-// of the tile over the CL copies through DSMEM in rank order (deterministic).  With one cluster per tile (P == 1) the slice
-// goes straight through the STE mask / alpha term (quant.py:80-92) into grad_W and the launch also finishes grad_alpha
-// (ticketed last CTA) and grad_bias (every CTA reduces its share of the prep kernel's column sums): ONE launch, no partials.
-// With P > 1 clusters per tile the P slice sums are the partials of the (much smaller) finaliser.
-constexpr int kDwcThreads = 256;
-constexpr int kDwcPitch = 129;                  // floats per staged column: (col * 129 + row) % 32 spreads both axes over the banks
-
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
-  return v;
-}
-
-struct DwcArgs {
-  float* out;                 // finalize: grad_W [N, K];  else partials [P][N][K]
-  const float* W;
-  const float* alpha;
-  int alpha_mode, bitwidth;
-  float* alpha_parts;         // [ctas] (finalize)
-  float* grad_alpha;
-  const float* colsum;        // [n_col_blocks][N] or nullptr
-  int n_col_blocks;
-  float* grad_bias;           // nullptr -> no bias gradient
-  int* counter;               // zero on entry, reset on exit (finalize)
-  int M, N, K, tb_per_cta, P, finalize;
-  uint32_t lbo, sbo;
-};
-
-// grid: x = CL * P (cluster along x: rank = token split inside the cluster, blockIdx.x / CL = cluster index p),
-//       y = n_tile * k_tiles + k_tile.  Warp roles: 0 producer, 1 MMA, 2 TMEM alloc, 4..7 TMEM -> staging; then all.
-template <int BLOCK_N, int STAGES, int CL>
-__global__ void __launch_bounds__(kDwcThreads, 1)
-dw_cluster_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ CUtensorMap map_qb, const DwcArgs a) {
-  using L = DwSmem<BLOCK_N, STAGES>;
-  static_assert(BLOCK_N * kDwcPitch * 4 <= STAGES * (L::kATileBytes + L::kBTileBytes), "staging tile must fit in the operand ring");
-  static_assert(BLOCK_N % CL == 0, "column slices");
-  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
-  constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 1, 1, 128, BLOCK_N);
-  constexpr int SL = BLOCK_N / CL;              // columns of the tile this CTA reduces
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* done_bar = full_bar + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
-  __shared__ float red[8];
-  __shared__ int is_last;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k_tiles = (a.K + BLOCK_N - 1) / BLOCK_N;
-  const int n0 = (blockIdx.y / k_tiles) * 128, k0 = (blockIdx.y % k_tiles) * BLOCK_N;
-  const uint32_t rank = cluster_ctarank();
-  const int p = blockIdx.x / CL;
-  const int num_tb = (a.M + kDwTokBlock - 1) / kDwTokBlock;
-  const int tb0 = min(num_tb, static_cast<int>(blockIdx.x) * a.tb_per_cta);
-  const int tb1 = min(num_tb, tb0 + a.tb_per_cta);
-  const int nkb = tb1 - tb0;                     // may be 0 for the last splits
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_dys);
-    tma_prefetch_desc(&map_qb);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(done_bar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int t0 = (tb0 + kb) * kDwTokBlock;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], L::kATileBytes + L::kBTileBytes);
-        uint8_t* sa = smem + L::kOffA + stage * L::kATileBytes;
-        uint8_t* sb = smem + L::kOffB + stage * L::kBTileBytes;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) tma_load_2d(sa + j * kDwAtomBytes, &map_dys, &full_bar[stage], n0 + 64 * j, t0);
-#pragma unroll
-        for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * kDwAtomBytes, &map_qb, &full_bar[stage], k0 + 64 * j, t0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + L::kOffA + stage * L::kATileBytes), a.lbo, a.sbo);
-        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + L::kOffB + stage * L::kBTileBytes), a.lbo, a.sbo);
-#pragma unroll
-        for (int k = 0; k < kDwTokBlock / 16; ++k)
-          umma_f16(tmem_base, a_desc + 128 * k, b_desc + 128 * k, kIdesc, (kb | k) != 0);
-        umma_commit(&empty_bar[stage]);
-        if (kb == nkb - 1) umma_commit(done_bar);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    // accumulator -> staging tile in shared memory, [col][row] with a pitch of 129 floats (the ring is idle: every load
-    // has been consumed by an MMA that retired before done_bar fired)
-    const int e = warp - 4;
-    const int row = e * 32 + lane;
-    float* stage_f = reinterpret_cast<float*>(smem);
-    if (nkb > 0) {
-      mbar_wait(done_bar, 0);
-      tc_fence_after();
-    }
-#pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      uint32_t r[32];
-      if (nkb > 0) {
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + c * 32, r);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stage_f[(c * 32 + j) * kDwcPitch + row] = __uint_as_float(r[j]);
-    }
-    tc_fence_before();
-  }
-  cluster_sync_all();                           // every CTA's tile is parked; also orders the generic-proxy smem writes
-
-  // ---- slice reduction over the cluster, rank order; thread t -> (col fastest) so that global I/O is row segments
-  const float a_eff = load_alpha_eff(a.alpha, a.alpha_mode);
-  float acc_alpha = 0.f;
-  const uint32_t stage_base = smem_u32(smem);
-  for (int e = threadIdx.x; e < SL * 128; e += kDwcThreads) {
-    const int col_l = e % SL, row = e / SL;
-    const int col = rank * SL + col_l;
-    const uint32_t off = stage_base + static_cast<uint32_t>((col * kDwcPitch + row) * 4);
-    float v = 0.f;
-#pragma unroll
-    for (int c = 0; c < CL; ++c) v += ld_dsmem_f32(mapa_u32(off, c));
-    const int n = n0 + row, k = k0 + col;
-    if (n < a.N && k < a.K) {
-      const int64_t idx = static_cast<int64_t>(n) * a.K + k;
-      if (a.finalize) a.out[idx] = ste_elem(v, __ldg(a.W + idx), a_eff, a.bitwidth, acc_alpha);
-      else            a.out[static_cast<int64_t>(p) * a.N * a.K + idx] = v;
-    }
-  }
-  cluster_sync_all();                           // nobody leaves (or reuses its tile) while a peer may still read it
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-  if (!a.finalize) return;
-
-  // ---- tails of the backward in the same launch
-  const int ncta = gridDim.x * gridDim.y;
-  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-  const float tot = block_sum<kDwcThreads>(acc_alpha, red);
-  if (a.grad_bias != nullptr) {                 // grad_bias[c] = sum over row blocks of the prep kernel's column sums
-    const int per = (a.N + ncta - 1) / ncta;
-    const int c_lo = cta * per, c_hi = min(a.N, c_lo + per);
-    for (int c = c_lo; c < c_hi; ++c) {
-      float s = 0.f;
-      for (int b = threadIdx.x; b < a.n_col_blocks; b += kDwcThreads) s += __ldg(a.colsum + static_cast<int64_t>(b) * a.N + c);
-      s = block_sum<kDwcThreads>(s, red);
-      if (threadIdx.x == 0) a.grad_bias[c] = s;
-    }
-  }
-  if (threadIdx.x == 0) {
-    a.alpha_parts[cta] = tot;
-    __threadfence();
-    is_last = atomicAdd(a.counter, 1) == ncta - 1;
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    float s = 0.f;
-    for (int i = threadIdx.x; i < ncta; i += kDwcThreads) s += __ldcg(a.alpha_parts + i);
-    s = block_sum<kDwcThreads>(s, red);
-    if (threadIdx.x == 0) {
-      if (a.alpha_mode == OB_ALPHA_RAW) {
-        const float al = __ldg(a.alpha);
-        s = al > 0.f ? s : (al < 0.f ? -s : 0.f);
-      }
-      a.grad_alpha[0] = s;
-      *a.counter = 0;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
@@ -984,92 +775,6 @@ static int launch_dw(const CUtensorMap& map_dys, const CUtensorMap& map_qb, floa
   return OB_OK;
 }
 
-
-constexpr int kDwClusterSize = 8;
-
-struct DwcPlan {
-  bool use;
-  int block_n, k_tiles, n_tiles, P, tb_per_cta;
-};
-
-template <int BLOCK_N, int STAGES>
-static int dwc_query_clusters() {
-  using L = DwSmem<BLOCK_N, STAGES>;
-  auto kern = dw_cluster_kernel<BLOCK_N, STAGES, kDwClusterSize>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes) != cudaSuccess) return 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kDwClusterSize * 64, 1);
-  cfg.blockDim = dim3(kDwcThreads);
-  cfg.dynamicSmemBytes = L::kDynBytes;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kDwClusterSize;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
-  return n;
-}
-
-// co-resident clusters of 8 for the kernel variant of this tile width (GPC granularity: fewer than sm_count / 8), cached
-static int dwc_max_clusters(int block_n) {
-  static int cached[3] = {-1, -1, -1};
-  const int i = block_n == 256 ? 0 : (block_n == 128 ? 1 : 2);
-  if (cached[i] < 0)
-    cached[i] = i == 0 ? dwc_query_clusters<256, 4>() : (i == 1 ? dwc_query_clusters<128, 6>() : dwc_query_clusters<64, 8>());
-  return cached[i];
-}
-
-// clusters of 8 CTAs per output tile, as many clusters per tile as can be resident at once (one wave); only when every CTA
-// still gets a few token blocks (tiny M keeps the plain split kernel)
-static DwcPlan plan_dw_cluster(int M, int N, int K) {
-  DwcPlan p;
-  p.block_n = K >= 256 ? 256 : (K >= 128 ? 128 : 64);
-  p.k_tiles = (K + p.block_n - 1) / p.block_n;
-  p.n_tiles = (N + 127) / 128;
-  p.P = 0;
-  p.tb_per_cta = 0;
-  p.use = false;
-  if (g_dbg_dw_cluster == 1) return p;
-  const int tiles = p.k_tiles * p.n_tiles;
-  const int num_tb = (M + kDwTokBlock - 1) / kDwTokBlock;
-  int max_clusters = dwc_max_clusters(p.block_n);
-  if (g_dbg_max_ctas > 0 && max_clusters > g_dbg_max_ctas / kDwClusterSize) max_clusters = g_dbg_max_ctas / kDwClusterSize;
-  p.P = max_clusters / tiles;
-  if (g_dbg_force_splits > 0) p.P = g_dbg_force_splits;
-  const int max_p = num_tb / (2 * kDwClusterSize);          // at least two token blocks per CTA
-  if (p.P > max_p) p.P = max_p;
-  p.use = p.P >= 1;
-  if (!p.use) return p;
-  const int ctas = p.P * kDwClusterSize;
-  p.tb_per_cta = (num_tb + ctas - 1) / ctas;
-  return p;
-}
-
-template <int BLOCK_N, int STAGES>
-static int launch_dw_cluster(const CUtensorMap& map_dys, const CUtensorMap& map_qb, const DwcArgs& args, const DwcPlan& p,
-                             cudaStream_t st) {
-  using L = DwSmem<BLOCK_N, STAGES>;
-  auto kern = dw_cluster_kernel<BLOCK_N, STAGES, kDwClusterSize>;     // smem attribute set by dwc_query_clusters (plan)
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kDwClusterSize * p.P, p.n_tiles * p.k_tiles);
-  cfg.blockDim = dim3(kDwcThreads);
-  cfg.dynamicSmemBytes = L::kDynBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kDwClusterSize;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_dys, map_qb, args));
-  count_launch();
-  return OB_OK;
-}
-
 }  // namespace ob
 
 // =============================================================================================
@@ -1088,7 +793,6 @@ extern "C" int ob_debug_set(int key, int value) {
     case kDbgF32Epilogue: f32_gemm_debug_epilogue(value); return OB_OK;
     case kDbgF32Pair: f32_gemm_debug_pair(value); return OB_OK;
     case kDbgSmallM: g_dbg_small_m = value; return OB_OK;
-    case kDbgDwCluster: g_dbg_dw_cluster = value; return OB_OK;
     default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;
   }
 }
@@ -1153,11 +857,8 @@ extern "C" int ob_bwd_dx(const void* dys_bf16, const float* scale, const uint8_t
 extern "C" size_t ob_bwd_dw_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const DwPlan p = plan_dw(M, N, K);
-  const DwcPlan c = plan_dw_cluster(M, N, K);
-  size_t parts = (size_t)p.splits;                           // either kernel may run (debug switch): size for the larger
-  if (c.use && (size_t)c.P > parts) parts = (size_t)c.P;
-  const size_t partials = parts * N * K * sizeof(float);
-  return partials + ob_ste_workspace_bytes((int64_t)N * K) + bwd_tail_workspace_bytes(N) + 1024 * sizeof(float) + 256;
+  const size_t partials = (size_t)p.splits * N * K * sizeof(float);
+  return partials + ob_ste_workspace_bytes((int64_t)N * K) + bwd_tail_workspace_bytes(N) + 256;
 }
 
 extern "C" int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float* colsum, const float* W,
@@ -1185,26 +886,6 @@ extern "C" int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float*
   rc = make_map(&map_qb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qb_bf16, K, M, (uint64_t)K * 2, 64, kDwTokBlock,
                 CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != OB_OK) return rc;
-  const DwcPlan c = plan_dw_cluster(M, N, K);
-  if (c.use) {
-    // cluster-reduced path: one launch when a single cluster covers a tile's tokens, else P partials + the small finaliser
-    float* partials = static_cast<float*>(ws);
-    const bool fin = c.P == 1;
-    float* alpha_parts = partials + (fin ? 0 : (size_t)c.P * N * K);
-    int* counter = reinterpret_cast<int*>(alpha_parts + 1024);            // <= 148 CTAs of partial sums in front of it
-    DwcArgs args = {fin ? grad_W : partials, W, alpha, alpha_mode, bitwidth, alpha_parts, grad_alpha, colsum,
-                    ob_bwd_colsum_blocks(M), grad_bias, counter, M, N, K, c.tb_per_cta, c.P, fin ? 1 : 0, kDwAtomBytes, 1024u};
-    if (g_dbg_swap_lbo_sbo) { args.lbo = 1024u; args.sbo = kDwAtomBytes; }
-    if (fin) OB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    switch (c.block_n) {
-      case 256: rc = launch_dw_cluster<256, 4>(map_dys, map_qb, args, c, st); break;
-      case 128: rc = launch_dw_cluster<128, 6>(map_dys, map_qb, args, c, st); break;
-      default:  rc = launch_dw_cluster<64, 8>(map_dys, map_qb, args, c, st); break;
-    }
-    if (rc != OB_OK || fin) return rc;
-    return launch_ste_and_tail(partials, c.P, W, alpha, alpha_mode, (int64_t)N * K, bitwidth, grad_W, grad_alpha,
-                               alpha_parts, colsum, ob_bwd_colsum_blocks(M), N, grad_bias, st);
-  }
   float* partials = static_cast<float*>(ws);
   float* alpha_parts = partials + (size_t)p.splits * N * K;
   switch (p.block_n) {

@@ -18,6 +18,22 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// Deterministic block sum (fixed tree); result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* smem /* THREADS/32 floats */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (wid == 0) {
+    r = lane < THREADS / 32 ? smem[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mean |W|   (alpha initialisation, quant.py:111-113)
 // ---------------------------------------------------------------------------------------------
@@ -124,6 +140,25 @@ __global__ void __launch_bounds__(256) weight_dense_kernel(const float* __restri
   }
   if (blockIdx.x == 0)
     for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += 256) out[i] = dense_code(W[i], a_eff, bitwidth);
+}
+
+// ---------------------------------------------------------------------------------------------
+// STE backward pieces (quant.py:80-92), shared by the dense path and the grad_W finalizer
+// ---------------------------------------------------------------------------------------------
+// returns masked gradient; adds g*term to acc
+__device__ __forceinline__ float ste_elem(float g, float w, float a_eff, int bitwidth, float& acc) {
+  const float wa = __fdiv_rn(w, a_eff);
+  const float mag = fabsf(wa);
+  const float sgn = wa > 0.f ? 1.f : (wa < 0.f ? -1.f : 0.f);
+  float term;
+  if (mag < 1.0f) {                                                     // strict, quant.py:87
+    const float proj = (bitwidth == 2) ? (mag >= 0.5f ? sgn : 0.f) : sgn;   // quant.py:88
+    term = __fadd_rn(-wa, proj);
+  } else {
+    term = sgn;                                                         // quant.py:89
+  }
+  acc = __fmaf_rn(g, term, acc);
+  return mag <= 1.0f ? g : 0.f;                                         // quant.py:81-82
 }
 
 constexpr int kSteBlockElems = 4096;   // elements per block (256 threads x 4 float4)

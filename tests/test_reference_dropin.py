@@ -6,7 +6,7 @@
   * ``oracle/torch_oracle.py``'s layer          -> Oracle-A / Oracle-B model on the CPU,
   * ``onebit_b200.quant`` on a B200             -> the product, compared with Oracle-B (``-m gpu``).
 
-tolerances (GPU): the first routed modules (block 0: ff1, mhsa) rel <= 1e-5 of max - fp32 model around an exact integer GEMM;
+tolerances (GPU): the first routed projection (block 0, ff1.lin1: identical inputs on both sides) rel <= 1e-5 of max;
                   encoder output / CTC logits rel <= 3e-2: the int8 activation quantiser is discontinuous, so a last-bit
                   difference in an activation eventually flips a code (one step = 1/127 of the row's absmax) and the flip is
                   amplified by every later quantiser and LayerNorm - measured growth 4e-7 -> 1e-4 -> 8e-3 over three blocks
@@ -132,9 +132,8 @@ def test_unmodified_reference_conformer_on_the_cuda_layer(precision, sp_mask):
     m_same = copy.deepcopy(m_cpu).cuda()             # Oracle-B on the SAME device: isolates the layer from CPU/GPU conv rounding
     first = {}
     for tag, m in (("same", m_same), ("gpu", m_gpu)):
-        for name in ("ff1", "mhsa"):
-            getattr(m.encoder.blocks[0], name).register_forward_hook(
-                lambda mod, i, o, key=(tag, name): first.__setitem__(key, o.detach().float().cpu()))
+        m.encoder.blocks[0].ff1.lin1.register_forward_hook(
+            lambda mod, i, o, key=tag: first.__setitem__(key, o.detach().float().cpu()))
     enc_c, mask_c, ctc_c = m_cpu(batch, precision=precision, sp_mask=sp_mask)
     g = torch.Generator().manual_seed(5)
     w_enc, w_ctc = torch.randn(enc_c.shape, generator=g), torch.randn(ctc_c.shape, generator=g)
@@ -144,8 +143,8 @@ def test_unmodified_reference_conformer_on_the_cuda_layer(precision, sp_mask):
     assert torch.equal(mask_c, mask_g.cpu())
     with torch.no_grad():
         m_same(batch_gpu, precision=precision, sp_mask=sp_mask)
-    for name in ("ff1", "mhsa"):                     # before any int8 code flip has been amplified: fp32-level agreement
-        assert _rel(first[("gpu", name)], first[("same", name)]) < 1e-5, name
+    # the first routed projection sees bit-identical inputs on both sides, so no int8 code can differ: fp32-level agreement
+    assert _rel(first["gpu"], first["same"]) < 1e-5
     assert _rel(enc_g.detach().cpu(), enc_c.detach()) < 3e-2
     assert _rel(ctc_g.detach().cpu(), ctc_c.detach()) < 3e-2
     grads_c = dict(m_cpu.named_parameters())
