@@ -310,8 +310,8 @@ def sweep_summary(rows, peaks):
 
 def small_batch_table(peaks):
     """north_star: "at small batch, the packed-weight GEMV-like regime is also reported as achieved GB/s".  M token rows in
-    {1, 8, 64, 256} x the model's three routed shapes; M <= 64 runs the weight-streaming DP4A kernel (csrc/ob_gemv.cu), 256 the
-    tcgen05 kernel.  Device time per launch from a CUDA-graph replay over 8 rotating weight/activation sets (the layers of a
+    {1, 8, 64, 256} x the model's three routed shapes (+ 2048^2); small M runs the weight-streaming DP4A kernel
+    (csrc/ob_gemv.cu) where it beats the 128-row tcgen05 tile (M * K <= 32 K codes), both timings are listed.  Device time per launch from a CUDA-graph replay over 8 rotating weight/activation sets (the layers of a
     model are distinct: 8 x 64 KB..1 MB stays in L2, as it does in a real 108-layer forward at this batch); bytes = packed W
     (N K / 4) + int8 activations (M K) + fp32 output (4 M N) + scales and bias."""
     import onebit_b200 as ob
@@ -336,18 +336,21 @@ def small_batch_table(peaks):
                 obq.gemm_fwd(q, sc, pks[j], layers[j].alpha, layers[j].bias, N, torch.float32)
             us = _graph_time_us(gemm, 64)
             us_layer = _graph_time_us(layer_fwd, 64)
-            us_tc = None
-            if M <= 64:                                        # the same call forced onto the 128-row tcgen05 tile, for comparison
-                _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, 1)
+            us_tc = us_dp4a = None
+            if M <= 64:                                        # the same call forced onto either kernel, for comparison
                 try:
+                    _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, 1)
                     us_tc = round(_graph_time_us(gemm, 64), 2)
+                    _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, 2)
+                    us_dp4a = round(_graph_time_us(gemm, 64), 2)
                 finally:
                     _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, 0)
             by = N * K / 4 + M * K + 4.0 * M * N + 4 * M + 4 * N
-            rows.append({"M": M, "K": K, "N": N, "kernel": "gemv_tern_i8 (DP4A)" if M <= 64 else "gemm_expand (tcgen05)",
+            dp4a = us_dp4a is not None and abs(us - us_dp4a) <= abs(us - us_tc)      # which one the dispatcher picked
+            rows.append({"M": M, "K": K, "N": N, "kernel": "gemv_tern_i8 (DP4A)" if dp4a else "gemm_expand (tcgen05)",
                          "us": round(us, 2), "gbs": round(by / us / 1e3, 1), "frac_hbm": round(by / us / 1e3 / peaks["hbm_gbs"], 4),
                          "weight_gbs": round(N * K / 4 / us / 1e3, 1), "layer_fwd_us": round(us_layer, 2),
-                         "tcgen05_tile_us": us_tc, "algorithmic_bytes": int(by)})
+                         "tcgen05_tile_us": us_tc, "dp4a_us": us_dp4a, "algorithmic_bytes": int(by)})
     return {"note": "packed-weight GEMV-like regime; at these sizes (16 KB - 1 MB of weights) a launch is latency-bound: "
                     "the floor is the ~2 us launch + one dependent HBM/L2 round trip, not bandwidth", "rows": rows}
 

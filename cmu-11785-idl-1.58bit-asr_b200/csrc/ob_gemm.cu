@@ -27,9 +27,10 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
 enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5,
                 kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9 };
 int small_m_limit(int K);              // ob_gemv.cu
+int small_m_capacity(int K);
 int launch_gemv_tern_i8(const int8_t* q, const float* scale, const uint8_t* packed, const float* alpha, int alpha_mode,
                         const float* bias, int M, int N, int K, void* y, int out_bf16, cudaStream_t st);
-static int g_dbg_small_m = 0;          // 0: M <= 64 takes the DP4A kernel (ob_gemv.cu), 1: always the tcgen05 kernel
+static int g_dbg_small_m = 0;          // 0: small M takes the DP4A kernel where it wins (ob_gemv.cu), 1: always tcgen05, 2: DP4A whenever it can
 void f32_gemm_debug(int split_mode);   // ob_gemm_f32.cu
 void f32_gemm_debug_epilogue(int mode);
 void f32_gemm_debug_pair(int on);
@@ -811,7 +812,7 @@ extern "C" int ob_gemm_tern_i8_fwd(const int8_t* q, const float* scale, const ui
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   OB_REQUIRE(y_dtype == OB_F32 || y_dtype == OB_BF16, "ob_gemm_tern_i8_fwd: unknown dtype tag %d", y_dtype);
   // small-batch regime: weight-streaming DP4A kernel instead of a mostly empty 128-row UMMA tile (same epilogue bits)
-  if (M <= small_m_limit(K) && g_dbg_small_m != 1)
+  if (g_dbg_small_m != 1 && M <= (g_dbg_small_m == 2 ? small_m_capacity(K) : small_m_limit(K)))
     return launch_gemv_tern_i8(q, scale, packed_i8, alpha, alpha_mode, bias, M, N, K, y, y_dtype == OB_BF16, st);
   if (y_dtype == OB_F32)
     return dispatch_gemm_expand<kFwdI8, 0>(q, packed_i8, scale, alpha, alpha_mode, bias, y, M, N, K, st);

@@ -105,8 +105,15 @@ gemv_tern_i8_kernel(const int8_t* __restrict__ q, const float* __restrict__ scal
   }
 }
 
-// largest M served by this kernel for a given K (the staged activations must fit in shared memory)
+// largest M served by this kernel for a given K.  Measured against the 128-row tcgen05 tile (bench.py `small_batch`): the
+// DP4A kernel wins while the staged activations are small - M * K <= 32 K codes (M = 64 at K <= 512, M = 8 at K = 2048:
+// 2.2-4.8 us vs 4.7-9.7 us) - and loses beyond (M = 64, K = 1024: 8.7 vs 7.3 us), where the tensor cores take over.
 int small_m_limit(int K) {
+  const int by_work = 32768 / K;
+  return by_work < kGemvMaxM ? by_work : kGemvMaxM;
+}
+// what the kernel CAN serve (tests / measurements force it with ob_debug_set): activations staged in shared memory
+int small_m_capacity(int K) {
   const int by_smem = kGemvMaxSmem / (K + 16);
   return by_smem < kGemvMaxM ? by_smem : kGemvMaxM;
 }

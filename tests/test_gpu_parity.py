@@ -182,7 +182,7 @@ def test_small_batch_gemv_kernel(ob, M, N, K):
     a_eff = np.float32(abs(np.float32(-0.0625))) + np.float32(1e-8)
     ref = (q.double() @ codes.cuda().double().t()) * (float(a_eff) / scale.double())[:, None] + bias.double()
     outs = {}
-    for mode in (0, 1):                                      # 0: GEMV kernel, 1: forced tcgen05 kernel
+    for mode in (2, 1):                                      # 2: forced DP4A kernel, 1: forced tcgen05 kernel
         _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, mode)
         try:
             outs[mode] = (obq.gemm_fwd(q, scale, packed, alpha, bias, N, torch.float32),
@@ -190,9 +190,9 @@ def test_small_batch_gemv_kernel(ob, M, N, K):
             torch.cuda.synchronize()
         finally:
             _cabi.lib.ob_debug_set(_cabi.DBG_SMALL_M, 0)
-    assert rel_err(outs[0][0].cpu().numpy(), ref.cpu().numpy()) < 1e-6
-    assert torch.equal(outs[0][0], outs[1][0])
-    assert torch.equal(outs[0][1], outs[1][1])
+    assert rel_err(outs[2][0].cpu().numpy(), ref.cpu().numpy()) < 1e-6
+    assert torch.equal(outs[2][0], outs[1][0])
+    assert torch.equal(outs[2][1], outs[1][1])
 
 
 # ------------------------------------------------------------------ whole layer vs golden fixtures
