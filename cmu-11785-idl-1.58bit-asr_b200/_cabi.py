@@ -76,6 +76,8 @@ SIGNATURES = {
     "ob_ctc_state_pitch": (_i, [_i]),
     "ob_ctc_loss_fwd": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "ob_ctc_loss_bwd": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "ob_colsum_workspace_bytes": (_sz, [_i64, _i]),
+    "ob_colsum": (_i, [_p, _i64, _i, _p, _p, _p]),
     "ob_debug_set": (_i, [_i, _i]),
 }
 

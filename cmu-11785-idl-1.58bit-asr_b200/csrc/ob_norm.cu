@@ -232,6 +232,50 @@ __global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restr
   }
 }
 
+// Column sums of a row-major [M, N] fp32 matrix (bias gradients of the non-routed linears: dY.sum(0)), deterministic:
+// a fixed grid of blocks each reduces a contiguous range of rows into one partial row, ln_param_grad_kernel adds the
+// partial rows in fixed order.  torch's column reduction reaches ~0.8 TB/s on [76608, 256]; this streams at HBM speed.
+constexpr int kColsumBlocks = 592;
+
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t M, int N, int rows_per_block,
+                                                             float* __restrict__ part /* [blocks][N] */) {
+  __shared__ float4 red[256];
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  for (int c0 = 0; c0 < N; c0 += 1024) {
+    const int cw = min(1024, N - c0);
+    const int tpr = cw >> 2;                       // threads per row (one float4 each)
+    const int rpi = 256 / tpr;                     // rows per pass
+    const int rg = threadIdx.x / tpr;
+    const int c = c0 + (threadIdx.x - rg * tpr) * 4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    if (rg < rpi) {
+      int64_t r = r0 + rg;
+      for (; r + rpi < r1; r += 2 * rpi) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(x + r * N + c));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(x + (r + rpi) * N + c));
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      }
+      if (r < r1) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(x + r * N + c));
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      }
+      a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
+    }
+    red[threadIdx.x] = a0;
+    __syncthreads();
+    if (rg == 0) {
+      for (int g = 1; g < rpi; ++g) {
+        const float4 o = red[g * tpr + threadIdx.x];
+        a0.x += o.x; a0.y += o.y; a0.z += o.z; a0.w += o.w;
+      }
+      *reinterpret_cast<float4*>(part + (int64_t)blockIdx.x * N + c) = a0;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace ob
 
 using namespace ob;
@@ -310,5 +354,30 @@ extern "C" int ob_layernorm_quant_fwd(const float* x, const float* gamma, const 
     default:   ln_quant_fwd_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
   }
   OB_LAUNCH_CHECK("ln_quant_fwd_kernel");
+  return OB_OK;
+}
+
+static int colsum_blocks(int64_t M) {
+  const int64_t want = (M + 31) / 32;
+  return (int)(want < kColsumBlocks ? want : kColsumBlocks);
+}
+
+extern "C" size_t ob_colsum_workspace_bytes(int64_t M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  return (size_t)colsum_blocks(M) * N * sizeof(float);
+}
+
+extern "C" int ob_colsum(const float* x, int64_t M, int N, float* out, void* ws, ob_stream_t stream) {
+  OB_REQUIRE(x && out && ws && M > 0 && N > 0 && N % 4 == 0, "ob_colsum: null pointer, M <= 0 or N (%d) not a multiple of 4", N);
+  OB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "ob_colsum: x must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = colsum_blocks(M);
+  const int rows_per_block = (int)((M + blocks - 1) / blocks);
+  float* part = static_cast<float*>(ws);
+  colsum_partial_kernel<<<blocks, 256, 0, st>>>(x, M, N, rows_per_block, part);
+  OB_LAUNCH_CHECK("colsum_partial_kernel");
+  const int used = (int)((M + rows_per_block - 1) / rows_per_block);          // blocks that own at least one row
+  ln_param_grad_kernel<<<dim3((N + 31) / 32, 1), 256, 0, st>>>(part, used, N, out, out);
+  OB_LAUNCH_CHECK("ln_param_grad_kernel(colsum)");
   return OB_OK;
 }

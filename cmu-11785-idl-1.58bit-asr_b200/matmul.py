@@ -110,6 +110,17 @@ def bmm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None, bias: tor
     return result
 
 
+def column_sums(g2: torch.Tensor) -> torch.Tensor:
+    """``g2.sum(0)`` of a contiguous fp32 ``[M, N]`` CUDA matrix on the library's streaming kernel (fixed summation order)."""
+    M, N = g2.shape
+    if not (g2.is_cuda and g2.dtype == torch.float32 and g2.is_contiguous() and N % 4 == 0 and M > 0 and g2.data_ptr() % 16 == 0):
+        return g2.sum(0)
+    out = torch.empty((N,), device=g2.device, dtype=torch.float32)
+    ws = torch.empty(lib.ob_colsum_workspace_bytes(M, N), device=g2.device, dtype=torch.uint8)
+    check(lib.ob_colsum(g2.data_ptr(), M, N, out.data_ptr(), ws.data_ptr(), _stream()))
+    return out
+
+
 class _LinearFn(torch.autograd.Function):
     """``F.linear`` of the non-routed fp32 layers (vocabulary projections, front-end output) on ``bmm_nt``."""
 
@@ -137,7 +148,7 @@ class _LinearFn(torch.autograd.Function):
             if not gw.is_contiguous():
                 gw = gw.contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0)
+            gb = column_sums(g2)
         return gx, gw, gb
 
 

@@ -46,10 +46,12 @@ _weight_epoch = [0]
 def invalidate_packed_weights() -> None:
     """Declare every cached packed code stale (call after writing latent weights or alpha behind autograd's back)."""
     _weight_epoch[0] += 1
+    _ActQuantCache.clear()
 
 
 def _optimizer_step_hook(optimizer, args, kwargs) -> None:
     _weight_epoch[0] += 1
+    _ActQuantCache.clear()
 
 
 from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook  # noqa: E402
@@ -142,27 +144,41 @@ def gemm_fwd(q, scale, packed, alpha, bias, N, out_dtype=torch.float32, alpha_mo
 # autograd: the whole layer (act quant -> GEMM -> epilogue) is one Function
 # ----------------------------------------------------------------------------------------------
 class _ActQuantCache:
-    """q/k/v projections receive the same tensor (conformer.py:110-112): quantise it once."""
-    x = None          # keeps the storage alive so (data_ptr, version) cannot be recycled under us
+    """q/k/v projections of the reference's own ``MHSA.forward`` receive the same tensor three times in a row
+    (conformer.py:110-112): quantise it once.  (This repo's model quantises inside the fused LayerNorm kernel and hands the
+    codes to the three GEMMs explicitly - ``fused.ln_projections`` - and never comes here.)
+
+    One entry, scoped as tightly as the call pattern allows: the key carries the tensor's storage pointer, version, shape,
+    dtype AND the stream it was quantised on; the entry is dropped after its third use (q, k, v), at every optimiser step /
+    ``invalidate_packed_weights()`` and by ``clear()``, so an activation is not kept alive past the module that made it.  A
+    write that bypasses autograd's version counter (``.data`` edits, raw-pointer writes) between two of the three calls is
+    not detectable - the same caveat as for the packed weights above."""
+    x = None          # keeps the storage alive so (data_ptr, version) cannot be recycled while the entry exists
     key = None
     q = None
     s = None
+    uses = 0
 
     @classmethod
     def get(cls, x2: torch.Tensor):
-        key = (x2.data_ptr(), x2._version, tuple(x2.shape), x2.dtype)
+        key = (x2.data_ptr(), x2._version, tuple(x2.shape), x2.dtype, _stream())
         if cls.key == key:
-            return cls.q, cls.s
+            q, s = cls.q, cls.s
+            cls.uses += 1
+            if cls.uses >= 3:
+                cls.clear()
+            return q, s
         M, K = x2.shape
         q = torch.empty((M, K), device=x2.device, dtype=torch.int8)
         s = torch.empty((M,), device=x2.device, dtype=torch.float32)
         check(lib.ob_act_quant_i8(x2.data_ptr(), _tag(x2), M, K, q.data_ptr(), s.data_ptr(), _stream()))
-        cls.x, cls.key, cls.q, cls.s = x2, key, q, s
+        cls.x, cls.key, cls.q, cls.s, cls.uses = x2, key, q, s, 1
         return q, s
 
     @classmethod
     def clear(cls):
         cls.x = cls.key = cls.q = cls.s = None
+        cls.uses = 0
 
 
 class _QuantLinearFn(torch.autograd.Function):

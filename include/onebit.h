@@ -299,6 +299,11 @@ int ob_bn_swish_bwd(const float* gs, const float* d, const float* mean, const fl
 int ob_glu_dwconv_bwd(const float* gd, const float* a, const float* w, int B, int T, int C, int ks, float* ga,
                       float* gw, float* gbias, void* ws, ob_stream_t stream);
 
+/* Column sums of a row-major fp32 [M, N] matrix (N % 4 == 0): out[n] = sum_m x[m, n], fixed summation order.  Used for the
+ * bias gradients of the non-routed linears around the layer.  ws >= ob_colsum_workspace_bytes(M, N). */
+size_t ob_colsum_workspace_bytes(int64_t M, int N);
+int ob_colsum(const float* x, int64_t M, int N, float* out, void* ws, ob_stream_t stream);
+
 /* Debug/tuning knob (tests and profiling only): key/value pairs, see csrc/ob_gemm.cu. */
 int ob_debug_set(int key, int value);
 

@@ -282,3 +282,16 @@ def test_frontend_conv1_relu_matches_torch(ob, B, T, F):
         err = ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
         assert err < (1e-5 if name == "y" else 2e-4), (name, err)
     assert outs[0][0].is_contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("M,N", [(1, 4), (37, 256), (25536, 512), (4160, 5004), (76608, 256)])
+def test_column_sums_kernel(M, N):
+    """ob_colsum (bias gradients of the non-routed linears) vs float64, and bitwise run-to-run (fixed summation order)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from onebit_b200.matmul import column_sums
+    x = torch.randn(M, N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(M + N))
+    got = column_sums(x)
+    want = x.double().sum(0)
+    assert (got.double() - want).abs().max().item() <= 1e-5 * (x.double().abs().sum(0).max().item() + 1e-30)
+    assert torch.equal(got, column_sums(x))
