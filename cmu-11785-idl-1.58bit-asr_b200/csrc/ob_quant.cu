@@ -562,42 +562,59 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ dY,
     }
     float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_a;
     if (rg < rpi) {
-#pragma unroll 2
-      for (int r = rg; r < rows; r += rpi) {
-        const int64_t off = (int64_t)(r0 + r) * N;
-        float4 va = load4<T>(dY + off + ca), vb = load4<T>(dY + off + cb);
-        if (MODE == 1) {
-          const float f = rowf[r];
-          uint32_t kb = 0xFFu;
-          if (op.rng.threshold != 0u)
-            kb = philox_keep8(static_cast<unsigned long long>(((op.row_base + r0 + r) * N + ca) >> 3), op.rng);
-          va.x = (kb & 1u) ? va.x * f : 0.f;   va.y = (kb & 2u) ? va.y * f : 0.f;
-          va.z = (kb & 4u) ? va.z * f : 0.f;   va.w = (kb & 8u) ? va.w * f : 0.f;
-          vb.x = (kb & 16u) ? vb.x * f : 0.f;  vb.y = (kb & 32u) ? vb.y * f : 0.f;
-          vb.z = (kb & 64u) ? vb.z * f : 0.f;  vb.w = (kb & 128u) ? vb.w * f : 0.f;
-        } else if (MODE == 2) {
-          const float4 ha = __ldg(reinterpret_cast<const float4*>(op.h + off + ca));
-          const float4 hb = __ldg(reinterpret_cast<const float4*>(op.h + off + cb));
-          uint32_t kb = 0xFFu;
-          if (op.rng.threshold != 0u)
-            kb = philox_keep8(static_cast<unsigned long long>(((op.row_base + r0 + r) * N + ca) >> 2), op.rng);
-          const float ik = op.factor;
-          const float hs[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-          const float gs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-          float o[8];
+      // U rows per step: all their 16-byte loads are issued before the first one is consumed (memory-level parallelism)
+      constexpr int U = MODE == 2 ? 2 : 4;
+      for (int rb = rg; rb < rows; rb += U * rpi) {
+        float4 va_[U], vb_[U], ha_[U], hb_[U];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float sg = __fdividef(1.0f, 1.0f + __expf(-hs[u]));
-            o[u] = ((kb >> u) & 1u) ? gs[u] * ik * (sg + hs[u] * sg * (1.0f - sg)) : 0.f;
+        for (int u = 0; u < U; ++u) {
+          const int r = min(rb + u * rpi, rows - 1);               // clamped: the tail re-reads the last row, result unused
+          const int64_t off = (int64_t)(r0 + r) * N;
+          va_[u] = load4<T>(dY + off + ca);
+          vb_[u] = load4<T>(dY + off + cb);
+          if (MODE == 2) {
+            ha_[u] = __ldg(reinterpret_cast<const float4*>(op.h + off + ca));
+            hb_[u] = __ldg(reinterpret_cast<const float4*>(op.h + off + cb));
           }
-          va = make_float4(o[0], o[1], o[2], o[3]);
-          vb = make_float4(o[4], o[5], o[6], o[7]);
         }
-        acc_a.x += va.x; acc_a.y += va.y; acc_a.z += va.z; acc_a.w += va.w;
-        acc_b.x += vb.x; acc_b.y += vb.y; acc_b.z += vb.z; acc_b.w += vb.w;
-        const float is = inv_s[r];
-        *reinterpret_cast<uint2*>(dys + off + ca) = pack_bf16x4(va.x * is, va.y * is, va.z * is, va.w * is);
-        *reinterpret_cast<uint2*>(dys + off + cb) = pack_bf16x4(vb.x * is, vb.y * is, vb.z * is, vb.w * is);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = rb + u * rpi;
+          if (r >= rows) break;
+          const int64_t off = (int64_t)(r0 + r) * N;
+          float4 va = va_[u], vb = vb_[u];
+          if (MODE == 1) {
+            const float f = rowf[r];
+            uint32_t kb = 0xFFu;
+            if (op.rng.threshold != 0u)
+              kb = philox_keep8(static_cast<unsigned long long>(((op.row_base + r0 + r) * N + ca) >> 3), op.rng);
+            va.x = (kb & 1u) ? va.x * f : 0.f;   va.y = (kb & 2u) ? va.y * f : 0.f;
+            va.z = (kb & 4u) ? va.z * f : 0.f;   va.w = (kb & 8u) ? va.w * f : 0.f;
+            vb.x = (kb & 16u) ? vb.x * f : 0.f;  vb.y = (kb & 32u) ? vb.y * f : 0.f;
+            vb.z = (kb & 64u) ? vb.z * f : 0.f;  vb.w = (kb & 128u) ? vb.w * f : 0.f;
+          } else if (MODE == 2) {
+            const float4 ha = ha_[u], hb = hb_[u];
+            uint32_t kb = 0xFFu;
+            if (op.rng.threshold != 0u)
+              kb = philox_keep8(static_cast<unsigned long long>(((op.row_base + r0 + r) * N + ca) >> 2), op.rng);
+            const float ik = op.factor;
+            const float hs[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            const float gs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float sg = __fdividef(1.0f, 1.0f + __expf(-hs[e]));
+              o[e] = ((kb >> e) & 1u) ? gs[e] * ik * (sg + hs[e] * sg * (1.0f - sg)) : 0.f;
+            }
+            va = make_float4(o[0], o[1], o[2], o[3]);
+            vb = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          acc_a.x += va.x; acc_a.y += va.y; acc_a.z += va.z; acc_a.w += va.w;
+          acc_b.x += vb.x; acc_b.y += vb.y; acc_b.z += vb.z; acc_b.w += vb.w;
+          const float is = inv_s[r];
+          *reinterpret_cast<uint2*>(dys + off + ca) = pack_bf16x4(va.x * is, va.y * is, va.z * is, va.w * is);
+          *reinterpret_cast<uint2*>(dys + off + cb) = pack_bf16x4(vb.x * is, vb.y * is, vb.z * is, vb.w * is);
+        }
       }
     }
     if (colsum != nullptr) {
