@@ -7,7 +7,8 @@ stream with the oracle's Philox restatement (oracle/onebit_oracle.py: ``dropout_
 ``dropout_keep_groups8`` for the module tails, ``dropout_keep_relattn`` for the attention weights).  The positional-encoding
 dropout (torch's own RNG on either device) is switched off on both sides.
 
-tolerances: first feed-forward module rel <= 2e-3 of max (identical masks; only int8 code flips at lin2's input separate the two),
+tolerances: first feed-forward module rel <= 1e-2 of max (identical masks; int8 code flips at the two quantisers - the front-end
+            runs on different devices - separate the two; measured 4.5e-3; a wrong mask gives O(1)),
             encoder output rel <= 3e-2 (flip amplification, see tests/test_reference_dropin.py), gradient norms rel <= 3e-2.
 """
 import numpy as np
@@ -100,7 +101,7 @@ def test_encoder_under_dropout_matches_oracle_with_the_same_masks(precision):
     for h in hooks:
         h.remove()
     assert torch.equal(valid_c, valid_g.cpu())
-    assert _rel(first["gpu"], first["cpu"]) < 2e-3
+    assert _rel(first["gpu"], first["cpu"]) < 1e-2
     assert _rel(enc_g.detach().cpu(), enc_c.detach()) < 3e-2
     # dropout really happened, and the same one on both sides: a run without it differs by far more than the tolerance
     m_cpu.eval()
