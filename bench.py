@@ -615,6 +615,7 @@ def run_train(args, world, rank):
         torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(0)                                   # same weights and (CPU RNG) precision masks on every rank
     model = ob.ConformerASR(TRAIN["mel"], TRAIN["vocab"], enc_dropout=args.dropout, dec_dropout=args.dropout).train().to(dev)
+    model.use_packed_code_arena()                          # all 108 layers x 2 bitwidths re-quantised by ONE launch per step
     torch.cuda.manual_seed(1234 + rank)                    # dropout streams differ per replica (weights were drawn on the CPU)
     opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), weight_decay=1e-2,
                             fused=not getattr(args, "foreach_adamw", False))

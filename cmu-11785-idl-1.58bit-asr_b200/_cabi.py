@@ -30,6 +30,7 @@ SIGNATURES = {
     "ob_absmean_workspace_bytes": (_sz, []),
     "ob_weight_absmean": (_i, [_p, _i64, _p, _p, _p]),
     "ob_weight_quant_pack": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "ob_weight_quant_pack_multi": (_i, [_p, _i, _i, _i, _p]),
     "ob_weight_quant_dense": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
     "ob_ste_workspace_bytes": (_sz, [_i64]),
     "ob_weight_ste_backward": (_i, [_p, _p, _p, _i, _i64, _i, _p, _p, _p, _p]),

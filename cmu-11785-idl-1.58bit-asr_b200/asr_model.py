@@ -243,9 +243,13 @@ class MHSA(nn.Module):
             routes.taken("attention", True, x)
             routes.taken("mhsa_module_fused", True, x)
             x_res, (q_flat, k_flat, v_flat) = fused.ln_projections(x, self.ln.ln, qkv, rows2)
-            pos_flat = self._positions(pos_emb, bitwidth, batch)
+            if isinstance(bitwidth, StackedBits) and 0 < bitwidth.utt2 < batch:
+                # two bitwidth groups: the positional table is projected once per bitwidth and used by its group, broadcast
+                pos_flat, pos_b, split = self.pos_proj(pos_emb, 2), self.pos_proj(pos_emb, 1), bitwidth.utt2
+            else:
+                pos_flat, pos_b, split = self._positions(pos_emb, bitwidth, batch), None, 0
             mixed = attention.rel_attention(q_flat, k_flat, v_flat, pos_flat, self.pos_bias_u, self.pos_bias_v, mask,
-                                            self.n_heads, self.dropout.p, self.training)
+                                            self.n_heads, self.dropout.p, self.training, pos_b=pos_b, split=split)
             return fused.proj_tail(mixed, x_res, self.out_proj, rows2, _row_mask(mask), self.dropout.p, self.training)
         normed = self.ln(x)
         q_flat, k_flat, v_flat = (_routed(p, normed, bitwidth) for p in qkv)
@@ -512,3 +516,9 @@ class ConformerASR(nn.Module):
 
     def quantized_layers(self):
         return [m for m in self.modules() if isinstance(m, QuantizedLinear)]
+
+    def use_packed_code_arena(self):
+        """Re-quantise all routed layers (both bitwidths) with ONE launch per optimiser step instead of two per layer; call after
+        the model is on its device.  Returns the arena (``.repacks`` counts the launches)."""
+        from .quant import PackedCodeArena
+        return PackedCodeArena(self.quantized_layers())

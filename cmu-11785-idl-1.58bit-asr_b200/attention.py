@@ -111,13 +111,18 @@ def _heads(t: torch.Tensor, H: int) -> torch.Tensor:
 class _RelAttentionFn(torch.autograd.Function):
     """out[b, t, h*d:(h+1)*d] = dropout(softmax(mask((q+u) k^T + shift((q+w) pos^T)) * scale)) v   per head.
 
-    q, k, v: [B, T, H*d] (projection outputs, read in place), pos: [1, T, H*d], u, w: [H, d]."""
+    q, k, v: [B, T, H*d] (projection outputs, read in place), pos: [1, T, H*d] (or [B, T, H*d]), u, w: [H, d].
+    ``pos_b`` / ``split``: a second positional table [1, T, H*d] used by the utterances ``[split, B)`` - the stacked co-training
+    passes project the table once per bitwidth; the positional product runs once per group with the table broadcast, instead
+    of materialising a per-utterance copy of it."""
 
     @staticmethod
-    def forward(ctx, q, k, v, pos, u, w, mask, keep, inv_keep, scale, rng, n_heads):
+    def forward(ctx, q, k, v, pos, u, w, mask, keep, inv_keep, scale, rng, n_heads, pos_b=None, split=0):
         B, T, W = q.shape
         H = n_heads
         q, k, v, pos = q.contiguous(), k.contiguous(), v.contiguous(), pos.contiguous()
+        if pos_b is not None:
+            pos_b = pos_b.contiguous()
         if W % 64 == 0:
             qu, qw = torch.empty_like(q), torch.empty_like(q)
             check(lib.ob_add_bias2(q.data_ptr(), u.contiguous().data_ptr(), w.contiguous().data_ptr(), B * T, W, qu.data_ptr(),
@@ -125,19 +130,25 @@ class _RelAttentionFn(torch.autograd.Function):
         else:
             qu, qw = q + u.reshape(1, 1, W), q + w.reshape(1, 1, W)
         ac = bmm_nt(_heads(qu, H), _heads(k, H), out=_scores_like(B, H, T, q.device))
-        bd = bmm_nt(_heads(qw, H), _heads(pos, H), out=_scores_like(B, H, T, q.device))
+        bd = _scores_like(B, H, T, q.device)
+        if pos_b is None:
+            bmm_nt(_heads(qw, H), _heads(pos, H), out=bd)
+        else:
+            bmm_nt(_heads(qw[:split], H), _heads(pos, H), out=bd[:split])
+            bmm_nt(_heads(qw[split:], H), _heads(pos_b, H), out=bd[split:])
         y, attn_d = _softmax_fwd(ac, bd, mask, keep, inv_keep, scale, rng)
         probs = y if attn_d is None else attn_d
         out = torch.empty_like(q)
         bmm_nt(probs, _heads(v, H).transpose(-1, -2), out=_heads(out, H))
-        ctx.save_for_backward(qu, qw, k, v, pos, y, probs, *(() if keep is None else (keep,)))
+        ctx.save_for_backward(qu, qw, k, v, pos, y, probs, pos if pos_b is None else pos_b, *(() if keep is None else (keep,)))
         ctx.inv_keep, ctx.scale, ctx.rng, ctx.H = inv_keep, scale, rng, H
+        ctx.two_tables, ctx.split = pos_b is not None, split
         return out
 
     @staticmethod
     def backward(ctx, g):
-        qu, qw, k, v, pos, y, probs = ctx.saved_tensors[:7]
-        keep = ctx.saved_tensors[7] if len(ctx.saved_tensors) > 7 else None
+        qu, qw, k, v, pos, y, probs, pos_second = ctx.saved_tensors[:8]
+        keep = ctx.saved_tensors[8] if len(ctx.saved_tensors) > 8 else None
         H = ctx.H
         B, T, W = qu.shape
         g = g.contiguous()
@@ -149,10 +160,19 @@ class _RelAttentionFn(torch.autograd.Function):
         g_qu, g_qw, g_k = torch.empty_like(qu), torch.empty_like(qu), torch.empty_like(k)
         bmm_nt(d_ac, _heads(k, H).transpose(-1, -2), out=_heads(g_qu, H))                      # dS_ac . k
         bmm_nt(d_ac.transpose(-1, -2), _heads(qu, H).transpose(-1, -2), out=_heads(g_k, H))    # dS_ac^T . (q+u)
-        bmm_nt(d_bd, _heads(pos, H).transpose(-1, -2), out=_heads(g_qw, H))                    # dS_bd . pos
+        pos_b, split = (pos_second if ctx.two_tables else None), ctx.split
+        if pos_b is None:
+            bmm_nt(d_bd, _heads(pos, H).transpose(-1, -2), out=_heads(g_qw, H))                # dS_bd . pos
+        else:
+            bmm_nt(d_bd[:split], _heads(pos, H).transpose(-1, -2), out=_heads(g_qw[:split], H))
+            bmm_nt(d_bd[split:], _heads(pos_b, H).transpose(-1, -2), out=_heads(g_qw[split:], H))
         g_pos_b = torch.empty_like(qw)                                                         # per utterance, then summed
         bmm_nt(d_bd.transpose(-1, -2), _heads(qw, H).transpose(-1, -2), out=_heads(g_pos_b, H))
-        g_pos = g_pos_b.sum(dim=0, keepdim=True) if pos.shape[0] == 1 else g_pos_b        # shared table: sum over the batch
+        g_pos2 = None
+        if pos_b is not None:                                                                  # one table per group
+            g_pos, g_pos2 = g_pos_b[:split].sum(dim=0, keepdim=True), g_pos_b[split:].sum(dim=0, keepdim=True)
+        else:
+            g_pos = g_pos_b.sum(dim=0, keepdim=True) if pos.shape[0] == 1 else g_pos_b    # shared table: sum over the batch
         if W % 64 == 0:
             g_q, sums = torch.empty_like(qu), torch.empty(2, W, device=g.device, dtype=torch.float32)
             ws = torch.empty(lib.ob_add_colsum2_workspace_bytes(B * T, W), device=g.device, dtype=torch.uint8)
@@ -162,7 +182,7 @@ class _RelAttentionFn(torch.autograd.Function):
         else:
             g_q = g_qu + g_qw
             g_u, g_w = g_qu.sum(dim=(0, 1)).view(H, W // H), g_qw.sum(dim=(0, 1)).view(H, W // H)
-        return g_q, g_k, g_v, g_pos, g_u, g_w, None, None, None, None, None, None
+        return g_q, g_k, g_v, g_pos, g_u, g_w, None, None, None, None, None, None, g_pos2, None
 
 
 def rel_attention_usable(q: torch.Tensor, mask, n_heads: int) -> bool:
@@ -171,11 +191,16 @@ def rel_attention_usable(q: torch.Tensor, mask, n_heads: int) -> bool:
             and q.shape[2] % (4 * n_heads) == 0 and "attn" not in DISABLED)
 
 
-def rel_attention(q, k, v, pos, u, w, mask, n_heads: int, p: float = 0.0, training: bool = False, keep=None):
+def rel_attention(q, k, v, pos, u, w, mask, n_heads: int, p: float = 0.0, training: bool = False, keep=None, pos_b=None,
+                  split: int = 0):
     """The attention core of ``MHSA.forward`` (conformer.py:113-129) without the projections.
 
     q, k, v: ``[B, T, H*d]``; pos: ``[1, T, H*d]`` (projected positional encoding) or ``[B, T, H*d]``; u, w: ``[H, d]`` (``pos_bias_u``,
-    ``pos_bias_v``); mask: ``[B, T, T]`` bool.  Returns ``[B, T, H*d]``."""
+    ``pos_bias_v``); mask: ``[B, T, T]`` bool.  ``pos_b`` ``[1, T, H*d]`` + ``split``: utterances ``[split, B)`` use this second table
+    (stacked passes at two bitwidths).  Returns ``[B, T, H*d]``."""
     d = q.shape[2] // n_heads
     keep, inv_keep, rng = _dropout_args(q.device, p, training, keep)
-    return _RelAttentionFn.apply(q, k, v, pos, u, w, mask.contiguous(), keep, inv_keep, 1.0 / (d ** 0.5), rng, n_heads)
+    if pos_b is not None and not (0 < split < q.shape[0] and pos.shape[0] == 1 and pos_b.shape[0] == 1):
+        raise ValueError("rel_attention: pos_b needs 0 < split < batch and two [1, T, W] tables")
+    return _RelAttentionFn.apply(q, k, v, pos, u, w, mask.contiguous(), keep, inv_keep, 1.0 / (d ** 0.5), rng, n_heads, pos_b,
+                                 split)

@@ -118,6 +118,52 @@ __global__ void __launch_bounds__(256) weight_pack_tile_kernel(const float* __re
   }
 }
 
+// Every routed layer of a model, both bitwidths, in ONE launch (the co-training step of train.py:83-103 needs the 2-bit and the
+// 1-bit codes of all 108 layers once per optimiser step: 216 launches of the kernel above otherwise).  W is read once per
+// tile and quantised both ways (the two code sets share W / alpha_eff and differ only in the 0.5 threshold).  Blocks map to
+// (layer, 64 x 64 tile) through the descriptors' running tile offsets.
+__global__ void __launch_bounds__(256) weight_pack_multi_kernel(const ob_pack_desc* __restrict__ descs, int count, int alpha_mode) {
+  __shared__ uint8_t fields[2][64][65];            // [0]: 2-bit codes, [1]: 1-bit codes
+  int lo = 0, hi = count - 1;                      // last descriptor with tile0 <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].tile0 <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+  }
+  const ob_pack_desc d = descs[lo];
+  const int t = blockIdx.x - d.tile0, tiles_k = d.K / 64;
+  const int n0 = (t / tiles_k) * 64, k0 = (t % tiles_k) * 64;
+  const float a_eff = load_alpha_eff(d.alpha, alpha_mode);
+  for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+    const int r = i >> 4, c4 = i & 15;
+    const float4 f = __ldg(reinterpret_cast<const float4*>(d.W + (int64_t)(n0 + r) * d.K + k0) + c4);
+    const float w[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      fields[0][r][c4 * 4 + u] = (uint8_t)code_field(w[u], a_eff, 2);
+      fields[1][r][c4 * 4 + u] = (uint8_t)code_field(w[u], a_eff, 1);
+    }
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 2, g = threadIdx.x & 3;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    uint32_t* packed = reinterpret_cast<uint32_t*>(b == 0 ? d.packed2 : d.packed1);
+    uint32_t* packed_t = reinterpret_cast<uint32_t*>(b == 0 ? d.packed2_t : d.packed1_t);
+    if (packed != nullptr) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int tt = 0; tt < 16; ++tt) word |= (uint32_t)fields[b][r][g * 16 + tt] << field_pos_i8(tt);
+      packed[(int64_t)(n0 + r) * (d.K / 16) + k0 / 16 + g] = word;
+    }
+    if (packed_t != nullptr) {
+      uint32_t wt = 0;
+#pragma unroll
+      for (int tt = 0; tt < 16; ++tt) wt |= (uint32_t)fields[b][g * 16 + tt][r] << field_pos_bf16(tt);
+      packed_t[(int64_t)(k0 + r) * (d.N / 16) + n0 / 16 + g] = wt;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // dense W_hat = alpha_eff * Q   (quantize_weight, quant.py:45-70)
 // ---------------------------------------------------------------------------------------------
@@ -692,6 +738,15 @@ extern "C" int ob_weight_quant_pack(const float* W, const float* alpha, int alph
   weight_pack_rows_kernel<<<blocks, 256, 0, st>>>(W, alpha, alpha_mode, nwords, bitwidth,
                                                  reinterpret_cast<uint32_t*>(packed_i8));
   OB_LAUNCH_CHECK("weight_pack_rows_kernel");
+  return OB_OK;
+}
+
+extern "C" int ob_weight_quant_pack_multi(const ob_pack_desc* descs_dev, int count, int total_tiles, int alpha_mode,
+                                          ob_stream_t stream) {
+  OB_REQUIRE(descs_dev && count > 0 && total_tiles > 0, "ob_weight_quant_pack_multi: null descriptor table or empty");
+  OB_REQUIRE(alpha_mode == OB_ALPHA_RAW || alpha_mode == OB_ALPHA_EFF, "ob_weight_quant_pack_multi: unknown alpha mode %d", alpha_mode);
+  weight_pack_multi_kernel<<<total_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(descs_dev, count, alpha_mode);
+  OB_LAUNCH_CHECK("weight_pack_multi_kernel");
   return OB_OK;
 }
 

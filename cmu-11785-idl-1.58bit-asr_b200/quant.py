@@ -424,6 +424,53 @@ def quantize_weight(W: torch.Tensor, alpha: torch.Tensor, bitwidth: int) -> torc
     return _QuantizeWeightFn.apply(W, alpha, bitwidth)
 
 
+class PackedCodeArena:
+    """Persistent 2-bit code buffers of MANY layers, refreshed by one kernel launch.
+
+    The co-training step (train.py:83-103) needs the 2-bit and the 1-bit codes of every routed layer once per optimiser step.
+    Layer by layer that is 2 launches x 108 layers; with an arena the first ``packed_weight()`` call after the weights changed
+    (same staleness rule as the per-layer cache: weight epoch + tensor versions) re-quantises ALL registered layers with
+    ``ob_weight_quant_pack_multi`` - each W read once, both bitwidths, both layouts - into buffers that stay allocated.  The
+    buffers are rewritten in place, in stream order: a backward that still holds them sees the same codes unless the weights
+    changed in between, which no training loop does between a forward and its backward."""
+
+    def __init__(self, layers):
+        import struct
+        self.layers = [l for l in layers if l.in_features % 64 == 0 and l.out_features % 64 == 0]
+        if not self.layers:
+            raise ValueError("PackedCodeArena: no layer with feature counts that are multiples of 64")
+        dev = self.layers[0].weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("PackedCodeArena: move the model to a B200 device first")
+        self.buffers, blob, tile0 = [], b"", 0
+        for l in self.layers:
+            N, K = l.out_features, l.in_features
+            bufs = tuple(torch.empty(shape, device=dev, dtype=torch.uint8) for shape in ((N, K // 4), (K, N // 4), (N, K // 4), (K, N // 4)))
+            self.buffers.append(bufs)
+            blob += struct.pack("<6Q4i", l.weight.data_ptr(), l.alpha.data_ptr(), *(b.data_ptr() for b in bufs), N, K, tile0, 0)
+            tile0 += (N // 64) * (K // 64)
+        self.total_tiles = tile0
+        self.descs = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        self.ptrs = [(l.weight.data_ptr(), l.alpha.data_ptr()) for l in self.layers]
+        self.stamps = [None] * len(self.layers)           # (weight epoch, weight version, alpha version) at the last repack
+        self.repacks = 0
+        for i, l in enumerate(self.layers):
+            l._arena, l._arena_index = self, i
+
+    def codes(self, index: int, bitwidth: int):
+        layer = self.layers[index]
+        w, a = layer.weight, layer.alpha
+        if (w.data_ptr(), a.data_ptr()) != self.ptrs[index]:
+            raise RuntimeError("PackedCodeArena: a parameter was re-allocated (module moved or re-created); build a new arena")
+        if self.stamps[index] != (_weight_epoch[0], w._version, a._version):      # this layer's codes are stale: redo them all
+            check(lib.ob_weight_quant_pack_multi(self.descs.data_ptr(), len(self.layers), self.total_tiles, OB_ALPHA_RAW, _stream()))
+            epoch = _weight_epoch[0]
+            self.stamps = [(epoch, l.weight._version, l.alpha._version) for l in self.layers]
+            self.repacks += 1
+        b = self.buffers[index]
+        return (b[0], b[1]) if bitwidth == 2 else (b[2], b[3])
+
+
 class QuantizedLinear(nn.Module):
     """Linear layer with 1-bit / 2-bit (ternary) weights chosen per call; drop-in for quant.py:99-127."""
 
@@ -437,6 +484,7 @@ class QuantizedLinear(nn.Module):
         self.alpha = nn.Parameter(w.abs().mean())         # 0-dim, learnable (quant.py:111-113)
         self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
         self._packed = {}                                 # bitwidth -> (key, packed, packed_t)
+        self._arena, self._arena_index = None, -1         # set by PackedCodeArena: codes of many layers from one launch
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"
@@ -450,6 +498,8 @@ class QuantizedLinear(nn.Module):
         """2-bit packed codes for ``bitwidth``, cached while the latent weights are known to be unchanged (tensor versions
         and the weight epoch above): one quantiser launch per optimiser step and bitwidth, instead of one per forward as
         in quant.py:124."""
+        if self._arena is not None:
+            return self._arena.codes(self._arena_index, bitwidth)
         w, a = self.weight, self.alpha
         key = (_weight_epoch[0], w._version, a._version, w.data_ptr(), a.data_ptr())
         hit = self._packed.get(bitwidth)

@@ -73,6 +73,20 @@ int ob_weight_absmean(const float* W, int64_t n, float* out, void* ws, ob_stream
 int ob_weight_quant_pack(const float* W, const float* alpha, int alpha_mode, int N, int K,
                          int bitwidth, uint8_t* packed_i8, uint8_t* packed_t, ob_stream_t stream);
 
+/* The same for MANY layers and BOTH bitwidths in one launch.  descs_dev: device array of `count` descriptors sorted by
+ * tile0 = number of 64 x 64 tiles of all earlier layers (N and K multiples of 64); total_tiles = sum of (N/64)*(K/64).
+ * Each W is read once; any of the four outputs may be NULL.  Codes are bit-identical to ob_weight_quant_pack. */
+typedef struct ob_pack_desc {
+  const float* W;          /* [N, K] fp32 */
+  const float* alpha;      /* device scalar */
+  uint8_t* packed2;        /* [N, K/4] OB_ORDER_I8, 2-bit (ternary) codes */
+  uint8_t* packed2_t;      /* [K, N/4] OB_ORDER_BF16 */
+  uint8_t* packed1;        /* 1-bit (binary) codes, same layouts */
+  uint8_t* packed1_t;
+  int32_t N, K, tile0, reserved;
+} ob_pack_desc;
+int ob_weight_quant_pack_multi(const ob_pack_desc* descs_dev, int count, int total_tiles, int alpha_mode, ob_stream_t stream);
+
 /* Dense W_hat = alpha_eff * Q in fp32 over n elements: `quantize_weight` / _QuantizeSTE.forward
  * (quant.py:45-70, 95-96). */
 int ob_weight_quant_dense(const float* W, const float* alpha, int alpha_mode, int64_t n,

@@ -25,8 +25,8 @@ def fx():
     return dict(np.load(os.path.join(GOLDEN, "conformer_step.npz")))
 
 
-@pytest.mark.parametrize("fused_adamw", [False, True])
-def test_cotraining_run_matches_reference(fx, fused_adamw):
+@pytest.mark.parametrize("fused_adamw,arena", [(False, False), (True, False), (True, True)])
+def test_cotraining_run_matches_reference(fx, fused_adamw, arena):
     """``fused_adamw``: torch's single-kernel AdamW (what bench.py uses) updates parameters without bumping their
     ``_version``; the packed codes must still follow the weights (losses of steps 1..3 depend on it)."""
     import onebit_b200 as ob
@@ -36,6 +36,7 @@ def test_cotraining_run_matches_reference(fx, fused_adamw):
     torch.manual_seed(int(fx["seed"]))
     model = ob.ConformerASR(**CFG).train().cuda()
     assert len(model.quantized_layers()) == 27
+    packed = model.use_packed_code_arena() if arena else None      # all layers re-quantised by one launch per step (bench.py's setting)
     batch = {k: torch.from_numpy(fx[k]).cuda() for k in ("feats", "feat_lens", "tokens", "token_lens")}
     batch["feat_lens_cpu"] = torch.from_numpy(fx["feat_lens"])
     batch["token_lens_cpu"] = torch.from_numpy(fx["token_lens"])
@@ -58,6 +59,8 @@ def test_cotraining_run_matches_reference(fx, fused_adamw):
         losses.append(loss.item())
     np.testing.assert_allclose(losses, fx["losses_B"], rtol=3e-3)
     np.testing.assert_allclose(losses, fx["losses_A"], rtol=1e-2)
+    if packed is not None:
+        assert packed.repacks == len(fx["sp_masks"])                # exactly one multi-layer launch per optimiser step
     total_ref = float(fx["norms_B"][list(fx["norm_names"]).index("__total__")])
     for name, ref in zip(fx["norm_names"], fx["norms_B"]):
         name = str(name)
@@ -145,3 +148,29 @@ def test_stacked_passes_equal_sequential_passes_on_device(fx):
         err = (g_seq[n] - g_stk[n]).abs().max().item()
         # same bound as the layer's backward (bf16 operands): stacking changes which sums are rounded to bf16 first
         assert err < 1e-2 * g_seq[n].abs().max().item() + 1e-6 * total, (n, err)
+
+
+def test_packed_code_arena_equals_per_layer_packing():
+    """ob_weight_quant_pack_multi (all layers, both bitwidths, one launch) writes the same bits as ob_weight_quant_pack per layer
+    and bitwidth, in both layouts; and follows in-place weight updates like the per-layer cache."""
+    import onebit_b200 as ob
+    from onebit_b200 import quant as obq
+    torch.manual_seed(2)
+    model = ob.ConformerASR(**CFG).train().cuda()
+    with torch.no_grad():
+        model.quantized_layers()[3].alpha.mul_(-1.0)               # a negative raw alpha: |alpha| + 1e-8 inside
+    arena = model.use_packed_code_arena()
+    for layer in model.quantized_layers():
+        for bw in (2, 1):
+            got, got_t = layer.packed_weight(bw)
+            ref, ref_t = obq.pack_weight(layer.weight, layer.alpha, bw)
+            assert torch.equal(got, ref) and torch.equal(got_t, ref_t)
+    assert arena.repacks == 1
+    layer = model.quantized_layers()[5]
+    before = layer.packed_weight(2)[0].clone()
+    opt = torch.optim.AdamW(model.parameters(), lr=0.05, fused=True)
+    layer(torch.randn(30, layer.in_features, device="cuda"), 2).square().mean().backward()
+    opt.step()
+    after, _ = layer.packed_weight(2)
+    assert arena.repacks == 2 and not torch.equal(after, before)
+    assert torch.equal(after, obq.pack_weight(layer.weight, layer.alpha, 2)[0])
