@@ -30,6 +30,8 @@ class _InjectedDropout(torch.nn.Module):
         self.streams, self.d_ff, self.p = streams, d_ff, P
 
     def forward(self, x):
+        if not self.training:
+            return x
         inv_keep, (seed, offset, thr) = self.streams.pop(0)
         if x.dim() == 4:                                              # attention weights [B, H, T, T]
             keep = orc.dropout_keep_relattn(x.shape[0], x.shape[1], x.shape[2], seed, offset, thr)
