@@ -535,6 +535,80 @@ def hot_kernel_rooflines(peaks, M):
     return {"shape": {"M": M, "K": K, "N": N, "attention": [Bq, Hh, Tt, Tt]}, "kernels": out}
 
 
+def layer_core_rooflines(peaks, M):
+    """The quantised layer's own kernels at the token count one launch of the timed step really sees when the three co-training passes
+    are stacked (M rows = 3 x batch x frames/4; a bitwidth group is one or two thirds of that), for the model's three routed shapes.
+    Same method as hot_kernel_rooflines: CUDA events over rotating operand sets larger than L2."""
+    import onebit_b200 as ob
+    from onebit_b200 import _cabi, fused
+    lib = _cabi.lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    thr = int(round(0.1 * 65536))
+    ik = 65536.0 / (65536 - thr)
+    for K, N in ((256, 1024), (1024, 256), (256, 256)):
+        torch.manual_seed(0)
+        layer = ob.QuantizedLinear(K, N).to(dev)
+        pk, pkt = layer.packed_weight(2)
+        a, nb = layer.alpha, 3
+        xs = [torch.randn(M, K, device=dev) for _ in range(nb)]
+        gys = [torch.randn(M, N, device=dev) for _ in range(nb)]
+        qs = [ob.act_quant_int8(x) for x in xs]
+        ys = [torch.empty(M, N, device=dev) for _ in range(nb)]
+        dys = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
+        qbs = [torch.empty(M, K, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
+        dxs = [torch.empty(M, K, device=dev) for _ in range(nb)]
+        lnw, lnb = torch.ones(K, device=dev), torch.zeros(K, device=dev)
+        stats = torch.empty(2, M, device=dev)
+        colsum = torch.empty(lib.ob_bwd_colsum_blocks(M), N, device=dev)
+        gw, ga, gb = torch.empty(N, K, device=dev), torch.empty((), device=dev), torch.empty(N, device=dev)
+        nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        fns = {
+            "ln_quant_fwd": (lambda j: lib.ob_layernorm_quant_fwd(xs[j].data_ptr(), lnw.data_ptr(), lnb.data_ptr(), 1e-5, M, K, qs[j][0].data_ptr(),
+                                                                  qs[j][1].data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), st),
+                             5.0 * M * K + 12 * M),
+            "gemm_fwd": (lambda j: lib.ob_gemm_tern_i8_fwd(qs[j][0].data_ptr(), qs[j][1].data_ptr(), pk.data_ptr(), a.data_ptr(), 1,
+                                                           layer.bias.data_ptr(), M, N, K, ys[j].data_ptr(), 0, st),
+                         M * K + N * K / 4 + 4.0 * M * N + 4 * M + 4 * N),
+            "gemm_fwd_tail": (lambda j: lib.ob_gemm_tern_i8_fwd_tail(qs[j][0].data_ptr(), qs[j][1].data_ptr(), pk.data_ptr(), a.data_ptr(), 1,
+                                                                     layer.bias.data_ptr(), M, N, K, gys[j].data_ptr(), None, 0.5 * ik, 7, 4 * j, thr,
+                                                                     0, ys[j].data_ptr(), st),
+                              M * K + N * K / 4 + 8.0 * M * N + 4 * M + 4 * N),
+            "bwd_prep": (lambda j: lib.ob_bwd_prep(gys[j].data_ptr(), 0, qs[j][1].data_ptr(), qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(),
+                                                   qbs[j].data_ptr(), colsum.data_ptr(), st), 6.0 * M * N + 3.0 * M * K + 4 * M),
+            "bwd_prep_tail": (lambda j: lib.ob_bwd_prep_fused(gys[j].data_ptr(), 1, None, None, 0.5 * ik, 7, 4 * j, thr, 0, qs[j][1].data_ptr(),
+                                                              qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(), qbs[j].data_ptr(), colsum.data_ptr(), st),
+                              6.0 * M * N + 3.0 * M * K + 4 * M),
+            "bwd_dx": (lambda j: lib.ob_bwd_dx(dys[j].data_ptr(), qs[j][1].data_ptr(), pkt.data_ptr(), a.data_ptr(), 1, M, N, K, dxs[j].data_ptr(), 0, st),
+                       2.0 * M * N + N * K / 4 + 4.0 * M * K + 4 * M),
+            "bwd_dw": (lambda j: lib.ob_bwd_dw(dys[j].data_ptr(), qbs[j].data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(), a.data_ptr(), 1, 2,
+                                               M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, st),
+                       2.0 * M * N + 2.0 * M * K + 8.0 * N * K),
+        }
+        if N % 256 == 0:
+            fns["bwd_prep_swish"] = (lambda j: lib.ob_bwd_prep_fused(gys[j].data_ptr(), 2, None, ys[j].data_ptr(), ik, 7, 4 * j, thr, 0,
+                                                                     qs[j][1].data_ptr(), qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(), None,
+                                                                     colsum.data_ptr(), st), 10.0 * M * N + 4 * M)
+        i = [0]
+        rows = {}
+        for name, (fn, nbytes_alg) in fns.items():
+            def call(fn=fn):
+                i[0] = (i[0] + 1) % nb
+                rc = fn(i[0])
+                if rc != 0:
+                    raise RuntimeError(_cabi.last_error())
+            for _ in range(3):
+                call()
+            ms = timed_region(1, call, 20) / 20
+            gbs = nbytes_alg / (ms * 1e-3) / 1e9
+            rows[name] = {"us": round(ms * 1e3, 1), "gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 3)}
+        out[f"{K}->{N}"] = rows
+        del xs, gys, qs, ys, dys, qbs, dxs, ws
+    return {"M": M, "peak_gbs": peaks["hbm_gbs"], "shapes": out}
+
+
 def ctc_kernel_rooflines(peaks, B, T, V, L, blank=3):
     """The CTC loss kernels (csrc/ob_ctc.cu) at the step's shape through the C ABI: forward (row log-sum-exp + alpha/beta recursion
     + mean) and backward (gradient pass); the 0.5 GB logits exceed L2 by themselves."""
@@ -731,6 +805,11 @@ def run_train(args, world, rank):
                                     "shape; every kernel of the step, incl. the fp32 tensor-core GEMM of the non-routed matmuls "
                                     "(the largest single family of the step), is in layer_kernels")
         out["layer_kernels"] = hk
+        if cfg.stack_passes:
+            try:
+                out["layer_kernels_stacked"] = layer_core_rooflines(peaks, 3 * M)
+            except Exception as e:  # noqa: BLE001
+                out["layer_kernels_stacked"] = {"error": f"{type(e).__name__}: {e}"}
         try:                                                # added late in round 1: a failure here must not cost the bench line
             hk["kernels"].update(ctc_kernel_rooflines(peaks, Bm, ((T - 1) // 2 - 1) // 2, TRAIN["vocab"], TRAIN["tokens"]))
         except Exception as e:  # noqa: BLE001

@@ -287,16 +287,42 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
   }
 }
 
-// g_g = transposed depthwise convolution of g_d, then the GLU backward into both halves of g_a
+// g_g = transposed depthwise convolution of g_d, then the GLU backward into both halves of g_a.  The a tile the GLU backward
+// needs (both halves, 2 x [64 x 64]) is fetched with the g_d tile in one round of 128-bit loads and kept in shared memory, so
+// the stencil is followed by shared-memory reads instead of a second, late round of global loads (the kernel is latency-bound:
+// ~100 registers allow two blocks per SM).
+constexpr int kCvBwdSmemBytes = (kCvRows * kCvC + 2 * kCvT * kCvC) * 4;
+
 __global__ void __launch_bounds__(256) dwconv_bwd_data_glu_kernel(const float* __restrict__ gd, const float* __restrict__ a,
                                                                   const float* __restrict__ w, int B, int T, int C, int ks,
                                                                   float* __restrict__ ga) {
-  __shared__ __align__(16) float tile[kCvRows * kCvC];
+  extern __shared__ __align__(16) float cv_smem[];
+  float* tile = cv_smem;                              // [94][64] g_d with halo
+  float* a_tile = cv_smem + kCvRows * kCvC;           // [2][64][64]: a1 (values), a2 (gates)
   const int tblocks = (T + kCvT - 1) / kCvT;
   const int b = blockIdx.x / tblocks, tb = blockIdx.x % tblocks;
   const int t0 = tb * kCvT, c0 = blockIdx.y * kCvC;
   const int c = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  load_plain_tile(gd, b, T, C, t0, c0, tile);
+  {                                                   // a tile: 64 rows x (16 + 16) float4, all loads issued before the g_d tile's
+    const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
+    float4 v1[4], v2[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int t = t0 + r0 + 16 * p;
+      v1[p] = v2[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < T) {
+        const float* row = a + (static_cast<int64_t>(b) * T + t) * (2 * C) + c0 + c4;
+        v1[p] = __ldg(reinterpret_cast<const float4*>(row));
+        v2[p] = __ldg(reinterpret_cast<const float4*>(row + C));
+      }
+    }
+    load_plain_tile(gd, b, T, C, t0, c0, tile);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      *reinterpret_cast<float4*>(a_tile + (r0 + 16 * p) * kCvC + c4) = v1[p];
+      *reinterpret_cast<float4*>(a_tile + kCvT * kCvC + (r0 + 16 * p) * kCvC + c4) = v2[p];
+    }
+  }
   float wr[kCvTaps];
   load_taps(w, c0 + c, ks, true, wr);
   __syncthreads();
@@ -305,13 +331,13 @@ __global__ void __launch_bounds__(256) dwconv_bwd_data_glu_kernel(const float* _
   for (int i = 0; i < kCvWin; ++i) win[i] = tile[(tg * kCvPer + i) * kCvC + c];
 #pragma unroll
   for (int o = 0; o < kCvPer; ++o) {
-    const int t = t0 + tg * kCvPer + o;
+    const int tl = tg * kCvPer + o, t = t0 + tl;
     if (t >= T) break;
     float gg = 0.f;
 #pragma unroll
     for (int j = 0; j < kCvTaps; ++j) gg = fmaf(wr[j], win[o + j], gg);
     const int64_t idx = (static_cast<int64_t>(b) * T + t) * (2 * C) + c0 + c;
-    const float a1 = __ldg(a + idx), sg = sigmoid_f(__ldg(a + idx + C));
+    const float a1 = a_tile[tl * kCvC + c], sg = sigmoid_f(a_tile[kCvT * kCvC + tl * kCvC + c]);
     ga[idx] = gg * sg;
     ga[idx + C] = gg * a1 * sg * (1.0f - sg);
   }
@@ -531,7 +557,12 @@ extern "C" int ob_glu_dwconv_bwd(const float* gd, const float* a, const float* w
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* part = static_cast<float*>(ws);
   dim3 grid(B * conv_tblocks(T), C / kCvC);
-  dwconv_bwd_data_glu_kernel<<<grid, 256, 0, st>>>(gd, a, w, B, T, C, ks, ga);
+  static bool attr_set = false;
+  if (!attr_set) {
+    OB_CUDA(cudaFuncSetAttribute(dwconv_bwd_data_glu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvBwdSmemBytes));
+    attr_set = true;
+  }
+  dwconv_bwd_data_glu_kernel<<<grid, 256, kCvBwdSmemBytes, st>>>(gd, a, w, B, T, C, ks, ga);
   OB_LAUNCH_CHECK("dwconv_bwd_data_glu_kernel");
   dwconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(gd, a, B, T, C, part);
   OB_LAUNCH_CHECK("dwconv_bwd_weight_kernel");
