@@ -536,8 +536,9 @@ def hot_kernel_rooflines(peaks, M):
 
 
 def layer_core_rooflines(peaks, M):
-    """The quantised layer's own kernels at the token count one launch of the timed step really sees when the three co-training passes
-    are stacked (M rows = 3 x batch x frames/4; a bitwidth group is one or two thirds of that), for the model's three routed shapes.
+    """The quantised layer's own kernels at the token count of the LARGER bitwidth group of the stacked co-training passes (the stack
+    holds 3 x batch x frames/4 rows; in every block one bitwidth owns one third of them and the other two thirds - one launch per
+    group; `layer_kernels` above is quoted at the smaller group), for the model's three routed shapes.
     Same method as hot_kernel_rooflines: CUDA events over rotating operand sets larger than L2."""
     import onebit_b200 as ob
     from onebit_b200 import _cabi, fused
@@ -807,7 +808,7 @@ def run_train(args, world, rank):
         out["layer_kernels"] = hk
         if cfg.stack_passes:
             try:
-                out["layer_kernels_stacked"] = layer_core_rooflines(peaks, 3 * M)
+                out["layer_kernels_stacked"] = layer_core_rooflines(peaks, 2 * M)
             except Exception as e:  # noqa: BLE001
                 out["layer_kernels_stacked"] = {"error": f"{type(e).__name__}: {e}"}
         try:                                                # added late in round 1: a failure here must not cost the bench line

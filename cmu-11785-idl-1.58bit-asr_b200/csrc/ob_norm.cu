@@ -125,7 +125,7 @@ constexpr int kLnBwdBlocks = 296;      // persistent grid (2 per SM); fixed so t
 // dy = dy0 (+ dy1 + dy2): the gradients of up to three projections that read the same normalised tensor (q, k, v) are
 // summed on load; `resid` is the gradient that reached the module's input along the residual path, added on store - both
 // spare a separate element-wise kernel over [M, C].
-template <int V>
+template <int V, int NDY, int RESID>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy1,
                                                      const float* __restrict__ dy2, const float* __restrict__ x,
                                                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -153,11 +153,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     for (int j = 0; j < V; ++j) {
       const float4 xv = __ldg(xr + lane + 32 * j);
       float4 dv = __ldg(dr + lane + 32 * j);
-      if (dy1 != nullptr) {
+      if (NDY >= 2) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(dy1 + row * C) + lane + 32 * j);
         dv.x += t.x; dv.y += t.y; dv.z += t.z; dv.w += t.w;
       }
-      if (dy2 != nullptr) {
+      if (NDY >= 3) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(dy2 + row * C) + lane + 32 * j);
         dv.x += t.x; dv.y += t.y; dv.z += t.z; dv.w += t.w;
       }
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       o.y = rstd * (gg[j].y - m1 - xh[j].y * m2);
       o.z = rstd * (gg[j].z - m1 - xh[j].z * m2);
       o.w = rstd * (gg[j].w - m1 - xh[j].w * m2);
-      if (resid != nullptr) {
+      if (RESID) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(resid + row * C) + lane + 32 * j);
         o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
       }
@@ -309,12 +309,26 @@ static int launch_ln_bwd(const float* dy, const float* dy1, const float* dy2, co
   const int64_t want = (M + 7) / 8;
   const int blocks = (int)(want < kLnBwdBlocks ? want : kLnBwdBlocks);
   float* part = static_cast<float*>(ws);
+  const int ndy = dy2 != nullptr ? 3 : (dy1 != nullptr ? 2 : 1);
+#define OB_LN_BWD(V)                                                                                                          \
+  do {                                                                                                                        \
+    if (resid != nullptr) {                                                                                                   \
+      if (ndy == 1) ln_bwd_kernel<V, 1, 1><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
+      else if (ndy == 2) ln_bwd_kernel<V, 2, 1><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
+      else ln_bwd_kernel<V, 3, 1><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part);          \
+    } else {                                                                                                                  \
+      if (ndy == 1) ln_bwd_kernel<V, 1, 0><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
+      else if (ndy == 2) ln_bwd_kernel<V, 2, 0><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
+      else ln_bwd_kernel<V, 3, 0><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part);          \
+    }                                                                                                                         \
+  } while (0)
   switch (C) {
-    case 128:  ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); break;
-    case 256:  ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); break;
-    case 512:  ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); break;
-    default:   ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); break;
+    case 128:  OB_LN_BWD(1); break;
+    case 256:  OB_LN_BWD(2); break;
+    case 512:  OB_LN_BWD(4); break;
+    default:   OB_LN_BWD(8); break;
   }
+#undef OB_LN_BWD
   OB_LAUNCH_CHECK("ln_bwd_kernel");
   dim3 grid((C + 31) / 32, 2);
   ln_param_grad_kernel<<<grid, 256, 0, st>>>(part, blocks, C, dgamma, dbeta);
