@@ -381,28 +381,31 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint32_t obuf = out_buf + (buf * G + g) * kStageOutBytes + out_row;
 #pragma unroll
           for (int h = 0; h < (OUT_BF16 ? 2 : 1); ++h) {
+            // fused tail: the residual row segment (8 x 16 B, straight from HBM) is requested BEFORE the accumulator is read
+            // from TMEM, so its latency overlaps the tcgen05.ld and the previous chunk's stores
+            float4 res[TAIL ? 8 : 1];
+            if (TAIL) {
+              const float* rrow = tail.resid + static_cast<int64_t>(row) * NC + col0;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                res[j4] = row < M ? __ldg(reinterpret_cast<const float4*>(rrow) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             uint32_t r[32];
             tmem_ld_32x32(taddr + h * 32, r);
             tmem_ld_wait();
             if (dbg & 2) continue;
             if (TAIL) {
-              // 32 columns = four Philox blocks of 8 elements; the residual row segment comes straight from global memory
+              // 32 columns = four Philox blocks of 8 elements
               const int64_t e0 = (tail.row_base + row) * static_cast<int64_t>(NC) + col0;
-              const float* rrow = tail.resid + static_cast<int64_t>(row) * NC + col0;
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
-                float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
-                if (row < M) {
-                  ra = __ldg(reinterpret_cast<const float4*>(rrow) + 2 * j8);
-                  rb = __ldg(reinterpret_cast<const float4*>(rrow) + 2 * j8 + 1);
-                }
                 const uint32_t kb = tail.rng.threshold != 0u
                                         ? philox_keep8(static_cast<unsigned long long>((e0 >> 3) + j8), tail.rng) : 0xFFu;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   const int j4 = 2 * j8 + u;
                   const float4 b = lds128f(bias_addr + (c * kChunkCols + j4 * 4) * 4);
-                  const float4 rr = u == 0 ? ra : rb;
+                  const float4 rr = res[j4];
                   const uint32_t k4 = kb >> (4 * u);
                   float v0 = fmaf(__uint_as_float(r[4 * j4 + 0] + 0x4B400000u) - 12582912.0f, factor, b.x);
                   float v1 = fmaf(__uint_as_float(r[4 * j4 + 1] + 0x4B400000u) - 12582912.0f, factor, b.y);
