@@ -42,6 +42,8 @@ SIGNATURES = {
     "ob_bwd_dx": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
     "ob_bwd_dw_workspace_bytes": (_sz, [_i, _i, _i]),
     "ob_bwd_dw": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "ob_bwd_dw_q8": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "ob_bwd_dw_q8_groups": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "ob_swish_drop_quant": (_i, [_p, _p, ctypes.c_float, _u64, _u64, _u32, _i64, _i, _p, _p, _p]),
     "ob_swish_drop_bwd": (_i, [_p, _p, _p, ctypes.c_float, _u64, _u64, _u32, _i64, _p, _p]),
     "ob_layernorm_fwd": (_i, [_p, _p, _p, ctypes.c_float, _i64, _i, _p, _p, _p, _p]),

@@ -20,6 +20,9 @@ size_t bwd_tail_workspace_bytes(int N);
 int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const float* alpha, int alpha_mode, int64_t n,
                         int bitwidth, float* grad_W, float* grad_alpha, float* alpha_parts, const float* colsum,
                         int n_col_blocks, int N, float* grad_bias, cudaStream_t st);
+int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, const float* W, const float* alpha, int alpha_mode,
+                              int64_t n, int bw_a, int bw_b, float* grad_W, float* grad_alpha, float* alpha_parts,
+                              const float* colsum, int n_col_blocks, int N, float* grad_bias, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // debug / tuning knobs (ob_debug_set)
@@ -626,6 +629,203 @@ dw_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ C
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// dW_hat partials = dys^T . q   on CTA pairs, with the int8 activation codes converted to bf16 in shared memory
+// ---------------------------------------------------------------------------------------------
+// A pair (cluster of 2, cta_group::2) owns a [256 layer-N rows x 256 layer-K columns] tile of one token split.  Each CTA
+// loads its own 128 N-rows of dys (two [64 tokens][64 n] bf16 atoms by TMA, MN-major as in dw_kernel) and its own half
+// of the tile's K-columns of q as INT8 ([64 tokens][128 features], 8 KB, un-swizzled); eight converter warps rewrite the
+// codes as bf16 (exact) in the MN-major SWIZZLE_128B atom layout.  Against dw_kernel the operand bytes a CTA pulls from
+// L2 per token drop from 768 to 384 (the kernel is bound by that stream), and the bf16 copy of q no longer exists in HBM.
+// Signalling as in the CTA-pair fp32 GEMM: each CTA's TMA completes on its own `full` barrier, the converter warps of
+// both CTAs arrive on the leader's `ready` barrier (the peer's dys tile is covered: its converters waited for the
+// barrier that tile completes on), tcgen05.commit multicasts `empty` / `done` to both CTAs.
+constexpr int kDw2Threads = 384;               // warps: 0 producer, 1 MMA (leader), 2 TMEM, 3 idle, 4..11 converters + epilogue
+constexpr int kDw2ConvWarps = 8;
+
+template <int STAGES>
+struct Dw2Smem {
+  static constexpr int kATileBytes = 2 * kDwAtomBytes;        // this CTA's 128 N-rows: two [64 tok][64 n] atoms
+  static constexpr int kBTileBytes = 2 * kDwAtomBytes;        // this CTA's 128 K-columns, converted
+  static constexpr int kQTileBytes = kDwTokBlock * 128;       // [64 tok][128 features] int8
+  static constexpr int kOffA = 0;
+  static constexpr int kOffB = STAGES * kATileBytes;
+  static constexpr int kOffQ = kOffB + STAGES * kBTileBytes;
+  static constexpr int kOffBar = kOffQ + STAGES * kQTileBytes;
+  static constexpr int kNumBars = 3 * STAGES + 1;
+  static constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
+  static constexpr int kBytes = kOffTmemSlot + 16;
+  static constexpr int kDynBytes = kBytes + 1024;
+};
+
+// eight int8 codes -> eight bf16 (exact): u = code + 128 placed in the mantissa of 2^23, minus (2^23 + 128)
+__device__ __forceinline__ uint4 i8x8_to_bf16x8(uint2 raw) {
+  const uint32_t w0 = raw.x ^ 0x80808080u, w1 = raw.y ^ 0x80808080u;
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[k] = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7540u | k)) - 8388736.0f;
+    f[4 + k] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7540u | k)) - 8388736.0f;
+  }
+  uint4 o;
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&p0);
+  o.y = *reinterpret_cast<uint32_t*>(&p1);
+  o.z = *reinterpret_cast<uint32_t*>(&p2);
+  o.w = *reinterpret_cast<uint32_t*>(&p3);
+  return o;
+}
+
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+// Two token groups per launch (the 2-bit and the 1-bit rows of a stacked batch, each with its own tensor maps so that a
+// group's last token block is zero-filled instead of running into the other group): splits [0, splits_a) walk group A,
+// the rest group B; the finaliser sums the two ranges of partials separately (the alpha term depends on the bitwidth).
+// grid: x = 2 * (n_tile * k_tiles + k_tile) + cluster rank, y = split
+template <int STAGES>
+__global__ void __launch_bounds__(kDw2Threads, 1)
+dw_pair_kernel(const __grid_constant__ CUtensorMap map_dys_a, const __grid_constant__ CUtensorMap map_q_a,
+               const __grid_constant__ CUtensorMap map_dys_b, const __grid_constant__ CUtensorMap map_q_b,
+               float* __restrict__ partials, int M_a, int M_b, int splits_a, int N, int K, int tb_per_split) {
+  using L = Dw2Smem<STAGES>;
+  constexpr uint32_t kTmemCols = 256;
+  constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 1, 1, 256, 256);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* ready_bar = full_bar + STAGES;         // leader's: converter warps of both CTAs
+  uint64_t* empty_bar = full_bar + 2 * STAGES;
+  uint64_t* done_bar = full_bar + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int k_tiles = (K + 255) / 256;
+  const int tile = blockIdx.x >> 1;
+  const int n0 = (tile / k_tiles) * 256 + static_cast<int>(rank) * 128;      // this CTA's rows of the output tile
+  const int kt0 = (tile % k_tiles) * 256;                                     // the tile's columns
+  const int kq0 = kt0 + static_cast<int>(rank) * 128;                         // the half this CTA converts
+  const int split = blockIdx.y;
+  const bool in_a = split < splits_a;
+  const CUtensorMap* map_dys = in_a ? &map_dys_a : &map_dys_b;
+  const CUtensorMap* map_q = in_a ? &map_q_a : &map_q_b;
+  const int num_tb = ((in_a ? M_a : M_b) + kDwTokBlock - 1) / kDwTokBlock;
+  const int tb0 = (in_a ? split : split - splits_a) * tb_per_split;
+  const int nkb = min(num_tb, tb0 + tb_per_split) - tb0;      // >= 1 by construction of the split counts
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(map_dys);
+    tma_prefetch_desc(map_q);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], kDw2ConvWarps * 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int t0 = (tb0 + kb) * kDwTokBlock;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], L::kATileBytes + L::kQTileBytes);
+        uint8_t* a = smem + L::kOffA + stage * L::kATileBytes;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_2d(a + j * kDwAtomBytes, map_dys, &full_bar[stage], n0 + 64 * j, t0);
+        tma_load_2d(smem + L::kOffQ + stage * L::kQTileBytes, map_q, &full_bar[stage], kq0, t0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait_cluster(&ready_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t a_desc = make_smem_desc_sw128(sbase + L::kOffA + stage * L::kATileBytes, kDwAtomBytes, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(sbase + L::kOffB + stage * L::kBTileBytes, kDwAtomBytes, 1024);
+#pragma unroll
+        for (int k = 0; k < kDwTokBlock / 16; ++k)     // 16 tokens = 2048 B -> +128 in the address field
+          umma_f16_pair(tmem_base, a_desc + 128 * k, b_desc + 128 * k, kIdesc, (kb | k) != 0);
+        umma_commit_pair(&empty_bar[stage]);
+        if (kb == nkb - 1) umma_commit_pair(done_bar);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- converters: [64 tok][128 features] int8 -> two [64 tok][64 features] bf16 atoms (16-byte chunk c of token row t
+    //      lands at chunk c ^ (t & 7)); 16 lanes read one token row (128 B), 8 lanes write one atom row ----
+    const int tc = threadIdx.x - 128;
+    const uint32_t ready_addr0 = mapa_u32(smem_u32(&ready_bar[0]), 0);
+    uint32_t stage = 0, phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      const uint32_t src = sbase + L::kOffQ + stage * L::kQTileBytes;
+      const uint32_t dst = sbase + L::kOffB + stage * L::kBTileBytes;
+      uint2 raw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) raw[i] = lds64(src + (tc + 256 * i) * 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int task = tc + 256 * i, t = task >> 4, cc = task & 15;
+        sts128(dst + (cc >> 3) * kDwAtomBytes + t * 128 + (((cc & 7) ^ (t & 7)) << 4), i8x8_to_bf16x8(raw[i]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ready_addr0 + stage * 8);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ---- epilogue: this CTA's 128 rows x 256 columns of the partial product ----
+    const int e = warp & 3, half = (warp - 4) >> 2;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int n = n0 + e * 32 + lane;
+    float* dst_row = partials + (static_cast<int64_t>(split) * N + n) * K;
+#pragma unroll 1
+    for (int c = half * 4; c < half * 4 + 4; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      const int col0 = kt0 + c * 32;
+      if (n < N && col0 < K) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        store_row_chunk_f32(dst_row + col0, v, K - col0);
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                 // the peer's shared memory is read until the last MMA retires
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
@@ -760,6 +960,64 @@ static DwPlan plan_dw(int M, int N, int K) {
   return p;
 }
 
+// pair kernel: [256 x 256] output tiles, token splits over the CTA pairs; token rows [0, rows_a) and [rows_a, M) are split
+// separately with a common number of token blocks per split (no split spans both groups)
+struct DwPairPlan {
+  int k_tiles, n_tiles, splits_a, splits, tb_per_split;
+};
+
+static DwPairPlan plan_dw_pair(int M, int rows_a, int N, int K) {
+  DwPairPlan p;
+  p.k_tiles = (K + 255) / 256;
+  p.n_tiles = (N + 255) / 256;
+  const int tb_a = (rows_a + kDwTokBlock - 1) / kDwTokBlock, tb_b = (M - rows_a + kDwTokBlock - 1) / kDwTokBlock;
+  int want = (sm_count() / 2) / (p.k_tiles * p.n_tiles);
+  if (g_dbg_force_splits > 0) want = g_dbg_force_splits;
+  if (want < 1) want = 1;
+  if (want > tb_a + tb_b) want = tb_a + tb_b;
+  p.tb_per_split = (tb_a + tb_b + want - 1) / want;
+  p.splits_a = (tb_a + p.tb_per_split - 1) / p.tb_per_split;
+  p.splits = p.splits_a + (tb_b + p.tb_per_split - 1) / p.tb_per_split;
+  return p;
+}
+// upper bound of plan_dw_pair(...).splits over every position of the group boundary: ceil(a/t) + ceil(b/t) <= want + 2
+static int max_pair_splits(int M, int N, int K) {
+  (void)M;
+  int want = (sm_count() / 2) / (((K + 255) / 256) * ((N + 255) / 256));
+  if (g_dbg_force_splits > 0) want = g_dbg_force_splits;
+  return (want < 1 ? 1 : want) + 2;
+}
+
+static int launch_dw_pair(const CUtensorMap& map_dys_a, const CUtensorMap& map_q_a, const CUtensorMap& map_dys_b,
+                          const CUtensorMap& map_q_b, float* partials, int M, int rows_a, int N, int K, const DwPairPlan& p,
+                          cudaStream_t st) {
+  constexpr int kStages = 5;
+  using L = Dw2Smem<kStages>;
+  static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
+  auto kern = dw_pair_kernel<kStages>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * p.n_tiles * p.k_tiles, p.splits);
+  cfg.blockDim = dim3(kDw2Threads);
+  cfg.dynamicSmemBytes = L::kDynBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_dys_a, map_q_a, map_dys_b, map_q_b, partials, rows_a, M - rows_a, p.splits_a, N,
+                             K, p.tb_per_split));
+  count_launch();
+  return OB_OK;
+}
+
 template <int BLOCK_N, int STAGES>
 static int launch_dw(const CUtensorMap& map_dys, const CUtensorMap& map_qb, float* partials, int M, int N, int K,
                      const DwPlan& p, cudaStream_t st) {
@@ -862,7 +1120,8 @@ extern "C" int ob_bwd_dx(const void* dys_bf16, const float* scale, const uint8_t
 extern "C" size_t ob_bwd_dw_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const DwPlan p = plan_dw(M, N, K);
-  const size_t partials = (size_t)p.splits * N * K * sizeof(float);
+  const int s2 = max_pair_splits(M, N, K);
+  const size_t partials = (size_t)(p.splits > s2 ? p.splits : s2) * N * K * sizeof(float);
   return partials + ob_ste_workspace_bytes((int64_t)N * K) + bwd_tail_workspace_bytes(N) + 256;
 }
 
@@ -901,4 +1160,62 @@ extern "C" int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float*
   if (rc != OB_OK) return rc;
   return launch_ste_and_tail(partials, p.splits, W, alpha, alpha_mode, (int64_t)N * K, bitwidth, grad_W, grad_alpha,
                              alpha_parts, colsum, ob_bwd_colsum_blocks(M), N, grad_bias, st);
+}
+
+// rows [0, rows2) of dys / q belong to the 2-bit pass, rows [rows2, M) to the 1-bit pass (rows2 = M or 0: one group)
+static int bwd_dw_q8_groups(const char* who, const void* dys_bf16, const int8_t* q, const float* colsum, const float* W,
+                            const float* alpha, int alpha_mode, int rows2, int M, int N, int K, float* grad_W,
+                            float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream) {
+  OB_REQUIRE(dys_bf16 && q && W && alpha && grad_W && grad_alpha && ws, "%s: null pointer", who);
+  OB_REQUIRE((grad_bias == nullptr) || (colsum != nullptr), "%s: grad_bias requested without colsum partials", who);
+  OB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0, "%s: need K %% 64 == 0 and N %% 64 == 0 (M=%d N=%d K=%d)",
+             who, M, N, K);
+  OB_REQUIRE(rows2 >= 0 && rows2 <= M, "%s: rows2 (%d) outside [0, M = %d]", who, rows2, M);
+  OB_REQUIRE(aligned16(dys_bf16) && aligned16(q) && aligned16(W) && aligned16(grad_W) && aligned16(ws),
+             "%s: pointers must be 16-byte aligned", who);
+  if (ws_bytes < ob_bwd_dw_workspace_bytes(M, N, K)) {
+    set_error("%s: workspace too small (%zu < %zu)", who, ws_bytes, ob_bwd_dw_workspace_bytes(M, N, K));
+    return OB_ERR_WORKSPACE;
+  }
+  int rc = check_device();
+  if (rc != OB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DwPairPlan p = plan_dw_pair(M, rows2, N, K);
+  // an empty group gets the other group's maps (never dereferenced: it has no splits)
+  const int ra = rows2 > 0 ? rows2 : M, rb = M - rows2 > 0 ? M - rows2 : M;
+  const int off_b = M - rows2 > 0 ? rows2 : 0;
+  const uint8_t* dys_b = static_cast<const uint8_t*>(dys_bf16) + (size_t)off_b * N * 2;
+  CUtensorMap map_dys_a, map_q_a, map_dys_b, map_q_b;
+  rc = make_map(&map_dys_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dys_bf16, N, ra, (uint64_t)N * 2, 64, kDwTokBlock,
+                CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != OB_OK) return rc;
+  rc = make_map(&map_q_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, q, K, ra, (uint64_t)K, 128, kDwTokBlock, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc != OB_OK) return rc;
+  rc = make_map(&map_dys_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dys_b, N, rb, (uint64_t)N * 2, 64, kDwTokBlock,
+                CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != OB_OK) return rc;
+  rc = make_map(&map_q_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, q + (size_t)off_b * K, K, rb, (uint64_t)K, 128, kDwTokBlock,
+                CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc != OB_OK) return rc;
+  float* partials = static_cast<float*>(ws);
+  float* alpha_parts = partials + (size_t)p.splits * N * K;
+  rc = launch_dw_pair(map_dys_a, map_q_a, map_dys_b, map_q_b, partials, M, rows2, N, K, p, st);
+  if (rc != OB_OK) return rc;
+  return launch_dw_finalize_groups(partials, p.splits_a, p.splits, W, alpha, alpha_mode, (int64_t)N * K, 2, 1, grad_W, grad_alpha,
+                                   alpha_parts, colsum, ob_bwd_colsum_blocks(M), N, grad_bias, st);
+}
+
+extern "C" int ob_bwd_dw_q8(const void* dys_bf16, const int8_t* q, const float* colsum, const float* W,
+                            const float* alpha, int alpha_mode, int bitwidth, int M, int N, int K, float* grad_W,
+                            float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream) {
+  OB_REQUIRE(bitwidth == 1 || bitwidth == 2, "bitwidth must be one of {1,2,32}");
+  return bwd_dw_q8_groups("ob_bwd_dw_q8", dys_bf16, q, colsum, W, alpha, alpha_mode, bitwidth == 2 ? M : 0, M, N, K, grad_W,
+                          grad_alpha, grad_bias, ws, ws_bytes, stream);
+}
+
+extern "C" int ob_bwd_dw_q8_groups(const void* dys_bf16, const int8_t* q, const float* colsum, const float* W,
+                                   const float* alpha, int alpha_mode, int rows2, int M, int N, int K, float* grad_W,
+                                   float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream) {
+  return bwd_dw_q8_groups("ob_bwd_dw_q8_groups", dys_bf16, q, colsum, W, alpha, alpha_mode, rows2, M, N, K, grad_W, grad_alpha,
+                          grad_bias, ws, ws_bytes, stream);
 }

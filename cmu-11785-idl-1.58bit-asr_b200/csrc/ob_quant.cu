@@ -315,14 +315,18 @@ constexpr int kFinBlockElems = 256;
 // Blocks [0, fin_blocks) finalise 256 elements each; the last of them to finish (ticket) reduces the alpha partials.
 // Blocks >= fin_blocks reduce the grad_bias column sums.  One launch for the whole tail of the backward.
 // tail_ws: [kTailRowChunks][N] floats, then 1 + ceil(N/32) int tickets (zero on entry, reset on exit).
-__global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restrict__ g_parts, int splits,
+// Two groups of splits: [0, splits_a) are partials of token rows quantised at bw_a, [splits_a, splits) at bw_b (the stacked
+// co-training passes; one group when splits_a == splits).  grad_W is the masked sum of both groups (the STE mask does not
+// depend on the bitwidth), the alpha term is taken per group (quant.py:86-91 depends on the codes).
+__global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restrict__ g_parts, int splits_a, int splits,
                                                           const float* __restrict__ W, const float* __restrict__ alpha,
-                                                          int alpha_mode, int64_t n, int bitwidth,
+                                                          int alpha_mode, int64_t n, int bw_a, int bw_b,
                                                           float* __restrict__ grad_W, float* __restrict__ alpha_parts,
                                                           int fin_blocks, float* __restrict__ grad_alpha,
                                                           const float* __restrict__ colsum, int n_col_blocks, int N,
                                                           float* __restrict__ grad_bias, float* __restrict__ tail_ws) {
   __shared__ float4 part[3][64];
+  __shared__ float4 part_b[3][64];
   __shared__ float red[8];
   __shared__ int last_fin;
   int* tickets = reinterpret_cast<int*>(tail_ws + (int64_t)kTailRowChunks * N);
@@ -333,20 +337,30 @@ __global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restric
   }
   const int eg = threadIdx.x & 63, sl = threadIdx.x >> 6;
   const int64_t i = (int64_t)blockIdx.x * kFinBlockElems + eg * 4;      // n % 256 == 0 (N, K multiples of 64)
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-  int s = sl;
-  for (; s + 4 < splits; s += 8) {
-    const float4 p0 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)s * n + i));
-    const float4 p1 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)(s + 4) * n + i));
-    a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
-    a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
+  // splits s0 + sl, s0 + sl + 4, ... < s1 of this thread's float4, two accumulators in flight
+  auto lane_sum = [&](int s0, int s1) {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    int s = s0 + sl;
+    for (; s + 4 < s1; s += 8) {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)s * n + i));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)(s + 4) * n + i));
+      a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
+      a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
+    }
+    if (s < s1) {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)s * n + i));
+      a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
+    }
+    a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
+    return a0;
+  };
+  const bool two = splits_a < splits;                                   // block-uniform
+  float4 a0 = lane_sum(0, splits_a), b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (two) b0 = lane_sum(splits_a, splits);
+  if (sl > 0) {
+    part[sl - 1][eg] = a0;
+    if (two) part_b[sl - 1][eg] = b0;
   }
-  if (s < splits) {
-    const float4 p0 = __ldg(reinterpret_cast<const float4*>(g_parts + (int64_t)s * n + i));
-    a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
-  }
-  a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
-  if (sl > 0) part[sl - 1][eg] = a0;
   __syncthreads();
   float acc = 0.f;
   if (sl == 0) {
@@ -358,10 +372,21 @@ __global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restric
     const float a_eff = load_alpha_eff(alpha, alpha_mode);
     const float4 w = __ldg(reinterpret_cast<const float4*>(W + i));
     float4 o;
-    o.x = ste_elem(a0.x, w.x, a_eff, bitwidth, acc);
-    o.y = ste_elem(a0.y, w.y, a_eff, bitwidth, acc);
-    o.z = ste_elem(a0.z, w.z, a_eff, bitwidth, acc);
-    o.w = ste_elem(a0.w, w.w, a_eff, bitwidth, acc);
+    o.x = ste_elem(a0.x, w.x, a_eff, bw_a, acc);
+    o.y = ste_elem(a0.y, w.y, a_eff, bw_a, acc);
+    o.z = ste_elem(a0.z, w.z, a_eff, bw_a, acc);
+    o.w = ste_elem(a0.w, w.w, a_eff, bw_a, acc);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float4 ob2 = part_b[j][eg];
+        b0.x += ob2.x; b0.y += ob2.y; b0.z += ob2.z; b0.w += ob2.w;
+      }
+      o.x += ste_elem(b0.x, w.x, a_eff, bw_b, acc);
+      o.y += ste_elem(b0.y, w.y, a_eff, bw_b, acc);
+      o.z += ste_elem(b0.z, w.z, a_eff, bw_b, acc);
+      o.w += ste_elem(b0.w, w.w, a_eff, bw_b, acc);
+    }
     *reinterpret_cast<float4*>(grad_W + i) = o;
   }
   const float tot = block_sum<256>(acc, red);
@@ -785,8 +810,8 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
     OB_CUDA(cudaMemsetAsync(tail_ws + (size_t)kTailRowChunks * N, 0, (size_t)(1 + col_groups) * sizeof(int), st));
   if (fused) {
     dw_finalize_kernel<<<blocks + col_groups * kTailRowChunks, 256, 0, st>>>(
-        g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts, blocks, grad_alpha, colsum, n_col_blocks,
-        N, grad_bias, tail_ws);
+        g_parts, splits, splits, W, alpha, alpha_mode, n, bitwidth, bitwidth, grad_W, alpha_parts, blocks, grad_alpha, colsum,
+        n_col_blocks, N, grad_bias, tail_ws);
     OB_LAUNCH_CHECK("dw_finalize_kernel");
     return OB_OK;
   }
@@ -795,6 +820,26 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
   bwd_tail_kernel<<<1 + col_groups * kTailRowChunks, 256, 0, st>>>(alpha_parts, blocks, alpha, alpha_mode, grad_alpha,
                                                                    colsum, n_col_blocks, N, grad_bias, tail_ws);
   OB_LAUNCH_CHECK("bwd_tail_kernel");
+  return OB_OK;
+}
+
+// the fused finaliser over two groups of splits (any split count; n % 256 == 0 holds for N, K multiples of 64)
+int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, const float* W, const float* alpha, int alpha_mode,
+                              int64_t n, int bw_a, int bw_b, float* grad_W, float* grad_alpha, float* alpha_parts,
+                              const float* colsum, int n_col_blocks, int N, float* grad_bias, cudaStream_t st) {
+  if (n % kFinBlockElems != 0) {
+    set_error("grad_W finaliser: N * K must be a multiple of %d", kFinBlockElems);
+    return OB_ERR_ARG;
+  }
+  if (splits_a == 0) { splits_a = splits; bw_a = bw_b; }           // only the second group has rows
+  const int col_groups = (grad_bias != nullptr) ? (N + 31) / 32 : 0;
+  const int blocks = (int)(n / kFinBlockElems);
+  float* tail_ws = alpha_parts + blocks;
+  OB_CUDA(cudaMemsetAsync(tail_ws + (size_t)kTailRowChunks * N, 0, (size_t)(1 + col_groups) * sizeof(int), st));
+  dw_finalize_kernel<<<blocks + col_groups * kTailRowChunks, 256, 0, st>>>(
+      g_parts, splits_a, splits, W, alpha, alpha_mode, n, bw_a, bw_b, grad_W, alpha_parts, blocks, grad_alpha, colsum,
+      n_col_blocks, N, grad_bias, tail_ws);
+  OB_LAUNCH_CHECK("dw_finalize_kernel");
   return OB_OK;
 }
 }  // namespace ob

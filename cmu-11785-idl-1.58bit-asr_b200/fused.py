@@ -27,7 +27,8 @@ import numpy as np
 import torch
 
 from ._cabi import OB_ALPHA_RAW, OB_F32, OB_PREP_SWISH, OB_PREP_TAIL, check, lib
-from .quant import _FUSED_SWISH_K, _NO_RNG, _colsum_blocks, _dw_ws_bytes, _stream, _weight_epoch, draw_dropout_stream
+from .quant import (_FUSED_SWISH_K, _NO_RNG, _colsum_blocks, _dw_ws_bytes, _stream, _weight_epoch, draw_dropout_stream,
+                    dw_reads_codes)
 
 LN_WIDTHS = (128, 256, 512, 1024)
 
@@ -128,16 +129,12 @@ def _layer_backward(g, prep, q, s, qb, lc: LayerCodes, rows2: int, need_x: bool,
     N = lc.N
     dev, st = g.device, _stream()
     dys = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
-    make_qb = need_w and qb is None
-    if make_qb:
-        qb = torch.empty((M, K), device=dev, dtype=torch.bfloat16)
+    q8 = dw_reads_codes(K)                              # grad_W converts the int8 codes in shared memory: no bf16 copy of q
     gx = torch.empty((M, K), device=dev, dtype=torch.float32) if need_x else None
     gw = ga = gb = None
     gp, qp, sp, dp, ap = g.data_ptr(), q.data_ptr(), s.data_ptr(), dys.data_ptr(), lc.alpha.data_ptr()
-    for r0, r1, bw in _groups(rows2, M):
-        Mg = r1 - r0
-        colsum = torch.empty((_colsum_blocks(Mg), N), device=dev, dtype=torch.float32) if need_b else None
-        qb_out = qb.data_ptr() + 2 * r0 * K if make_qb else None
+
+    def run_prep(r0, Mg, qb_out, colsum):
         if prep is None:
             check(lib.ob_bwd_prep(gp + 4 * r0 * N, OB_F32, sp + 4 * r0, qp + r0 * K, Mg, N, K, dp + 2 * r0 * N, qb_out,
                                   _ptr(colsum), st))
@@ -149,9 +146,38 @@ def _layer_backward(g, prep, q, s, qb, lc: LayerCodes, rows2: int, need_x: bool,
             _, h, inv_keep, rng = prep
             check(lib.ob_bwd_prep_fused(gp + 4 * r0 * N, OB_PREP_SWISH, None, h.data_ptr() + 4 * r0 * N, inv_keep, *rng, r0,
                                         sp + 4 * r0, qp + r0 * K, Mg, N, K, dp + 2 * r0 * N, qb_out, _ptr(colsum), st))
+
+    def run_dx(r0, Mg, bw):
+        pkt = (lc.pkt2 if bw == 2 else lc.pkt1).data_ptr()
+        check(lib.ob_bwd_dx(dp + 2 * r0 * N, sp + 4 * r0, pkt, ap, OB_ALPHA_RAW, Mg, N, K, gx.data_ptr() + 4 * r0 * K, OB_F32, st))
+
+    if q8:
+        # one pass over the upstream gradient for all rows (nothing in it depends on the bitwidth), grad_x per bitwidth
+        # group, then ONE grad_W launch + finaliser over both groups: no per-group partial results to add up
+        colsum = torch.empty((_colsum_blocks(M), N), device=dev, dtype=torch.float32) if need_b else None
+        run_prep(0, M, None, colsum)
         if need_x:
-            pkt = (lc.pkt2 if bw == 2 else lc.pkt1).data_ptr()
-            check(lib.ob_bwd_dx(dp + 2 * r0 * N, sp + 4 * r0, pkt, ap, OB_ALPHA_RAW, Mg, N, K, gx.data_ptr() + 4 * r0 * K, OB_F32, st))
+            for r0, r1, bw in _groups(rows2, M):
+                run_dx(r0, r1 - r0, bw)
+        if need_w:
+            gw = torch.empty((N, K), device=dev, dtype=torch.float32)
+            ga = torch.empty((), device=dev, dtype=torch.float32)
+            gb = torch.empty((N,), device=dev, dtype=torch.float32) if need_b else None
+            nbytes = _dw_ws_bytes(M, N, K)
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            check(lib.ob_bwd_dw_q8_groups(dp, qp, _ptr(colsum), lc.weight.data_ptr(), ap, OB_ALPHA_RAW, min(max(rows2, 0), M), M, N, K,
+                                          gw.data_ptr(), ga.data_ptr(), _ptr(gb), ws.data_ptr(), nbytes, st))
+        return gx, gw, ga, gb, qb
+
+    make_qb = need_w and qb is None
+    if make_qb:
+        qb = torch.empty((M, K), device=dev, dtype=torch.bfloat16)
+    for r0, r1, bw in _groups(rows2, M):
+        Mg = r1 - r0
+        colsum = torch.empty((_colsum_blocks(Mg), N), device=dev, dtype=torch.float32) if need_b else None
+        run_prep(r0, Mg, qb.data_ptr() + 2 * r0 * K if make_qb else None, colsum)
+        if need_x:
+            run_dx(r0, Mg, bw)
         if need_w:
             gw_g = torch.empty((N, K), device=dev, dtype=torch.float32)
             ga_g = torch.empty((), device=dev, dtype=torch.float32)

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import functools
 import math
+import os
 import sys
 
 import torch
@@ -223,6 +224,15 @@ def _dw_ws_bytes(M: int, N: int, K: int) -> int:
     return lib.ob_bwd_dw_workspace_bytes(M, N, K)
 
 
+# grad_W reads the saved int8 codes directly (CTA-pair kernel, codes converted to bf16 in shared memory) when the layer is at
+# least one 256-column tile wide; OB_DW_Q8=0 restores the bf16 copy of q made by the prep kernel (A/B measurements).
+DW_Q8 = os.environ.get("OB_DW_Q8", "1") != "0"
+
+
+def dw_reads_codes(K: int) -> bool:
+    return DW_Q8 and K >= 256
+
+
 def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w, need_b, gx_out=None):
     """Shared backward of the quantised linear: prep (bf16 casts + column sums), grad_x GEMM, grad_W GEMM + fused
     STE / alpha / bias reductions.  Returns (grad_x [M,K] | None, grad_W | None, grad_alpha | None, grad_bias | None)."""
@@ -233,7 +243,8 @@ def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w
         g2 = g2.contiguous()
     dev, st = g2.device, _stream()
     dys = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
-    qb = torch.empty((M, K), device=dev, dtype=torch.bfloat16) if need_w else None
+    q8 = dw_reads_codes(K)
+    qb = torch.empty((M, K), device=dev, dtype=torch.bfloat16) if need_w and not q8 else None
     colsum = torch.empty((_colsum_blocks(M), N), device=dev, dtype=torch.float32) if need_b else None
     check(lib.ob_bwd_prep(g2.data_ptr(), _tag(g2), s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(),
                           None if qb is None else qb.data_ptr(), None if colsum is None else colsum.data_ptr(), st))
@@ -248,13 +259,45 @@ def _linear_backward(gy, q, s, weight, alpha, packed_t, bitwidth, need_x, need_w
         gb = torch.empty((N,), device=dev, dtype=torch.float32) if need_b else None
         nbytes = _dw_ws_bytes(M, N, K)
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-        check(lib.ob_bwd_dw(dys.data_ptr(), qb.data_ptr(), None if colsum is None else colsum.data_ptr(),
+        dw = lib.ob_bwd_dw_q8 if q8 else lib.ob_bwd_dw
+        check(dw(dys.data_ptr(), (q if q8 else qb).data_ptr(), None if colsum is None else colsum.data_ptr(),
                             weight.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW, bitwidth, M, N, K,
                             gw.data_ptr(), ga.data_ptr(), None if gb is None else gb.data_ptr(), ws.data_ptr(),
                             nbytes, st))
     elif need_b:
         gb = g2.sum(0, dtype=torch.float32)
     return gx, gw, ga, gb
+
+
+def _grouped_backward_q8(g2, q, s, weight, alpha, pkt2, pkt1, rows2, gx, need_w, need_b):
+    """Layer backward over a stacked batch (rows [0, rows2) at 2 bits, the rest at 1 bit): one prep pass over all rows, grad_x
+    per bitwidth group into ``gx`` (or skipped when None), one grad_W launch + finaliser over both groups."""
+    M, K = q.shape
+    N = weight.shape[0]
+    dev, st = g2.device, _stream()
+    dys = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+    colsum = torch.empty((_colsum_blocks(M), N), device=dev, dtype=torch.float32) if need_b else None
+    check(lib.ob_bwd_prep(g2.data_ptr(), _tag(g2), s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(), None,
+                          None if colsum is None else colsum.data_ptr(), st))
+    if gx is not None:
+        for r0, r1, pkt in ((0, rows2, pkt2), (rows2, M, pkt1)):
+            if r1 > r0:
+                check(lib.ob_bwd_dx(dys.data_ptr() + 2 * r0 * N, s.data_ptr() + 4 * r0, pkt.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW,
+                                    r1 - r0, N, K, gx.data_ptr() + r0 * K * gx.element_size(), _tag(gx), st))
+    gw = ga = gb = None
+    if need_w:
+        gw = torch.empty((N, K), device=dev, dtype=torch.float32)
+        ga = torch.empty((), device=dev, dtype=torch.float32)
+        gb = torch.empty((N,), device=dev, dtype=torch.float32) if need_b else None
+        nbytes = _dw_ws_bytes(M, N, K)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        check(lib.ob_bwd_dw_q8_groups(dys.data_ptr(), q.data_ptr(), None if colsum is None else colsum.data_ptr(),
+                                      weight.data_ptr(), alpha.data_ptr(), OB_ALPHA_RAW, min(max(rows2, 0), M), M, N, K,
+                                      gw.data_ptr(), ga.data_ptr(), None if gb is None else gb.data_ptr(), ws.data_ptr(),
+                                      nbytes, st))
+    elif need_b:
+        gb = g2.sum(0, dtype=torch.float32)
+    return gw, ga, gb
 
 
 _FUSED_SWISH_K = (256, 512, 1024, 2048)
@@ -367,7 +410,10 @@ class _GroupedQuantLinearFn(torch.autograd.Function):
             g2 = g2.contiguous()
         gx = torch.empty((M, K), device=g2.device, dtype=gy.dtype) if need_x else None
         gw = ga = gb = None
-        for r0, r1, pkt, bw in ((0, ctx.rows2, pkt2, 2), (ctx.rows2, M, pkt1, 1)):
+        if dw_reads_codes(K):
+            gw, ga, gb = _grouped_backward_q8(g2, q, s, weight, alpha, pkt2, pkt1, ctx.rows2, gx, need_w or need_a,
+                                              need_b and ctx.has_bias)
+        for r0, r1, pkt, bw in () if dw_reads_codes(K) else ((0, ctx.rows2, pkt2, 2), (ctx.rows2, M, pkt1, 1)):
             if r1 <= r0:
                 continue
             _, gw_g, ga_g, gb_g = _linear_backward(g2[r0:r1], q[r0:r1], s[r0:r1], weight, alpha, pkt, bw, need_x,

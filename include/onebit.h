@@ -141,6 +141,21 @@ int ob_bwd_dw(const void* dys_bf16, const void* qb_bf16, const float* colsum, co
               const float* alpha, int alpha_mode, int bitwidth, int M, int N, int K, float* grad_W,
               float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream);
 
+/* ob_bwd_dw reading the saved int8 activation codes q [M, K] themselves (round 2): CTA pairs on [256 x 256] output tiles
+ * convert the codes to bf16 (exact) in shared memory, so ob_bwd_prep / ob_bwd_prep_fused are called with qb_bf16 = NULL and
+ * the bf16 copy of q never exists in HBM.  Same results as ob_bwd_dw up to the fp32 summation order of the token splits;
+ * same workspace size. */
+int ob_bwd_dw_q8(const void* dys_bf16, const int8_t* q, const float* colsum, const float* W,
+                 const float* alpha, int alpha_mode, int bitwidth, int M, int N, int K, float* grad_W,
+                 float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream);
+/* The same over a stacked batch whose token rows [0, rows2) went through the 2-bit codes and rows [rows2, M) through the
+ * 1-bit codes (train.py:83-103 evaluated side by side): one GEMM launch whose token splits never span the boundary and one
+ * finaliser - grad_W is the masked sum over all rows, grad_alpha the sum of the two bitwidths' alpha terms, grad_bias the
+ * column sums of all rows (colsum from ONE ob_bwd_prep* call over the M rows). */
+int ob_bwd_dw_q8_groups(const void* dys_bf16, const int8_t* q, const float* colsum, const float* W,
+                        const float* alpha, int alpha_mode, int rows2, int M, int N, int K, float* grad_W,
+                        float* grad_alpha, float* grad_bias, void* ws, size_t ws_bytes, ob_stream_t stream);
+
 /* Fused FFN mid-section (conformer.py:36-39): z = dropout(swish(h)) followed by the
  * activation quantiser of the next layer, in one pass.  h [M, K] fp32, K in {256, 512, 1024, 2048}; inv_keep = 1/(1-p).
  * The dropout mask (nn.Dropout of conformer.py:38) comes from one of two places:

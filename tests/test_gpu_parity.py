@@ -323,6 +323,87 @@ def test_backward_at_bench_token_counts(ob, M, rows2, K, N):
     assert math.isclose(layer.alpha.grad.item(), ga_ref, rel_tol=1e-2, abs_tol=1e-2 * g_hat_norm)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 256, 256), (4100, 1024, 256), (4100, 256, 1024), (1000, 320, 512), (2049, 576, 320),
+                                   (64, 256, 256), (25536, 1024, 256)])
+@pytest.mark.parametrize("bw", [1, 2])
+def test_grad_w_from_int8_codes_matches_bf16_copy(ob, M, N, K, bw):
+    """ob_bwd_dw_q8 (CTA pairs, int8 codes converted to bf16 in shared memory) against ob_bwd_dw on the bf16 copy of q made by the
+    prep kernel, and both against float64 of the same bf16 operands: the conversion is exact, so the only difference is the
+    fp32 summation order of the token splits."""
+    from onebit_b200 import _cabi
+    lib, check = _cabi.lib, _cabi.check
+    torch.manual_seed(M + N + K)
+    layer = ob.QuantizedLinear(K, N).cuda()
+    q, s = ob.act_quant_int8(torch.randn(M, K, device="cuda"))
+    g = torch.randn(M, N, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    dys = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    qb = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+    colsum = torch.empty(lib.ob_bwd_colsum_blocks(M), N, device="cuda")
+    check(lib.ob_bwd_prep(g.data_ptr(), 0, s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(), qb.data_ptr(), colsum.data_ptr(), st))
+    assert torch.equal(qb.float(), q.float())
+    nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
+    ws = torch.empty(nbytes, device="cuda", dtype=torch.uint8)
+    res = []
+    for fn, src in ((lib.ob_bwd_dw, qb), (lib.ob_bwd_dw_q8, q)):
+        gw = torch.full((N, K), float("nan"), device="cuda")
+        ga, gb = torch.empty((), device="cuda"), torch.empty(N, device="cuda")
+        check(fn(dys.data_ptr(), src.data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(), layer.alpha.data_ptr(), 1, bw, M, N, K,
+                 gw.data_ptr(), ga.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, st))
+        res.append((gw.cpu().double(), ga.item(), gb.cpu()))
+    (gw0, ga0, gb0), (gw1, ga1, gb1) = res
+    mask = (layer.weight.double() / (layer.alpha.abs().double() + 1e-8)).abs() <= 1.0
+    ref = ((dys.double().t() @ qb.double()) * mask).cpu()
+    scale = ref.abs().max().item()
+    assert not torch.isnan(gw1).any()
+    assert (gw1 - ref).abs().max().item() <= 2e-5 * scale
+    assert (gw0 - gw1).abs().max().item() <= 2e-5 * scale
+    assert torch.equal(gw0 != 0, gw1 != 0)
+    g_hat_norm = float(torch.linalg.norm(ref)) * 2 ** 0.5
+    assert math.isclose(ga0, ga1, rel_tol=1e-4, abs_tol=1e-5 * g_hat_norm)
+    assert torch.equal(gb0, gb1)
+
+
+@pytest.mark.parametrize("M,rows2,N,K", [(4100, 1500, 1024, 256), (4100, 4100, 256, 1024), (4100, 0, 256, 256), (2049, 1, 320, 512),
+                                         (76608, 25536 + 7 * 399, 256, 256), (1000, 999, 256, 256)])
+def test_grad_w_over_two_bitwidth_groups_in_one_launch(ob, M, rows2, N, K):
+    """ob_bwd_dw_q8_groups (one GEMM launch whose token splits stop at the 2-bit / 1-bit boundary + one finaliser) against the
+    sum of two single-group calls on the row ranges; grad_bias against the column sums of all rows."""
+    from onebit_b200 import _cabi
+    lib, check = _cabi.lib, _cabi.check
+    torch.manual_seed(M + rows2 + N)
+    layer = ob.QuantizedLinear(K, N).cuda()
+    q, s = ob.act_quant_int8(torch.randn(M, K, device="cuda"))
+    g = torch.randn(M, N, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    dys = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    colsum = torch.empty(lib.ob_bwd_colsum_blocks(M), N, device="cuda")
+    check(lib.ob_bwd_prep(g.data_ptr(), 0, s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(), None, colsum.data_ptr(), st))
+    nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
+    ws = torch.empty(nbytes, device="cuda", dtype=torch.uint8)
+    gw = torch.full((N, K), float("nan"), device="cuda")
+    ga, gb = torch.empty((), device="cuda"), torch.empty(N, device="cuda")
+    check(lib.ob_bwd_dw_q8_groups(dys.data_ptr(), q.data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(), layer.alpha.data_ptr(), 1,
+                                  rows2, M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, st))
+    gw_ref, ga_ref = torch.zeros(N, K, dtype=torch.float64), 0.0
+    for r0, r1, bw in ((0, rows2, 2), (rows2, M, 1)):
+        if r1 <= r0:
+            continue
+        gw_g, ga_g = torch.empty(N, K, device="cuda"), torch.empty((), device="cuda")
+        nb = lib.ob_bwd_dw_workspace_bytes(r1 - r0, N, K)
+        ws_g = torch.empty(nb, device="cuda", dtype=torch.uint8)
+        check(lib.ob_bwd_dw_q8(dys.data_ptr() + 2 * r0 * N, q.data_ptr() + r0 * K, None, layer.weight.data_ptr(), layer.alpha.data_ptr(),
+                               1, bw, r1 - r0, N, K, gw_g.data_ptr(), ga_g.data_ptr(), None, ws_g.data_ptr(), nb, st))
+        gw_ref += gw_g.cpu().double()
+        ga_ref += ga_g.item()
+    scale = gw_ref.abs().max().item()
+    assert not torch.isnan(gw).any()
+    assert (gw.cpu().double() - gw_ref).abs().max().item() <= 2e-5 * scale
+    assert torch.equal(gw.cpu() != 0, gw_ref != 0)
+    assert math.isclose(ga.item(), ga_ref, rel_tol=1e-4, abs_tol=1e-5 * float(torch.linalg.norm(gw_ref)))
+    assert rel_err(gb.cpu().numpy(), g.double().sum(0).cpu().numpy()) < 1e-5
+
+
 def test_size_independent_properties_at_bench_size(ob):
     """BASELINE config sizes (M = 65536 tokens, 2048 x 2048): linearity in the activation scale and a
     checksum identity  sum_n y[m,n] = (q[m,:] . colsum(Q)) * alpha/s[m] + sum(b)  instead of a CPU re-run."""

@@ -33,14 +33,14 @@ def graph_time(fn, n=20):
     return e0.elapsed_time(e1) / 3 / n * 1e3
 
 
-for (M, K, N, odt) in [(25536, 256, 1024, torch.float32)]:
+for (M, K, N, odt) in [(25536, 256, 1024, torch.float32), (76608, 256, 1024, torch.float32), (76608, 1024, 256, torch.float32), (76608, 256, 256, torch.float32)]:
     torch.manual_seed(0)
     layer = ob.QuantizedLinear(K, N).cuda()
     pk, _ = layer.packed_weight(2)
     q, s = ob.act_quant_int8(torch.randn(M, K, device="cuda"))
     for bn in (0,):
         lib.ob_debug_set(_cabi.DBG_FORCE_BLOCK_N, bn)
-        for flags, name in [(0, "full"), (1, "no TMA store"), (8, "no fence"), (16, "no wait_read"), (24, "no fence, no wait"), (25, "no fence/wait/store"), (3, "no math no store")]:
+        for flags, name in [(0, "full"), (1, "no TMA store"), (8, "no fence"), (16, "no wait_read"), (24, "no fence, no wait"), (25, "no fence/wait/store"), (2, "no math"), (3, "no math no store"), (4, "no expansion"), (7, "no expansion no epilogue")]:
             lib.ob_debug_set(5, flags)
             t = graph_time(lambda: obq.gemm_fwd(q, s, pk, layer.alpha, layer.bias, N, odt))
             print(f"M={M} K={K} N={N} {str(odt)[6:]} bn={bn} {name:30s}: {t:7.1f} us", flush=True)
