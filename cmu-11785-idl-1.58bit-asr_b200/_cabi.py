@@ -99,6 +99,8 @@ def _load():
 
 
 lib = _load()
+if os.environ.get("OB_PDL", "1") == "0":       # A/B switch: launch every kernel fully serialised (no programmatic dependent launch)
+    lib.ob_debug_set(13, 0)
 
 
 def last_error() -> str:

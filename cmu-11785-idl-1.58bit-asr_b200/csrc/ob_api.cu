@@ -12,6 +12,10 @@ static std::atomic<long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static int g_pdl = 1;
+int pdl_enabled() { return g_pdl; }
+void set_pdl(int on) { g_pdl = on != 0; }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_fwd_kernel(const float
                                                                   const uint8_t* __restrict__ keep /* [B,H,T,T] | null */,
                                                                   float inv_keep, DropRng rng, float scale, int B, int H, int T, int ld,
                                                                   float* __restrict__ y, float* __restrict__ attn_d) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * T;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256, 3) relattn_softmax_bwd_kernel(const float
                                                                   const uint8_t* __restrict__ keep, float inv_keep,
                                                                   DropRng rng, float scale, int B, int H, int T, int ld,
                                                                   float* __restrict__ d_ac, float* __restrict__ d_bd) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * T;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -176,11 +178,11 @@ static int attn_blocks(int64_t rows) {
 #define OB_ATTN_DISPATCH(KERNEL, ...)                                         \
   do {                                                                        \
     const int nj = (T + 31) / 32;                                             \
-    if (nj <= 8) KERNEL<8><<<blocks, 256, 0, st>>>(__VA_ARGS__);              \
-    else if (nj <= 13) KERNEL<13><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
-    else if (nj <= 16) KERNEL<16><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
-    else if (nj <= 32) KERNEL<32><<<blocks, 256, 0, st>>>(__VA_ARGS__);       \
-    else KERNEL<64><<<blocks, 256, 0, st>>>(__VA_ARGS__);                     \
+    if (nj <= 8) launch_k((KERNEL<8>), dim3(blocks), dim3(256), 0, st, __VA_ARGS__);              \
+    else if (nj <= 13) launch_k((KERNEL<13>), dim3(blocks), dim3(256), 0, st, __VA_ARGS__);       \
+    else if (nj <= 16) launch_k((KERNEL<16>), dim3(blocks), dim3(256), 0, st, __VA_ARGS__);       \
+    else if (nj <= 32) launch_k((KERNEL<32>), dim3(blocks), dim3(256), 0, st, __VA_ARGS__);       \
+    else launch_k((KERNEL<64>), dim3(blocks), dim3(256), 0, st, __VA_ARGS__);                     \
   } while (0)
 
 extern "C" int ob_relattn_softmax_fwd(const float* ac, const float* bd, const uint8_t* mask, const uint8_t* keep,

@@ -19,6 +19,33 @@ void set_error(const char* fmt, ...);
 int check_device();   // OB_OK when the current device is sm_100
 void count_launch();  // bumps the library-wide kernel launch counter (ob_launch_count)
 int sm_count();       // SMs of the current device (ob_debug_set can cap it)
+int pdl_enabled();    // 1: kernels are launched with programmatic stream serialization (ob_debug_set key 13 turns it off)
+void set_pdl(int on);
+
+// Every kernel of the library goes through this launcher.  With programmatic dependent launch the grid may be scheduled
+// while the previous kernel of the stream is still draining: its blocks run up to their griddepcontrol.wait (pdl_entry /
+// pdl_wait, executed before the first access to global memory) and continue once the predecessor has completed and its
+// writes are visible, so the launch latency and the block prologues overlap the predecessor's tail.
+static inline cudaLaunchAttribute pdl_attribute() {
+  cudaLaunchAttribute a;
+  a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a.val.programmaticStreamSerializationAllowed = pdl_enabled();
+  return a;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // cuTensorMapEncodeTiled resolved at run time (no link-time dependency on libcuda); nullptr when unavailable
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -223,6 +250,15 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: block until the preceding kernel of the stream has completed (no-op without the launch
+// attribute); then let the NEXT kernel's blocks be scheduled as soon as resources free up
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -406,6 +442,27 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem], fp32 operands read as tf32: A = 128 lanes (rows) x 8 consecutive 32-bit columns (K-major)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // ---- thread-block cluster / CTA-pair (cta_group::2) variants ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {

@@ -83,6 +83,7 @@ __device__ __forceinline__ void load_plain_tile(const float* __restrict__ x, int
 __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w,
                                                              const float* __restrict__ bias, int B, int T, int C, int ks,
                                                              float* __restrict__ d, float* __restrict__ part) {
+  pdl_entry();
   __shared__ __align__(16) float tile[kCvRows * kCvC];
   __shared__ float red[4][kCvC];
   const int tblocks = (T + kCvT - 1) / kCvT;
@@ -138,6 +139,7 @@ constexpr int kFinGroups = 16;
 __global__ void __launch_bounds__(64 * kFinGroups) bn_stats_finalize_kernel(const float* __restrict__ part, int B, int T, int C,
                                                                           float eps, float* __restrict__ mean,
                                                                           float* __restrict__ rstd) {
+  pdl_entry();
   // total M2 = sum_tiles [ M2_tile + n_tile * (mean_tile - mean)^2 ]  (the pairwise Chan update, summed in closed form)
   __shared__ double sh[kFinGroups][64];
   const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(256) bn_swish_fwd_kernel(const float* __restri
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, int64_t n4, int C4,
                                                            float* __restrict__ s) {
+  pdl_entry();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * 256) {
     const int c4 = static_cast<int>(i % C4);
     const float4 x = __ldg(reinterpret_cast<const float4*>(d) + i);
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_reduce_kernel(const float* _
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   int64_t M, int C, float* __restrict__ part) {
+  pdl_entry();
   // a thread owns 4 channels (128-bit loads) of every 16th row of the block; fixed-order fold over the 16 row groups
   __shared__ float4 red[2][16][16];
   const int c4 = threadIdx.x & 15, rg = threadIdx.x >> 4;
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_reduce_kernel(const float* _
 // sums[0][c] = sum g_y (= g_beta), sums[1][c] = sum g_y * xhat (= g_gamma).  grid: 2C / 64 blocks of 1024 threads
 __global__ void __launch_bounds__(64 * kFinGroups) bn_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int C,
                                                                         float* __restrict__ sums) {
+  pdl_entry();
   __shared__ double sh[kFinGroups][64];
   const int item = blockIdx.x * 64 + (threadIdx.x & 63);
   const double acc = grouped_block_sum(part, nblocks, 2 * static_cast<int64_t>(C), item, sh);
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  const float* __restrict__ sums, float inv_m, int64_t n4, int C4,
                                                                  float* __restrict__ gd) {
+  pdl_entry();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * 256) {
     const int c4 = static_cast<int>(i % C4);
     const float4 x = __ldg(reinterpret_cast<const float4*>(d) + i), g = __ldg(reinterpret_cast<const float4*>(gs) + i);
@@ -296,6 +302,7 @@ constexpr int kCvBwdSmemBytes = (kCvRows * kCvC + 2 * kCvT * kCvC) * 4;
 __global__ void __launch_bounds__(256) dwconv_bwd_data_glu_kernel(const float* __restrict__ gd, const float* __restrict__ a,
                                                                   const float* __restrict__ w, int B, int T, int C, int ks,
                                                                   float* __restrict__ ga) {
+  pdl_entry();
   extern __shared__ __align__(16) float cv_smem[];
   float* tile = cv_smem;                              // [94][64] g_d with halo
   float* a_tile = cv_smem + kCvRows * kCvC;           // [2][64][64]: a1 (values), a2 (gates)
@@ -347,6 +354,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_data_glu_kernel(const float* _
 // part: [B * tblocks][32][C], slot 31 = bias.  grid: x = b * tblocks + tb, y = channel tile.
 __global__ void __launch_bounds__(256) dwconv_bwd_weight_kernel(const float* __restrict__ gd, const float* __restrict__ a, int B,
                                                                 int T, int C, float* __restrict__ part) {
+  pdl_entry();
   __shared__ __align__(16) float buf[4 * 32 * kCvC];               // the GLU tile (94 x 64) first, then the cross-group reduction
   const int tblocks = (T + kCvT - 1) / kCvT;
   const int b = blockIdx.x / tblocks, tb = blockIdx.x % tblocks;
@@ -387,6 +395,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_weight_kernel(const float* __r
 __global__ void __launch_bounds__(64 * kFinGroups) dwconv_bwd_weight_finalize_kernel(const float* __restrict__ part, int nblocks,
                                                                                    int C, int ks, float* __restrict__ gw,
                                                                                    float* __restrict__ gbias) {
+  pdl_entry();
   __shared__ double sh[kFinGroups][64];
   const int item = blockIdx.x * 64 + (threadIdx.x & 63);      // slot * C + c
   const double acc = grouped_block_sum(part, nblocks, 32 * static_cast<int64_t>(C), item, sh);
@@ -405,6 +414,7 @@ __global__ void __launch_bounds__(64 * kFinGroups) dwconv_bwd_weight_finalize_ke
 __global__ void __launch_bounds__(256) add_bias2_kernel(const float* __restrict__ q, const float* __restrict__ u,
                                                         const float* __restrict__ w, int64_t n4, int W4, float* __restrict__ qu,
                                                         float* __restrict__ qw) {
+  pdl_entry();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * 256) {
     const int c4 = static_cast<int>(i % W4);
     const float4 x = __ldg(reinterpret_cast<const float4*>(q) + i);
@@ -417,6 +427,7 @@ __global__ void __launch_bounds__(256) add_bias2_kernel(const float* __restrict_
 // g = ga + gb; part[blk][0][c] = sum of ga, part[blk][1][c] = sum of gb over the block's rows
 __global__ void __launch_bounds__(256) add_colsum2_kernel(const float* __restrict__ ga, const float* __restrict__ gb, int64_t M,
                                                           int W, float* __restrict__ g, float* __restrict__ part) {
+  pdl_entry();
   __shared__ float red[2][4][kCvC];
   const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int cc = blockIdx.y * kCvC + c;
@@ -444,6 +455,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256) residual_dropout_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                                const float* __restrict__ rowmask, float scale, float inv_keep,
                                                                DropRng rng, int64_t n8, int C8, float* __restrict__ out) {
+  pdl_entry();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
     const float rm = rowmask != nullptr ? __ldg(rowmask + i / C8) : 1.0f;
     const uint32_t kb = rng.threshold != 0u ? philox_keep8(static_cast<unsigned long long>(i), rng) : 0xFFu;
@@ -499,11 +511,11 @@ extern "C" int ob_glu_dwconv_bn_fwd(const float* a, const float* w, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* part = static_cast<float*>(ws);
   dim3 grid(B * conv_tblocks(T), C / kCvC);
-  glu_dwconv_fwd_kernel<<<grid, 256, 0, st>>>(a, w, bias, B, T, C, ks, d, part);
+  launch_k((glu_dwconv_fwd_kernel), dim3(grid), dim3(256), 0, st, a, w, bias, B, T, C, ks, d, part);
   OB_LAUNCH_CHECK("glu_dwconv_fwd_kernel");
   const int Bg = B / groups;
   for (int g = 0; g < groups; ++g) {                     // mean, rstd: [groups][C]
-    bn_stats_finalize_kernel<<<C / 64, 64 * kFinGroups, 0, st>>>(part + static_cast<size_t>(g) * Bg * conv_tblocks(T) * 2 * C, Bg, T,
+    launch_k((bn_stats_finalize_kernel), dim3(C / 64), dim3(64 * kFinGroups), 0, st, part + static_cast<size_t>(g) * Bg * conv_tblocks(T) * 2 * C, Bg, T,
                                                                C, eps, mean + g * C, rstd + g * C);
     OB_LAUNCH_CHECK("bn_stats_finalize_kernel");
   }
@@ -517,7 +529,7 @@ extern "C" int ob_bn_swish_fwd(const float* d, const float* mean, const float* r
   OB_REQUIRE(groups >= 1 && M % groups == 0, "ob_bn_swish_fwd: M must be a multiple of groups (%d)", groups);
   const int64_t Mg = M / groups, n4 = Mg * C / 4;
   for (int g = 0; g < groups; ++g) {
-    bn_swish_fwd_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(d + g * Mg * C, mean + g * C, rstd + g * C,
+    launch_k((bn_swish_fwd_kernel), dim3(ew_blocks(n4)), dim3(256), 0, static_cast<cudaStream_t>(stream), d + g * Mg * C, mean + g * C, rstd + g * C,
                                                                                       gamma, beta, n4, C / 4, s + g * Mg * C);
     OB_LAUNCH_CHECK("bn_swish_fwd_kernel");
   }
@@ -539,11 +551,11 @@ extern "C" int ob_bn_swish_bwd(const float* gs, const float* d, const float* mea
   for (int g = 0; g < groups; ++g) {
     const float *gs_g = gs + g * Mg * C, *d_g = d + g * Mg * C, *mean_g = mean + g * C, *rstd_g = rstd + g * C;
     float* sums_g = g_gamma_beta + static_cast<size_t>(g) * 2 * C;
-    bn_swish_bwd_reduce_kernel<<<dim3(rblocks, C / kCvC), 256, 0, st>>>(gs_g, d_g, mean_g, rstd_g, gamma, beta, Mg, C, part);
+    launch_k((bn_swish_bwd_reduce_kernel), dim3(dim3(rblocks, C / kCvC)), dim3(256), 0, st, gs_g, d_g, mean_g, rstd_g, gamma, beta, Mg, C, part);
     OB_LAUNCH_CHECK("bn_swish_bwd_reduce_kernel");
-    bn_bwd_finalize_kernel<<<2 * C / 64, 64 * kFinGroups, 0, st>>>(part, rblocks, C, sums_g);
+    launch_k((bn_bwd_finalize_kernel), dim3(2 * C / 64), dim3(64 * kFinGroups), 0, st, part, rblocks, C, sums_g);
     OB_LAUNCH_CHECK("bn_bwd_finalize_kernel");
-    bn_swish_bwd_apply_kernel<<<ew_blocks(n4), 256, 0, st>>>(gs_g, d_g, mean_g, rstd_g, gamma, beta, sums_g,
+    launch_k((bn_swish_bwd_apply_kernel), dim3(ew_blocks(n4)), dim3(256), 0, st, gs_g, d_g, mean_g, rstd_g, gamma, beta, sums_g,
                                                             1.0f / static_cast<float>(Mg), n4, C / 4, gd + g * Mg * C);
     OB_LAUNCH_CHECK("bn_swish_bwd_apply_kernel");
   }
@@ -562,11 +574,11 @@ extern "C" int ob_glu_dwconv_bwd(const float* gd, const float* a, const float* w
     OB_CUDA(cudaFuncSetAttribute(dwconv_bwd_data_glu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvBwdSmemBytes));
     attr_set = true;
   }
-  dwconv_bwd_data_glu_kernel<<<grid, 256, kCvBwdSmemBytes, st>>>(gd, a, w, B, T, C, ks, ga);
+  launch_k((dwconv_bwd_data_glu_kernel), dim3(grid), dim3(256), kCvBwdSmemBytes, st, gd, a, w, B, T, C, ks, ga);
   OB_LAUNCH_CHECK("dwconv_bwd_data_glu_kernel");
-  dwconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(gd, a, B, T, C, part);
+  launch_k((dwconv_bwd_weight_kernel), dim3(grid), dim3(256), 0, st, gd, a, B, T, C, part);
   OB_LAUNCH_CHECK("dwconv_bwd_weight_kernel");
-  dwconv_bwd_weight_finalize_kernel<<<32 * C / 64, 64 * kFinGroups, 0, st>>>(part, B * conv_tblocks(T), C, ks, gw, gbias);
+  launch_k((dwconv_bwd_weight_finalize_kernel), dim3(32 * C / 64), dim3(64 * kFinGroups), 0, st, part, B * conv_tblocks(T), C, ks, gw, gbias);
   OB_LAUNCH_CHECK("dwconv_bwd_weight_finalize_kernel");
   return OB_OK;
 }
@@ -576,7 +588,7 @@ extern "C" int ob_add_bias2(const float* q, const float* u, const float* w, int6
   OB_REQUIRE(q && u && w && qu && qw, "ob_add_bias2: null pointer");
   OB_REQUIRE(M > 0 && W > 0 && W % 4 == 0, "ob_add_bias2: need M > 0 and W a positive multiple of 4 (W=%d)", W);
   const int64_t n4 = M * W / 4;
-  add_bias2_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, u, w, n4, W / 4, qu, qw);
+  launch_k((add_bias2_kernel), dim3(ew_blocks(n4)), dim3(256), 0, static_cast<cudaStream_t>(stream), q, u, w, n4, W / 4, qu, qw);
   OB_LAUNCH_CHECK("add_bias2_kernel");
   return OB_OK;
 }
@@ -593,9 +605,9 @@ extern "C" int ob_add_colsum2(const float* ga, const float* gb, int64_t M, int W
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* part = static_cast<float*>(ws);
   const int rblocks = static_cast<int>((M + kBnRows - 1) / kBnRows);
-  add_colsum2_kernel<<<dim3(rblocks, W / kCvC), 256, 0, st>>>(ga, gb, M, W, g, part);
+  launch_k((add_colsum2_kernel), dim3(dim3(rblocks, W / kCvC)), dim3(256), 0, st, ga, gb, M, W, g, part);
   OB_LAUNCH_CHECK("add_colsum2_kernel");
-  bn_bwd_finalize_kernel<<<2 * W / 64, 64 * kFinGroups, 0, st>>>(part, rblocks, W, sums);   // sums[0] = colsum(ga), [1] = colsum(gb)
+  launch_k((bn_bwd_finalize_kernel), dim3(2 * W / 64), dim3(64 * kFinGroups), 0, st, part, rblocks, W, sums);   // sums[0] = colsum(ga), [1] = colsum(gb)
   OB_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   return OB_OK;
 }
@@ -608,7 +620,7 @@ extern "C" int ob_residual_dropout_fwd(const float* x, const float* y, const flo
   OB_REQUIRE(drop_threshold < 65536u, "ob_residual_dropout_fwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
   const DropRng rng = {seed, offset, drop_threshold};
   const int64_t n8 = M * C / 8;
-  residual_dropout_kernel<false><<<ew_blocks(n8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rowmask, scale, inv_keep, rng,
+  launch_k((residual_dropout_kernel<false>), dim3(ew_blocks(n8)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, y, rowmask, scale, inv_keep, rng,
                                                                                                 n8, C / 8, out);
   OB_LAUNCH_CHECK("residual_dropout_kernel");
   return OB_OK;
@@ -622,7 +634,7 @@ extern "C" int ob_residual_dropout_bwd(const float* g, const float* rowmask, flo
   OB_REQUIRE(drop_threshold < 65536u, "ob_residual_dropout_bwd: drop_threshold (%u) is a 16-bit value", drop_threshold);
   const DropRng rng = {seed, offset, drop_threshold};
   const int64_t n8 = M * C / 8;
-  residual_dropout_kernel<true><<<ew_blocks(n8), 256, 0, static_cast<cudaStream_t>(stream)>>>(nullptr, g, rowmask, scale, inv_keep,
+  launch_k((residual_dropout_kernel<true>), dim3(ew_blocks(n8)), dim3(256), 0, static_cast<cudaStream_t>(stream), nullptr, g, rowmask, scale, inv_keep,
                                                                                                rng, n8, C / 8, gy);
   OB_LAUNCH_CHECK("residual_dropout_kernel");
   return OB_OK;

@@ -42,6 +42,7 @@ __device__ __forceinline__ void lse_combine(float& m, float& s, float om, float 
 __global__ void __launch_bounds__(kCtcRowThreads)
 ctc_row_lse_kernel(const float* __restrict__ x, int64_t ld, const int64_t* __restrict__ in_lens, int Tn, int V,
                    float* __restrict__ lse) {
+  pdl_entry();
   const int64_t row = blockIdx.x;
   const int b = static_cast<int>(row / Tn), t = static_cast<int>(row % Tn);
   if (t >= in_lens[b]) {                                   // padded frame: never read
@@ -84,6 +85,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ x, int64_t ld, c
                                       int64_t tgt_ld, const int64_t* __restrict__ tgt_lens, int B, int Tn, int V, int Lmax,
                                       int blank, int Sp, float* __restrict__ alpha, float* __restrict__ beta,
                                       float* __restrict__ nll) {
+  pdl_entry();
   extern __shared__ float sh[];
   const bool backward = blockIdx.x >= B;
   const int b = backward ? blockIdx.x - B : blockIdx.x;
@@ -176,6 +178,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ x, int64_t ld, c
 // loss = (1/B) sum_b (isinf(nll_b) ? 0 : nll_b / max(L_b, 1)); one warp, fixed order
 __global__ void __launch_bounds__(32)
 ctc_mean_kernel(const float* __restrict__ nll, const int64_t* __restrict__ tgt_lens, int B, int Lmax, float* __restrict__ loss) {
+  pdl_entry();
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += 32) {
     const float v = nll[b];
@@ -193,6 +196,7 @@ ctc_grad_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict
                 const int64_t* __restrict__ targets, int64_t tgt_ld, const int64_t* __restrict__ tgt_lens, int B, int Tn,
                 int V, int Lmax, int blank, int Sp, const float* __restrict__ alpha, const float* __restrict__ beta,
                 const float* __restrict__ nll, const float* __restrict__ grad_out, float* __restrict__ dx, int64_t ldg) {
+  pdl_entry();
   extern __shared__ float sh[];
   float* occ = sh;                                         // [Sp]
   int* lab = reinterpret_cast<int*>(sh + Sp);              // [Lmax]
@@ -283,14 +287,14 @@ extern "C" int ob_ctc_loss_fwd(const float* logits, int64_t ld, const int64_t* i
   if (rc != OB_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Sp = ob_ctc_state_pitch(Lmax);
-  ctc_row_lse_kernel<<<B * T, kCtcRowThreads, 0, st>>>(logits, ld, in_lens, T, V, lse);
+  launch_k((ctc_row_lse_kernel), dim3(B * T), dim3(kCtcRowThreads), 0, st, logits, ld, in_lens, T, V, lse);
   OB_LAUNCH_CHECK("ctc_row_lse_kernel");
   const int threads = ctc_block_threads(Lmax);
   const size_t smem = 2 * static_cast<size_t>(threads + 4) * sizeof(float);
-  ctc_alpha_beta_kernel<<<2 * B, threads, smem, st>>>(logits, ld, lse, in_lens, targets, tgt_ld, tgt_lens, B, T, V, Lmax, blank,
+  launch_k((ctc_alpha_beta_kernel), dim3(2 * B), dim3(threads), smem, st, logits, ld, lse, in_lens, targets, tgt_ld, tgt_lens, B, T, V, Lmax, blank,
                                                       Sp, alpha, beta, nll);
   OB_LAUNCH_CHECK("ctc_alpha_beta_kernel");
-  ctc_mean_kernel<<<1, 32, 0, st>>>(nll, tgt_lens, B, Lmax, loss);
+  launch_k((ctc_mean_kernel), dim3(1), dim3(32), 0, st, nll, tgt_lens, B, Lmax, loss);
   OB_LAUNCH_CHECK("ctc_mean_kernel");
   return OB_OK;
 }
@@ -309,7 +313,7 @@ extern "C" int ob_ctc_loss_bwd(const float* logits, int64_t ld, const int64_t* i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Sp = ob_ctc_state_pitch(Lmax);
   const size_t smem = static_cast<size_t>(Sp) * sizeof(float) + static_cast<size_t>(Lmax > 0 ? Lmax : 1) * sizeof(int);
-  ctc_grad_kernel<<<B * T, kCtcRowThreads, smem, st>>>(logits, ld, lse, in_lens, targets, tgt_ld, tgt_lens, B, T, V, Lmax, blank,
+  launch_k((ctc_grad_kernel), dim3(B * T), dim3(kCtcRowThreads), smem, st, logits, ld, lse, in_lens, targets, tgt_ld, tgt_lens, B, T, V, Lmax, blank,
                                                        Sp, alpha, beta, nll, grad_out, grad_logits, ldg);
   OB_LAUNCH_CHECK("ctc_grad_kernel");
   return OB_OK;

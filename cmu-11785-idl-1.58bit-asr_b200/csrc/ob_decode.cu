@@ -21,6 +21,7 @@ __device__ __forceinline__ void take(float v, int i, float& best, int& bi) {
 template <typename T>
 __global__ void __launch_bounds__(256) frame_argmax_kernel(const T* __restrict__ logits, int B, int Tn, int V,
                                                            const int32_t* __restrict__ lens, int32_t* __restrict__ pred) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) frame_argmax_kernel(const T* __restrict__
 __global__ void __launch_bounds__(256) ctc_collapse_kernel(const int32_t* __restrict__ pred, int Tn,
                                                            const int32_t* __restrict__ lens, int blank_id,
                                                            int32_t* __restrict__ out_tokens, int32_t* __restrict__ out_lens) {
+  pdl_entry();
   __shared__ int warp_cnt[8];
   __shared__ int base_s;
   const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -115,13 +117,13 @@ extern "C" int ob_ctc_greedy_decode(const void* logits, int dtype, int B, int T,
   const int64_t want = (frames + 7) / 8;
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
   if (dtype == OB_F32)
-    frame_argmax_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(logits), B, T, V, lens, pred);
+    launch_k((frame_argmax_kernel<float>), dim3(blocks), dim3(256), 0, st, static_cast<const float*>(logits), B, T, V, lens, pred);
   else if (dtype == OB_BF16)
-    frame_argmax_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), B, T, V, lens, pred);
+    launch_k((frame_argmax_kernel<__nv_bfloat16>), dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(logits), B, T, V, lens, pred);
   else
     OB_REQUIRE(false, "ob_ctc_greedy_decode: unknown dtype tag %d", dtype);
   OB_LAUNCH_CHECK("frame_argmax_kernel");
-  ctc_collapse_kernel<<<B, 256, 0, st>>>(pred, T, lens, blank_id, out_tokens, out_lens);
+  launch_k((ctc_collapse_kernel), dim3(B), dim3(256), 0, st, pred, T, lens, blank_id, out_tokens, out_lens);
   OB_LAUNCH_CHECK("ctc_collapse_kernel");
   return OB_OK;
 }

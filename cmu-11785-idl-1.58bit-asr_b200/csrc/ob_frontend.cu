@@ -43,6 +43,7 @@ __device__ __forceinline__ void conv1_load_inputs(const float* __restrict__ x, i
 __global__ void __launch_bounds__(256) conv1_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, int B, int T, int F, int T1, int F1,
                                                              float* __restrict__ y) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   float wr[9][kC1Lane], br[kC1Lane];
   conv1_load_params(w, bias, lane, wr, br);
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256) conv1_relu_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) conv1_relu_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
                                                              const float* __restrict__ w, const float* __restrict__ bias, int B,
                                                              int T, int F, int T1, int F1, float* __restrict__ part) {
+  pdl_entry();
   __shared__ float red[10][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float wr[9][kC1Lane], br[kC1Lane];
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(256) conv1_relu_bwd_kernel(const float* __rest
 // gw[c][tap], gb[c] = sums of the block partials, fp64, fixed order.  grid: 2560 / 64 blocks of 1024 threads
 __global__ void __launch_bounds__(1024) conv1_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, float* __restrict__ gw,
                                                                   float* __restrict__ gb) {
+  pdl_entry();
   __shared__ double sh[16][64];
   const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int item = blockIdx.x * 64 + cl;                      // tap * 256 + c
@@ -165,7 +168,7 @@ extern "C" int ob_conv1_relu_fwd(const float* x, const float* w, const float* bi
   const int64_t warps = static_cast<int64_t>(B) * T1 * F1;
   const int64_t want = (warps + 7) / 8;
   const int blocks = static_cast<int>(want < kC1Blocks ? want : kC1Blocks);
-  conv1_relu_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, B, T, F, T1, F1, y);
+  launch_k((conv1_relu_fwd_kernel), dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), x, w, bias, B, T, F, T1, F1, y);
   OB_LAUNCH_CHECK("conv1_relu_fwd_kernel");
   return OB_OK;
 }
@@ -180,9 +183,9 @@ extern "C" int ob_conv1_relu_bwd(const float* g, const float* x, const float* w,
   const int64_t warps = static_cast<int64_t>(B) * T1 * F1;
   const int64_t want = (warps + 7) / 8;
   const int blocks = static_cast<int>(want < kC1Blocks ? want : kC1Blocks);
-  conv1_relu_bwd_kernel<<<blocks, 256, 0, st>>>(g, x, w, bias, B, T, F, T1, F1, part);
+  launch_k((conv1_relu_bwd_kernel), dim3(blocks), dim3(256), 0, st, g, x, w, bias, B, T, F, T1, F1, part);
   OB_LAUNCH_CHECK("conv1_relu_bwd_kernel");
-  conv1_bwd_finalize_kernel<<<2560 / 64, 1024, 0, st>>>(part, blocks, gw, gb);
+  launch_k((conv1_bwd_finalize_kernel), dim3(2560 / 64), dim3(1024), 0, st, part, blocks, gw, gb);
   OB_LAUNCH_CHECK("conv1_bwd_finalize_kernel");
   return OB_OK;
 }

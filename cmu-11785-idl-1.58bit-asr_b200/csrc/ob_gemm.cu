@@ -28,7 +28,7 @@ int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, co
 // debug / tuning knobs (ob_debug_set)
 // ---------------------------------------------------------------------------------------------
 enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5,
-                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9 };
+                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9, kDbgF32Atm = 11, kDbgF32Promo = 12, kDbgPdl = 13 };
 int small_m_limit(int K);              // ob_gemv.cu
 int small_m_capacity(int K);
 int launch_gemv_tern_i8(const int8_t* q, const float* scale, const uint8_t* packed, const float* alpha, int alpha_mode,
@@ -37,6 +37,8 @@ static int g_dbg_small_m = 0;          // 0: small M takes the DP4A kernel where
 void f32_gemm_debug(int split_mode);   // ob_gemm_f32.cu
 void f32_gemm_debug_epilogue(int mode);
 void f32_gemm_debug_pair(int on);
+void f32_gemm_debug_atm(int on);
+void f32_gemm_debug_promo(int v);
 static int g_dbg_kernel_flags = 0;   // bit0 skip TMA stores, bit1 skip epilogue math/STS, bit2 skip expansion (timing experiments)
 static int g_dbg_swap_lbo_sbo = 0;
 static int g_dbg_force_block_n = 0;
@@ -210,6 +212,7 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_entry();       // everything above touched no global memory: it overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -566,6 +569,7 @@ dw_kernel(const __grid_constant__ CUtensorMap map_dys, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_entry();       // everything above touched no global memory: it overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -742,6 +746,7 @@ dw_pair_kernel(const __grid_constant__ CUtensorMap map_dys_a, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_entry();       // everything above touched no global memory: it overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -881,13 +886,14 @@ static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_b
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = L::kDynBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1] = pdl_attribute();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC,
                              g_dbg_kernel_flags, tail));
   count_launch();
@@ -1005,13 +1011,14 @@ static int launch_dw_pair(const CUtensorMap& map_dys_a, const CUtensorMap& map_q
   cfg.blockDim = dim3(kDw2Threads);
   cfg.dynamicSmemBytes = L::kDynBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1] = pdl_attribute();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_dys_a, map_q_a, map_dys_b, map_q_b, partials, rows_a, M - rows_a, p.splits_a, N,
                              K, p.tb_per_split));
   count_launch();
@@ -1033,7 +1040,7 @@ static int launch_dw(const CUtensorMap& map_dys, const CUtensorMap& map_qb, floa
   uint32_t lbo = kDwAtomBytes, sbo = 1024;
   if (g_dbg_swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
   dim3 grid(p.n_tiles * p.k_tiles, p.splits);
-  kern<<<grid, kDwThreads, L::kDynBytes, st>>>(map_dys, map_qb, partials, M, N, K, p.tb_per_split, lbo, sbo);
+  launch_k((kern), dim3(grid), dim3(kDwThreads), L::kDynBytes, st, map_dys, map_qb, partials, M, N, K, p.tb_per_split, lbo, sbo);
   OB_LAUNCH_CHECK("dw_kernel");
   return OB_OK;
 }
@@ -1056,6 +1063,9 @@ extern "C" int ob_debug_set(int key, int value) {
     case kDbgF32Epilogue: f32_gemm_debug_epilogue(value); return OB_OK;
     case kDbgF32Pair: f32_gemm_debug_pair(value); return OB_OK;
     case kDbgSmallM: g_dbg_small_m = value; return OB_OK;
+    case kDbgF32Atm: f32_gemm_debug_atm(value); return OB_OK;
+    case kDbgF32Promo: f32_gemm_debug_promo(value); return OB_OK;
+    case kDbgPdl: set_pdl(value); return OB_OK;
     default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;
   }
 }

@@ -34,18 +34,30 @@ constexpr int kFStageOutBytes = 32 * 128;          // one epilogue chunk: 32 row
 // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a [256 x BLOCK_N] tile.  Each CTA loads and splits its own
 // 128 rows of A and its own half (BLOCK_N / 2 rows) of B, so per output element the splitter traffic and the tensor
 // core's operand reads of B are halved - the shared-memory pipe is what limits the deep shapes.
-template <int BLOCK_N, int STAGES, int PASSES, int CTAS = 1>
+// ATM = 1 ("A through TMEM", single CTA, PASSES = 3): the splitter warps read the raw A tile from shared memory once and
+// write its hi / lo parts into tensor memory (128 lanes = rows, 32 + 32 columns per stage); the MMAs take A from TMEM, so the
+// three passes of a k-step no longer read A from shared memory and no lo copy of A is written there.  This is what binds
+// the attention products (a [T x T] operand streamed against a 64-wide one): 144 KB -> 80 KB of shared-memory traffic per
+// k-block.  The A tile needs no UMMA layout any more: a transposed (MN-major) A is read from un-swizzled [32 k][32 m] boxes.
+template <int BLOCK_N, int STAGES, int PASSES, int CTAS = 1, int ATM = 0>
 struct F32Smem {
   static constexpr int kRowsB = BLOCK_N / CTAS;                        // B rows held by this CTA
   static constexpr int kBTileBytes = kRowsB * 128;
   static constexpr int kHiBytes = kFATileBytes + kBTileBytes;          // [A_hi | B_hi], then [A_lo | B_lo] behind it
-  static constexpr int kStageBytes = (PASSES == 3 ? 2 : 1) * kHiBytes;
-  static constexpr int kOffOut = STAGES * kStageBytes;                 // 8 epilogue warps x 4 KB
+  // ATM: a stage of the (deep) raw ring is just the TMA-written [A | B]; what the splitters produce - A hi / lo in tensor
+  // memory, B lo in shared memory - lives in a short second ring of kProc stages, so that the bytes in flight from HBM / L2
+  // are not limited by the space the split copies take (these products are bound by exactly that latency x depth).
+  static constexpr int kProc = ATM ? (BLOCK_N <= 64 ? 3 : 2) : 0;
+  static constexpr int kStageBytes = ATM ? kHiBytes : (PASSES == 3 ? 2 : 1) * kHiBytes;
+  static constexpr int kOffBLo = kHiBytes + kFATileBytes;              // B_lo within a stage (not ATM)
+  static constexpr int kOffBLoRing = STAGES * kStageBytes;             // ATM: kProc x B_lo
+  static constexpr int kOffOut = kOffBLoRing + kProc * kBTileBytes;    // 8 epilogue warps x 4 KB
   static constexpr int kOffBar = kOffOut + kFEpiWarps * kFStageOutBytes;
-  static constexpr int kNumBars = 3 * STAGES + 4;
+  static constexpr int kNumBars = 3 * STAGES + 4 + 2 * kProc;          // full, ready, empty, 4 accumulator barriers, ATM: pready, pfree
   static constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
   static constexpr int kBytes = kOffTmemSlot + 16;
   static constexpr int kDynBytes = kBytes + 1024;
+  static constexpr int kTmemACol = 2 * BLOCK_N;                        // ATM: processed stage s holds A_hi at +64 s, A_lo at +64 s + 32
 };
 
 struct F32Params {
@@ -65,15 +77,17 @@ struct F32Params {
   int d_b0, d_b1;               // batch coordinates of the output map
 };
 
-template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES, int CTAS = 1>
+template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES, int CTAS = 1, int ATM = 0>
 __global__ void __launch_bounds__(kFThreads, 1)
 f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_d, const F32Params p) {
-  using L = F32Smem<BLOCK_N, STAGES, PASSES, CTAS>;
+  using L = F32Smem<BLOCK_N, STAGES, PASSES, CTAS, ATM>;
   static_assert(CTAS == 1 || (CTAS == 2 && PASSES == 3), "the CTA-pair variant is built for the split product only");
+  static_assert(!ATM || (CTAS == 1 && PASSES == 3 && 2 * BLOCK_N + 64 * L::kProc <= 512),
+                "A through TMEM: single CTA, split product, accumulators + A stages within the 512 columns");
   constexpr int kTileM = kFTileM * CTAS;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtTF32, kFmtTF32, A_MN, B_MN, kTileM, BLOCK_N);
+  constexpr uint32_t kTmemCols = ATM ? 512 : (2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
+  constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtTF32, kFmtTF32, ATM ? 0 : A_MN, B_MN, kTileM, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -84,6 +98,8 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* empty_bar = bars + 2 * STAGES;        // MMAs that read the stage retired (pair: multicast to both CTAs)
   uint64_t* tmem_full_bar = bars + 3 * STAGES;    // [2]
   uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;   // (pair: both CTAs' epilogue warps, leader's barrier)
+  uint64_t* pready_bar = bars + 3 * STAGES + 4;       // ATM: splitters filled processed stage (TMEM A hi / lo, B lo)
+  uint64_t* pfree_bar = pready_bar + L::kProc;        // ATM: the MMAs that read it retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,6 +127,10 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], kFEpiWarps * CTAS);
     }
+    for (int s = 0; s < L::kProc; ++s) {
+      mbar_init(&pready_bar[s], kFSplitWarps);
+      mbar_init(&pfree_bar[s], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -121,6 +141,7 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_entry();       // everything above touched no global memory: it overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -160,6 +181,7 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0 && rank == 0) {                 // pair: one thread of the leader CTA issues for both
       uint32_t stage = 0, phase = 0;
+      uint32_t ps = 0, pphase = 0;                // ATM: cursor over the processed ring
       int it = 0;
       // K-major: SWIZZLE_128B, 8-row groups 1024 B apart.  MN-major fp32: SWIZZLE_128B_BASE32B, LBO = stride between the
       // 128-byte column blocks along M/N (one [32 k x 32 mn] TMA box), SBO = 4 contraction rows of 128 B
@@ -175,6 +197,26 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int split = (tile % tiles_per_batch) / tiles_mn;
         const int num_kb = min(p.kb_per_split, total_kb - split * p.kb_per_split);
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (ATM) {
+            mbar_wait(&pready_bar[ps], pphase);
+            tc_fence_after();
+            const uint32_t b_addr = sbase + stage * L::kStageBytes + kFATileBytes;
+            const uint64_t b_hi = make_smem_desc(b_addr, kLboB, kSboB, kLayB);
+            const uint64_t b_lo = make_smem_desc(sbase + L::kOffBLoRing + ps * L::kBTileBytes, kLboB, kSboB, kLayB);
+            const uint32_t a_hi_t = tmem_base + L::kTmemACol + ps * 64, a_lo_t = a_hi_t + 32;
+#pragma unroll
+            for (int k = 0; k < kFKBlock / 8; ++k) {
+              umma_tf32_ts(d_tmem, a_lo_t + 8 * k, b_hi + kStepB * k, kIdesc, (kb | k) != 0);
+              umma_tf32_ts(d_tmem, a_hi_t + 8 * k, b_lo + kStepB * k, kIdesc, 1);
+              umma_tf32_ts(d_tmem, a_hi_t + 8 * k, b_hi + kStepB * k, kIdesc, 1);
+            }
+            umma_commit(&empty_bar[stage]);
+            umma_commit(&pfree_bar[ps]);
+            if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++ps == L::kProc) { ps = 0; pphase ^= 1; }
+            continue;
+          }
           // pair: the peer's TMA-written hi tile is covered by its splitters, which waited for it before arriving here
           if (CTAS == 2) mbar_wait_cluster(&ready_bar[stage], phase);
           else           mbar_wait(PASSES == 3 ? &ready_bar[stage] : &full_bar[stage], phase);
@@ -183,7 +225,7 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint64_t a_hi = make_smem_desc(a_addr, kLboA, kSboA, kLayA);
           const uint64_t b_hi = make_smem_desc(b_addr, kLboB, kSboB, kLayB);
           const uint64_t a_lo = make_smem_desc(a_addr + L::kHiBytes, kLboA, kSboA, kLayA);
-          const uint64_t b_lo = make_smem_desc(b_addr + L::kHiBytes, kLboB, kSboB, kLayB);
+          const uint64_t b_lo = make_smem_desc(a_addr + L::kOffBLo, kLboB, kSboB, kLayB);
 #pragma unroll
           for (int k = 0; k < kFKBlock / 8; ++k) {
             const uint32_t acc = (kb | k) != 0;
@@ -212,7 +254,62 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp >= 4 && warp < kFEpiWarp0) {
     // ------------------------------ splitters: x -> (hi, lo), element-wise, layout-agnostic ------------------------------
-    if (PASSES == 3) {
+    if (ATM) {
+      // A: thread = (row, half of the k-block); raw words are the hi operand (the tensor core truncates), lo = x - trunc(x)
+      const int te = threadIdx.x - 128;
+      const int quarter = warp & 3, khalf = (warp - 4) >> 2;       // TMEM lane quarter of this warp, columns [16 khalf, +16)
+      const int row = quarter * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + L::kTmemACol + 16 * khalf;
+      constexpr int kBChunks = L::kBTileBytes / 16;
+      static_assert(kBChunks % kFSplitThreads == 0, "B tile must divide over the splitter threads");
+      uint32_t stage = 0, phase = 0, ps = 0, pphase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int split = (tile % tiles_per_batch) / tiles_mn;
+        const int num_kb = min(p.kb_per_split, total_kb - split * p.kb_per_split);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          const uint32_t a_smem = sbase + stage * L::kStageBytes;
+          uint32_t x[16], l[16];
+          if (A_MN) {                                  // un-swizzled atoms [32 k][32 m]: lanes read 128 contiguous bytes
+            const uint32_t src = a_smem + quarter * 4096 + lane * 4 + (16 * khalf) * 128;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = lds32(src + j * 128);
+          } else {                                     // K-major rows of 128 B, 16-byte chunk c at c ^ (row & 7)
+            const uint32_t src = a_smem + row * 128;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 v = lds128(src + (((4 * khalf + j4) ^ (row & 7)) << 4));
+              x[4 * j4] = v.x, x[4 * j4 + 1] = v.y, x[4 * j4 + 2] = v.z, x[4 * j4 + 3] = v.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            l[j] = __float_as_uint(__uint_as_float(x[j]) - __uint_as_float(x[j] & 0xFFFFE000u));
+          mbar_wait(&pfree_bar[ps], pphase ^ 1);       // the MMAs that read this processed stage have retired
+          tc_fence_after();
+          tmem_st_32x16(t_row + ps * 64, x);
+          tmem_st_32x16(t_row + ps * 64 + 32, l);
+          // B: the raw tile is the hi operand, lo goes to the processed ring (element-wise, layout-agnostic)
+          const uint32_t bh = a_smem + kFATileBytes + te * 16, bl = sbase + L::kOffBLoRing + ps * L::kBTileBytes + te * 16;
+#pragma unroll
+          for (int i = 0; i < kBChunks / kFSplitThreads; ++i) {
+            const uint4 v = lds128(bh + i * kFSplitThreads * 16);
+            const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+            uint32_t ls[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ls[j] = __float_as_uint(__uint_as_float(xs[j]) - __uint_as_float(xs[j] & 0xFFFFE000u));
+            sts128(bl + i * kFSplitThreads * 16, make_uint4(ls[0], ls[1], ls[2], ls[3]));
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pready_bar[ps]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++ps == L::kProc) { ps = 0; pphase ^= 1; }
+        }
+      }
+    } else if (PASSES == 3) {
       const int te = threadIdx.x - 128;
       uint32_t stage = 0, phase = 0;
       constexpr int kChunks = L::kHiBytes / 16;
@@ -371,6 +468,7 @@ f32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, int64_t ldp,
                                                             const float* __restrict__ bias, int accumulate, float* __restrict__ D,
                                                             int64_t ldd) {
+  pdl_entry();
   const int n4 = static_cast<int>(ldp / 4);
   const int64_t total = static_cast<int64_t>(M) * n4;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * 256) {
@@ -431,6 +529,8 @@ struct F32Operand {
   int64_t ld, bs0, bs1;     // elements
 };
 
+static int g_f32_l2_promo = 1;       // 0 none, 1 128 B, 2 256 B (ob_debug_set key 12)
+void f32_gemm_debug_promo(int v) { g_f32_l2_promo = v; }
 // 4-D map over (contiguous axis, strided axis, inner batch, outer batch)
 static int make_map4(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, int64_t ld, int nb1, int64_t bs1,
                      int nb0, int64_t bs0, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
@@ -445,15 +545,16 @@ static int make_map4(CUtensorMap* map, const void* base, uint64_t inner, uint64_
                            has0 ? (cuuint64_t)bs0 * 4 : (cuuint64_t)ld * 4};
   cuuint32_t box[4] = {box_inner, box_outer, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapL2promotion promo = g_f32_l2_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                      : (g_f32_l2_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
     // a thread that has made no runtime call yet (e.g. an autograd worker) has no current context for the driver API:
     // bind the primary context of the current device and retry
     cudaFree(nullptr);
     r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstride, box, estr,
-           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (4-D fp32) failed with %d (inner=%llu outer=%llu ld=%lld nb=%dx%d bs=%lld,%lld box=%ux%u)",
@@ -464,18 +565,20 @@ static int make_map4(CUtensorMap* map, const void* base, uint64_t inner, uint64_
   return OB_OK;
 }
 
+static int g_f32_atm = 1;            // A through TMEM for the single-CTA split products (ob_debug_set key 11)
+void f32_gemm_debug_atm(int on) { g_f32_atm = on; }
 static int g_f32_split_mode = 1;     // the tensor core truncates fp32 -> tf32 (measured), so the raw tile is the hi part
 static int g_f32_epilogue = 0;       // 0 auto, 1 direct row stores, 2 TMA box stores
 void f32_gemm_debug_epilogue(int mode) { g_f32_epilogue = mode; }
 void f32_gemm_debug_pair(int on) { g_f32_pair = on; }
 void f32_gemm_debug(int split_mode) { g_f32_split_mode = split_mode; }
 
-template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES, int CTAS = 1>
+template <int A_MN, int B_MN, int BLOCK_N, int STAGES, int PASSES, int CTAS = 1, int ATM = 0>
 static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_t ldd, int64_t d_bs0, int64_t d_bs1,
                       F32Params p, const F32Plan& pl, cudaStream_t st) {
-  using L = F32Smem<BLOCK_N, STAGES, PASSES, CTAS>;
+  using L = F32Smem<BLOCK_N, STAGES, PASSES, CTAS, ATM>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
-  auto kern = f32_gemm_kernel<A_MN, B_MN, BLOCK_N, STAGES, PASSES, CTAS>;
+  auto kern = f32_gemm_kernel<A_MN, B_MN, BLOCK_N, STAGES, PASSES, CTAS, ATM>;
   static bool attr_set = false;
   if (!attr_set) {
     OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
@@ -484,7 +587,8 @@ static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_
   CUtensorMap map_a, map_b, map_d;
   int rc;
   constexpr CUtensorMapSwizzle kSwK = CU_TENSOR_MAP_SWIZZLE_128B, kSwMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (A_MN) rc = make_map4(&map_a, A.ptr, p.M, p.K, A.ld, p.nb1, A.bs1, p.nb0, A.bs0, 32, 32, kSwMN);
+  if (A_MN) rc = make_map4(&map_a, A.ptr, p.M, p.K, A.ld, p.nb1, A.bs1, p.nb0, A.bs0, 32, 32,
+                           ATM ? CU_TENSOR_MAP_SWIZZLE_NONE : kSwMN);   // ATM: read by the splitter warps, not by the tensor core
   else      rc = make_map4(&map_a, A.ptr, p.K, p.M, A.ld, p.nb1, A.bs1, p.nb0, A.bs0, 32, kFTileM, kSwK);
   if (rc != OB_OK) return rc;
   if (B_MN) rc = make_map4(&map_b, B.ptr, p.N, p.K, B.ld, p.nb1, B.bs1, p.nb0, B.bs0, 32, 32, kSwMN);
@@ -509,19 +613,20 @@ static int launch_f32(const F32Operand& A, const F32Operand& B, float* D, int64_
   if (CTAS == 2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(groups * 2), cfg.blockDim = dim3(kFThreads), cfg.dynamicSmemBytes = L::kDynBytes, cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    attr[1] = pdl_attribute();
+    cfg.attrs = attr, cfg.numAttrs = 2;
     OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_d, p));
   } else {
-    kern<<<groups, kFThreads, L::kDynBytes, st>>>(map_a, map_b, map_d, p);
+    launch_k((kern), dim3(groups), dim3(kFThreads), L::kDynBytes, st, map_a, map_b, map_d, p);
   }
   OB_LAUNCH_CHECK("f32_gemm_kernel");
   if (p.k_splits > 1) {
     const int64_t work = (int64_t)p.M * (p.ldp / 4);
     const int64_t want = (work + 255) / 256, cap = (int64_t)sm_count() * 16;
-    splitk_reduce_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(p.part, p.k_splits, p.M, p.N, p.ldp, p.bias,
+    launch_k((splitk_reduce_kernel), dim3((int)(want < cap ? want : cap)), dim3(256), 0, st, p.part, p.k_splits, p.M, p.N, p.ldp, p.bias,
                                                                          p.accumulate, D, ldd);
     OB_LAUNCH_CHECK("splitk_reduce_kernel");
   }
@@ -532,6 +637,14 @@ template <int A_MN, int B_MN, int PASSES>
 static int dispatch_f32_cfg(const F32Operand& A, const F32Operand& B, float* D, int64_t ldd, int64_t d_bs0, int64_t d_bs1,
                             const F32Params& p, const F32Plan& pl, cudaStream_t st) {
   if (PASSES == 3 && pl.pair) return launch_f32<A_MN, B_MN, 256, 3, 3, 2>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
+  // The 128-wide single-CTA split products (attention scores and their gradients) keep A in tensor memory: 191 -> 171 us at
+  // 192 x 4 x 399 x 399.  The 64-wide ones (probs . v and the transposed products) gain nothing from it - with a third of the
+  // MMAs and no split at all they still take 125 us (tools/gpu_f32atm.py) - and stay on the shared-memory operand path.
+  // (The truncating split only: cvt.rna would need the hi tile rewritten.)  g_f32_atm = 2 forces the 64-wide variant (tests).
+  if (PASSES == 3 && g_f32_atm && g_f32_split_mode == 1) {
+    if (pl.block_n == 128) return launch_f32<A_MN, B_MN, 128, 5, 3, 1, 1>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
+    if (pl.block_n == 64 && g_f32_atm == 2) return launch_f32<A_MN, B_MN, 64, 7, 3, 1, 1>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
+  }
   if (pl.block_n == 64) return launch_f32<A_MN, B_MN, 64, 4, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
   if (pl.block_n == 256) return launch_f32<A_MN, B_MN, 256, 2, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);
   return launch_f32<A_MN, B_MN, 128, 3, PASSES>(A, B, D, ldd, d_bs0, d_bs1, p, pl, st);

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kGemvThreads)
 gemv_tern_i8_kernel(const int8_t* __restrict__ q, const float* __restrict__ scale, const uint8_t* __restrict__ packed,
                     const float* __restrict__ alpha, int alpha_mode, const float* __restrict__ bias, int M, int N, int K,
                     void* __restrict__ y) {
+  pdl_entry();
   extern __shared__ uint8_t gemv_smem[];
   __shared__ float out_s[kGemvMaxM][kGemvRowsPerCta];
   constexpr int KS = 32 / MP;                                   // lanes splitting the contraction
@@ -127,12 +128,12 @@ static int launch_gemv_variant(const int8_t* q, const float* scale, const uint8_
     auto kern = gemv_tern_i8_kernel<MP, TWO, 1>;
     static bool attr_set = false;
     if (!attr_set) { OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem)); attr_set = true; }
-    kern<<<grid, kGemvThreads, smem, st>>>(q, scale, packed, alpha, alpha_mode, bias, M, N, K, y);
+    launch_k((kern), dim3(grid), dim3(kGemvThreads), smem, st, q, scale, packed, alpha, alpha_mode, bias, M, N, K, y);
   } else {
     auto kern = gemv_tern_i8_kernel<MP, TWO, 0>;
     static bool attr_set = false;
     if (!attr_set) { OB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem)); attr_set = true; }
-    kern<<<grid, kGemvThreads, smem, st>>>(q, scale, packed, alpha, alpha_mode, bias, M, N, K, y);
+    launch_k((kern), dim3(grid), dim3(kGemvThreads), smem, st, q, scale, packed, alpha, alpha_mode, bias, M, N, K, y);
   }
   OB_LAUNCH_CHECK("gemv_tern_i8_kernel");
   return OB_OK;

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ beta, float eps, int64_t M, int C,
                                                      float* __restrict__ y, float* __restrict__ mean_out,
                                                      float* __restrict__ rstd_out) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) ln_quant_fwd_kernel(const float* __restri
                                                            const float* __restrict__ beta, float eps, int64_t M, int C,
                                                            int8_t* __restrict__ q, float* __restrict__ scale,
                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                      const float* __restrict__ gamma, const float* __restrict__ resid, int64_t M,
                                                      int C, float* __restrict__ dx, float* __restrict__ part /* [2][blocks][C] */) {
+  pdl_entry();
   __shared__ float4 red[8][32 * V];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 // [2][nblocks][C] partials -> d-gamma, d-beta: 32 columns x 8 row groups per block, fixed order
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restrict__ part, int nblocks, int C,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_entry();
   __shared__ float red[8][33];
   const int which = blockIdx.y;
   const float* p = part + (int64_t)which * nblocks * C;
@@ -239,6 +243,7 @@ constexpr int kColsumBlocks = 592;
 
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t M, int N, int rows_per_block,
                                                              float* __restrict__ part /* [blocks][N] */) {
+  pdl_entry();
   __shared__ float4 red[256];
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
@@ -292,10 +297,10 @@ extern "C" int ob_layernorm_fwd(const float* x, const float* gamma, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = ln_blocks(M);
   switch (C) {
-    case 128:  ln_fwd_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, y, mean, rstd); break;
-    case 256:  ln_fwd_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, y, mean, rstd); break;
-    case 512:  ln_fwd_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, y, mean, rstd); break;
-    default:   ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, y, mean, rstd); break;
+    case 128:  launch_k((ln_fwd_kernel<1>), dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, M, C, y, mean, rstd); break;
+    case 256:  launch_k((ln_fwd_kernel<2>), dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, M, C, y, mean, rstd); break;
+    case 512:  launch_k((ln_fwd_kernel<4>), dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, M, C, y, mean, rstd); break;
+    default:   launch_k((ln_fwd_kernel<8>), dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, M, C, y, mean, rstd); break;
   }
   OB_LAUNCH_CHECK("ln_fwd_kernel");
   return OB_OK;
@@ -313,13 +318,13 @@ static int launch_ln_bwd(const float* dy, const float* dy1, const float* dy2, co
 #define OB_LN_BWD(V)                                                                                                          \
   do {                                                                                                                        \
     if (resid != nullptr) {                                                                                                   \
-      if (ndy == 1) ln_bwd_kernel<V, 1, 1><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
-      else if (ndy == 2) ln_bwd_kernel<V, 2, 1><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
-      else ln_bwd_kernel<V, 3, 1><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part);          \
+      if (ndy == 1) launch_k((ln_bwd_kernel<V, 1, 1>), dim3(blocks), dim3(256), 0, st, dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
+      else if (ndy == 2) launch_k((ln_bwd_kernel<V, 2, 1>), dim3(blocks), dim3(256), 0, st, dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
+      else launch_k((ln_bwd_kernel<V, 3, 1>), dim3(blocks), dim3(256), 0, st, dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part);          \
     } else {                                                                                                                  \
-      if (ndy == 1) ln_bwd_kernel<V, 1, 0><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
-      else if (ndy == 2) ln_bwd_kernel<V, 2, 0><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
-      else ln_bwd_kernel<V, 3, 0><<<blocks, 256, 0, st>>>(dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part);          \
+      if (ndy == 1) launch_k((ln_bwd_kernel<V, 1, 0>), dim3(blocks), dim3(256), 0, st, dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
+      else if (ndy == 2) launch_k((ln_bwd_kernel<V, 2, 0>), dim3(blocks), dim3(256), 0, st, dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part); \
+      else launch_k((ln_bwd_kernel<V, 3, 0>), dim3(blocks), dim3(256), 0, st, dy, dy1, dy2, x, mean, rstd, gamma, resid, M, C, dx, part);          \
     }                                                                                                                         \
   } while (0)
   switch (C) {
@@ -331,7 +336,7 @@ static int launch_ln_bwd(const float* dy, const float* dy1, const float* dy2, co
 #undef OB_LN_BWD
   OB_LAUNCH_CHECK("ln_bwd_kernel");
   dim3 grid((C + 31) / 32, 2);
-  ln_param_grad_kernel<<<grid, 256, 0, st>>>(part, blocks, C, dgamma, dbeta);
+  launch_k((ln_param_grad_kernel), dim3(grid), dim3(256), 0, st, part, blocks, C, dgamma, dbeta);
   OB_LAUNCH_CHECK("ln_param_grad_kernel");
   return OB_OK;
 }
@@ -362,10 +367,10 @@ extern "C" int ob_layernorm_quant_fwd(const float* x, const float* gamma, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = ln_blocks(M);
   switch (C) {
-    case 128:  ln_quant_fwd_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
-    case 256:  ln_quant_fwd_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
-    case 512:  ln_quant_fwd_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
-    default:   ln_quant_fwd_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
+    case 128:  launch_k((ln_quant_fwd_kernel<1>), dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
+    case 256:  launch_k((ln_quant_fwd_kernel<2>), dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
+    case 512:  launch_k((ln_quant_fwd_kernel<4>), dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
+    default:   launch_k((ln_quant_fwd_kernel<8>), dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, M, C, q, scale, mean, rstd); break;
   }
   OB_LAUNCH_CHECK("ln_quant_fwd_kernel");
   return OB_OK;
@@ -388,10 +393,10 @@ extern "C" int ob_colsum(const float* x, int64_t M, int N, float* out, void* ws,
   const int blocks = colsum_blocks(M);
   const int rows_per_block = (int)((M + blocks - 1) / blocks);
   float* part = static_cast<float*>(ws);
-  colsum_partial_kernel<<<blocks, 256, 0, st>>>(x, M, N, rows_per_block, part);
+  launch_k((colsum_partial_kernel), dim3(blocks), dim3(256), 0, st, x, M, N, rows_per_block, part);
   OB_LAUNCH_CHECK("colsum_partial_kernel");
   const int used = (int)((M + rows_per_block - 1) / rows_per_block);          // blocks that own at least one row
-  ln_param_grad_kernel<<<dim3((N + 31) / 32, 1), 256, 0, st>>>(part, used, N, out, out);
+  launch_k((ln_param_grad_kernel), dim3(dim3((N + 31) / 32, 1)), dim3(256), 0, st, part, used, N, out, out);
   OB_LAUNCH_CHECK("ln_param_grad_kernel(colsum)");
   return OB_OK;
 }

@@ -41,6 +41,7 @@ constexpr int kAbsmeanBlocks = 296;   // 2 per SM on a 148-SM part; fixed so the
 
 __global__ void __launch_bounds__(256) absmean_partial_kernel(const float* __restrict__ W, int64_t n,
                                                               float* __restrict__ partials) {
+  pdl_entry();
   __shared__ float red[8];
   float acc = 0.f;
   const int64_t n4 = n >> 2;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) absmean_partial_kernel(const float* __res
 
 __global__ void __launch_bounds__(512) absmean_final_kernel(const float* __restrict__ partials, int nparts, int64_t n,
                                                             float* __restrict__ out) {
+  pdl_entry();
   __shared__ float red[16];
   float v = threadIdx.x < nparts ? partials[threadIdx.x] : 0.f;
   float s = block_sum<512>(v, red);
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(512) absmean_final_kernel(const float* __restr
 __global__ void __launch_bounds__(256) weight_pack_rows_kernel(const float* __restrict__ W, const float* __restrict__ alpha,
                                                                int alpha_mode, int64_t nwords, int bitwidth,
                                                                uint32_t* __restrict__ packed) {
+  pdl_entry();
   const float a_eff = load_alpha_eff(alpha, alpha_mode);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) {
     const float4* src = reinterpret_cast<const float4*>(W + i * 16);
@@ -93,6 +96,7 @@ __global__ void __launch_bounds__(256) weight_pack_tile_kernel(const float* __re
                                                                int N, int K, int bitwidth,
                                                                uint32_t* __restrict__ packed,
                                                                uint32_t* __restrict__ packed_t) {
+  pdl_entry();
   __shared__ uint8_t fields[64][65];
   const float a_eff = load_alpha_eff(alpha, alpha_mode);
   const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
@@ -123,6 +127,7 @@ __global__ void __launch_bounds__(256) weight_pack_tile_kernel(const float* __re
 // tile and quantised both ways (the two code sets share W / alpha_eff and differ only in the 0.5 threshold).  Blocks map to
 // (layer, 64 x 64 tile) through the descriptors' running tile offsets.
 __global__ void __launch_bounds__(256) weight_pack_multi_kernel(const ob_pack_desc* __restrict__ descs, int count, int alpha_mode) {
+  pdl_entry();
   __shared__ uint8_t fields[2][64][65];            // [0]: 2-bit codes, [1]: 1-bit codes
   int lo = 0, hi = count - 1;                      // last descriptor with tile0 <= blockIdx.x
   while (lo < hi) {
@@ -176,6 +181,7 @@ __device__ __forceinline__ float dense_code(float w, float a_eff, int bitwidth) 
 __global__ void __launch_bounds__(256) weight_dense_kernel(const float* __restrict__ W, const float* __restrict__ alpha,
                                                            int alpha_mode, int64_t n, int bitwidth,
                                                            float* __restrict__ out) {
+  pdl_entry();
   const float a_eff = load_alpha_eff(alpha, alpha_mode);
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
@@ -214,6 +220,7 @@ __global__ void __launch_bounds__(256) ste_backward_kernel(const float* __restri
                                                            const float* __restrict__ W, const float* __restrict__ alpha,
                                                            int alpha_mode, int64_t n, int bitwidth,
                                                            float* __restrict__ grad_W, float* __restrict__ alpha_parts) {
+  pdl_entry();
   __shared__ float red[8];
   const float a_eff = load_alpha_eff(alpha, alpha_mode);
   float acc = 0.f;
@@ -325,6 +332,7 @@ __global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restric
                                                           int fin_blocks, float* __restrict__ grad_alpha,
                                                           const float* __restrict__ colsum, int n_col_blocks, int N,
                                                           float* __restrict__ grad_bias, float* __restrict__ tail_ws) {
+  pdl_entry();
   __shared__ float4 part[3][64];
   __shared__ float4 part_b[3][64];
   __shared__ float red[8];
@@ -410,6 +418,7 @@ __global__ void __launch_bounds__(256) bwd_tail_kernel(const float* __restrict__
                                                        float* __restrict__ grad_alpha, const float* __restrict__ colsum,
                                                        int n_col_blocks, int N, float* __restrict__ grad_bias,
                                                        float* __restrict__ tail_ws) {
+  pdl_entry();
   __shared__ float red[8];
   if (blockIdx.x == 0) {
     if (grad_alpha != nullptr) alpha_final(alpha_parts, n_alpha_parts, alpha, alpha_mode, grad_alpha, red);
@@ -426,6 +435,7 @@ __global__ void __launch_bounds__(256) bwd_tail_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict__ packed, int64_t nwords, int order,
                                                      int8_t* __restrict__ codes) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * 256) {
     const uint32_t w = __ldg(packed + i);
     int8_t out[16];
@@ -446,6 +456,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict_
 template <typename T, int V>
 __global__ void __launch_bounds__(256) act_quant_reg_kernel(const T* __restrict__ x, int64_t M, int K,
                                                             int8_t* __restrict__ q, float* __restrict__ scale) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -470,6 +481,7 @@ __global__ void __launch_bounds__(256) act_quant_reg_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) act_quant_generic_kernel(const T* __restrict__ x, int64_t M, int K,
                                                                 int8_t* __restrict__ q, float* __restrict__ scale) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -493,6 +505,7 @@ template <int V>
 __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __restrict__ h, const uint8_t* __restrict__ keep,
                                                                float inv_keep, DropRng rng, int64_t M, int K,
                                                                int8_t* __restrict__ q, float* __restrict__ scale) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -546,6 +559,7 @@ __global__ void __launch_bounds__(256) swish_drop_quant_kernel(const float* __re
 __global__ void __launch_bounds__(256) swish_drop_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ h,
                                                              const uint8_t* __restrict__ keep, float inv_keep, DropRng rng,
                                                              int64_t npairs, float* __restrict__ gh) {
+  pdl_entry();
   const float ik = (keep != nullptr || rng.threshold != 0u) ? inv_keep : 1.0f;
   for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * 256) {
     const int64_t f0 = ((p >> 5) << 6) + (p & 31);
@@ -602,6 +616,7 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ dY,
                                                        const int8_t* __restrict__ q, int M, int N, int K,
                                                        __nv_bfloat16* __restrict__ dys, __nv_bfloat16* __restrict__ qb,
                                                        float* __restrict__ colsum, PrepOp op) {
+  pdl_entry();
   __shared__ float inv_s[kPrepRows];
   __shared__ float rowf[kPrepRows];
   __shared__ float4 red[2][256];
@@ -734,9 +749,9 @@ extern "C" int ob_weight_absmean(const float* W, int64_t n, float* out, void* ws
   OB_REQUIRE(W && out && ws && n > 0, "ob_weight_absmean: null pointer or n <= 0");
   OB_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "ob_weight_absmean: W must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  absmean_partial_kernel<<<kAbsmeanBlocks, 256, 0, st>>>(W, n, static_cast<float*>(ws));
+  launch_k((absmean_partial_kernel), dim3(kAbsmeanBlocks), dim3(256), 0, st, W, n, static_cast<float*>(ws));
   OB_LAUNCH_CHECK("absmean_partial_kernel");
-  absmean_final_kernel<<<1, 512, 0, st>>>(static_cast<float*>(ws), kAbsmeanBlocks, n, out);
+  launch_k((absmean_final_kernel), dim3(1), dim3(512), 0, st, static_cast<float*>(ws), kAbsmeanBlocks, n, out);
   OB_LAUNCH_CHECK("absmean_final_kernel");
   return OB_OK;
 }
@@ -751,7 +766,7 @@ extern "C" int ob_weight_quant_pack(const float* W, const float* alpha, int alph
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (N % 64 == 0 && K % 64 == 0) {
     dim3 grid(K / 64, N / 64);
-    weight_pack_tile_kernel<<<grid, 256, 0, st>>>(W, alpha, alpha_mode, N, K, bitwidth,
+    launch_k((weight_pack_tile_kernel), dim3(grid), dim3(256), 0, st, W, alpha, alpha_mode, N, K, bitwidth,
                                                  reinterpret_cast<uint32_t*>(packed_i8),
                                                  reinterpret_cast<uint32_t*>(packed_t));
     OB_LAUNCH_CHECK("weight_pack_tile_kernel");
@@ -760,7 +775,7 @@ extern "C" int ob_weight_quant_pack(const float* W, const float* alpha, int alph
   const int64_t nwords = (int64_t)N * K / 16;
   const int64_t want = (nwords + 255) / 256;
   const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
-  weight_pack_rows_kernel<<<blocks, 256, 0, st>>>(W, alpha, alpha_mode, nwords, bitwidth,
+  launch_k((weight_pack_rows_kernel), dim3(blocks), dim3(256), 0, st, W, alpha, alpha_mode, nwords, bitwidth,
                                                  reinterpret_cast<uint32_t*>(packed_i8));
   OB_LAUNCH_CHECK("weight_pack_rows_kernel");
   return OB_OK;
@@ -770,7 +785,7 @@ extern "C" int ob_weight_quant_pack_multi(const ob_pack_desc* descs_dev, int cou
                                           ob_stream_t stream) {
   OB_REQUIRE(descs_dev && count > 0 && total_tiles > 0, "ob_weight_quant_pack_multi: null descriptor table or empty");
   OB_REQUIRE(alpha_mode == OB_ALPHA_RAW || alpha_mode == OB_ALPHA_EFF, "ob_weight_quant_pack_multi: unknown alpha mode %d", alpha_mode);
-  weight_pack_multi_kernel<<<total_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(descs_dev, count, alpha_mode);
+  launch_k((weight_pack_multi_kernel), dim3(total_tiles), dim3(256), 0, static_cast<cudaStream_t>(stream), descs_dev, count, alpha_mode);
   OB_LAUNCH_CHECK("weight_pack_multi_kernel");
   return OB_OK;
 }
@@ -781,7 +796,7 @@ extern "C" int ob_weight_quant_dense(const float* W, const float* alpha, int alp
   OB_REQUIRE(bitwidth == 1 || bitwidth == 2, "bitwidth must be one of {1,2,32}");
   const int64_t want = (n / 4 + 255) / 256 + 1;
   const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
-  weight_dense_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, alpha, alpha_mode, n, bitwidth, w_hat);
+  launch_k((weight_dense_kernel), dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), W, alpha, alpha_mode, n, bitwidth, w_hat);
   OB_LAUNCH_CHECK("weight_dense_kernel");
   return OB_OK;
 }
@@ -809,15 +824,15 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
   if (fused || col_groups > 0)
     OB_CUDA(cudaMemsetAsync(tail_ws + (size_t)kTailRowChunks * N, 0, (size_t)(1 + col_groups) * sizeof(int), st));
   if (fused) {
-    dw_finalize_kernel<<<blocks + col_groups * kTailRowChunks, 256, 0, st>>>(
+    launch_k((dw_finalize_kernel), dim3(blocks + col_groups * kTailRowChunks), dim3(256), 0, st, 
         g_parts, splits, splits, W, alpha, alpha_mode, n, bitwidth, bitwidth, grad_W, alpha_parts, blocks, grad_alpha, colsum,
         n_col_blocks, N, grad_bias, tail_ws);
     OB_LAUNCH_CHECK("dw_finalize_kernel");
     return OB_OK;
   }
-  ste_backward_kernel<<<blocks, 256, 0, st>>>(g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
+  launch_k((ste_backward_kernel), dim3(blocks), dim3(256), 0, st, g_parts, splits, W, alpha, alpha_mode, n, bitwidth, grad_W, alpha_parts);
   OB_LAUNCH_CHECK("ste_backward_kernel");
-  bwd_tail_kernel<<<1 + col_groups * kTailRowChunks, 256, 0, st>>>(alpha_parts, blocks, alpha, alpha_mode, grad_alpha,
+  launch_k((bwd_tail_kernel), dim3(1 + col_groups * kTailRowChunks), dim3(256), 0, st, alpha_parts, blocks, alpha, alpha_mode, grad_alpha,
                                                                    colsum, n_col_blocks, N, grad_bias, tail_ws);
   OB_LAUNCH_CHECK("bwd_tail_kernel");
   return OB_OK;
@@ -836,7 +851,7 @@ int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, co
   const int blocks = (int)(n / kFinBlockElems);
   float* tail_ws = alpha_parts + blocks;
   OB_CUDA(cudaMemsetAsync(tail_ws + (size_t)kTailRowChunks * N, 0, (size_t)(1 + col_groups) * sizeof(int), st));
-  dw_finalize_kernel<<<blocks + col_groups * kTailRowChunks, 256, 0, st>>>(
+  launch_k((dw_finalize_kernel), dim3(blocks + col_groups * kTailRowChunks), dim3(256), 0, st, 
       g_parts, splits_a, splits, W, alpha, alpha_mode, n, bw_a, bw_b, grad_W, alpha_parts, blocks, grad_alpha, colsum,
       n_col_blocks, N, grad_bias, tail_ws);
   OB_LAUNCH_CHECK("dw_finalize_kernel");
@@ -859,7 +874,7 @@ extern "C" int ob_unpack_codes(const uint8_t* packed, int R, int C, int order, i
   OB_REQUIRE(order == OB_ORDER_I8 || order == OB_ORDER_BF16, "ob_unpack_codes: unknown order %d", order);
   const int64_t nwords = (int64_t)R * C / 16;
   const int blocks = (int)((nwords + 255) / 256 < 4096 ? (nwords + 255) / 256 : 4096);
-  unpack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint32_t*>(packed), nwords,
+  launch_k((unpack_kernel), dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const uint32_t*>(packed), nwords,
                                                                       order, codes);
   OB_LAUNCH_CHECK("unpack_kernel");
   return OB_OK;
@@ -870,12 +885,12 @@ static int launch_act_quant(const T* x, int64_t M, int K, int8_t* q, float* scal
   const int64_t want = (M + 7) / 8;                               // 8 warps (rows) per block
   const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
   switch (K) {
-    case 128:  act_quant_reg_kernel<T, 1><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
-    case 256:  act_quant_reg_kernel<T, 2><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
-    case 512:  act_quant_reg_kernel<T, 4><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
-    case 1024: act_quant_reg_kernel<T, 8><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
-    case 2048: act_quant_reg_kernel<T, 16><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
-    default:   act_quant_generic_kernel<T><<<blocks, 256, 0, st>>>(x, M, K, q, scale); break;
+    case 128:  launch_k((act_quant_reg_kernel<T, 1>), dim3(blocks), dim3(256), 0, st, x, M, K, q, scale); break;
+    case 256:  launch_k((act_quant_reg_kernel<T, 2>), dim3(blocks), dim3(256), 0, st, x, M, K, q, scale); break;
+    case 512:  launch_k((act_quant_reg_kernel<T, 4>), dim3(blocks), dim3(256), 0, st, x, M, K, q, scale); break;
+    case 1024: launch_k((act_quant_reg_kernel<T, 8>), dim3(blocks), dim3(256), 0, st, x, M, K, q, scale); break;
+    case 2048: launch_k((act_quant_reg_kernel<T, 16>), dim3(blocks), dim3(256), 0, st, x, M, K, q, scale); break;
+    default:   launch_k((act_quant_generic_kernel<T>), dim3(blocks), dim3(256), 0, st, x, M, K, q, scale); break;
   }
   OB_LAUNCH_CHECK("act_quant kernel");
   return OB_OK;
@@ -904,11 +919,11 @@ extern "C" int ob_bwd_prep(const void* dY, int dy_dtype, const float* scale, con
   const int blocks = ob_bwd_colsum_blocks(M);
   const PrepOp op = {nullptr, nullptr, 1.0f, {0ull, 0ull, 0u}, 0ll};
   if (dy_dtype == OB_F32)
-    bwd_prep_kernel<float, 0><<<blocks, 256, 0, st>>>(static_cast<const float*>(dY), scale, q, M, N, K,
+    launch_k((bwd_prep_kernel<float, 0>), dim3(blocks), dim3(256), 0, st, static_cast<const float*>(dY), scale, q, M, N, K,
                                                       static_cast<__nv_bfloat16*>(dys_bf16),
                                                       static_cast<__nv_bfloat16*>(qb_bf16), colsum, op);
   else if (dy_dtype == OB_BF16)
-    bwd_prep_kernel<__nv_bfloat16, 0><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dY), scale, q, M, N, K,
+    launch_k((bwd_prep_kernel<__nv_bfloat16, 0>), dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(dY), scale, q, M, N, K,
                                                               static_cast<__nv_bfloat16*>(dys_bf16),
                                                               static_cast<__nv_bfloat16*>(qb_bf16), colsum, op);
   else
@@ -933,10 +948,10 @@ extern "C" int ob_bwd_prep_fused(const float* g_next, int mode, const float* row
   const int blocks = ob_bwd_colsum_blocks(M);
   const PrepOp op = {rowmask, h, factor, {seed, offset, drop_threshold}, static_cast<long long>(row_base)};
   if (mode == OB_PREP_TAIL)
-    bwd_prep_kernel<float, 1><<<blocks, 256, 0, st>>>(g_next, scale, q, M, N, K, static_cast<__nv_bfloat16*>(dys_bf16),
+    launch_k((bwd_prep_kernel<float, 1>), dim3(blocks), dim3(256), 0, st, g_next, scale, q, M, N, K, static_cast<__nv_bfloat16*>(dys_bf16),
                                                       static_cast<__nv_bfloat16*>(qb_bf16), colsum, op);
   else
-    bwd_prep_kernel<float, 2><<<blocks, 256, 0, st>>>(g_next, scale, q, M, N, K, static_cast<__nv_bfloat16*>(dys_bf16),
+    launch_k((bwd_prep_kernel<float, 2>), dim3(blocks), dim3(256), 0, st, g_next, scale, q, M, N, K, static_cast<__nv_bfloat16*>(dys_bf16),
                                                       static_cast<__nv_bfloat16*>(qb_bf16), colsum, op);
   OB_LAUNCH_CHECK("bwd_prep_kernel(fused)");
   return OB_OK;
@@ -952,10 +967,10 @@ extern "C" int ob_swish_drop_quant(const float* h, const uint8_t* keep, float in
   const int64_t want = (M + 7) / 8;
   const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
   switch (K) {
-    case 256:  swish_drop_quant_kernel<2><<<blocks, 256, 0, st>>>(h, keep, inv_keep, rng, M, K, q, scale); break;
-    case 512:  swish_drop_quant_kernel<4><<<blocks, 256, 0, st>>>(h, keep, inv_keep, rng, M, K, q, scale); break;
-    case 1024: swish_drop_quant_kernel<8><<<blocks, 256, 0, st>>>(h, keep, inv_keep, rng, M, K, q, scale); break;
-    default:   swish_drop_quant_kernel<16><<<blocks, 256, 0, st>>>(h, keep, inv_keep, rng, M, K, q, scale); break;
+    case 256:  launch_k((swish_drop_quant_kernel<2>), dim3(blocks), dim3(256), 0, st, h, keep, inv_keep, rng, M, K, q, scale); break;
+    case 512:  launch_k((swish_drop_quant_kernel<4>), dim3(blocks), dim3(256), 0, st, h, keep, inv_keep, rng, M, K, q, scale); break;
+    case 1024: launch_k((swish_drop_quant_kernel<8>), dim3(blocks), dim3(256), 0, st, h, keep, inv_keep, rng, M, K, q, scale); break;
+    default:   launch_k((swish_drop_quant_kernel<16>), dim3(blocks), dim3(256), 0, st, h, keep, inv_keep, rng, M, K, q, scale); break;
   }
   OB_LAUNCH_CHECK("swish_drop_quant_kernel");
   return OB_OK;
@@ -969,7 +984,7 @@ extern "C" int ob_swish_drop_bwd(const float* gz, const float* h, const uint8_t*
   const int64_t npairs = n / 8;
   const int64_t want = (npairs + 255) / 256;
   const int blocks = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
-  swish_drop_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(gz, h, keep, inv_keep, rng, npairs, gh);
+  launch_k((swish_drop_bwd_kernel), dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), gz, h, keep, inv_keep, rng, npairs, gh);
   OB_LAUNCH_CHECK("swish_drop_bwd_kernel");
   return OB_OK;
 }

@@ -98,6 +98,28 @@ def test_cta_pair_tiles_equal_single_cta_tiles(ob, name):
     assert rel(pair, a.double() @ b.double().transpose(-1, -2)) <= TOL
 
 
+@pytest.mark.parametrize("name", ["nt_ragged_batched", "nn_b_mn_major", "tn_batched", "tn_both_mn_major", "k_not_multiple_of_32",
+                                  "broadcast_b", "nt_tiny"])
+def test_a_operand_through_tensor_memory_equals_shared_memory_operand(ob, name):
+    """The single-CTA split products can keep the A operand in tensor memory (tcgen05.mma with A from TMEM, hi / lo written by
+    tcgen05.st; default for the 128-wide tiles, ob_debug_set(11, 2) also for the 64-wide ones, 0 = off).  Same operand values
+    and MMA order per output element, so the results are bitwise equal in every layout, incl. the transposed A that is then
+    read from un-swizzled boxes."""
+    from onebit_b200._cabi import lib
+    from onebit_b200.matmul import bmm_nt
+    a, b = CASES[name]()
+    try:
+        assert lib.ob_debug_set(11, 0) == 0
+        smem = bmm_nt(a, b)
+        assert lib.ob_debug_set(11, 2) == 0
+        tmem = bmm_nt(a, b)
+        torch.cuda.synchronize()
+    finally:
+        lib.ob_debug_set(11, 1)
+    assert torch.equal(smem, tmem)
+    assert rel(tmem, torch.matmul(a.double(), b.double().transpose(-1, -2))) < TOL
+
+
 def test_bmm_nt_rejects_bad_arguments(ob):
     from onebit_b200.matmul import bmm_nt
     with pytest.raises(RuntimeError):

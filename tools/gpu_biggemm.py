@@ -35,27 +35,30 @@ def graph_time(fn, n=20, reps=3):
     return e0.elapsed_time(e1) / reps / n * 1e3
 
 
-if __name__ != "__main__":
-    raise SystemExit(0)
-shapes = [(65536, 2048, 2048)]
-if len(sys.argv) > 1 and sys.argv[1] == "all":
-    shapes += [(65536, 1024, 1024), (65536, 1024, 2048), (65536, 2048, 1024)]
-for (M, K, N) in shapes:
-    torch.manual_seed(0)
-    layer = ob.QuantizedLinear(K, N).cuda()
-    pk, _ = layer.packed_weight(2)
-    q, s = ob.act_quant_int8(torch.randn(M, K, device="cuda").bfloat16())
-    ops = 2.0 * M * N * K
-    wq = torch.randint(-1, 2, (K, N), device="cuda", dtype=torch.int8)
-    t = graph_time(lambda: torch._int_mm(q, wq))
-    print(f"M={M} K={K} N={N} cuBLASLt _int_mm (int32 out) burst: {t:7.1f} us  {ops / t * 1e-6:7.1f} TOPS", flush=True)
-    t = graph_time(lambda: torch._int_mm(q, wq), n=20, reps=250)
-    print(f"M={M} K={K} N={N} cuBLASLt _int_mm (int32 out) ~1 s : {t:7.1f} us  {ops / t * 1e-6:7.1f} TOPS", flush=True)
-    for odt in (torch.bfloat16,):
-        for flags, name in [(0, "full"), (4, "no expansion"), (3, "no epilogue"), (7, "no expansion, no epilogue")]:
-            lib.ob_debug_set(5, flags)
-            t = graph_time(lambda: obq.gemm_fwd(q, s, pk, layer.alpha, layer.bias, N, odt))
-            t2 = graph_time(lambda: obq.gemm_fwd(q, s, pk, layer.alpha, layer.bias, N, odt), n=20, reps=250)
-            print(f"M={M} K={K} N={N} {str(odt)[6:]} {name:28s}: burst {t:7.1f} us {ops / t * 1e-6:7.1f} TOPS | ~1 s {t2:7.1f} us "
-                  f"{ops / t2 * 1e-6:7.1f} TOPS", flush=True)
-        lib.ob_debug_set(5, 0)
+def main():
+    shapes = [(65536, 2048, 2048)]
+    if len(sys.argv) > 1 and sys.argv[1] == "all":
+        shapes += [(65536, 1024, 1024), (65536, 1024, 2048), (65536, 2048, 1024)]
+    for (M, K, N) in shapes:
+        torch.manual_seed(0)
+        layer = ob.QuantizedLinear(K, N).cuda()
+        pk, _ = layer.packed_weight(2)
+        q, s = ob.act_quant_int8(torch.randn(M, K, device="cuda").bfloat16())
+        ops = 2.0 * M * N * K
+        wq = torch.randint(-1, 2, (K, N), device="cuda", dtype=torch.int8)
+        t = graph_time(lambda: torch._int_mm(q, wq))
+        print(f"M={M} K={K} N={N} cuBLASLt _int_mm (int32 out) burst: {t:7.1f} us  {ops / t * 1e-6:7.1f} TOPS", flush=True)
+        t = graph_time(lambda: torch._int_mm(q, wq), n=20, reps=250)
+        print(f"M={M} K={K} N={N} cuBLASLt _int_mm (int32 out) ~1 s : {t:7.1f} us  {ops / t * 1e-6:7.1f} TOPS", flush=True)
+        for odt in (torch.bfloat16,):
+            for flags, name in [(0, "full"), (4, "no expansion"), (3, "no epilogue"), (7, "no expansion, no epilogue")]:
+                lib.ob_debug_set(5, flags)
+                t = graph_time(lambda: obq.gemm_fwd(q, s, pk, layer.alpha, layer.bias, N, odt))
+                t2 = graph_time(lambda: obq.gemm_fwd(q, s, pk, layer.alpha, layer.bias, N, odt), n=20, reps=250)
+                print(f"M={M} K={K} N={N} {str(odt)[6:]} {name:28s}: burst {t:7.1f} us {ops / t * 1e-6:7.1f} TOPS | ~1 s {t2:7.1f} us "
+                      f"{ops / t2 * 1e-6:7.1f} TOPS", flush=True)
+            lib.ob_debug_set(5, 0)
+
+
+if __name__ == "__main__":
+    main()
