@@ -398,7 +398,6 @@ def hot_kernel_rooflines(peaks, M):
     qs = [ob.act_quant_int8(x) for x in xs]
     ys = [torch.empty(M, N, device=dev) for _ in range(nbuf)]
     dys = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
-    qbs = [torch.empty(M, K, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
     dxs = [torch.empty(M, K, device=dev) for _ in range(nbuf)]
     colsum = torch.empty(lib.ob_bwd_colsum_blocks(M), N, device=dev)
     gw, ga, gb = torch.empty(N, K, device=dev), torch.empty((), device=dev), torch.empty(N, device=dev)
@@ -417,16 +416,17 @@ def hot_kernel_rooflines(peaks, M):
         "gemm_fwd": (lambda j: lib.ob_gemm_tern_i8_fwd(qs[j][0].data_ptr(), qs[j][1].data_ptr(), pk.data_ptr(), a.data_ptr(), 1,
                                                        layer.bias.data_ptr(), M, N, K, ys[j].data_ptr(), 0, st),
                      M * K + N * K / 4 + 4.0 * M * N + 4 * M + 4 * N, 2.0 * M * N * K),
+        # round 2: grad_W converts the int8 codes in shared memory, so the prep pass no longer reads q or writes a bf16 copy of it
         "bwd_prep": (lambda j: lib.ob_bwd_prep(gys[j].data_ptr(), 0, qs[j][1].data_ptr(), qs[j][0].data_ptr(), M, N, K,
-                                               dys[j].data_ptr(), qbs[j].data_ptr(), colsum.data_ptr(), st),
-                     6.0 * M * N + 3.0 * M * K + 4 * M, 0.0),
+                                               dys[j].data_ptr(), None, colsum.data_ptr(), st),
+                     6.0 * M * N + 4 * M, 0.0),
         "bwd_dx": (lambda j: lib.ob_bwd_dx(dys[j].data_ptr(), qs[j][1].data_ptr(), pkt.data_ptr(), a.data_ptr(), 1, M, N, K,
                                            dxs[j].data_ptr(), 0, st),
                    2.0 * M * N + N * K / 4 + 4.0 * M * K + 4 * M, 2.0 * M * N * K),
-        "bwd_dw": (lambda j: lib.ob_bwd_dw(dys[j].data_ptr(), qbs[j].data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(),
-                                           a.data_ptr(), 1, 2, M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(),
-                                           ws.data_ptr(), nbytes, st),
-                   2.0 * M * N + 2.0 * M * K + 8.0 * N * K, 2.0 * M * N * K),
+        "bwd_dw": (lambda j: lib.ob_bwd_dw_q8(dys[j].data_ptr(), qs[j][0].data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(),
+                                              a.data_ptr(), 1, 2, M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                              ws.data_ptr(), nbytes, st),
+                   2.0 * M * N + 1.0 * M * K + 8.0 * N * K, 2.0 * M * N * K),
     }
     # kernels around the layer (same token count): FFN mid-section, LayerNorm, attention chain, weight quantiser
     from onebit_b200.attention import rel_attention_probs  # noqa: F401
@@ -558,7 +558,6 @@ def layer_core_rooflines(peaks, M):
         qs = [ob.act_quant_int8(x) for x in xs]
         ys = [torch.empty(M, N, device=dev) for _ in range(nb)]
         dys = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
-        qbs = [torch.empty(M, K, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
         dxs = [torch.empty(M, K, device=dev) for _ in range(nb)]
         lnw, lnb = torch.ones(K, device=dev), torch.zeros(K, device=dev)
         stats = torch.empty(2, M, device=dev)
@@ -578,15 +577,17 @@ def layer_core_rooflines(peaks, M):
                                                                      0, ys[j].data_ptr(), st),
                               M * K + N * K / 4 + 8.0 * M * N + 4 * M + 4 * N),
             "bwd_prep": (lambda j: lib.ob_bwd_prep(gys[j].data_ptr(), 0, qs[j][1].data_ptr(), qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(),
-                                                   qbs[j].data_ptr(), colsum.data_ptr(), st), 6.0 * M * N + 3.0 * M * K + 4 * M),
+                                                   None, colsum.data_ptr(), st), 6.0 * M * N + 4 * M),
             "bwd_prep_tail": (lambda j: lib.ob_bwd_prep_fused(gys[j].data_ptr(), 1, None, None, 0.5 * ik, 7, 4 * j, thr, 0, qs[j][1].data_ptr(),
-                                                              qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(), qbs[j].data_ptr(), colsum.data_ptr(), st),
-                              6.0 * M * N + 3.0 * M * K + 4 * M),
+                                                              qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(), None, colsum.data_ptr(), st),
+                              6.0 * M * N + 4 * M),
             "bwd_dx": (lambda j: lib.ob_bwd_dx(dys[j].data_ptr(), qs[j][1].data_ptr(), pkt.data_ptr(), a.data_ptr(), 1, M, N, K, dxs[j].data_ptr(), 0, st),
                        2.0 * M * N + N * K / 4 + 4.0 * M * K + 4 * M),
-            "bwd_dw": (lambda j: lib.ob_bwd_dw(dys[j].data_ptr(), qbs[j].data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(), a.data_ptr(), 1, 2,
-                                               M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, st),
-                       2.0 * M * N + 2.0 * M * K + 8.0 * N * K),
+            # both bitwidth groups of the stack in one launch + one finaliser (rows [0, 2M/3) at 2 bits, the rest at 1 bit)
+            "bwd_dw": (lambda j: lib.ob_bwd_dw_q8_groups(dys[j].data_ptr(), qs[j][0].data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(),
+                                                         a.data_ptr(), 1, (2 * M) // 3, M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                                         ws.data_ptr(), nbytes, st),
+                       2.0 * M * N + 1.0 * M * K + 8.0 * N * K),
         }
         if N % 256 == 0:
             fns["bwd_prep_swish"] = (lambda j: lib.ob_bwd_prep_fused(gys[j].data_ptr(), 2, None, ys[j].data_ptr(), ik, 7, 4 * j, thr, 0,
@@ -606,7 +607,7 @@ def layer_core_rooflines(peaks, M):
             gbs = nbytes_alg / (ms * 1e-3) / 1e9
             rows[name] = {"us": round(ms * 1e3, 1), "gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 3)}
         out[f"{K}->{N}"] = rows
-        del xs, gys, qs, ys, dys, qbs, dxs, ws
+        del xs, gys, qs, ys, dys, dxs, ws
     return {"M": M, "peak_gbs": peaks["hbm_gbs"], "shapes": out}
 
 

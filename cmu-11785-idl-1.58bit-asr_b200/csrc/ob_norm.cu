@@ -81,14 +81,25 @@ __global__ void __launch_bounds__(256) ln_quant_fwd_kernel(const float* __restri
     b[j] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
   }
   const float inv_c = 1.0f / static_cast<float>(C);
+  // the next row of this warp is loaded while the current one goes through its three dependent warp reductions
+  constexpr bool kPre = V <= 4;                         // up to 512 columns; wider rows have enough loads in flight per lane
+  float4 nx[V];
+  if (kPre && warp0 < M) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) nx[j] = __ldg(reinterpret_cast<const float4*>(x + warp0 * C) + lane + 32 * j);
+  }
   for (int64_t row = warp0; row < M; row += nwarps) {
-    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
     float4 v[V];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      v[j] = __ldg(xr + lane + 32 * j);
+      v[j] = kPre ? nx[j] : __ldg(reinterpret_cast<const float4*>(x + row * C) + lane + 32 * j);
       s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    if (kPre && row + nwarps < M) {
+      const float4* xn = reinterpret_cast<const float4*>(x + (row + nwarps) * C);
+#pragma unroll
+      for (int j = 0; j < V; ++j) nx[j] = __ldg(xn + lane + 32 * j);
     }
     const float mean = wsum(s) * inv_c;
     float ss = 0.f;
