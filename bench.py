@@ -403,7 +403,7 @@ def hot_kernel_rooflines(peaks, M):
     gw, ga, gb = torch.empty(N, K, device=dev), torch.empty((), device=dev), torch.empty(N, device=dev)
     nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-    st = torch.cuda.current_stream().cuda_stream
+    cur = lambda: torch.cuda.current_stream().cuda_stream        # noqa: E731  (looked up per call: the timing graphs capture on a side stream)
     a = layer.alpha
     i = [0]
 
@@ -411,21 +411,21 @@ def hot_kernel_rooflines(peaks, M):
         i[0] = (i[0] + 1) % nbuf
         return i[0]
     fns = {
-        "act_quant_i8": (lambda j: lib.ob_act_quant_i8(xs[j].data_ptr(), 0, M, K, qs[j][0].data_ptr(), qs[j][1].data_ptr(), st),
+        "act_quant_i8": (lambda j: lib.ob_act_quant_i8(xs[j].data_ptr(), 0, M, K, qs[j][0].data_ptr(), qs[j][1].data_ptr(), cur()),
                          4 * M * K + M * K + 4 * M, 0.0),
         "gemm_fwd": (lambda j: lib.ob_gemm_tern_i8_fwd(qs[j][0].data_ptr(), qs[j][1].data_ptr(), pk.data_ptr(), a.data_ptr(), 1,
-                                                       layer.bias.data_ptr(), M, N, K, ys[j].data_ptr(), 0, st),
+                                                       layer.bias.data_ptr(), M, N, K, ys[j].data_ptr(), 0, cur()),
                      M * K + N * K / 4 + 4.0 * M * N + 4 * M + 4 * N, 2.0 * M * N * K),
         # round 2: grad_W converts the int8 codes in shared memory, so the prep pass no longer reads q or writes a bf16 copy of it
         "bwd_prep": (lambda j: lib.ob_bwd_prep(gys[j].data_ptr(), 0, qs[j][1].data_ptr(), qs[j][0].data_ptr(), M, N, K,
-                                               dys[j].data_ptr(), None, colsum.data_ptr(), st),
+                                               dys[j].data_ptr(), None, colsum.data_ptr(), cur()),
                      6.0 * M * N + 4 * M, 0.0),
         "bwd_dx": (lambda j: lib.ob_bwd_dx(dys[j].data_ptr(), qs[j][1].data_ptr(), pkt.data_ptr(), a.data_ptr(), 1, M, N, K,
-                                           dxs[j].data_ptr(), 0, st),
+                                           dxs[j].data_ptr(), 0, cur()),
                    2.0 * M * N + N * K / 4 + 4.0 * M * K + 4 * M, 2.0 * M * N * K),
         "bwd_dw": (lambda j: lib.ob_bwd_dw_q8(dys[j].data_ptr(), qs[j][0].data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(),
                                               a.data_ptr(), 1, 2, M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(),
-                                              ws.data_ptr(), nbytes, st),
+                                              ws.data_ptr(), nbytes, cur()),
                    2.0 * M * N + 1.0 * M * K + 8.0 * N * K, 2.0 * M * N * K),
     }
     # kernels around the layer (same token count): FFN mid-section, LayerNorm, attention chain, weight quantiser
@@ -447,22 +447,22 @@ def hot_kernel_rooflines(peaks, M):
     pk2, pkt2 = torch.empty_like(pk), torch.empty_like(pkt)
     fns.update({
         "swish_drop_quant": (lambda j: lib.ob_swish_drop_quant(h_mid[j % 2].data_ptr(), None, 1.0 / 0.9, 1234, 4 * j, drop_thr, M, N,
-                                                                q_mid.data_ptr(), s_mid.data_ptr(), st), 5.0 * M * N + 4 * M, 0.0),
+                                                                q_mid.data_ptr(), s_mid.data_ptr(), cur()), 5.0 * M * N + 4 * M, 0.0),
         "swish_drop_bwd": (lambda j: lib.ob_swish_drop_bwd(gys[j].data_ptr(), h_mid[j % 2].data_ptr(), None, 1.0 / 0.9, 1234, 4 * j,
-                                                            drop_thr, M * N, gh.data_ptr(), st), 12.0 * M * N, 0.0),
+                                                            drop_thr, M * N, gh.data_ptr(), cur()), 12.0 * M * N, 0.0),
         "layernorm_fwd": (lambda j: lib.ob_layernorm_fwd(xs[j].data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), 1e-5, M, K, ln_y.data_ptr(),
-                                                         ln_stats[0].data_ptr(), ln_stats[1].data_ptr(), st), 8.0 * M * K + 8 * M, 0.0),
+                                                         ln_stats[0].data_ptr(), ln_stats[1].data_ptr(), cur()), 8.0 * M * K + 8 * M, 0.0),
         "layernorm_bwd": (lambda j: lib.ob_layernorm_bwd(dxs[j].data_ptr(), xs[j].data_ptr(), ln_stats[0].data_ptr(), ln_stats[1].data_ptr(),
                                                          ln_w.data_ptr(), M, K, ln_dx.data_ptr(), ln_dp[0].data_ptr(), ln_dp[1].data_ptr(),
-                                                         ln_ws.data_ptr(), st), 12.0 * M * K + 8 * M, 0.0),
+                                                         ln_ws.data_ptr(), cur()), 12.0 * M * K + 8 * M, 0.0),
         "relattn_softmax_fwd": (lambda j: lib.ob_relattn_softmax_fwd(att[j % 2].data_ptr(), att[2 + j % 2].data_ptr(), att_mask.data_ptr(),
                                                                      None, 1.0 / 0.9, 1234, 4 * j, drop_thr, 0.125, Bq, Hh, Tt, Tt,
-                                                                     att_y.data_ptr(), att_o.data_ptr(), st), 16.0 * nat, 0.0),
+                                                                     att_y.data_ptr(), att_o.data_ptr(), cur()), 16.0 * nat, 0.0),
         "relattn_softmax_bwd": (lambda j: lib.ob_relattn_softmax_bwd(att[j % 2].data_ptr(), att_y.data_ptr(), None, 1.0 / 0.9, 1234, 4 * j,
-                                                                     drop_thr, 0.125, Bq, Hh, Tt, Tt, att[2].data_ptr(), att[3].data_ptr(), st),
+                                                                     drop_thr, 0.125, Bq, Hh, Tt, Tt, att[2].data_ptr(), att[3].data_ptr(), cur()),
                                 16.0 * nat, 0.0),
         "weight_quant_pack": (lambda j: lib.ob_weight_quant_pack(layer.weight.data_ptr(), a.data_ptr(), 1, N, K, 2, pk2.data_ptr(),
-                                                                 pkt2.data_ptr(), st), 4.5 * N * K, 0.0),
+                                                                 pkt2.data_ptr(), cur()), 4.5 * N * K, 0.0),
     })
     # fp32 tensor-core GEMM (3 x tf32 split) at the shapes the model uses it on, and the convolution-module kernels
     from onebit_b200.matmul import bmm_nt
@@ -505,14 +505,14 @@ def hot_kernel_rooflines(peaks, M):
     fns.update({
         "glu_dwconv_bn_fwd": (lambda j: lib.ob_glu_dwconv_bn_fwd(cv_a[j % 2].data_ptr(), cv_w.data_ptr(), cv_b.data_ptr(), Bc, Tc, K, 31,
                                                                  1e-5, 1, cv_s.data_ptr(), cv_stats[0].data_ptr(), cv_stats[1].data_ptr(),
-                                                                 cv_ws.data_ptr(), st), 12.0 * Mc * K, 0.0),
+                                                                 cv_ws.data_ptr(), cur()), 12.0 * Mc * K, 0.0),
         "bn_swish_fwd": (lambda j: lib.ob_bn_swish_fwd(cv_d[j % 2].data_ptr(), cv_stats[0].data_ptr(), cv_stats[1].data_ptr(), ln_w.data_ptr(),
-                                                       ln_b.data_ptr(), Mc, K, 1, cv_s.data_ptr(), st), 8.0 * Mc * K, 0.0),
+                                                       ln_b.data_ptr(), Mc, K, 1, cv_s.data_ptr(), cur()), 8.0 * Mc * K, 0.0),
         "bn_swish_bwd": (lambda j: lib.ob_bn_swish_bwd(cv_d[1 - j % 2].data_ptr(), cv_d[j % 2].data_ptr(), cv_stats[0].data_ptr(),
                                                        cv_stats[1].data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), Mc, K, 1, cv_gd.data_ptr(),
-                                                       cv_ggb.data_ptr(), cv_ws.data_ptr(), st), 20.0 * Mc * K, 0.0),
+                                                       cv_ggb.data_ptr(), cv_ws.data_ptr(), cur()), 20.0 * Mc * K, 0.0),
         "glu_dwconv_bwd": (lambda j: lib.ob_glu_dwconv_bwd(cv_d[j % 2].data_ptr(), cv_a[j % 2].data_ptr(), cv_w.data_ptr(), Bc, Tc, K, 31,
-                                                           cv_ga.data_ptr(), cv_gw.data_ptr(), cv_gb.data_ptr(), cv_ws.data_ptr(), st),
+                                                           cv_ga.data_ptr(), cv_gw.data_ptr(), cv_gb.data_ptr(), cv_ws.data_ptr(), cur()),
                            32.0 * Mc * K, 0.0),
     })
     out = {}
@@ -520,7 +520,10 @@ def hot_kernel_rooflines(peaks, M):
         fn, nbytes_alg, flops = spec[:3]
         for _ in range(3):
             fn(nxt())
-        ms = timed_region(1, lambda: fn(nxt()), 20) / 20
+        # device time per call from a CUDA-graph replay of 20 calls over the rotating operand sets: several entries are more than
+        # one launch (grad_W = GEMM + memset + finaliser) and their host-side enqueue (tensor-map encodes, ctypes) would otherwise
+        # be what a 30 us kernel is timed by
+        ms = _graph_time_us(lambda i: fn(i % nbuf), 20) / 1e3
         gbs = nbytes_alg / (ms * 1e-3) / 1e9
         out[name] = {"ms": round(ms, 4), "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": round(gbs / peaks["hbm_gbs"], 4), "algorithmic_bytes": int(nbytes_alg),
@@ -535,16 +538,17 @@ def hot_kernel_rooflines(peaks, M):
     return {"shape": {"M": M, "K": K, "N": N, "attention": [Bq, Hh, Tt, Tt]}, "kernels": out}
 
 
-def layer_core_rooflines(peaks, M):
-    """The quantised layer's own kernels at the token count of the LARGER bitwidth group of the stacked co-training passes (the stack
-    holds 3 x batch x frames/4 rows; in every block one bitwidth owns one third of them and the other two thirds - one launch per
-    group; `layer_kernels` above is quoted at the smaller group), for the model's three routed shapes.
-    Same method as hot_kernel_rooflines: CUDA events over rotating operand sets larger than L2."""
+def layer_core_rooflines(peaks, M, Mg):
+    """The quantised layer's own kernels at the token counts they run at in the stacked co-training step, for the model's three
+    routed shapes: the stack holds M = 3 x batch x frames/4 rows; the LayerNorm quantiser, the backward prep pass and grad_W (both
+    bitwidth groups in one launch) see all of them, the forward and grad_x GEMMs run once per bitwidth group - quoted at the
+    larger group, Mg = 2M/3 rows (`layer_kernels` above is quoted at the smaller one).
+    Same method as hot_kernel_rooflines: device time from a graph replay over rotating operand sets larger than L2."""
     import onebit_b200 as ob
     from onebit_b200 import _cabi, fused
     lib = _cabi.lib
     dev = torch.device("cuda", torch.cuda.current_device())
-    st = torch.cuda.current_stream().cuda_stream
+    cur = lambda: torch.cuda.current_stream().cuda_stream        # noqa: E731  (looked up per call: the timing graphs capture on a side stream)
     out = {}
     thr = int(round(0.1 * 65536))
     ik = 65536.0 / (65536 - thr)
@@ -567,48 +571,48 @@ def layer_core_rooflines(peaks, M):
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         fns = {
             "ln_quant_fwd": (lambda j: lib.ob_layernorm_quant_fwd(xs[j].data_ptr(), lnw.data_ptr(), lnb.data_ptr(), 1e-5, M, K, qs[j][0].data_ptr(),
-                                                                  qs[j][1].data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), st),
+                                                                  qs[j][1].data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), cur()),
                              5.0 * M * K + 12 * M),
             "gemm_fwd": (lambda j: lib.ob_gemm_tern_i8_fwd(qs[j][0].data_ptr(), qs[j][1].data_ptr(), pk.data_ptr(), a.data_ptr(), 1,
-                                                           layer.bias.data_ptr(), M, N, K, ys[j].data_ptr(), 0, st),
-                         M * K + N * K / 4 + 4.0 * M * N + 4 * M + 4 * N),
+                                                           layer.bias.data_ptr(), Mg, N, K, ys[j].data_ptr(), 0, cur()),
+                         Mg * K + N * K / 4 + 4.0 * Mg * N + 4 * Mg + 4 * N),
             "gemm_fwd_tail": (lambda j: lib.ob_gemm_tern_i8_fwd_tail(qs[j][0].data_ptr(), qs[j][1].data_ptr(), pk.data_ptr(), a.data_ptr(), 1,
-                                                                     layer.bias.data_ptr(), M, N, K, gys[j].data_ptr(), None, 0.5 * ik, 7, 4 * j, thr,
-                                                                     0, ys[j].data_ptr(), st),
-                              M * K + N * K / 4 + 8.0 * M * N + 4 * M + 4 * N),
+                                                                     layer.bias.data_ptr(), Mg, N, K, gys[j].data_ptr(), None, 0.5 * ik, 7, 4 * j, thr,
+                                                                     0, ys[j].data_ptr(), cur()),
+                              Mg * K + N * K / 4 + 8.0 * Mg * N + 4 * Mg + 4 * N),
             "bwd_prep": (lambda j: lib.ob_bwd_prep(gys[j].data_ptr(), 0, qs[j][1].data_ptr(), qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(),
-                                                   None, colsum.data_ptr(), st), 6.0 * M * N + 4 * M),
+                                                   None, colsum.data_ptr(), cur()), 6.0 * M * N + 4 * M),
             "bwd_prep_tail": (lambda j: lib.ob_bwd_prep_fused(gys[j].data_ptr(), 1, None, None, 0.5 * ik, 7, 4 * j, thr, 0, qs[j][1].data_ptr(),
-                                                              qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(), None, colsum.data_ptr(), st),
+                                                              qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(), None, colsum.data_ptr(), cur()),
                               6.0 * M * N + 4 * M),
-            "bwd_dx": (lambda j: lib.ob_bwd_dx(dys[j].data_ptr(), qs[j][1].data_ptr(), pkt.data_ptr(), a.data_ptr(), 1, M, N, K, dxs[j].data_ptr(), 0, st),
-                       2.0 * M * N + N * K / 4 + 4.0 * M * K + 4 * M),
+            "bwd_dx": (lambda j: lib.ob_bwd_dx(dys[j].data_ptr(), qs[j][1].data_ptr(), pkt.data_ptr(), a.data_ptr(), 1, Mg, N, K, dxs[j].data_ptr(), 0, cur()),
+                       2.0 * Mg * N + N * K / 4 + 4.0 * Mg * K + 4 * Mg),
             # both bitwidth groups of the stack in one launch + one finaliser (rows [0, 2M/3) at 2 bits, the rest at 1 bit)
             "bwd_dw": (lambda j: lib.ob_bwd_dw_q8_groups(dys[j].data_ptr(), qs[j][0].data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(),
                                                          a.data_ptr(), 1, (2 * M) // 3, M, N, K, gw.data_ptr(), ga.data_ptr(), gb.data_ptr(),
-                                                         ws.data_ptr(), nbytes, st),
+                                                         ws.data_ptr(), nbytes, cur()),
                        2.0 * M * N + 1.0 * M * K + 8.0 * N * K),
         }
         if N % 256 == 0:
             fns["bwd_prep_swish"] = (lambda j: lib.ob_bwd_prep_fused(gys[j].data_ptr(), 2, None, ys[j].data_ptr(), ik, 7, 4 * j, thr, 0,
                                                                      qs[j][1].data_ptr(), qs[j][0].data_ptr(), M, N, K, dys[j].data_ptr(), None,
-                                                                     colsum.data_ptr(), st), 10.0 * M * N + 4 * M)
+                                                                     colsum.data_ptr(), cur()), 10.0 * M * N + 4 * M)
         i = [0]
         rows = {}
         for name, (fn, nbytes_alg) in fns.items():
-            def call(fn=fn):
-                i[0] = (i[0] + 1) % nb
-                rc = fn(i[0])
+            def call(j, fn=fn):
+                rc = fn(j % nb)
                 if rc != 0:
                     raise RuntimeError(_cabi.last_error())
-            for _ in range(3):
-                call()
-            ms = timed_region(1, call, 20) / 20
+            for j in range(3):
+                call(j)
+            ms = _graph_time_us(call, 18) / 1e3                      # device time (graph replay), see hot_kernel_rooflines
             gbs = nbytes_alg / (ms * 1e-3) / 1e9
             rows[name] = {"us": round(ms * 1e3, 1), "gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 3)}
         out[f"{K}->{N}"] = rows
         del xs, gys, qs, ys, dys, dxs, ws
-    return {"M": M, "peak_gbs": peaks["hbm_gbs"], "shapes": out}
+    return {"M": M, "M_group": Mg, "rows": {"ln_quant_fwd, bwd_prep*, bwd_dw": M, "gemm_fwd*, bwd_dx": Mg}, "peak_gbs": peaks["hbm_gbs"],
+            "shapes": out}
 
 
 def ctc_kernel_rooflines(peaks, B, T, V, L, blank=3):
@@ -809,7 +813,20 @@ def run_train(args, world, rank):
         out["layer_kernels"] = hk
         if cfg.stack_passes:
             try:
-                out["layer_kernels_stacked"] = layer_core_rooflines(peaks, 2 * M)
+                stk = layer_core_rooflines(peaks, 3 * M, 2 * M)
+                out["layer_kernels_stacked"] = stk
+                # The step runs the layer on the stacked batch, so the line's roofline is the layer kernel with the largest device
+                # time there (widest routed shape): achieved = algorithmic bytes / device time of one launch, both from this table.
+                wide = stk["shapes"]["256->1024"]
+                name, row = max(wide.items(), key=lambda kv: kv[1]["us"])
+                rows_at = stk["M_group"] if name.startswith(("gemm_fwd", "bwd_dx")) else stk["M"]
+                out["roofline"] = dict(kernel=name, shape={"M": rows_at, "K": 256, "N": 1024},
+                                       traffic=ncu_traffic(f"{name}_{rows_at}x256x1024_f32"), bound="hbm", achieved=row["gbs"],
+                                       peak=peaks["hbm_gbs"], unit="GB/s", frac=row["frac"],
+                                       peak_source=f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)",
+                                       note="the kernel of the BitLinear layer (the north_star path) with the largest device time per launch "
+                                            "at the token counts of the stacked step (layer_kernels_stacked, widest routed shape); every "
+                                            "kernel of the step, incl. the fp32 tensor-core GEMM of the non-routed matmuls, is in layer_kernels")
             except Exception as e:  # noqa: BLE001
                 out["layer_kernels_stacked"] = {"error": f"{type(e).__name__}: {e}"}
         try:                                                # added late in round 1: a failure here must not cost the bench line

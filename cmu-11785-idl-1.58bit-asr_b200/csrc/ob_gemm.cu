@@ -28,7 +28,7 @@ int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, co
 // debug / tuning knobs (ob_debug_set)
 // ---------------------------------------------------------------------------------------------
 enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5,
-                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9, kDbgF32Atm = 11, kDbgF32Promo = 12, kDbgPdl = 13 };
+                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9, kDbgF32Atm = 11, kDbgF32Promo = 12, kDbgPdl = 13, kDbgTailTma = 14 };
 int small_m_limit(int K);              // ob_gemv.cu
 int small_m_capacity(int K);
 int launch_gemv_tern_i8(const int8_t* q, const float* scale, const uint8_t* packed, const float* alpha, int alpha_mode,
@@ -44,6 +44,7 @@ static int g_dbg_swap_lbo_sbo = 0;
 static int g_dbg_force_block_n = 0;
 static int g_dbg_force_splits = 0;
 static int g_dbg_max_ctas = 0;
+static int g_dbg_tail_tma = 1;        // fused tail: residual by TMA (ob_debug_set key 14, 0 = per-lane row loads)
 
 static int g_sms = 0;
 int sm_count() {
@@ -115,7 +116,7 @@ constexpr int kStageOutBytes = 32 * 128;                   // one epilogue chunk
 // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a [256 x BLOCK_N] tile; each CTA loads its own 128
 // rows of A and expands its own half (BLOCK_N/2 rows) of B, so the expansion work and the shared-memory operand
 // traffic per MMA are halved.
-template <int MODE, int BLOCK_N, int STAGES, int CTAS, int OUT_BUFS>
+template <int MODE, int BLOCK_N, int STAGES, int CTAS, int OUT_BUFS, int RES = 0>
 struct GemmSmem {
   static constexpr int kPackedRowBytes = MODE == kFwdI8 ? 32 : 16;   // 128 int8 / 64 bf16 codes per k-block
   static constexpr int kRowsB = BLOCK_N / CTAS;                      // B rows expanded by this CTA
@@ -124,10 +125,11 @@ struct GemmSmem {
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kOffA + STAGES * kATileBytes;
   static constexpr int kOffOut = kOffB + STAGES * kBTileBytes;       // 8 warps x OUT_BUFS buffers x 4 KB, 1024-aligned
-  static constexpr int kOffBp = kOffOut + kEpiWarps * OUT_BUFS * kStageOutBytes;
+  static constexpr int kOffRes = kOffOut + kEpiWarps * OUT_BUFS * kStageOutBytes;   // RES: one residual chunk per epilogue warp
+  static constexpr int kOffBp = kOffRes + (RES ? kEpiWarps * kStageOutBytes : 0);
   static constexpr int kOffBias = kOffBp + STAGES * kBpTileBytes;    // [2][BLOCK_N] floats
   static constexpr int kOffBar = kOffBias + 2 * BLOCK_N * 4;
-  static constexpr int kNumBars = 4 * STAGES + 4;
+  static constexpr int kNumBars = 4 * STAGES + 4 + (RES ? kEpiWarps : 0);
   static constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
   static constexpr int kBytes = kOffTmemSlot + 16;
   static constexpr int kDynBytes = kBytes + 1024;                    // slack for the 1024-byte alignment
@@ -150,14 +152,19 @@ struct TailArgs {
 // OUT_BF16: output element type (0 = fp32, 1 = bf16); the epilogue moves 128 bytes of a row per chunk.
 // OUT_BUFS: staging buffers per epilogue warp; the TMA stores of up to OUT_BUFS-1 earlier chunks stay in flight
 // (the store-read latency, not the instruction count, bounds the output rate with only two).
+// TAIL = 2: the residual chunk ([32 rows x 128 B], the geometry of the output box) arrives by TMA in a per-warp staging buffer
+// instead of by per-lane row loads - a lane owns a ROW of the accumulator, so its own loads touch 32 different 128-byte lines per
+// instruction and thrash the little L1 that is left beside the operand ring.  The next chunk's residual is requested as soon
+// as this one sits in registers, the first one of a tile before the wait for the accumulator.  One staging buffer (OUT_BUFS = 1).
 template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS, int OUT_BUFS, int TAIL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bp,
                    const __grid_constant__ CUtensorMap map_out, const float* __restrict__ row_scale,
                    const float* __restrict__ alpha, int alpha_mode, const float* __restrict__ bias, int M, int NC,
-                   int KC, int dbg, const TailArgs tail) {
+                   int KC, int dbg, const TailArgs tail, const __grid_constant__ CUtensorMap map_res) {
   static_assert(TAIL == 0 || (MODE == kFwdI8 && OUT_BF16 == 0), "the fused module tail exists for the fp32 forward only");
-  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS, OUT_BUFS>;
+  static_assert(TAIL != 2 || OUT_BUFS == 1, "the TMA-fed tail walks one chunk at a time");
+  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS, OUT_BUFS, TAIL == 2>;
   constexpr int kElemsPerKBlock = MODE == kFwdI8 ? 128 : 64;
   constexpr int kChunkCols = OUT_BF16 ? 64 : 32;          // output columns per 128-byte chunk
   constexpr int kTileM = kBlockM * CTAS;
@@ -176,6 +183,7 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* empty_bar = bars + 3 * STAGES;        // MMAs that read the stage retired
   uint64_t* tmem_full_bar = bars + 4 * STAGES;    // [2] accumulator ready for the epilogue
   uint64_t* tmem_empty_bar = bars + 4 * STAGES + 2;   // [2] epilogue drained the accumulator (leader's barrier)
+  uint64_t* res_bar = bars + 4 * STAGES + 4;          // TAIL = 2: [kEpiWarps] residual chunk landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,6 +198,7 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_bp);
     tma_prefetch_desc(&map_out);
+    if (TAIL == 2) tma_prefetch_desc(&map_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -202,6 +211,8 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], kEpiWarps * CTAS);
     }
+    if (TAIL == 2)
+      for (int s = 0; s < kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -343,6 +354,7 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t swz = (lane & 7) << 4;
     const uint32_t tmem_empty_addr0 = CTAS == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
     uint32_t buf = 0;
+    uint32_t res_phase = 0;                                  // TAIL = 2: parity of this warp's residual barrier
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
@@ -363,8 +375,6 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       named_bar_sync(1, kEpiWarps * 32);
       const uint32_t bias_addr = sbase + L::kOffBias + as * BLOCK_N * 4;
-      mbar_wait(&tmem_full_bar[as], aphase);
-      tc_fence_after();
       // chunks are staged and stored in groups of G (one fence / commit per group, NG groups in flight); the two
       // warps of a lane quarter split the tile's chunks in halves
       constexpr int NG = OUT_BUFS >= 2 ? 2 : 1;
@@ -372,6 +382,12 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       constexpr int kChunks = BLOCK_N / kChunkCols;
       constexpr int kPerHalf = (kChunks + 1) / 2;
       const int c_begin = half * kPerHalf, c_end = min(kChunks, c_begin + kPerHalf);
+      if (TAIL == 2 && lane == 0 && row0 < M && n_blk * BLOCK_N + c_begin * kChunkCols < NC) {
+        mbar_expect_tx(&res_bar[ew], kStageOutBytes);         // the tile's first residual chunk flies while the MMAs finish
+        tma_load_2d(smem + L::kOffRes + ew * kStageOutBytes, &map_res, &res_bar[ew], n_blk * BLOCK_N + c_begin * kChunkCols, row0);
+      }
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
 #pragma unroll 1
       for (int c0 = c_begin; c0 < c_end; c0 += G) {
         if (n_blk * BLOCK_N + c0 * kChunkCols >= NC) break;  // warp-uniform
@@ -390,7 +406,25 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             // fused tail: the residual row segment (8 x 16 B, straight from HBM) is requested BEFORE the accumulator is read
             // from TMEM, so its latency overlaps the tcgen05.ld and the previous chunk's stores
             float4 res[TAIL ? 8 : 1];
-            if (TAIL) {
+            if (TAIL == 2) {
+              if (row0 < M) {                                      // warp-uniform: rows beyond M have no chunk in flight
+                mbar_wait(&res_bar[ew], res_phase);
+                res_phase ^= 1;
+                const uint32_t rbuf = sbase + L::kOffRes + ew * kStageOutBytes + out_row;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) res[j4] = lds128f(rbuf + ((j4 << 4) ^ swz));
+                fence_proxy_async_smem();                          // these reads before the next TMA write into the buffer
+                __syncwarp();
+                const int ncol0 = col0 + kChunkCols;
+                if (lane == 0 && c + 1 < c_end && ncol0 < NC) {
+                  mbar_expect_tx(&res_bar[ew], kStageOutBytes);
+                  tma_load_2d(smem + L::kOffRes + ew * kStageOutBytes, &map_res, &res_bar[ew], ncol0, row0);
+                }
+              } else {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) res[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            } else if (TAIL) {
               const float* rrow = tail.resid + static_cast<int64_t>(row) * NC + col0;
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4)
@@ -869,7 +903,13 @@ template <int MODE, int BLOCK_N, int STAGES, int OUT_BF16, int CTAS, int OUT_BUF
 static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_bp, const CUtensorMap& map_out,
                               const float* row_scale, const float* alpha, int alpha_mode, const float* bias, int M,
                               int NC, int KC, cudaStream_t st, const TailArgs& tail) {
-  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS, OUT_BUFS>;
+  using L = GemmSmem<MODE, BLOCK_N, STAGES, CTAS, OUT_BUFS, TAIL == 2>;
+  CUtensorMap map_res = map_out;                             // TAIL = 2: the residual has the geometry of the output
+  if (TAIL == 2) {
+    const int rc = make_map(&map_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, tail.resid, NC, M, (uint64_t)NC * 4, 32, 32,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != OB_OK) return rc;
+  }
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
   auto kern = gemm_expand_kernel<MODE, BLOCK_N, STAGES, OUT_BF16, CTAS, OUT_BUFS, TAIL>;
   static bool attr_set = false;
@@ -895,7 +935,7 @@ static int launch_gemm_expand(const CUtensorMap& map_a, const CUtensorMap& map_b
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC,
-                             g_dbg_kernel_flags, tail));
+                             g_dbg_kernel_flags, tail, map_res));
   count_launch();
   return OB_OK;
 }
@@ -932,6 +972,9 @@ static int dispatch_gemm_expand(const void* a, const uint8_t* packed, const floa
 #define OB_GEMM_ARGS map_a, map_bp, map_out, row_scale, alpha, alpha_mode, bias, M, NC, KC, st, tail
   if (cfg.ctas == 2) {
     if (bn == 256) {
+      // the fused module tail takes its residual by TMA on the 256-wide pair tiles (one staging buffer, four operand stages)
+      constexpr int kTail2 = TAIL ? 2 : 0;
+      if (TAIL && g_dbg_tail_tma) return launch_gemm_expand<MODE, 256, 4, OUT_BF16, 2, 1, kTail2>(OB_GEMM_ARGS);
       // long contractions want the deeper operand ring; short ones are output-bound and want double-buffered staging
       // (four staging buffers + two operand stages at K <= 256 measured no better: forward equal, grad_x 15-35 % slower)
       if (KC >= 1024) return launch_gemm_expand<MODE, 256, 5, OUT_BF16, 2, 1, TAIL>(OB_GEMM_ARGS);
@@ -1066,6 +1109,7 @@ extern "C" int ob_debug_set(int key, int value) {
     case kDbgF32Atm: f32_gemm_debug_atm(value); return OB_OK;
     case kDbgF32Promo: f32_gemm_debug_promo(value); return OB_OK;
     case kDbgPdl: set_pdl(value); return OB_OK;
+    case kDbgTailTma: g_dbg_tail_tma = value; return OB_OK;
     default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;
   }
 }

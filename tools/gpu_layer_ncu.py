@@ -2,9 +2,9 @@
 large GEMM (65536 x 2048 x 2048), behind a cache flush, for `ncu --set full`:
 
     ncu --set full --clock-control none --import-source on -k regex:'gemm_expand|dw_|bwd_prep|act_quant|ln_quant|gemv|swish_drop_quant' \
-        -o gpurun_out/r02_layer python tools/gpu_layer_ncu.py
-    ncu -i gpurun_out/r02_layer.ncu-rep --page raw --csv > gpurun_out/r02_layer_raw.csv
-    python tools/ncu_traffic.py gpurun_out/r02_layer_raw.csv r02_layer_kernels_ncu_full_raw.csv   # -> profiles/ncu_traffic.json
+        -o gpurun_out/r02b_layer python tools/gpu_layer_ncu.py
+    ncu -i gpurun_out/r02b_layer.ncu-rep --page raw --csv > gpurun_out/r02b_layer_raw.csv
+    python tools/ncu_traffic.py gpurun_out/r02b_layer_raw.csv   # per-kernel table + gpurun_out/ncu_kernel_summary.json
 """
 import os
 import sys
@@ -46,9 +46,8 @@ def run(M, K, N, big=False):
         y = obq.gemm_fwd(q, s, pk, a, layer.bias, N, torch.float32)
         flush.zero_()
         dys = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        qb = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
         colsum = torch.empty(lib.ob_bwd_colsum_blocks(M), N, device=dev)
-        lib.ob_bwd_prep(gy.data_ptr(), 0, s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(), qb.data_ptr(), colsum.data_ptr(), st)
+        lib.ob_bwd_prep(gy.data_ptr(), 0, s.data_ptr(), q.data_ptr(), M, N, K, dys.data_ptr(), None, colsum.data_ptr(), st)
         flush.zero_()
         dx = torch.empty(M, K, device=dev)
         lib.ob_bwd_dx(dys.data_ptr(), s.data_ptr(), pkt.data_ptr(), a.data_ptr(), 1, M, N, K, dx.data_ptr(), 0, st)
@@ -56,8 +55,8 @@ def run(M, K, N, big=False):
         gw, ga, gb = torch.empty(N, K, device=dev), torch.empty((), device=dev), torch.empty(N, device=dev)
         nbytes = lib.ob_bwd_dw_workspace_bytes(M, N, K)
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-        lib.ob_bwd_dw(dys.data_ptr(), qb.data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(), a.data_ptr(), 1, 2, M, N, K,
-                      gw.data_ptr(), ga.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, st)
+        lib.ob_bwd_dw_q8(dys.data_ptr(), q.data_ptr(), colsum.data_ptr(), layer.weight.data_ptr(), a.data_ptr(), 1, 2, M, N, K,
+                         gw.data_ptr(), ga.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, st)
         flush.zero_()
         # fused neighbours: tail epilogue (1024 -> 256 as lin2), swish-mode prep, swish+dropout quantiser
         layer2 = ob.QuantizedLinear(N, K).to(dev)
@@ -77,6 +76,7 @@ def run(M, K, N, big=False):
 
 
 run(25536, 256, 1024)
+run(76608, 256, 1024)          # the stacked step's row count (prep, grad_W) for the bench line's roofline.traffic
 run(65536, 2048, 2048, big=True)
 # small batch (GEMV-like regime): M = 1, 8, 64 at 256 -> 1024
 layer = ob.QuantizedLinear(256, 1024).to(dev)
