@@ -28,7 +28,7 @@ int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, co
 // debug / tuning knobs (ob_debug_set)
 // ---------------------------------------------------------------------------------------------
 enum DebugKey { kDbgSwapLboSbo = 1, kDbgForceBlockN = 2, kDbgForceSplits = 3, kDbgMaxCtas = 4, kDbgKernelFlags = 5,
-                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9, kDbgF32Atm = 11, kDbgF32Promo = 12, kDbgPdl = 13, kDbgTailTma = 14 };
+                kDbgF32SplitMode = 6, kDbgF32Epilogue = 7, kDbgF32Pair = 8, kDbgSmallM = 9, kDbgF32Atm = 11, kDbgPdl = 13, kDbgTailTma = 14 };
 int small_m_limit(int K);              // ob_gemv.cu
 int small_m_capacity(int K);
 int launch_gemv_tern_i8(const int8_t* q, const float* scale, const uint8_t* packed, const float* alpha, int alpha_mode,
@@ -38,7 +38,6 @@ void f32_gemm_debug(int split_mode);   // ob_gemm_f32.cu
 void f32_gemm_debug_epilogue(int mode);
 void f32_gemm_debug_pair(int on);
 void f32_gemm_debug_atm(int on);
-void f32_gemm_debug_promo(int v);
 static int g_dbg_kernel_flags = 0;   // bit0 skip TMA stores, bit1 skip epilogue math/STS, bit2 skip expansion (timing experiments)
 static int g_dbg_swap_lbo_sbo = 0;
 static int g_dbg_force_block_n = 0;
@@ -1107,7 +1106,6 @@ extern "C" int ob_debug_set(int key, int value) {
     case kDbgF32Pair: f32_gemm_debug_pair(value); return OB_OK;
     case kDbgSmallM: g_dbg_small_m = value; return OB_OK;
     case kDbgF32Atm: f32_gemm_debug_atm(value); return OB_OK;
-    case kDbgF32Promo: f32_gemm_debug_promo(value); return OB_OK;
     case kDbgPdl: set_pdl(value); return OB_OK;
     case kDbgTailTma: g_dbg_tail_tma = value; return OB_OK;
     default: set_error("ob_debug_set: unknown key %d", key); return OB_ERR_ARG;

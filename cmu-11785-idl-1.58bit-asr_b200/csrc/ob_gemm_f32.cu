@@ -529,8 +529,6 @@ struct F32Operand {
   int64_t ld, bs0, bs1;     // elements
 };
 
-static int g_f32_l2_promo = 1;       // 0 none, 1 128 B, 2 256 B (ob_debug_set key 12)
-void f32_gemm_debug_promo(int v) { g_f32_l2_promo = v; }
 // 4-D map over (contiguous axis, strided axis, inner batch, outer batch)
 static int make_map4(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, int64_t ld, int nb1, int64_t bs1,
                      int nb0, int64_t bs0, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
@@ -545,8 +543,8 @@ static int make_map4(CUtensorMap* map, const void* base, uint64_t inner, uint64_
                            has0 ? (cuuint64_t)bs0 * 4 : (cuuint64_t)ld * 4};
   cuuint32_t box[4] = {box_inner, box_outer, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUtensorMapL2promotion promo = g_f32_l2_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                      : (g_f32_l2_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  // (L2 promotion none / 128 B / 256 B measured identical on the attention products: tools/gpu_f32atm.py)
+  const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
