@@ -228,16 +228,19 @@ __global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restr
   const float* p = part + (int64_t)which * nblocks * C;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
-  float a0 = 0.f, a1 = 0.f;
+  // eight loads in flight per thread (the kernel is a chain of L2 round trips: with two it took 9.3 us for 1184 partial rows)
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < C) {
     int b = ry;
-    for (; b + 8 < nblocks; b += 16) {
-      a0 += p[(int64_t)b * C + c];
-      a1 += p[(int64_t)(b + 8) * C + c];
+    for (; b + 56 < nblocks; b += 64) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += __ldg(p + (int64_t)(b + 8 * u) * C + c);
     }
-    if (b < nblocks) a0 += p[(int64_t)b * C + c];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (b + 8 * u < nblocks) a[u] += __ldg(p + (int64_t)(b + 8 * u) * C + c);
   }
-  red[ry][cx] = a0 + a1;
+  red[ry][cx] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   __syncthreads();
   if (ry == 0 && c < C) {
     float t = 0.f;
