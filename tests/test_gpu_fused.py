@@ -50,10 +50,22 @@ def test_layernorm_quant_equals_layernorm_then_quant(ob, M, C):
 
 
 @pytest.mark.parametrize("p", [0.0, 0.1])
-@pytest.mark.parametrize("M,N,K,row_base", [(300, 256, 256, 0), (996, 256, 1024, 0), (513, 256, 256, 1400), (70, 192, 320, 64)])
-def test_gemm_tail_epilogue_equals_gemm_then_tail_kernel(ob, p, M, N, K, row_base):
+@pytest.mark.parametrize("M,N,K,row_base", [(300, 256, 256, 0), (996, 256, 1024, 0), (513, 256, 256, 1400), (70, 192, 320, 64),
+                                            (4100, 320, 512, 0), (5000, 256, 1024, 100)])
+@pytest.mark.parametrize("tile", [0, 1256])     # 0: the launcher's choice; 1256: the 256-wide CTA-pair tile, whose tail takes the residual by TMA
+def test_gemm_tail_epilogue_equals_gemm_then_tail_kernel(ob, p, M, N, K, row_base, tile):
     """out = x + scale * dropout(layer(q)) * frame_mask from the GEMM epilogue: same bits as the GEMM followed by the
     residual_dropout kernel on the rows [row_base, row_base + M) of a taller tensor, and the mask is the oracle's."""
+    from onebit_b200 import _cabi, quant as obq
+    lib = _cabi.lib
+    lib.ob_debug_set(_cabi.DBG_FORCE_BLOCK_N, tile)
+    try:
+        _tail_epilogue_case(ob, p, M, N, K, row_base)
+    finally:
+        lib.ob_debug_set(_cabi.DBG_FORCE_BLOCK_N, 0)
+
+
+def _tail_epilogue_case(ob, p, M, N, K, row_base):
     from onebit_b200 import _cabi, quant as obq
     lib = _cabi.lib
     g = torch.Generator().manual_seed(M + N + K)
