@@ -410,18 +410,19 @@ class _GroupedQuantLinearFn(torch.autograd.Function):
             g2 = g2.contiguous()
         gx = torch.empty((M, K), device=g2.device, dtype=gy.dtype) if need_x else None
         gw = ga = gb = None
-        if dw_reads_codes(K):
+        if dw_reads_codes(K):                              # one prep pass, one grad_W launch + finaliser over both groups
             gw, ga, gb = _grouped_backward_q8(g2, q, s, weight, alpha, pkt2, pkt1, ctx.rows2, gx, need_w or need_a,
                                               need_b and ctx.has_bias)
-        for r0, r1, pkt, bw in () if dw_reads_codes(K) else ((0, ctx.rows2, pkt2, 2), (ctx.rows2, M, pkt1, 1)):
-            if r1 <= r0:
-                continue
-            _, gw_g, ga_g, gb_g = _linear_backward(g2[r0:r1], q[r0:r1], s[r0:r1], weight, alpha, pkt, bw, need_x,
-                                                   need_w or need_a, need_b and ctx.has_bias,
-                                                   gx_out=None if gx is None else gx[r0:r1])
-            gw = gw_g if gw is None or gw_g is None else gw.add_(gw_g)
-            ga = ga_g if ga is None or ga_g is None else ga.add_(ga_g)
-            gb = gb_g if gb is None or gb_g is None else gb.add_(gb_g)
+        else:                                              # narrow layers: per group, parameter gradients added here
+            for r0, r1, pkt, bw in ((0, ctx.rows2, pkt2, 2), (ctx.rows2, M, pkt1, 1)):
+                if r1 <= r0:
+                    continue
+                _, gw_g, ga_g, gb_g = _linear_backward(g2[r0:r1], q[r0:r1], s[r0:r1], weight, alpha, pkt, bw, need_x,
+                                                       need_w or need_a, need_b and ctx.has_bias,
+                                                       gx_out=None if gx is None else gx[r0:r1])
+                gw = gw_g if gw is None or gw_g is None else gw.add_(gw_g)
+                ga = ga_g if ga is None or ga_g is None else ga.add_(ga_g)
+                gb = gb_g if gb is None or gb_g is None else gb.add_(gb_g)
         if need_x and ctx.pre is not None:                # back through dropout and swish
             h2 = ctx.saved_tensors[6]
             gh = torch.empty_like(h2)
