@@ -431,6 +431,13 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             uint32_t r[32];
             tmem_ld_32x32(taddr + h * 32, r);
+            // the chunk's bias slice is fetched while the accumulator is on its way (the shared-memory accessors are volatile:
+            // inside the store loop every load would wait behind the previous store)
+            float4 bvec[TAIL ? 1 : 8];                              // (the tail variants hold the residual chunk in those registers)
+            if (!TAIL) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) bvec[j4] = lds128f(bias_addr + (c * kChunkCols + h * 32 + j4 * 4) * 4);
+            }
             tmem_ld_wait();
             if (dbg & 2) continue;
             if (TAIL) {
@@ -463,7 +470,7 @@ gemm_expand_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b = lds128f(bias_addr + (c * kChunkCols + h * 32 + j4 * 4) * 4);
+              const float4 b = bvec[TAIL ? 0 : j4];
               float v0, v1, v2, v3;
               if (MODE == kFwdI8) {
                 // exact int32 -> fp32 for |acc| < 2^22 (|acc| <= 128 K, K <= 32768) with two full-rate ops
