@@ -21,8 +21,9 @@ v = torch.randn(B, T, W, device=dev, generator=g)
 out = torch.empty_like(v)
 hv = v.view(B, T, H, d).permute(0, 2, 1, 3)
 ho = out.view(B, T, H, d).permute(0, 2, 1, 3)
-lib.ob_debug_set(11, 0)
-for passes in (3, 1):
+for atm, passes in ((0, 3), (0, 1), (2, 3)):          # shared-memory operands, plain tf32, A through tensor memory
+    lib.ob_debug_set(11, atm)
     bmm_nt(p, hv.transpose(-1, -2), out=ho, passes=passes)
+lib.ob_debug_set(11, 1)
 torch.cuda.synchronize()
 print("done")
