@@ -47,6 +47,14 @@ def test_argument_validation_without_gpu():
     assert lib.ob_debug_set(999, 1) == _cabi.OB_ERR_ARG
     assert lib.ob_bwd_dw_workspace_bytes(1000, 256, 256) >= 256 * 256 * 4
     assert lib.ob_bwd_colsum_blocks(129) == (129 + 31) // 32
+    # grad_W from the int8 codes: argument checks come before the device is touched
+    dw8 = lambda **kw: lib.ob_bwd_dw_q8_groups(16, 16, None, 16, 16, 1, kw.get("rows2", 10), kw.get("M", 100), kw.get("N", 256),  # noqa: E731
+                                               kw.get("K", 256), 16, 16, kw.get("gb", None), kw.get("ws", 16), kw.get("ws_bytes", 1 << 30), None)
+    assert dw8(rows2=101) == _cabi.OB_ERR_ARG and "rows2" in _cabi.last_error()
+    assert dw8(rows2=-1) == _cabi.OB_ERR_ARG and dw8(K=100) == _cabi.OB_ERR_ARG and dw8(ws=None) == _cabi.OB_ERR_ARG
+    assert dw8(gb=16) == _cabi.OB_ERR_ARG and "colsum" in _cabi.last_error()                     # grad_bias without column sums
+    assert dw8(ws_bytes=64) == _cabi.OB_ERR_WORKSPACE
+    assert lib.ob_bwd_dw_q8(16, 16, None, 16, 16, 1, 3, 100, 256, 256, 16, 16, None, 16, 1 << 30, None) == _cabi.OB_ERR_ARG   # bitwidth
     # entry points around the layer: shapes and strides are checked before anything touches the device
     E = _cabi.OB_ERR_ARG
     gemm = lambda **kw: lib.ob_gemm_f32(16, 0, kw.get("lda", 64), 0, 0, 32, 0, 64, 0, 0, 48, kw.get("ldd", 64), 0, 0, None, 1.0, 0,  # noqa: E731
