@@ -23,6 +23,7 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
 int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, const float* W, const float* alpha, int alpha_mode,
                               int64_t n, int bw_a, int bw_b, float* grad_W, float* grad_alpha, float* alpha_parts,
                               const float* colsum, int n_col_blocks, int N, float* grad_bias, cudaStream_t st);
+int* dw_finalize_tickets(float* alpha_parts, int64_t n, int N, int with_bias, int* count);
 
 // ---------------------------------------------------------------------------------------------
 // debug / tuning knobs (ob_debug_set)
@@ -736,7 +737,8 @@ template <int STAGES>
 __global__ void __launch_bounds__(kDw2Threads, 1)
 dw_pair_kernel(const __grid_constant__ CUtensorMap map_dys_a, const __grid_constant__ CUtensorMap map_q_a,
                const __grid_constant__ CUtensorMap map_dys_b, const __grid_constant__ CUtensorMap map_q_b,
-               float* __restrict__ partials, int M_a, int M_b, int splits_a, int N, int K, int tb_per_split) {
+               float* __restrict__ partials, int M_a, int M_b, int splits_a, int N, int K, int tb_per_split,
+               int* __restrict__ fin_tickets, int n_fin_tickets) {
   using L = Dw2Smem<STAGES>;
   constexpr uint32_t kTmemCols = 256;
   constexpr uint32_t kIdesc = make_idesc(kCFmtF32, kFmtBF16, kFmtBF16, 1, 1, 256, 256);
@@ -787,6 +789,10 @@ dw_pair_kernel(const __grid_constant__ CUtensorMap map_dys_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_entry();       // everything above touched no global memory: it overlaps the previous kernel's tail
+  // the finaliser that follows this grid counts its blocks in these tickets: zeroed here instead of by a memset node
+  if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 3 && lane < n_fin_tickets) {
+    for (int i = lane; i < n_fin_tickets; i += 32) fin_tickets[i] = 0;
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1045,7 +1051,7 @@ static int max_pair_splits(int M, int N, int K) {
 
 static int launch_dw_pair(const CUtensorMap& map_dys_a, const CUtensorMap& map_q_a, const CUtensorMap& map_dys_b,
                           const CUtensorMap& map_q_b, float* partials, int M, int rows_a, int N, int K, const DwPairPlan& p,
-                          cudaStream_t st) {
+                          int* fin_tickets, int n_fin_tickets, cudaStream_t st) {
   constexpr int kStages = 5;
   using L = Dw2Smem<kStages>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget exceeded");
@@ -1069,7 +1075,7 @@ static int launch_dw_pair(const CUtensorMap& map_dys_a, const CUtensorMap& map_q
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   OB_CUDA(cudaLaunchKernelEx(&cfg, kern, map_dys_a, map_q_a, map_dys_b, map_q_b, partials, rows_a, M - rows_a, p.splits_a, N,
-                             K, p.tb_per_split));
+                             K, p.tb_per_split, fin_tickets, n_fin_tickets));
   count_launch();
   return OB_OK;
 }
@@ -1258,7 +1264,9 @@ static int bwd_dw_q8_groups(const char* who, const void* dys_bf16, const int8_t*
   if (rc != OB_OK) return rc;
   float* partials = static_cast<float*>(ws);
   float* alpha_parts = partials + (size_t)p.splits * N * K;
-  rc = launch_dw_pair(map_dys_a, map_q_a, map_dys_b, map_q_b, partials, M, rows2, N, K, p, st);
+  int n_tickets = 0;
+  int* tickets = dw_finalize_tickets(alpha_parts, (int64_t)N * K, N, grad_bias != nullptr, &n_tickets);
+  rc = launch_dw_pair(map_dys_a, map_q_a, map_dys_b, map_q_b, partials, M, rows2, N, K, p, tickets, n_tickets, st);
   if (rc != OB_OK) return rc;
   return launch_dw_finalize_groups(partials, p.splits_a, p.splits, W, alpha, alpha_mode, (int64_t)N * K, 2, 1, grad_W, grad_alpha,
                                    alpha_parts, colsum, ob_bwd_colsum_blocks(M), N, grad_bias, st);

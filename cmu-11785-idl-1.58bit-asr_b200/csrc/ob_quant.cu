@@ -363,6 +363,13 @@ __global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restric
     return a0;
   };
   const bool two = splits_a < splits;                                   // block-uniform
+  // the latent weights and alpha of the STE are requested before the partial sums (one memory round trip instead of two)
+  float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+  float a_eff = 1.f;
+  if (sl == 0) {
+    w = __ldg(reinterpret_cast<const float4*>(W + i));
+    a_eff = load_alpha_eff(alpha, alpha_mode);
+  }
   float4 a0 = lane_sum(0, splits_a), b0 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (two) b0 = lane_sum(splits_a, splits);
   if (sl > 0) {
@@ -377,8 +384,6 @@ __global__ void __launch_bounds__(256) dw_finalize_kernel(const float* __restric
       const float4 o = part[j][eg];
       a0.x += o.x; a0.y += o.y; a0.z += o.z; a0.w += o.w;
     }
-    const float a_eff = load_alpha_eff(alpha, alpha_mode);
-    const float4 w = __ldg(reinterpret_cast<const float4*>(W + i));
     float4 o;
     o.x = ste_elem(a0.x, w.x, a_eff, bw_a, acc);
     o.y = ste_elem(a0.y, w.y, a_eff, bw_a, acc);
@@ -926,6 +931,14 @@ int launch_ste_and_tail(const float* g_parts, int splits, const float* W, const 
 }
 
 // the fused finaliser over two groups of splits (any split count; n % 256 == 0 holds for N, K multiples of 64)
+// Where the finaliser's tickets live inside the workspace (behind the alpha partials and the column-sum chunk rows) and how
+// many there are: the grad_W GEMM kernel zeroes them itself (one thread, before its main loop), which saves a memset node per layer.
+int* dw_finalize_tickets(float* alpha_parts, int64_t n, int N, int with_bias, int* count) {
+  const int col_groups = with_bias ? (N + 31) / 32 : 0;
+  *count = 1 + col_groups;
+  return reinterpret_cast<int*>(alpha_parts + n / kFinBlockElems + (size_t)kTailRowChunks * N);
+}
+
 int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, const float* W, const float* alpha, int alpha_mode,
                               int64_t n, int bw_a, int bw_b, float* grad_W, float* grad_alpha, float* alpha_parts,
                               const float* colsum, int n_col_blocks, int N, float* grad_bias, cudaStream_t st) {
@@ -937,7 +950,7 @@ int launch_dw_finalize_groups(const float* g_parts, int splits_a, int splits, co
   const int col_groups = (grad_bias != nullptr) ? (N + 31) / 32 : 0;
   const int blocks = (int)(n / kFinBlockElems);
   float* tail_ws = alpha_parts + blocks;
-  OB_CUDA(cudaMemsetAsync(tail_ws + (size_t)kTailRowChunks * N, 0, (size_t)(1 + col_groups) * sizeof(int), st));
+  (void)col_groups;                                  // tickets zeroed by dw_pair_kernel (dw_finalize_tickets)
   launch_k((dw_finalize_kernel), dim3(blocks + col_groups * kTailRowChunks), dim3(256), 0, st, 
       g_parts, splits_a, splits, W, alpha, alpha_mode, n, bw_a, bw_b, grad_W, alpha_parts, blocks, grad_alpha, colsum,
       n_col_blocks, N, grad_bias, tail_ws);
