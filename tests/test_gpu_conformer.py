@@ -174,3 +174,40 @@ def test_packed_code_arena_equals_per_layer_packing():
     after, _ = layer.packed_weight(2)
     assert arena.repacks == 2 and not torch.equal(after, before)
     assert torch.equal(after, obq.pack_weight(layer.weight, layer.alpha, 2)[0])
+
+
+def test_programmatic_dependent_launch_changes_nothing(fx):
+    """Every kernel of the library is launched with programmatic stream serialization and waits (griddepcontrol.wait) before its
+    first access to global memory, so nothing may depend on it: three stacked co-training steps under dropout (counter-based
+    streams, deterministic reductions) give bit-identical losses and gradient norms with the attribute on and off
+    (ob_debug_set key 13).  A kernel reading its predecessor's output too early would show here."""
+    import onebit_b200 as ob
+    from onebit_b200._cabi import lib
+    from onebit_b200.training import StepConfig, cotraining_loss
+    cfg_model = dict(CFG, enc_dropout=0.1)
+
+    def run(pdl):
+        assert lib.ob_debug_set(13, pdl) == 0
+        torch.manual_seed(int(fx["seed"]))
+        model = ob.ConformerASR(**cfg_model).train().cuda()
+        model.use_packed_code_arena()
+        batch = {k: torch.from_numpy(fx[k]).cuda() for k in ("feats", "feat_lens", "tokens", "token_lens")}
+        batch["feat_lens_cpu"] = torch.from_numpy(fx["feat_lens"])
+        batch["token_lens_cpu"] = torch.from_numpy(fx["token_lens"])
+        opt = torch.optim.AdamW(model.parameters(), lr=float(fx["lr"]), betas=(0.9, 0.98), weight_decay=1e-2, fused=True)
+        cfg = StepConfig(share_frontend=True, stack_passes=True)
+        out = []
+        for spm in fx["sp_masks"][:3]:
+            opt.zero_grad()
+            loss, _ = cotraining_loss(model, batch, cfg, list(spm))
+            loss.backward()
+            total = torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=5.0)
+            opt.step()
+            out.append((loss.item(), total.item()))
+        return out
+
+    try:
+        on, off = run(1), run(0)
+    finally:
+        lib.ob_debug_set(13, 1)
+    assert on == off, (on, off)
