@@ -136,28 +136,32 @@ __global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const float* __rest
 // 16th tile, then the 16 results are folded.  grid: C / 64 blocks of 1024 threads.
 constexpr int kFinGroups = 16;
 
-__global__ void __launch_bounds__(64 * kFinGroups) bn_stats_finalize_kernel(const float* __restrict__ part, int B, int T, int C,
+// (16 channels x 64 tile groups per block: C / 16 blocks instead of C / 64 - with four blocks the kernel was a 20 us chain of
+// dependent fp64 adds on the critical path between the depthwise convolution and the normalisation)
+constexpr int kStatCh = 16, kStatGroups = 64;
+
+__global__ void __launch_bounds__(kStatCh * kStatGroups) bn_stats_finalize_kernel(const float* __restrict__ part, int B, int T, int C,
                                                                           float eps, float* __restrict__ mean,
                                                                           float* __restrict__ rstd) {
   pdl_entry();
   // total M2 = sum_tiles [ M2_tile + n_tile * (mean_tile - mean)^2 ]  (the pairwise Chan update, summed in closed form)
-  __shared__ double sh[kFinGroups][64];
-  const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cl;
+  __shared__ double sh[kStatGroups][kStatCh];
+  const int cl = threadIdx.x & (kStatCh - 1), grp = threadIdx.x / kStatCh;
+  const int c = blockIdx.x * kStatCh + cl;
   const int tblocks = (T + kCvT - 1) / kCvT, nblk = B * tblocks;
   const double n_tail = static_cast<double>(T - (tblocks - 1) * kCvT);
   double s = 0.0;
 #pragma unroll 4
-  for (int blk = grp; blk < nblk; blk += kFinGroups) s += part[static_cast<int64_t>(blk) * 2 * C + c];
+  for (int blk = grp; blk < nblk; blk += kStatGroups) s += part[static_cast<int64_t>(blk) * 2 * C + c];
   sh[grp][cl] = s;
   __syncthreads();
   double tot = 0.0;
-  for (int g = 0; g < kFinGroups; ++g) tot += sh[g][cl];
+  for (int g = 0; g < kStatGroups; ++g) tot += sh[g][cl];
   const double n = static_cast<double>(B) * T, mu = tot / n;
   __syncthreads();
   double m2 = 0.0;
 #pragma unroll 4
-  for (int blk = grp; blk < nblk; blk += kFinGroups) {
+  for (int blk = grp; blk < nblk; blk += kStatGroups) {
     const bool tail = (blk % tblocks) == tblocks - 1;
     const double nb = tail ? n_tail : static_cast<double>(kCvT);
     const double dm = part[static_cast<int64_t>(blk) * 2 * C + c] * (tail ? 1.0 / n_tail : 1.0 / kCvT) - mu;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(64 * kFinGroups) bn_stats_finalize_kernel(cons
   __syncthreads();
   if (grp == 0) {
     double v = 0.0;
-    for (int g = 0; g < kFinGroups; ++g) v += sh[g][cl];
+    for (int g = 0; g < kStatGroups; ++g) v += sh[g][cl];
     mean[c] = static_cast<float>(mu);
     rstd[c] = static_cast<float>(1.0 / sqrt(v / n + static_cast<double>(eps)));
   }
@@ -515,7 +519,7 @@ extern "C" int ob_glu_dwconv_bn_fwd(const float* a, const float* w, const float*
   OB_LAUNCH_CHECK("glu_dwconv_fwd_kernel");
   const int Bg = B / groups;
   for (int g = 0; g < groups; ++g) {                     // mean, rstd: [groups][C]
-    launch_k((bn_stats_finalize_kernel), dim3(C / 64), dim3(64 * kFinGroups), 0, st, part + static_cast<size_t>(g) * Bg * conv_tblocks(T) * 2 * C, Bg, T,
+    launch_k((bn_stats_finalize_kernel), dim3(C / kStatCh), dim3(kStatCh * kStatGroups), 0, st, part + static_cast<size_t>(g) * Bg * conv_tblocks(T) * 2 * C, Bg, T,
                                                                C, eps, mean + g * C, rstd + g * C);
     OB_LAUNCH_CHECK("bn_stats_finalize_kernel");
   }
