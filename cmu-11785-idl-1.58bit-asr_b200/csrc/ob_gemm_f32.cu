@@ -474,25 +474,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * 256) {
     const int row = static_cast<int>(i / n4), col = static_cast<int>(i % n4) * 4;
     if (col >= N) continue;
-    // four partial sums (four loads in flight), combined in fixed order: the chunk products of up to 75 splits are L2 round trips
-    float4 a4[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) a4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int s = 0;
-    for (; s + 3 < splits; s += 4) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(part + (static_cast<int64_t>(s + u) * M + row) * ldp + col));
-        a4[u].x += v.x, a4[u].y += v.y, a4[u].z += v.z, a4[u].w += v.w;
-      }
-    }
-    for (; s < splits; ++s) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(part + (static_cast<int64_t>(s) * M + row) * ldp + col));
-      a4[0].x += v.x, a4[0].y += v.y, a4[0].z += v.z, a4[0].w += v.w;
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
     }
-    float4 acc;
-    acc.x = (a4[0].x + a4[1].x) + (a4[2].x + a4[3].x), acc.y = (a4[0].y + a4[1].y) + (a4[2].y + a4[3].y);
-    acc.z = (a4[0].z + a4[1].z) + (a4[2].z + a4[3].z), acc.w = (a4[0].w + a4[1].w) + (a4[2].w + a4[3].w);
     float* dst = D + static_cast<int64_t>(row) * ldd + col;
     const float vs[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
